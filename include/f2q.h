@@ -1,0 +1,200 @@
+/*
+ * f2q.h — C-ABI of libf2q.so, the B200 (sm_100a) read -> feature -> count engine.
+ *
+ * This is the drop-in boundary for ONE path of 2FAST2Q (reference v2.8.1): everything that
+ * happens between "uncompressed FASTQ bytes" and "per-feature count vector + 5 read statistics".
+ * The reference has no FFI; its seam is the Python function
+ *     reads_counter(i, raw, features, param, reads_stats, preprocess)      fast2q/fast2q.py:514-582
+ * which drives fastq_parser (fast2q.py:306-409), sequence_tinder (:215-285), border_finder
+ * (:628-658), features_all_vs_all (:660-690) and mismatch_search_handler (:692-750).
+ * The Python host layer (2fast2q_b200/fast2q.py) mirrors reads_counter and calls the entry
+ * points below through ctypes.  Each entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; no C++/torch/Python types cross the boundary.
+ *   - every call returns F2Q_OK (0) or a negative F2Q_E* code; text via f2q_last_error().
+ *   - CUDA errors are sticky per context.  Nothing here ever falls back to a CPU implementation:
+ *     without a usable sm_100 device f2q_create fails with F2Q_ENODEVICE.
+ *   - a context = one GPU, one sample in flight, used from one thread at a time.
+ *   - the caller owns every host buffer; the library owns all device memory it allocates.
+ */
+#ifndef F2Q_H_
+#define F2Q_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define F2Q_ABI_VERSION 1
+
+#define F2Q_MAX_ITER   8    /* max comma items in --st / --us / --ds (search_iterations, fast2q.py:541,558) */
+#define F2Q_MAX_DELIM  64   /* max bytes of one --us / --ds search sequence */
+
+/* error codes */
+#define F2Q_OK            0
+#define F2Q_EINVAL       -1  /* bad argument / configuration the reference would FATAL on (fast2q.py:555-556) */
+#define F2Q_ENOMEM       -2
+#define F2Q_ECUDA        -3  /* CUDA runtime/driver error (sticky) */
+#define F2Q_ESTATE       -4  /* call out of order (e.g. submit before begin_sample) */
+#define F2Q_EUNSUPPORTED -5  /* input outside what the device path implements; never silently approximated */
+#define F2Q_ETOOLONG     -6  /* one FASTQ record longer than the carry buffer (see f2q_set_option) */
+#define F2Q_ENODEVICE    -7  /* no CUDA device of compute capability 10.x */
+#define F2Q_EINTERNAL    -8  /* device-side invariant violated (reported, never ignored) */
+
+/* running mode: fast2q.py:1294-1297 ('C' / 'EC') */
+#define F2Q_MODE_COUNT          0
+#define F2Q_MODE_EXTRACT_COUNT  1
+
+/*
+ * Parameters of the hot path — the subset of the reference's `param` dict that fastq_parser,
+ * sequence_tinder and reads_counter read (fast2q.py:538-558, 1112-1129, 1246-1309).
+ * Values are the RAW command-line integers; clamping (ph<=0 -> 1, fast2q.py:1118-1125) and the
+ * fail-set construction (fast2q.py:1127-1129) happen inside the library exactly as in the reference.
+ * Fixed mode (has_up==0 && has_down==0): n_iter = number of --st items, starts[] = those ints.
+ * Delimiter mode: n_iter = max(#up, #down) (fast2q.py:558); up/down hold the UPPER-CASED search
+ * sequences (fast2q.py:547,550); when both are given their counts must match (fast2q.py:553-556).
+ */
+typedef struct f2q_config {
+    int32_t mode;        /* F2Q_MODE_* */
+    int32_t miss;        /* --m   mismatches allowed per feature (Counter mode only) */
+    int32_t phred;       /* --ph  */
+    int32_t qual_up;     /* --qsu */
+    int32_t qual_down;   /* --qsd */
+    int32_t miss_up;     /* --msu */
+    int32_t miss_down;   /* --msd */
+    int32_t length;      /* --l   */
+    int32_t n_iter;      /* search_iterations */
+    int32_t has_up;      /* --us given */
+    int32_t has_down;    /* --ds given */
+    int32_t starts[F2Q_MAX_ITER];     /* --st items (fixed mode) */
+    int32_t up_len[F2Q_MAX_ITER];
+    int32_t down_len[F2Q_MAX_ITER];
+    uint8_t up[F2Q_MAX_ITER][F2Q_MAX_DELIM];
+    uint8_t down[F2Q_MAX_ITER][F2Q_MAX_DELIM];
+} f2q_config;
+
+/* order of the five per-sample statistics (local_read_stats, fast2q.py:310-316) */
+#define F2Q_STAT_READS           0
+#define F2Q_STAT_PERFECT         1
+#define F2Q_STAT_IMPERFECT       2
+#define F2Q_STAT_NON_ALIGNED     3
+#define F2Q_STAT_QUALITY_FAILED  4
+#define F2Q_N_STATS              5
+
+typedef struct f2q_ctx f2q_ctx;
+
+/* ---- library / device ------------------------------------------------------------------- */
+int f2q_abi_version(void);
+/* number of usable devices (compute capability 10.x); 0 when there is none, never an error */
+int f2q_device_count(void);
+
+/*
+ * Create a context on `device`.  `stream` is a cudaStream_t the work is enqueued on (so a caller can
+ * bracket it with its own events) or NULL for a library-owned stream.
+ * Replaces: the per-call parameter derivation of reads_counter (fast2q.py:536-558).
+ */
+int f2q_create(const f2q_config* cfg, int device, void* stream, f2q_ctx** out);
+void f2q_destroy(f2q_ctx* ctx);
+const char* f2q_last_error(const f2q_ctx* ctx);   /* ctx may be NULL: last create-time error */
+
+/* tunables; must be set before the first f2q_begin_sample.  Unknown names -> F2Q_EINVAL.
+ *   "carry_bytes"     max bytes of one partial FASTQ record carried between submits (default 4 MiB)
+ *   "stage_bytes"     size of each internal pinned/device staging slot used by f2q_submit (default 64 MiB)
+ *   "stage_slots"     number of staging slots (default 3)
+ *   "resolver"        0 auto | 1 Hamming-1 neighbour probing | 2 pigeonhole seed index | 3 library tile scan
+ *   "queue_entries"   capacity of the deferred non-exact key queue (default: derived from stage_bytes)
+ */
+int f2q_set_option(f2q_ctx* ctx, const char* name, int64_t value);
+
+/*
+ * Counter mode library = the keys of the dict built by features_loader (fast2q.py:125-186), i.e. the
+ * upper-cased, space-stripped sequences, in file order, duplicates already removed.
+ * key i = key_bytes[key_offsets[i] .. key_offsets[i+1]).  Keys may contain any bytes (':' for
+ * multi-feature entries).  Builds the device tables that replace binary_converter (fast2q.py:188-213).
+ */
+int f2q_set_library(f2q_ctx* ctx, const uint8_t* key_bytes, const uint64_t* key_offsets, uint32_t n_keys);
+
+/* ---- one sample (= one FASTQ stream) ------------------------------------------------------ */
+/* zero the count vector / statistics / carried state.  Replaces the per-file entry of reads_counter. */
+int f2q_begin_sample(f2q_ctx* ctx);
+
+/*
+ * Feed the next `nbytes` of the UNCOMPRESSED stream, in file order, from HOST memory.  Chunks may cut
+ * records anywhere; the context carries the partial record (fast2q.py:324-328 — a record is every four
+ * '\n'-separated lines counted from byte 0).  The copy is staged through internal pinned slots and is
+ * asynchronous when host_chunk itself is pinned (f2q_host_alloc); the call may block until a slot frees.
+ * is_last != 0 marks end of stream (a final unterminated 4th line still completes a record).
+ */
+int f2q_submit(f2q_ctx* ctx, const uint8_t* host_chunk, uint64_t nbytes, int is_last);
+
+/* Same, but the chunk already lives in device memory of this context's GPU (resident mode).  The buffer
+ * must stay valid and unmodified until the next f2q_end_sample/f2q_sync returns. */
+int f2q_submit_device(f2q_ctx* ctx, const void* dptr, uint64_t nbytes, int is_last);
+
+/* block until everything submitted so far has been consumed (device buffers may be reused after) */
+int f2q_sync(f2q_ctx* ctx);
+
+/*
+ * Finish the sample: waits, then writes counts[n_keys] (Counter mode; may be NULL in EC mode) and the
+ * five statistics.  Replaces the return value of fastq_parser (fast2q.py:409).
+ * If the stream was never closed with is_last the carried partial record is dropped, exactly as the
+ * reference drops 1–3 left-over lines.
+ */
+int f2q_end_sample(f2q_ctx* ctx, uint64_t* counts, uint64_t stats[F2Q_N_STATS]);
+
+/* device address of the uint64 vector [counts[n_keys] | stats[5]] of the current sample, valid after
+ * the work was enqueued; for an in-place NCCL all-reduce over ranks (merge_feature_dicts,
+ * fast2q.py:439-445, 487-495).  After a reduce call f2q_end_sample as usual. */
+int f2q_result_device(f2q_ctx* ctx, void** dptr, uint64_t* n_words);
+
+/* ---- Extract + Count mode (fast2q.py:382-387) -------------------------------------------- */
+/* number of distinct keys and total key bytes of the current sample (synchronises) */
+int f2q_ec_size(f2q_ctx* ctx, uint64_t* n_keys, uint64_t* key_bytes);
+/* copy out keys (concatenated), offsets[n_keys+1] and counts[n_keys]; order unspecified */
+int f2q_ec_drain(f2q_ctx* ctx, uint8_t* key_bytes, uint64_t* key_offsets, uint64_t* counts);
+
+/* ---- pinned host memory for f2q_submit ------------------------------------------------------ */
+int f2q_host_alloc(void** ptr, uint64_t nbytes);
+int f2q_host_free(void* ptr);
+
+/* ---- primitives with public reference counterparts (README.md:259-298; tests/test_mainfunctions.py) ----
+ * Device implementations of border_finder (fast2q.py:628-658) and sequence_tinder (:215-285) run on one
+ * read; used by the host-side helpers of the same names and by the known-answer tests.
+ * f2q_border_finder: returns F2Q_OK and *pos = first index >= start_place with <= mismatch mismatches, or -1.
+ * f2q_sequence_tinder: *start/*end = trimmed window, or found=0 for the reference's (None, None).
+ */
+int f2q_border_finder(f2q_ctx* ctx, const uint8_t* seq, uint32_t seq_len, const uint8_t* read, uint32_t read_len,
+                      int32_t mismatch, int32_t start_place, int32_t* pos);
+int f2q_sequence_tinder(f2q_ctx* ctx, int32_t iteration, const uint8_t* read, uint32_t read_len,
+                        const uint8_t* qual, uint32_t qual_len, int32_t* found, int32_t* start, int32_t* end);
+
+/* ---- synthetic FASTQ generator K0 (bench/tests only) -------------------------- */
+typedef struct f2q_synth_spec {
+    uint64_t seed;
+    uint64_t first_read;     /* global index of the first read to generate */
+    uint64_t n_reads;
+    uint32_t read_len;       /* L; record = 2L+18 bytes */
+    uint32_t feat_len;       /* guide length placed at read offset 0 */
+    uint32_t n_guides;
+    /* cumulative class thresholds out of 65536: exact | 1 sub | 2 sub | 3 sub | one N | (rest = random) */
+    uint32_t cum_exact, cum_sub1, cum_sub2, cum_sub3, cum_n;
+    uint32_t lowq_per_65536; /* fraction of reads that get one low-quality byte */
+} f2q_synth_spec;
+/* writes n_reads*(2L+18) bytes at dptr (device); guides = n_guides*feat_len ASCII bytes on the HOST */
+int f2q_synth_fastq(f2q_ctx* ctx, const f2q_synth_spec* spec, const uint8_t* guides, void* dptr);
+
+/* device memory helpers so that a non-CUDA host language can hold resident chunks */
+int f2q_device_alloc(f2q_ctx* ctx, void** dptr, uint64_t nbytes);
+int f2q_device_free(f2q_ctx* ctx, void* dptr);
+int f2q_memcpy_d2h(f2q_ctx* ctx, void* host, const void* dptr, uint64_t nbytes);
+int f2q_memcpy_h2d(f2q_ctx* ctx, void* dptr, const void* host, uint64_t nbytes);
+
+/* number of kernel launches issued by this context so far (bench.py reports it as gpu_launches) */
+uint64_t f2q_launch_count(const f2q_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* F2Q_H_ */
