@@ -1,0 +1,725 @@
+// f2q_api.cu — C-ABI of libf2q.so (include/f2q.h): contexts, library tables, streaming submits.
+// Host code only orchestrates: every byte of FASTQ is parsed by the kernels in tile.cuh / generic.cuh /
+// resolve.cuh.  There is no CPU implementation of the path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "f2q_dev.cuh"
+#include "generic.cuh"
+#include "resolve.cuh"
+#include "stream.cuh"
+#include "tile.cuh"
+
+using namespace f2q;
+
+#define F2Q_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+std::mutex g_err_mu;
+std::string g_create_err;
+
+struct DevBuf {
+    void* p = nullptr; size_t n = 0;
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct f2q_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0;
+    f2q_config cfg{};
+    GenericCfg hG{};
+    GenericCfg* dG = nullptr;
+    int policy = POLICY_GENERIC;
+    int resolver = 0;                 // 0 auto, 1 probe, 2 seed, 3 scan
+    // library
+    bool lib_set = false;
+    uint32_t n_keys = 0;
+    LibTables T{};
+    std::vector<DevBuf> lib_bufs;
+    // results: [counts n_keys | stats 5]
+    DevBuf result;
+    uint32_t* d_error = nullptr;
+    DevState* dS = nullptr;
+    uint32_t* d_tickets = nullptr;
+    // streaming
+    uint64_t carry_cap = 4ull << 20;
+    DevBuf carry, status, status_stitch, queue, gqueue;
+    uint32_t q_cap = 0, g_cap = 0;
+    int64_t opt_queue_entries = 0;
+    // staging for host submits
+    uint64_t stage_bytes = 64ull << 20;
+    int stage_slots = 3;
+    std::vector<uint8_t*> d_stage;
+    std::vector<cudaEvent_t> ev_copied, ev_free;
+    int next_slot = 0;
+    // EC
+    EcTable E{};
+    DevBuf ec_slots, ec_counts, ec_arena, ec_meta;   // meta: [arena_used, n_keys]
+    uint64_t ec_cap = 0;
+    std::vector<uint64_t> ec_drain_off, ec_drain_cnt; std::vector<uint8_t> ec_drain_keys; bool ec_drained = false;
+    // state
+    bool in_sample = false, closed = false;
+    int sticky = F2Q_OK;
+    std::string err;
+    uint64_t launches = 0;
+    int tile_blocks[2] = {0, 0};
+};
+
+namespace {
+
+int fail(f2q_ctx* c, int code, const std::string& msg) {
+    if (c) { c->err = msg; if (code == F2Q_ECUDA) c->sticky = code; }
+    else { std::lock_guard<std::mutex> l(g_err_mu); g_create_err = msg; }
+    return code;
+}
+
+#define CU(ctx, call)                                                                                      \
+    do {                                                                                                   \
+        cudaError_t e__ = (call);                                                                          \
+        if (e__ != cudaSuccess)                                                                            \
+            return fail(ctx, F2Q_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));              \
+    } while (0)
+
+int dev_alloc(f2q_ctx* c, DevBuf& b, size_t n) {
+    if (b.n >= n && b.p) return F2Q_OK;
+    b.release();
+    cudaError_t e = cudaMalloc(&b.p, n ? n : 16);
+    if (e != cudaSuccess) return fail(c, e == cudaErrorMemoryAllocation ? F2Q_ENOMEM : F2Q_ECUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    b.n = n ? n : 16;
+    return F2Q_OK;
+}
+
+// largest failing byte of the fail set built at fast2q.py:1112-1129 (0 = empty set)
+int fail_max(int ph) {
+    if (ph <= 0) ph = 1;
+    int n = std::min(ph - 1, 94);
+    return n == 0 ? 0 : 33 + n - 1;
+}
+
+ByteSet fail_set(int ph) {
+    ByteSet s{{0, 0, 0, 0}};
+    int fm = fail_max(ph);
+    for (int b = 33; b <= fm; b++) s.w[b >> 6] |= 1ull << (b & 63);
+    return s;
+}
+
+int make_generic_cfg(const f2q_config* cfg, GenericCfg& G, std::string& why) {
+    if (cfg->n_iter < 1 || cfg->n_iter > F2Q_MAX_ITER) { why = "n_iter out of range"; return F2Q_EINVAL; }
+    if (cfg->mode != F2Q_MODE_COUNT && cfg->mode != F2Q_MODE_EXTRACT_COUNT) { why = "unknown mode"; return F2Q_EINVAL; }
+    memset(&G, 0, sizeof(G));
+    DevCfg& d = G.c;
+    d.mode = cfg->mode; d.miss = cfg->miss; d.length = cfg->length; d.n_iter = cfg->n_iter;
+    d.has_up = cfg->has_up != 0; d.has_down = cfg->has_down != 0; d.miss_up = cfg->miss_up; d.miss_down = cfg->miss_down;
+    d.fmax_ph = fail_max(cfg->phred); d.fmax_up = fail_max(cfg->qual_up); d.fmax_down = fail_max(cfg->qual_down);
+    for (int i = 0; i < F2Q_MAX_ITER; i++) {
+        d.starts[i] = cfg->starts[i];
+        d.up_len[i] = cfg->up_len[i]; d.down_len[i] = cfg->down_len[i];
+        if (d.up_len[i] < 0 || d.up_len[i] > F2Q_MAX_DELIM || d.down_len[i] < 0 || d.down_len[i] > F2Q_MAX_DELIM) {
+            why = "search sequence length out of range"; return F2Q_EINVAL;
+        }
+        memcpy(d.up[i], cfg->up[i], F2Q_MAX_DELIM); memcpy(d.down[i], cfg->down[i], F2Q_MAX_DELIM);
+    }
+    G.set_ph = fail_set(cfg->phred); G.set_up = fail_set(cfg->qual_up); G.set_down = fail_set(cfg->qual_down);
+    return F2Q_OK;
+}
+
+bool packable(const uint8_t* k, size_t n, uint64_t& key) {
+    if (n > 32) return false;
+    key = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint8_t ch = k[i];
+        if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') return false;
+        key |= (uint64_t)((ch >> 1) & 3) << (2 * i);
+    }
+    return true;
+}
+
+template <class Tv>
+int upload(f2q_ctx* c, const std::vector<Tv>& v, const Tv** out) {
+    c->lib_bufs.emplace_back();
+    DevBuf& b = c->lib_bufs.back();
+    int rc = dev_alloc(c, b, std::max<size_t>(v.size(), 1) * sizeof(Tv));
+    if (rc) return rc;
+    if (!v.empty()) CU(c, cudaMemcpy(b.p, v.data(), v.size() * sizeof(Tv), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const Tv*>(b.p);
+    return F2Q_OK;
+}
+
+uint32_t pow2_at_least(uint64_t n) { uint64_t p = 16; while (p < n) p <<= 1; return (uint32_t)p; }
+
+void decide_policy(f2q_ctx* c) {
+    const f2q_config& g = c->cfg;
+    c->policy = POLICY_GENERIC;
+    if (g.mode == F2Q_MODE_COUNT && !g.has_up && !g.has_down && g.n_iter == 1 && g.length >= 0 && g.length <= 32) c->policy = POLICY_FAST1;
+}
+
+template <int POLICY>
+int launch_tile(f2q_ctx* c, const TileParams& P, Outputs O, uint64_t n_tiles_upper) {
+    const bool hist = (POLICY == POLICY_FAST1) && c->n_keys > 0 && c->n_keys <= 8192;
+    TileParams p = P; p.hist_smem = hist;
+    const size_t smem = tile_smem_bytes(hist ? c->n_keys : 0);
+    int& blocks_per_sm = c->tile_blocks[POLICY];
+    if (blocks_per_sm == 0) {
+        CU(c, cudaFuncSetAttribute(k_tile<POLICY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tile_smem_bytes(8192))));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_tile<POLICY>, TILE_THREADS, smem));
+        if (blocks_per_sm < 1) return fail(c, F2Q_EINTERNAL, "tile kernel does not fit on an SM");
+    }
+    uint64_t grid = (uint64_t)c->sm_count * blocks_per_sm;
+    grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, n_tiles_upper));
+    k_tile<POLICY><<<(unsigned)grid, TILE_THREADS, smem, c->stream>>>(p, c->dG, c->T, c->E, O);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return F2Q_OK;
+}
+
+Outputs outputs_of(f2q_ctx* c) {
+    Outputs O;
+    O.counts = reinterpret_cast<unsigned long long*>(c->result.p);
+    O.stats = O.counts + c->n_keys;
+    O.error = c->d_error;
+    return O;
+}
+
+// grow the Extract+Count table so that `extra` more distinct keys and `extra_bytes` more key bytes fit
+int ec_reserve(f2q_ctx* c, uint64_t extra, uint64_t extra_bytes) {
+    unsigned long long meta[2] = {0, 0};
+    if (c->ec_meta.p) {
+        CU(c, cudaStreamSynchronize(c->stream));
+        CU(c, cudaMemcpy(meta, c->ec_meta.p, sizeof(meta), cudaMemcpyDeviceToHost));
+    } else {
+        int rc = dev_alloc(c, c->ec_meta, sizeof(meta));
+        if (rc) return rc;
+        CU(c, cudaMemset(c->ec_meta.p, 0, sizeof(meta)));
+    }
+    const uint64_t need_slots = 2 * (meta[1] + extra) + 1024, need_arena = meta[0] + extra_bytes + 1024;
+    if (need_arena > c->ec_arena.n) {
+        DevBuf nb; nb.p = nullptr;
+        size_t sz = std::max<size_t>(need_arena, c->ec_arena.n * 2);
+        cudaError_t e = cudaMalloc(&nb.p, sz);
+        if (e != cudaSuccess) return fail(c, F2Q_ENOMEM, "Extract+Count key arena: out of device memory");
+        nb.n = sz;
+        if (c->ec_arena.p && meta[0]) CU(c, cudaMemcpy(nb.p, c->ec_arena.p, meta[0], cudaMemcpyDeviceToDevice));
+        c->ec_arena.release(); c->ec_arena = nb;
+    }
+    if (need_slots > c->ec_cap) {
+        uint64_t cap = 1 << 16; while (cap < need_slots) cap <<= 1;
+        // rehash through the host: the table is small next to the FASTQ stream and growth is geometric
+        std::vector<unsigned long long> hs, hc;
+        std::vector<uint8_t> ar;
+        const uint64_t old = c->ec_cap;
+        if (old && meta[1]) {
+            hs.resize(old); hc.resize(old); ar.resize(meta[0] + 1);
+            CU(c, cudaMemcpy(hs.data(), c->ec_slots.p, old * 8, cudaMemcpyDeviceToHost));
+            CU(c, cudaMemcpy(hc.data(), c->ec_counts.p, old * 8, cudaMemcpyDeviceToHost));
+            if (meta[0]) CU(c, cudaMemcpy(ar.data(), c->ec_arena.p, meta[0], cudaMemcpyDeviceToHost));
+        }
+        c->ec_slots.release(); c->ec_counts.release();
+        int rc = dev_alloc(c, c->ec_slots, cap * 8); if (rc) return rc;
+        rc = dev_alloc(c, c->ec_counts, cap * 8); if (rc) return rc;
+        std::vector<unsigned long long> ns(cap, 0), nc(cap, 0);
+        for (uint64_t i = 0; i < old && meta[1]; i++) {
+            if (!hs[i]) continue;
+            const uint64_t off = (hs[i] - 1) >> 24, len = (hs[i] - 1) & 0xFFFFFF;
+            uint32_t h = FNV_INIT;
+            for (uint64_t k = 0; k < len; k++) h = fnv_step(h, ar[off + k]);
+            uint64_t j = (uint64_t)fnv_final(h) * 0x9E3779B1ull; j = (j ^ (j >> 29)) & (cap - 1);
+            while (ns[j]) j = (j + 1) & (cap - 1);
+            ns[j] = hs[i]; nc[j] = hc[i];
+        }
+        CU(c, cudaMemcpy(c->ec_slots.p, ns.data(), cap * 8, cudaMemcpyHostToDevice));
+        CU(c, cudaMemcpy(c->ec_counts.p, nc.data(), cap * 8, cudaMemcpyHostToDevice));
+        c->ec_cap = cap;
+    }
+    c->E.slots = reinterpret_cast<unsigned long long*>(c->ec_slots.p);
+    c->E.counts = reinterpret_cast<unsigned long long*>(c->ec_counts.p);
+    c->E.mask = c->ec_cap - 1;
+    c->E.arena = reinterpret_cast<uint8_t*>(c->ec_arena.p);
+    c->E.arena_cap = c->ec_arena.n;
+    c->E.arena_used = reinterpret_cast<unsigned long long*>(c->ec_meta.p);
+    c->E.n_keys = c->E.arena_used + 1;
+    return F2Q_OK;
+}
+
+// enqueue everything for one chunk that already sits in device memory at dptr[0, n)
+int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_last) {
+    const uint64_t addr = reinterpret_cast<uint64_t>(dptr);
+    const uint64_t delta = n ? (addr & 127ull) : 0;
+    const uint8_t* base = n ? reinterpret_cast<const uint8_t*>(addr - delta) : reinterpret_cast<const uint8_t*>(c->carry.p);
+    const uint64_t n_tiles = (delta + n) / OWN_BYTES + 2;
+    const uint64_t stitch_tiles = c->carry_cap / OWN_BYTES + 2;
+    int rc;
+    if ((rc = dev_alloc(c, c->status, n_tiles * 4))) return rc;
+    // queues sized for the chunk: one entry per 64 bytes covers every non-exact read of ordinary FASTQ; anything
+    // beyond that is resolved in place by the tile kernel, so capacity never changes results
+    uint64_t want_q = c->opt_queue_entries > 0 ? (uint64_t)c->opt_queue_entries : std::max<uint64_t>(1 << 16, n / 64 + 1024);
+    want_q = std::min<uint64_t>(want_q, 0x7FFFFFFFull);
+    if (c->policy == POLICY_GENERIC) want_q = 16;
+    if (want_q > c->q_cap) { if ((rc = dev_alloc(c, c->queue, want_q * sizeof(QEntry)))) return rc; c->q_cap = (uint32_t)want_q; }
+    uint64_t want_g = c->policy == POLICY_GENERIC ? 16 : std::max<uint64_t>(1 << 14, want_q / 8);
+    if (want_g > c->g_cap) { if ((rc = dev_alloc(c, c->gqueue, want_g * sizeof(GEntry)))) return rc; c->g_cap = (uint32_t)want_g; }
+    if (c->cfg.mode == F2Q_MODE_EXTRACT_COUNT) {
+        // worst case every record is 4 bytes and every key is new; key bytes are bounded by n_iter * stream bytes
+        if ((rc = ec_reserve(c, (n + c->carry_cap) / 4 + 16, (uint64_t)c->cfg.n_iter * (n + c->carry_cap) + 64))) return rc;
+    }
+
+    CU(c, cudaMemsetAsync(c->status.p, 0, n_tiles * 4, c->stream));
+    CU(c, cudaMemsetAsync(c->status_stitch.p, 0, stitch_tiles * 4, c->stream));
+    k_prepare<<<1, PREP_THREADS, 0, c->stream>>>(c->dS, base, delta, n, is_last ? 1u : 0u, reinterpret_cast<uint8_t*>(c->carry.p),
+                                                 c->carry_cap, c->d_tickets, c->q_cap, c->g_cap);
+    c->launches++;
+    Outputs O = outputs_of(c);
+    TileParams P{};
+    P.S = c->dS; P.queue = reinterpret_cast<QEntry*>(c->queue.p); P.gqueue = reinterpret_cast<GEntry*>(c->gqueue.p);
+    // 1. the record stitched from the carried tail and the head of this chunk (lives in the carry buffer)
+    P.buf = reinterpret_cast<const uint8_t*>(c->carry.p); P.status = reinterpret_cast<uint32_t*>(c->status_stitch.p);
+    P.ticket = c->d_tickets; P.stitch = 1;
+    rc = c->policy == POLICY_FAST1 ? launch_tile<POLICY_FAST1>(c, P, O, 4) : launch_tile<POLICY_GENERIC>(c, P, O, 4);
+    if (rc) return rc;
+    // 2. the chunk itself
+    if (n) {
+        P.buf = base; P.status = reinterpret_cast<uint32_t*>(c->status.p); P.ticket = c->d_tickets + 1; P.stitch = 0;
+        rc = c->policy == POLICY_FAST1 ? launch_tile<POLICY_FAST1>(c, P, O, n_tiles) : launch_tile<POLICY_GENERIC>(c, P, O, n_tiles);
+        if (rc) return rc;
+    }
+    // 3. deferred work
+    if (c->policy == POLICY_FAST1) {
+        if (c->cfg.miss > 0) {
+            int res = c->resolver ? c->resolver : (c->cfg.miss == 1 ? 1 : 3);
+            if (res == 1 && c->cfg.miss != 1) res = 3;
+            if (res == 2) res = 3;    // TODO(seed index): falls back to the exact tile scan
+            const unsigned grid = (unsigned)c->sm_count * 4;
+            if (res == 1) k_resolve_probe<<<grid, 256, 0, c->stream>>>(c->T, P.queue, c->dS, O.counts, O.stats);
+            else k_resolve_scan<<<grid, SCAN_THREADS, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, c->dS, O.counts, O.stats);
+            c->launches++;
+        }
+        k_generic_queue<<<(unsigned)c->sm_count, 128, 0, c->stream>>>(c->dG, c->T, c->E, O, P.gqueue, c->dS);
+        c->launches++;
+    }
+    // 4. carry the new partial record
+    k_carry<<<1, PREP_THREADS, 0, c->stream>>>(c->dS, base, reinterpret_cast<uint8_t*>(c->carry.p), c->carry_cap);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    if (is_last) c->closed = true;
+    return F2Q_OK;
+}
+
+int ensure_staging(f2q_ctx* c) {
+    if (!c->d_stage.empty()) return F2Q_OK;
+    CU(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < c->stage_slots; i++) {
+        uint8_t* p = nullptr;
+        cudaError_t e = cudaMalloc(&p, c->stage_bytes + 256);
+        if (e != cudaSuccess) return fail(c, F2Q_ENOMEM, "staging slot: out of device memory");
+        c->d_stage.push_back(p);
+        cudaEvent_t a, b;
+        CU(c, cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CU(c, cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        c->ev_copied.push_back(a); c->ev_free.push_back(b);
+    }
+    return F2Q_OK;
+}
+
+int check_ctx(f2q_ctx* c) {
+    if (!c) return F2Q_EINVAL;
+    if (c->sticky) return c->sticky;
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(c, F2Q_ECUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return F2Q_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+F2Q_EXPORT int f2q_abi_version(void) { return F2Q_ABI_VERSION; }
+
+F2Q_EXPORT int f2q_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; d++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+F2Q_EXPORT const char* f2q_last_error(const f2q_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> l(g_err_mu);
+    return g_create_err.c_str();
+}
+
+F2Q_EXPORT int f2q_create(const f2q_config* cfg, int device, void* stream, f2q_ctx** out) {
+    if (!cfg || !out) return fail(nullptr, F2Q_EINVAL, "null argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(nullptr, F2Q_ENODEVICE, "no CUDA device: libf2q has no CPU path"); }
+    if (device < 0 || device >= ndev) return fail(nullptr, F2Q_EINVAL, "device index out of range");
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (major != 10) return fail(nullptr, F2Q_ENODEVICE, "device is not compute capability 10.x (B200, sm_100a)");
+    if (cfg->has_up && cfg->has_down) {
+        // counts are checked by the host layer (fast2q.py:553-556); here both lists have n_iter entries
+    }
+    std::string why;
+    GenericCfg G;
+    int rc = make_generic_cfg(cfg, G, why);
+    if (rc) return fail(nullptr, rc, why);
+    f2q_ctx* c = new f2q_ctx();
+    c->device = device; c->cfg = *cfg; c->hG = G;
+    auto bail = [&](int code, const std::string& m) { fail(nullptr, code, m.empty() ? c->err : m); f2q_destroy(c); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(F2Q_ECUDA, "cudaSetDevice failed");
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (stream) c->stream = reinterpret_cast<cudaStream_t>(stream);
+    else { if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(F2Q_ECUDA, "cudaStreamCreate failed"); c->own_stream = true; }
+    if (cudaMalloc(&c->dG, sizeof(GenericCfg)) != cudaSuccess || cudaMalloc(&c->d_error, 4) != cudaSuccess ||
+        cudaMalloc(&c->dS, sizeof(DevState)) != cudaSuccess || cudaMalloc(&c->d_tickets, 8) != cudaSuccess)
+        return bail(F2Q_ENOMEM, "cudaMalloc failed");
+    cudaMemcpy(c->dG, &G, sizeof(G), cudaMemcpyHostToDevice);
+    cudaMemset(c->d_error, 0, 4); cudaMemset(c->dS, 0, sizeof(DevState)); cudaMemset(c->d_tickets, 0, 8);
+    decide_policy(c);
+    if (cfg->mode == F2Q_MODE_EXTRACT_COUNT) {
+        // no library in this mode: results are [stats 5]
+        if ((rc = dev_alloc(c, c->result, 5 * 8))) return bail(rc, "");
+        std::vector<uint32_t> gh(16, 0); std::vector<uint64_t> ko(1, 0); std::vector<uint8_t> kb(1, 0);
+        if ((rc = upload(c, gh, &c->T.ghash)) || (rc = upload(c, ko, &c->T.key_off)) || (rc = upload(c, kb, &c->T.key_bytes))) return bail(rc, "");
+        c->T.ghash_mask = 15; c->lib_set = true;
+    }
+    *out = c;
+    return F2Q_OK;
+}
+
+F2Q_EXPORT void f2q_destroy(f2q_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto& b : c->lib_bufs) b.release();
+    c->result.release(); c->carry.release(); c->status.release(); c->status_stitch.release(); c->queue.release(); c->gqueue.release();
+    c->ec_slots.release(); c->ec_counts.release(); c->ec_arena.release(); c->ec_meta.release();
+    for (auto p : c->d_stage) cudaFree(p);
+    for (auto e : c->ev_copied) cudaEventDestroy(e);
+    for (auto e : c->ev_free) cudaEventDestroy(e);
+    if (c->dG) cudaFree(c->dG);
+    if (c->d_error) cudaFree(c->d_error);
+    if (c->dS) cudaFree(c->dS);
+    if (c->d_tickets) cudaFree(c->d_tickets);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    cudaGetLastError();
+    delete c;
+}
+
+F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (!name) return fail(c, F2Q_EINVAL, "null option name");
+    if (c->in_sample) return fail(c, F2Q_ESTATE, "options must be set before f2q_begin_sample");
+    std::string n(name);
+    if (n == "carry_bytes") { if (value < 4096 || value > (1ll << 31)) return fail(c, F2Q_EINVAL, "carry_bytes out of range"); c->carry_cap = (uint64_t)value; c->carry.release(); c->status_stitch.release(); }
+    else if (n == "stage_bytes") { if (value < 4096 || !c->d_stage.empty()) return fail(c, F2Q_EINVAL, "stage_bytes invalid or staging already allocated"); c->stage_bytes = (uint64_t)value; }
+    else if (n == "stage_slots") { if (value < 1 || value > 16 || !c->d_stage.empty()) return fail(c, F2Q_EINVAL, "stage_slots invalid or staging already allocated"); c->stage_slots = (int)value; }
+    else if (n == "resolver") { if (value < 0 || value > 3) return fail(c, F2Q_EINVAL, "resolver must be 0..3"); c->resolver = (int)value; }
+    else if (n == "queue_entries") { if (value < 0) return fail(c, F2Q_EINVAL, "queue_entries < 0"); c->opt_queue_entries = value; c->q_cap = 0; c->g_cap = 0; c->queue.release(); c->gqueue.release(); }
+    else if (n == "force_generic") { if (value) c->policy = POLICY_GENERIC; else decide_policy(c); }
+    else return fail(c, F2Q_EINVAL, "unknown option " + n);
+    return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint64_t* key_offsets, uint32_t n_keys) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (c->cfg.mode != F2Q_MODE_COUNT) return fail(c, F2Q_ESTATE, "Extract+Count mode takes no library (fast2q.py:1700-1702)");
+    if (c->in_sample) return fail(c, F2Q_ESTATE, "set_library inside a sample");
+    if (n_keys && (!key_bytes || !key_offsets)) return fail(c, F2Q_EINVAL, "null library arrays");
+    for (auto& b : c->lib_bufs) b.release();
+    c->lib_bufs.clear(); c->T = LibTables{}; c->lib_set = false;
+    c->tile_blocks[0] = c->tile_blocks[1] = 0;
+
+    std::vector<uint64_t> off(n_keys + 1, 0);
+    for (uint32_t i = 0; i <= n_keys && n_keys; i++) off[i] = key_offsets[i] - key_offsets[0];
+    const uint8_t* kb = n_keys ? key_bytes + key_offsets[0] : nullptr;
+    const uint64_t total = off[n_keys];
+    std::vector<uint8_t> bytes(kb, kb + total);
+    bytes.push_back(0);
+
+    // uniqueness (the reference's dict has unique keys by construction)
+    {
+        std::unordered_set<std::string> seen;
+        seen.reserve(n_keys * 2);
+        for (uint32_t i = 0; i < n_keys; i++)
+            if (!seen.emplace(reinterpret_cast<const char*>(bytes.data() + off[i]), off[i + 1] - off[i]).second)
+                return fail(c, F2Q_EINVAL, "duplicate library key at index " + std::to_string(i));
+    }
+    // packed table + arrays
+    std::vector<uint64_t> fk; std::vector<uint32_t> fl, fi;
+    uint64_t gmask = 0; uint32_t n_generic = 0;
+    for (uint32_t i = 0; i < n_keys; i++) {
+        uint64_t key; const size_t len = off[i + 1] - off[i];
+        if (packable(bytes.data() + off[i], len, key)) { fk.push_back(key); fl.push_back((uint32_t)len); fi.push_back(i); }
+        else { n_generic++; gmask |= 1ull << std::min<size_t>(len, 63); }
+    }
+    const uint32_t cap = pow2_at_least(2 * (uint64_t)fk.size() + 2);
+    std::vector<FastSlot> slots(cap, FastSlot{0, 0, SLOT_EMPTY});
+    for (size_t k = 0; k < fk.size(); k++) {
+        uint32_t h = mix32(fk[k], fl[k]) & (cap - 1);
+        while (slots[h].idx != SLOT_EMPTY) h = (h + 1) & (cap - 1);
+        slots[h] = FastSlot{fk[k], fl[k], fi[k]};
+    }
+    const uint32_t gcap = pow2_at_least(2 * (uint64_t)n_keys + 2);
+    std::vector<uint32_t> gh(gcap, 0);
+    for (uint32_t i = 0; i < n_keys; i++) {
+        uint32_t h = FNV_INIT;
+        for (uint64_t k = off[i]; k < off[i + 1]; k++) h = fnv_step(h, bytes[k]);
+        uint32_t j = fnv_final(h) & (gcap - 1);
+        while (gh[j]) j = (j + 1) & (gcap - 1);
+        gh[j] = i + 1;
+    }
+    if ((rc = upload(c, slots, &c->T.slots)) || (rc = upload(c, fk, &c->T.fast_keys)) || (rc = upload(c, fl, &c->T.fast_lens)) ||
+        (rc = upload(c, fi, &c->T.fast_idx)) || (rc = upload(c, bytes, &c->T.key_bytes)) || (rc = upload(c, off, &c->T.key_off)) ||
+        (rc = upload(c, gh, &c->T.ghash)))
+        return rc;
+    c->T.slot_mask = cap - 1; c->T.n_fast = (uint32_t)fk.size(); c->T.n_keys = n_keys; c->T.ghash_mask = gcap - 1;
+    c->T.n_generic = n_generic; c->T.generic_len_mask = gmask;
+    c->n_keys = n_keys;
+    c->result.release();
+    if ((rc = dev_alloc(c, c->result, ((size_t)n_keys + 5) * 8))) return rc;
+    c->lib_set = true;
+    return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_begin_sample(f2q_ctx* c) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (!c->lib_set) return fail(c, F2Q_ESTATE, "f2q_set_library must be called first in Counter mode");
+    if ((rc = dev_alloc(c, c->carry, c->carry_cap + 256))) return rc;
+    if ((rc = dev_alloc(c, c->status_stitch, (c->carry_cap / OWN_BYTES + 2) * 4))) return rc;
+    CU(c, cudaMemsetAsync(c->result.p, 0, ((size_t)c->n_keys + 5) * 8, c->stream));
+    CU(c, cudaMemsetAsync(c->d_error, 0, 4, c->stream));
+    CU(c, cudaMemsetAsync(c->dS, 0, sizeof(DevState), c->stream));
+    if (c->cfg.mode == F2Q_MODE_EXTRACT_COUNT) {
+        if (c->ec_meta.p) CU(c, cudaMemsetAsync(c->ec_meta.p, 0, 16, c->stream));
+        if (c->ec_slots.p) { CU(c, cudaMemsetAsync(c->ec_slots.p, 0, c->ec_cap * 8, c->stream)); CU(c, cudaMemsetAsync(c->ec_counts.p, 0, c->ec_cap * 8, c->stream)); }
+        c->ec_drained = false;
+    }
+    c->in_sample = true; c->closed = false;
+    return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_submit_device(f2q_ctx* c, const void* dptr, uint64_t nbytes, int is_last) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (!c->in_sample) return fail(c, F2Q_ESTATE, "f2q_submit_device outside a sample");
+    if (c->closed) return fail(c, F2Q_ESTATE, "stream already closed with is_last");
+    if (nbytes && !dptr) return fail(c, F2Q_EINVAL, "null chunk");
+    return process_device_chunk(c, reinterpret_cast<const uint8_t*>(dptr), nbytes, is_last);
+}
+
+F2Q_EXPORT int f2q_submit(f2q_ctx* c, const uint8_t* host_chunk, uint64_t nbytes, int is_last) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (!c->in_sample) return fail(c, F2Q_ESTATE, "f2q_submit outside a sample");
+    if (c->closed) return fail(c, F2Q_ESTATE, "stream already closed with is_last");
+    if (nbytes && !host_chunk) return fail(c, F2Q_EINVAL, "null chunk");
+    if ((rc = ensure_staging(c))) return rc;
+    uint64_t done = 0;
+    do {
+        const uint64_t len = std::min<uint64_t>(c->stage_bytes, nbytes - done);
+        const int s = c->next_slot; c->next_slot = (c->next_slot + 1) % c->stage_slots;
+        // the copy engine may refill slot s only after the kernels that read it have finished
+        CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free[s], 0));
+        if (len) CU(c, cudaMemcpyAsync(c->d_stage[s], host_chunk + done, len, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(c, cudaEventRecord(c->ev_copied[s], c->copy_stream));
+        CU(c, cudaStreamWaitEvent(c->stream, c->ev_copied[s], 0));
+        done += len;
+        if ((rc = process_device_chunk(c, c->d_stage[s], len, is_last && done == nbytes))) return rc;
+        CU(c, cudaEventRecord(c->ev_free[s], c->stream));
+    } while (done < nbytes);
+    return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_sync(f2q_ctx* c) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (c->copy_stream) CU(c, cudaStreamSynchronize(c->copy_stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_result_device(f2q_ctx* c, void** dptr, uint64_t* n_words) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (!dptr || !n_words) return fail(c, F2Q_EINVAL, "null argument");
+    *dptr = c->result.p; *n_words = (uint64_t)c->n_keys + 5;
+    return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_end_sample(f2q_ctx* c, uint64_t* counts, uint64_t* stats) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (!c->in_sample) return fail(c, F2Q_ESTATE, "f2q_end_sample outside a sample");
+    if (!stats) return fail(c, F2Q_EINVAL, "null stats");
+    if (!c->closed && (rc = process_device_chunk(c, nullptr, 0, 1))) return rc;     // flush a carried final record
+    if ((rc = f2q_sync(c))) return rc;
+    c->in_sample = false;
+    uint32_t err = 0;
+    CU(c, cudaMemcpy(&err, c->d_error, 4, cudaMemcpyDeviceToHost));
+    DevState hs;
+    CU(c, cudaMemcpy(&hs, c->dS, sizeof(hs), cudaMemcpyDeviceToHost));
+    err |= hs.error;
+    if (err & ERR_RECORD_TOO_LONG) return fail(c, F2Q_ETOOLONG, "a FASTQ record is longer than carry_bytes; raise it with f2q_set_option");
+    if (err) return fail(c, F2Q_EINTERNAL, "device-side failure, flags=" + std::to_string(err));
+    if (counts && c->n_keys) CU(c, cudaMemcpy(counts, c->result.p, (size_t)c->n_keys * 8, cudaMemcpyDeviceToHost));
+    CU(c, cudaMemcpy(stats, reinterpret_cast<uint8_t*>(c->result.p) + (size_t)c->n_keys * 8, 5 * 8, cudaMemcpyDeviceToHost));
+    return F2Q_OK;
+}
+
+// ---- Extract+Count results ---------------------------------------------------------------------------
+static int ec_fetch(f2q_ctx* c) {
+    if (c->ec_drained) return F2Q_OK;
+    int rc = f2q_sync(c); if (rc) return rc;
+    c->ec_drain_off.assign(1, 0); c->ec_drain_cnt.clear(); c->ec_drain_keys.clear();
+    if (c->ec_cap) {
+        unsigned long long meta[2];
+        CU(c, cudaMemcpy(meta, c->ec_meta.p, 16, cudaMemcpyDeviceToHost));
+        std::vector<unsigned long long> hs(c->ec_cap), hc(c->ec_cap);
+        std::vector<uint8_t> ar(meta[0] + 1);
+        CU(c, cudaMemcpy(hs.data(), c->ec_slots.p, c->ec_cap * 8, cudaMemcpyDeviceToHost));
+        CU(c, cudaMemcpy(hc.data(), c->ec_counts.p, c->ec_cap * 8, cudaMemcpyDeviceToHost));
+        if (meta[0]) CU(c, cudaMemcpy(ar.data(), c->ec_arena.p, meta[0], cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < c->ec_cap; i++) {
+            if (!hs[i]) continue;
+            const uint64_t off = (hs[i] - 1) >> 24, len = (hs[i] - 1) & 0xFFFFFF;
+            c->ec_drain_keys.insert(c->ec_drain_keys.end(), ar.begin() + off, ar.begin() + off + len);
+            c->ec_drain_off.push_back(c->ec_drain_keys.size());
+            c->ec_drain_cnt.push_back(hc[i]);
+        }
+    }
+    c->ec_drained = true;
+    return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_ec_size(f2q_ctx* c, uint64_t* n_keys, uint64_t* key_bytes) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (c->cfg.mode != F2Q_MODE_EXTRACT_COUNT) return fail(c, F2Q_ESTATE, "not in Extract+Count mode");
+    if (!n_keys || !key_bytes) return fail(c, F2Q_EINVAL, "null argument");
+    if ((rc = ec_fetch(c))) return rc;
+    *n_keys = c->ec_drain_cnt.size(); *key_bytes = c->ec_drain_keys.size();
+    return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_ec_drain(f2q_ctx* c, uint8_t* key_bytes, uint64_t* key_offsets, uint64_t* counts) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (c->cfg.mode != F2Q_MODE_EXTRACT_COUNT) return fail(c, F2Q_ESTATE, "not in Extract+Count mode");
+    if ((rc = ec_fetch(c))) return rc;
+    if (!key_offsets || !counts || (!key_bytes && !c->ec_drain_keys.empty())) return fail(c, F2Q_EINVAL, "null argument");
+    if (!c->ec_drain_keys.empty()) memcpy(key_bytes, c->ec_drain_keys.data(), c->ec_drain_keys.size());
+    memcpy(key_offsets, c->ec_drain_off.data(), c->ec_drain_off.size() * 8);
+    if (!c->ec_drain_cnt.empty()) memcpy(counts, c->ec_drain_cnt.data(), c->ec_drain_cnt.size() * 8);
+    return F2Q_OK;
+}
+
+// ---- memory helpers --------------------------------------------------------------------------------------
+F2Q_EXPORT int f2q_host_alloc(void** ptr, uint64_t nbytes) {
+    if (!ptr) return F2Q_EINVAL;
+    cudaError_t e = cudaHostAlloc(ptr, nbytes ? nbytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return fail(nullptr, F2Q_ENOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+    return F2Q_OK;
+}
+F2Q_EXPORT int f2q_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); return F2Q_OK; }
+
+F2Q_EXPORT int f2q_device_alloc(f2q_ctx* c, void** dptr, uint64_t nbytes) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (!dptr) return fail(c, F2Q_EINVAL, "null argument");
+    cudaError_t e = cudaMalloc(dptr, nbytes ? nbytes : 16);
+    if (e != cudaSuccess) { cudaGetLastError(); *dptr = nullptr; return fail(c, F2Q_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    return F2Q_OK;
+}
+F2Q_EXPORT int f2q_device_free(f2q_ctx* c, void* dptr) {
+    int rc = check_ctx(c); if (rc) return rc;
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (dptr) CU(c, cudaFree(dptr));
+    return F2Q_OK;
+}
+F2Q_EXPORT int f2q_memcpy_d2h(f2q_ctx* c, void* host, const void* dptr, uint64_t nbytes) {
+    int rc = check_ctx(c); if (rc) return rc;
+    CU(c, cudaMemcpyAsync(host, dptr, nbytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return F2Q_OK;
+}
+F2Q_EXPORT int f2q_memcpy_h2d(f2q_ctx* c, void* dptr, const void* host, uint64_t nbytes) {
+    int rc = check_ctx(c); if (rc) return rc;
+    CU(c, cudaMemcpyAsync(dptr, host, nbytes, cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    return F2Q_OK;
+}
+
+F2Q_EXPORT uint64_t f2q_launch_count(const f2q_ctx* c) { return c ? c->launches : 0; }
+
+// ---- K0 synthetic generator ------------------------------------------------------------------------------
+F2Q_EXPORT int f2q_synth_fastq(f2q_ctx* c, const f2q_synth_spec* spec, const uint8_t* guides, void* dptr) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (!spec || !guides || !dptr) return fail(c, F2Q_EINVAL, "null argument");
+    if (spec->feat_len < 4 || spec->feat_len > 32 || spec->read_len < spec->feat_len || spec->read_len > 150 || spec->n_guides == 0)
+        return fail(c, F2Q_EINVAL, "synthetic spec out of range");
+    DevBuf g;
+    if ((rc = dev_alloc(c, g, (size_t)spec->n_guides * spec->feat_len))) return rc;
+    CU(c, cudaMemcpyAsync(g.p, guides, (size_t)spec->n_guides * spec->feat_len, cudaMemcpyHostToDevice, c->stream));
+    if (spec->n_reads) {
+        const unsigned grid = (unsigned)std::min<uint64_t>((spec->n_reads + 255) / 256, (uint64_t)c->sm_count * 16);
+        k_synth<<<grid, 256, 0, c->stream>>>(*spec, reinterpret_cast<const uint8_t*>(g.p), reinterpret_cast<uint8_t*>(dptr));
+        c->launches++;
+    }
+    CU(c, cudaGetLastError());
+    CU(c, cudaStreamSynchronize(c->stream));
+    g.release();
+    return F2Q_OK;
+}
+
+// ---- single-read helpers (README.md:259-298 public helpers of the reference) -----------------------------
+F2Q_EXPORT int f2q_border_finder(int device, const uint8_t* seq, uint32_t seq_len, const uint8_t* read, uint32_t read_len,
+                                 int32_t mismatch, int32_t start_place, int32_t* pos) {
+    if (!pos || (seq_len && !seq) || (read_len && !read)) return fail(nullptr, F2Q_EINVAL, "null argument");
+    if (f2q_device_count() == 0) return fail(nullptr, F2Q_ENODEVICE, "no CUDA device: libf2q has no CPU path");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, F2Q_ECUDA, "cudaSetDevice failed");
+    uint8_t* d = nullptr; int* dout = nullptr;
+    if (cudaMalloc(&d, (size_t)seq_len + read_len + 16) != cudaSuccess || cudaMalloc(&dout, 16) != cudaSuccess) { cudaFree(d); return fail(nullptr, F2Q_ENOMEM, "cudaMalloc failed"); }
+    if (seq_len) cudaMemcpy(d, seq, seq_len, cudaMemcpyHostToDevice);
+    if (read_len) cudaMemcpy(d + seq_len, read, read_len, cudaMemcpyHostToDevice);
+    k_border_finder<<<1, 32>>>(d, (int)seq_len, d + seq_len, (int)read_len, mismatch, start_place, dout);
+    int out = -1;
+    cudaError_t e = cudaMemcpy(&out, dout, 4, cudaMemcpyDeviceToHost);
+    cudaFree(d); cudaFree(dout);
+    if (e != cudaSuccess) return fail(nullptr, F2Q_ECUDA, std::string("k_border_finder: ") + cudaGetErrorString(e));
+    *pos = out;
+    return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_sequence_tinder(int device, const f2q_config* cfg, int32_t iteration, const uint8_t* read, uint32_t read_len,
+                                   const uint8_t* qual, uint32_t qual_len, const uint64_t* set_up, const uint64_t* set_down,
+                                   int32_t* found, int32_t* start, int32_t* end) {
+    if (!cfg || !found || !start || !end || (read_len && !read) || (qual_len && !qual)) return fail(nullptr, F2Q_EINVAL, "null argument");
+    if (iteration < 0 || iteration >= F2Q_MAX_ITER) return fail(nullptr, F2Q_EINVAL, "iteration out of range");
+    if (f2q_device_count() == 0) return fail(nullptr, F2Q_ENODEVICE, "no CUDA device: libf2q has no CPU path");
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, F2Q_ECUDA, "cudaSetDevice failed");
+    GenericCfg G; std::string why;
+    f2q_config tmp = *cfg; if (tmp.n_iter < 1) tmp.n_iter = 1;
+    int rc = make_generic_cfg(&tmp, G, why);
+    if (rc) return fail(nullptr, rc, why);
+    if (set_up) memcpy(G.set_up.w, set_up, 32);
+    if (set_down) memcpy(G.set_down.w, set_down, 32);
+    uint8_t* d = nullptr; int* dout = nullptr;
+    if (cudaMalloc(&d, (size_t)read_len + qual_len + 16) != cudaSuccess || cudaMalloc(&dout, 16) != cudaSuccess) { cudaFree(d); return fail(nullptr, F2Q_ENOMEM, "cudaMalloc failed"); }
+    if (read_len) cudaMemcpy(d, read, read_len, cudaMemcpyHostToDevice);
+    if (qual_len) cudaMemcpy(d + read_len, qual, qual_len, cudaMemcpyHostToDevice);
+    k_sequence_tinder<<<1, 32>>>(G, iteration, d, (int)read_len, d + read_len, (int)qual_len, dout);
+    int out[3] = {0, 0, 0};
+    cudaError_t e = cudaMemcpy(out, dout, 12, cudaMemcpyDeviceToHost);
+    cudaFree(d); cudaFree(dout);
+    if (e != cudaSuccess) return fail(nullptr, F2Q_ECUDA, std::string("k_sequence_tinder: ") + cudaGetErrorString(e));
+    *found = out[0]; *start = out[1]; *end = out[2];
+    return F2Q_OK;
+}

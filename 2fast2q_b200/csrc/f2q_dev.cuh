@@ -1,0 +1,192 @@
+// f2q_dev.cuh — shared device-side definitions of libf2q (sm_100a).
+//
+// Everything here is integer / byte work; the path is HBM-bound (one pass over the FASTQ bytes), so there is
+// no tensor-core code.  Reference semantics cited as fast2q.py:<lines> (2FAST2Q v2.8.1).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/f2q.h"
+
+namespace f2q {
+
+// ------------------------------------------------------------------------------------------------
+// geometry of one tile of the FASTQ byte stream in shared memory
+//   a tile = TILE_ROWS rows of 128 bytes; rows [0, OWN_ROWS) are owned, the rest is read-ahead (halo) so that
+//   a record that starts in the owned part can be finished without leaving shared memory.
+//   Rows are stored with the 128-byte XOR swizzle (16-byte chunk c of row r lives at chunk c ^ (r & 7)), the same
+//   pattern as CU_TENSOR_MAP_SWIZZLE_128B, so that "thread t scans row t" is bank-conflict free.
+// ------------------------------------------------------------------------------------------------
+constexpr int ROW_BYTES = 128;
+constexpr int TILE_ROWS = 256;
+constexpr int HALO_ROWS = 8;
+constexpr int OWN_ROWS = TILE_ROWS - HALO_ROWS;            // 248
+constexpr int TILE_BYTES = TILE_ROWS * ROW_BYTES;          // 32768 bytes resident per tile
+constexpr int OWN_BYTES = OWN_ROWS * ROW_BYTES;            // 31744 bytes advanced per tile
+constexpr int TILE_THREADS = 256;                          // one thread per row
+constexpr int NL_CAP = 4096;                               // newline positions kept per pass (u16 each)
+
+// status word of the decoupled look-back over tiles: [31:30] flag, [29:0] newline count (mod 2^30; only mod 4 is used)
+constexpr uint32_t LB_FLAG_AGG = 1u << 30;
+constexpr uint32_t LB_FLAG_PREFIX = 2u << 30;
+constexpr uint32_t LB_VALUE_MASK = (1u << 30) - 1;
+
+// device error bits (sticky, reported by f2q_end_sample as F2Q_EINTERNAL / F2Q_ETOOLONG)
+constexpr uint32_t ERR_LOOKBACK_TIMEOUT = 1u;
+constexpr uint32_t ERR_RECORD_TOO_LONG = 2u;
+constexpr uint32_t ERR_QUEUE = 4u;
+constexpr uint32_t ERR_EC_FULL = 8u;
+
+// ------------------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------------------
+struct DevCfg {
+    int32_t mode, miss, length, n_iter, has_up, has_down, miss_up, miss_down;
+    int32_t fmax_ph, fmax_up, fmax_down;   // largest failing quality byte (0 = empty fail set): fail iff 33 <= b <= fmax
+    int32_t starts[F2Q_MAX_ITER];
+    int32_t up_len[F2Q_MAX_ITER], down_len[F2Q_MAX_ITER];
+    uint8_t up[F2Q_MAX_ITER][F2Q_MAX_DELIM], down[F2Q_MAX_ITER][F2Q_MAX_DELIM];
+};
+
+// one slot of the packed-key hash table: 2-bit packed bases (<= 32), key length, feature index
+struct __align__(16) FastSlot {
+    uint64_t key;
+    uint32_t len;
+    uint32_t idx;      // 0xFFFFFFFF = empty
+};
+constexpr uint32_t SLOT_EMPTY = 0xFFFFFFFFu;
+
+// library tables on the device (replace binary_converter, fast2q.py:188-213)
+struct LibTables {
+    // packed (ACGT-only, <= 32 symbols, single piece) keys
+    const FastSlot* slots;
+    uint32_t slot_mask;        // capacity - 1 (power of two)
+    uint32_t n_fast;
+    const uint64_t* fast_keys; // n_fast packed keys grouped by length (for the tile-scan resolver)
+    const uint32_t* fast_lens;
+    const uint32_t* fast_idx;
+    // every key as bytes (generic path)
+    const uint8_t* key_bytes;
+    const uint64_t* key_off;   // n_keys + 1
+    uint32_t n_keys;
+    const uint32_t* ghash;     // byte-hash table: key index + 1, 0 = empty
+    uint32_t ghash_mask;
+    uint32_t n_generic;        // keys that are NOT in the packed table
+    uint64_t generic_len_mask; // bit L set: some non-packed key has length L (L < 64); bit 63: some length >= 63
+    // pigeonhole seed index over the packed keys (resolver 2)
+    const uint2* seed_slots;   // {tag, start|count} hash of (len, segment, value) -> range in seed_items
+    uint32_t seed_mask;
+    const uint32_t* seed_items;   // indices into fast_keys
+    uint32_t seed_parts;       // miss + 1
+};
+
+// entry of the deferred non-exact key queue (filled by the tile kernel, drained by the resolver kernel)
+struct __align__(16) QEntry {
+    uint64_t key;      // 2-bit packed, bad positions hold 0
+    uint32_t bad;      // bit p set: symbol p is not A/C/G/T
+    uint32_t len;
+};
+
+// a read the packed path cannot decide (record longer than the tile halo, odd key shape, non-packed library keys):
+// location of its sequence and quality lines (absolute device addresses), handled by the generic kernel
+struct __align__(8) GEntry {
+    uint64_t seq_addr;     // device address of the first byte of the sequence line
+    uint64_t qual_addr;
+    uint32_t seq_len;
+    uint32_t qual_len;
+};
+
+// per-sample, per-launch device state
+struct DevState {
+    // carried partial record
+    uint32_t tail_len;
+    uint32_t tail_nl;
+    // current launch
+    uint64_t beg, end;             // byte range of the buffer the tile kernel parses; beg is a record start
+    uint32_t is_last;              // the range ends at end-of-stream
+    uint32_t stitch_len;           // bytes of the stitched record in the carry buffer (0 = none)
+    uint32_t stitch_eof;           // the stitched bytes end the stream
+    uint32_t appended;             // the whole chunk was appended to the carry buffer (nothing else to parse)
+    unsigned long long last_rec_end;   // atomicMax: offset just behind the last complete record
+    uint32_t nl_total;             // newlines in [beg, end) (mod 2^30)
+    uint32_t ticket;
+    uint32_t error;
+    uint32_t q_count, q_cap;       // non-exact key queue
+    uint32_t g_count, g_cap;       // generic read queue
+    uint32_t pad;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t mix32(uint64_t key, uint32_t len) {
+    uint64_t h = (key ^ (0x9E3779B97F4A7C15ull * (uint64_t)(len + 1))) * 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 29;
+    h *= 0x94D049BB133111EBull;
+    return (uint32_t)(h >> 32);
+}
+
+// Python slice bounds seq[a:b] for a sequence of length n (fast2q.py:354-355)
+__host__ __device__ __forceinline__ void py_slice(int n, int a, int b, int& lo, int& hi) {
+    if (a < 0) { a += n; if (a < 0) a = 0; } else if (a > n) a = n;
+    if (b < 0) { b += n; if (b < 0) b = 0; } else if (b > n) b = n;
+    if (b < a) b = a;
+    lo = a; hi = b;
+}
+
+// bytes.rstrip() whitespace set: b" \t\n\r\x0b\x0c" (fast2q.py:326)
+__host__ __device__ __forceinline__ bool is_py_space(uint32_t c) { return c == 32u || (c - 9u) <= 4u; }
+
+__host__ __device__ __forceinline__ uint32_t upper8(uint32_t c) { return (c - 97u) <= 25u ? c - 32u : c; }
+
+// 2-bit code of an (upper- or lower-case) base: A=0 C=1 T=2 G=3  ((c >> 1) & 3); valid iff upper8(c) in ACGT
+__host__ __device__ __forceinline__ bool base_code(uint32_t c, uint32_t& code) {
+    uint32_t u = c & 0xDFu;
+    code = (c >> 1) & 3u;
+    return u == 'A' || u == 'C' || u == 'G' || u == 'T';
+}
+
+#ifdef __CUDACC__
+// swizzled address of the byte at tile offset o (see the tile geometry above)
+__device__ __forceinline__ uint32_t swz(uint32_t o) { return o ^ ((o >> 3) & 0x70u); }
+
+// exact per-byte equality flags (0x80 in every byte of w that equals the byte replicated in c4); 3 instructions
+__device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t c4) {
+    uint32_t x = (w ^ c4);
+    uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | x) & 0x80808080u;
+}
+
+// streaming 16-byte global load (read once, do not keep in L1)
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// probe the packed-key table; returns feature index or SLOT_EMPTY
+__device__ __forceinline__ uint32_t fast_lookup(const LibTables& T, uint64_t key, uint32_t len) {
+    uint32_t h = mix32(key, len) & T.slot_mask;
+    #pragma unroll 1
+    for (;;) {
+        uint4 raw = __ldg(reinterpret_cast<const uint4*>(T.slots + h));
+        uint64_t k = ((uint64_t)raw.y << 32) | raw.x;
+        if (raw.w == SLOT_EMPTY) return SLOT_EMPTY;
+        if (k == key && raw.z == len) return raw.w;
+        h = (h + 1) & T.slot_mask;
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace f2q

@@ -1,0 +1,174 @@
+// resolve.cuh — <= m mismatch resolution of packed keys that missed the exact table.
+// Rule (fast2q.py:692-750 + 660-690): among library entries of the SAME length take the minimum Hamming
+// distance d*; the read is assigned iff d* <= m and exactly one entry attains it.  A symbol of the read that is
+// not A/C/G/T ("bad") mismatches every packed library symbol.
+//
+// Three exact strategies over the same tables:
+//   probe  (m == 1)  enumerate the 3*L Hamming-1 neighbours, probe the exact hash table        k_resolve_probe
+//   seed   (any m)   pigeonhole: m+1 segments, one must match exactly -> candidates -> XOR+popc  k_resolve_seed
+//   scan   (any m)   XOR+popc against library tiles staged in shared memory                      k_resolve_scan
+// plus resolve_thread(), the one-thread version used when a queue overflows.
+#pragma once
+
+#include "f2q_dev.cuh"
+
+namespace f2q {
+
+constexpr uint32_t RES_NONE = 0xFFFFFFFFu;
+
+// spread the low 32 bits to the even bit positions of a 64-bit word
+__host__ __device__ __forceinline__ uint64_t spread_even(uint32_t v) {
+    uint64_t x = v;
+    x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+    x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+    x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+    x = (x | (x << 2)) & 0x3333333333333333ull;
+    x = (x | (x << 1)) & 0x5555555555555555ull;
+    return x;
+}
+
+// number of differing symbols between two 2-bit packed keys, ignoring positions flagged in notbad_even's complement
+__host__ __device__ __forceinline__ int packed_distance(uint64_t a, uint64_t b, uint64_t good_even) {
+    uint64_t x = a ^ b;
+    x = (x | (x >> 1)) & good_even;
+#ifdef __CUDA_ARCH__
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+
+struct Best {
+    int d; uint32_t n, idx;
+    __host__ __device__ __forceinline__ void add(int dist, uint32_t i, int m) {
+        if (dist < d) { d = dist; n = 1; idx = i; }
+        else if (dist == d && dist <= m) n++;
+    }
+};
+
+#ifdef __CUDACC__
+// ---- one thread, any m (overflow fallback; also the reference implementation of the two kernels below) ----
+__device__ inline uint32_t resolve_thread(const LibTables& T, int m, uint64_t key, uint32_t bad, uint32_t len) {
+    const int nbad = __popc(bad);
+    if (m <= 0 || nbad > m) return RES_NONE;
+    if (m == 1) {
+        uint32_t hits = 0, idx = RES_NONE;
+        if (nbad == 1) {
+            int p = __ffs(bad) - 1;
+            for (uint64_t c = 0; c < 4; c++) {
+                uint32_t r = fast_lookup(T, key | (c << (2 * p)), len);
+                if (r != SLOT_EMPTY) { hits++; idx = r; }
+            }
+        } else {
+            for (uint32_t p = 0; p < len; p++) {
+                uint64_t cur = (key >> (2 * p)) & 3ull;
+                for (uint64_t c = 1; c < 4; c++) {
+                    uint64_t k2 = key ^ (c << (2 * p));       // cur ^ c runs over the three other bases
+                    uint32_t r = fast_lookup(T, k2, len);
+                    if (r != SLOT_EMPTY) { hits++; idx = r; }
+                }
+                (void)cur;
+            }
+        }
+        return hits == 1 ? idx : RES_NONE;
+    }
+    const uint64_t good = (len >= 32 ? 0x5555555555555555ull : ((1ull << (2 * len)) - 1) & 0x5555555555555555ull) & ~spread_even(bad);
+    Best b{m + 1, 0, 0};
+    for (uint32_t i = 0; i < T.n_fast; i++) {
+        if (__ldg(T.fast_lens + i) != len) continue;
+        int d = packed_distance(key, __ldg(T.fast_keys + i), good) + nbad;
+        b.add(d, __ldg(T.fast_idx + i), m);
+    }
+    return (b.d <= m && b.n == 1) ? b.idx : RES_NONE;
+}
+
+// ---- Hamming-1 neighbour probing: one warp per queued key, lane p owns position p -----------------
+__global__ void __launch_bounds__(256) k_resolve_probe(LibTables T, const QEntry* __restrict__ q, const DevState* S,
+                                                       unsigned long long* counts, unsigned long long* stats) {
+    const uint32_t n = S->q_count < S->q_cap ? S->q_count : S->q_cap;
+    const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t imperfect = 0, nonal = 0;
+    for (uint32_t i = warp; i < n; i += nwarps) {
+        const QEntry e = q[i];
+        const int nbad = __popc(e.bad);
+        uint32_t hits = 0, idx = 0;
+        if (nbad <= 1) {
+            if (nbad == 1) {
+                const int p = __ffs(e.bad) - 1;
+                if (lane < 4) {
+                    uint32_t r = fast_lookup(T, e.key | ((uint64_t)lane << (2 * p)), e.len);
+                    if (r != SLOT_EMPTY) { hits = 1; idx = r; }
+                }
+            } else if (lane < e.len) {
+                #pragma unroll
+                for (uint64_t c = 1; c < 4; c++) {
+                    uint32_t r = fast_lookup(T, e.key ^ (c << (2 * lane)), e.len);
+                    if (r != SLOT_EMPTY) { hits++; idx = r; }
+                }
+            }
+        }
+        const uint32_t total = __reduce_add_sync(0xffffffffu, hits);
+        const uint32_t who = __ballot_sync(0xffffffffu, hits != 0);
+        if (total == 1) {
+            if (lane == (uint32_t)(__ffs(who) - 1)) atomicAdd(counts + idx, 1ull);
+            imperfect++;
+        } else nonal++;
+    }
+    if (lane == 0) {
+        if (imperfect) atomicAdd(stats + F2Q_STAT_IMPERFECT, (unsigned long long)imperfect);
+        if (nonal) atomicAdd(stats + F2Q_STAT_NON_ALIGNED, (unsigned long long)nonal);
+    }
+}
+
+// ---- library tile scan: XOR + popc of every queued key against shared-memory tiles of the packed library ----
+constexpr int SCAN_TILE = 2048;     // library entries per shared-memory tile (16 KB keys + 8 KB lens + 8 KB idx)
+constexpr int SCAN_THREADS = 256;
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_resolve_scan(LibTables T, int m, const QEntry* __restrict__ q, const DevState* S,
+                                                               unsigned long long* counts, unsigned long long* stats) {
+    __shared__ __align__(16) uint64_t s_key[SCAN_TILE];
+    __shared__ uint32_t s_len[SCAN_TILE];
+    __shared__ uint32_t s_idx[SCAN_TILE];
+    const uint32_t n = S->q_count < S->q_cap ? S->q_count : S->q_cap;
+    uint32_t imperfect = 0, nonal = 0;
+    for (uint32_t base = blockIdx.x * SCAN_THREADS; base < n; base += gridDim.x * SCAN_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        const bool live = i < n;
+        QEntry e{0, 0, 0};
+        if (live) e = q[i];
+        const int nbad = __popc(e.bad);
+        const uint64_t good = (e.len >= 32 ? 0x5555555555555555ull : ((1ull << (2 * e.len)) - 1) & 0x5555555555555555ull) & ~spread_even(e.bad);
+        Best b{m + 1, 0, 0};
+        for (uint32_t t0 = 0; t0 < T.n_fast; t0 += SCAN_TILE) {
+            const uint32_t cnt = min((uint32_t)SCAN_TILE, T.n_fast - t0);
+            __syncthreads();
+            for (uint32_t k = threadIdx.x; k < cnt; k += SCAN_THREADS) {
+                s_key[k] = __ldg(T.fast_keys + t0 + k);
+                s_len[k] = __ldg(T.fast_lens + t0 + k);
+                s_idx[k] = __ldg(T.fast_idx + t0 + k);
+            }
+            __syncthreads();
+            if (live && nbad <= m) {
+                for (uint32_t k = 0; k < cnt; k++) {                 // every lane reads the same entry: smem broadcast
+                    if (s_len[k] != e.len) continue;
+                    int d = packed_distance(e.key, s_key[k], good) + nbad;
+                    b.add(d, s_idx[k], m);
+                }
+            }
+        }
+        if (live) {
+            if (b.d <= m && b.n == 1) { atomicAdd(counts + b.idx, 1ull); imperfect++; }
+            else nonal++;
+        }
+    }
+    imperfect = __reduce_add_sync(0xffffffffu, imperfect);
+    nonal = __reduce_add_sync(0xffffffffu, nonal);
+    if ((threadIdx.x & 31) == 0) {
+        if (imperfect) atomicAdd(stats + F2Q_STAT_IMPERFECT, (unsigned long long)imperfect);
+        if (nonal) atomicAdd(stats + F2Q_STAT_NON_ALIGNED, (unsigned long long)nonal);
+    }
+}
+#endif  // __CUDACC__
+
+}  // namespace f2q

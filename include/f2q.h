@@ -104,7 +104,9 @@ const char* f2q_last_error(const f2q_ctx* ctx);   /* ctx may be NULL: last creat
  *   "stage_bytes"     size of each internal pinned/device staging slot used by f2q_submit (default 64 MiB)
  *   "stage_slots"     number of staging slots (default 3)
  *   "resolver"        0 auto | 1 Hamming-1 neighbour probing | 2 pigeonhole seed index | 3 library tile scan
- *   "queue_entries"   capacity of the deferred non-exact key queue (default: derived from stage_bytes)
+ *   "queue_entries"   capacity of the deferred non-exact key queue (default: derived from the chunk size;
+ *                     capacity never changes results — overflow is resolved in place)
+ *   "force_generic"   1: run every read through the byte-wise generic kernels (cross-check of the packed path)
  */
 int f2q_set_option(f2q_ctx* ctx, const char* name, int64_t value);
 
@@ -160,15 +162,19 @@ int f2q_host_alloc(void** ptr, uint64_t nbytes);
 int f2q_host_free(void* ptr);
 
 /* ---- primitives with public reference counterparts (README.md:259-298; tests/test_mainfunctions.py) ----
- * Device implementations of border_finder (fast2q.py:628-658) and sequence_tinder (:215-285) run on one
- * read; used by the host-side helpers of the same names and by the known-answer tests.
- * f2q_border_finder: returns F2Q_OK and *pos = first index >= start_place with <= mismatch mismatches, or -1.
- * f2q_sequence_tinder: *start/*end = trimmed window, or found=0 for the reference's (None, None).
+ * Device implementations of border_finder (fast2q.py:628-658) and sequence_tinder (:215-285) run on ONE read
+ * (context-free: they allocate, launch and free on `device`); used by the host-side helpers of the same names
+ * and by the known-answer tests.
+ * f2q_border_finder: *pos = first index >= start_place with <= mismatch mismatches, or -1 for the reference's None.
+ * f2q_sequence_tinder: cfg supplies up/down/miss_up/miss_down/length/qual_up/qual_down; set_up/set_down optionally
+ *   override the delimiter fail sets with explicit 256-bit byte sets (uint64[4], bit b of word b>>6) because the
+ *   reference helper takes arbitrary sets.  *found = 0 for the reference's (None, None).
  */
-int f2q_border_finder(f2q_ctx* ctx, const uint8_t* seq, uint32_t seq_len, const uint8_t* read, uint32_t read_len,
+int f2q_border_finder(int device, const uint8_t* seq, uint32_t seq_len, const uint8_t* read, uint32_t read_len,
                       int32_t mismatch, int32_t start_place, int32_t* pos);
-int f2q_sequence_tinder(f2q_ctx* ctx, int32_t iteration, const uint8_t* read, uint32_t read_len,
-                        const uint8_t* qual, uint32_t qual_len, int32_t* found, int32_t* start, int32_t* end);
+int f2q_sequence_tinder(int device, const f2q_config* cfg, int32_t iteration, const uint8_t* read, uint32_t read_len,
+                        const uint8_t* qual, uint32_t qual_len, const uint64_t* set_up, const uint64_t* set_down,
+                        int32_t* found, int32_t* start, int32_t* end);
 
 /* ---- synthetic FASTQ generator K0 (bench/tests only) -------------------------- */
 typedef struct f2q_synth_spec {

@@ -1,0 +1,179 @@
+"""
+-m gpu: the CUDA path (through the C-ABI) against the golden vectors of the unmodified reference and against the
+oracle.  Bit-exact: integer counts and the five statistics.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import cases
+import golden_io as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gu():
+    import gpu_util
+    assert gpu_util.lib.device_count() >= 1, "no B200 visible"
+    return gpu_util
+
+
+def test_kat_cases(gu):
+    for c in G.kat():
+        gu.check_case(c, c["fastq"])
+
+
+def test_kat_cases_generic_kernels(gu):
+    for c in G.kat():
+        gu.check_case(c, c["fastq"], force_generic=1)
+
+
+@pytest.mark.parametrize("chunk", [1, 3, 16, 127])
+def test_kat_cases_chunked(gu, chunk):
+    """records cut at arbitrary byte positions: the carry/stitch logic must give the same answer"""
+    for c in G.kat():
+        gu.check_case(c, c["fastq"], chunk)
+
+
+def test_fuzz_cases(gu):
+    for c in G.fuzz():
+        gu.check_case(c, c["fastq"])
+
+
+@pytest.mark.parametrize("chunk", [5, 64, 1000])
+def test_fuzz_cases_chunked(gu, chunk):
+    for c in G.fuzz()[::3]:
+        gu.check_case(c, c["fastq"], chunk)
+
+
+def test_fuzz_cases_generic_kernels(gu):
+    for c in G.fuzz()[::2]:
+        gu.check_case(c, c["fastq"], force_generic=1)
+
+
+@pytest.mark.parametrize("name", cases.SHAPED)
+def test_shaped_cases(gu, name):
+    c = [x for x in G.shaped() if x["name"] == name][0]
+    params, lib, data = cases.shaped_inputs(name)
+    assert cases.sha(data) == c["sha256"]
+    c = dict(c, library=lib)
+    gu.check_case(c, data)
+    gu.check_case(c, data, 100003)        # odd chunk size: every submit cuts a record
+
+
+@pytest.mark.parametrize("name,resolver", [("config2_slice", 1), ("config2_slice", 3), ("config3_slice", 3), ("config3_m3", 3)])
+def test_resolvers_agree(gu, name, resolver):
+    c = [x for x in G.shaped() if x["name"] == name][0]
+    params, lib, data = cases.shaped_inputs(name)
+    gu.check_case(dict(c, library=lib), data, resolver=resolver)
+
+
+def test_queue_overflow_resolves_in_place(gu):
+    """a 16-entry queue overflows immediately; results must not change"""
+    c = [x for x in G.shaped() if x["name"] == "config2_slice"][0]
+    params, lib, data = cases.shaped_inputs("config2_slice")
+    gu.check_case(dict(c, library=lib), data, queue_entries=16)
+
+
+def test_config1_surrogate_equals_reference_compiled_csv(gu):
+    g = G.config1()
+    lib, want, data = cases.config1_surrogate(os.path.join(G.HERE, "D39V_guides.csv"), os.path.join(G.HERE, "ref_compiled.csv"))
+    assert cases.sha(data) == g["sha256"]
+    got, stats = gu.run_case(cases.P(), lib, data)
+    assert {n: c for (n, _), c in zip(lib, got)} == want
+    assert stats == g["stats"]
+
+
+def test_primitives(gu):
+    p = G.primitives()
+    for v in p["border_finder"][::4]:
+        assert gu.lib.border_finder_device(v["seq"].encode(), v["read"].encode(), v["mismatch"], v["start_place"]) == v["expect"], v
+    for v in p["sequence_tinder"][::4] + p["sequence_tinder"][:5]:
+        cfg = gu.lib.make_config(upstream=v["upstream"], downstream=v["downstream"], miss_search_up=v["msu"],
+                                 miss_search_down=v["msd"], qual_up=v.get("qsu", 30), qual_down=v.get("qsd", 30), length=v["length"])
+        got = gu.lib.sequence_tinder_device(cfg, v["read"].encode(), v["qual"].encode(), v["i"], v.get("set_up"), v.get("set_down"))
+        assert list(got) == v["expect"], v
+
+
+def test_long_records_spill_path(gu, oracle):
+    """records longer than the tile halo (1 KiB) and than a whole tile take the global-memory path"""
+    from oracle import synth
+    r = synth.SM64(77)
+    guides = [r.dna(20) for _ in range(50)]
+    recs = []
+    for i in range(300):
+        L = r.choice([30, 600, 1500, 5000, 40000]) if i % 3 == 0 else 60
+        g = r.choice(guides)
+        if r.below(4) == 0:
+            g = synth.mutate(r, g, 1)
+        s = g + r.dna(L)
+        recs.append(b"@x%d\n" % i + s + b"\n+\n" + synth.qual_line(r, len(s), 0.1) + b"\n")
+    data = b"".join(recs)
+    params = cases.P()
+    lib = [("g%d" % i, g.decode()) for i, g in enumerate(dict.fromkeys(guides))]
+    want_c, want_s = oracle.count(oracle.make_config(**params), [s for _, s in lib], data)
+    for chunk in (None, 70001):
+        got, stats = gu.run_case(params, lib, data, chunk)
+        assert stats == want_s and got == [int(x) for x in want_c]
+
+
+def test_short_lines_many_newlines(gu, oracle):
+    """more newlines per tile than one rank window holds (lines of 0-3 bytes)"""
+    from oracle import synth
+    r = synth.SM64(5)
+    data = b"".join(r.dna(r.below(4)) + b"\n" for _ in range(60000))
+    params = cases.P(mode="EC", length=3)
+    want, want_s = oracle.extract_count(oracle.make_config(**params), data)
+    got, stats = gu.run_case(params, None, data)
+    assert stats == want_s and got == want
+    params = cases.P(length=2, miss=1)
+    lib = [("a", "AC"), ("b", "GT"), ("c", "A"), ("d", "")]
+    want_c, want_s = oracle.count(oracle.make_config(**params), [s for _, s in lib], data)
+    got, stats = gu.run_case(params, lib, data)
+    assert stats == want_s and got == [int(x) for x in want_c]
+
+
+def test_synth_generator_matches_numpy(gu):
+    from oracle import synth
+    for config in (2, 3):
+        spec = synth.default_spec(config)
+        names, keys = synth.make_library(config, 500, 20)
+        want = synth.fixed_reads(keys, 12345, 3000, **spec)
+        cfg = gu.lib.make_config()
+        with gu.lib.Engine(cfg) as e:
+            d = e.device_alloc(want.size)
+            e.synth(d, keys, 12345, 3000, **spec)
+            got = e.d2h(d, want.size)
+            e.device_free(d)
+        assert np.array_equal(got, want)
+
+
+def test_resident_device_submit_large(gu, oracle):
+    """config-2 shape, 2M reads generated on the device: one submit vs many odd-sized submits vs the oracle"""
+    from oracle import synth
+    spec = synth.default_spec(2)
+    names, keys = synth.make_library(2, 2000, 20)
+    n = 2_000_000
+    rec = 2 * spec["read_len"] + 18
+    cfg = gu.lib.make_config(miss=1)
+    with gu.lib.Engine(cfg) as e:
+        e.set_library(keys)
+        d = e.device_alloc(n * rec)
+        e.synth(d, keys, 0, n, **spec)
+        e.begin(); e.submit_device(d, n * rec, True); c1, s1 = e.end()
+        e.begin()
+        step, o = 7_777_777, 0
+        while o < n * rec:
+            m = min(step, n * rec - o)
+            e.submit_device(d + o, m, o + m >= n * rec)
+            o += m
+        c2, s2 = e.end()
+        host = e.d2h(d, n * rec)
+        e.device_free(d)
+    assert s1 == s2 and np.array_equal(c1, c2)
+    assert s1["reads"] == n and s1["reads"] == s1["perfect_counter"] + s1["imperfect_counter"] + s1["non_aligned_counter"] + s1["quality_failed"]
+    assert int(c1.sum()) == s1["perfect_counter"] + s1["imperfect_counter"]
+    want_c, want_s = oracle.count(oracle.make_config(miss=1), keys, host)
+    assert want_s == s1 and np.array_equal(want_c, c1)
