@@ -78,6 +78,7 @@ SYMBOLS = {
     "f2q_memcpy_d2h": (C.c_int, [_VP, _VP, _VP, C.c_uint64]),
     "f2q_memcpy_h2d": (C.c_int, [_VP, _VP, _VP, C.c_uint64]),
     "f2q_launch_count": (C.c_uint64, [_VP]),
+    "f2q_kernel_times": (C.c_int, [_VP, C.POINTER(C.c_double), _U64P]),
 }
 
 _lib = None
@@ -310,6 +311,12 @@ class Engine:
     @property
     def launches(self) -> int:
         return int(self.L.f2q_launch_count(self.h))
+
+    def kernel_times(self):
+        """{'tile': (ms, launches), 'resolve': ..., 'generic': ...} of the last finished sample (option time_kernels)"""
+        ms, n = (C.c_double * 3)(), (C.c_uint64 * 3)()
+        self._ck(self.L.f2q_kernel_times(self.h, ms, n))
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(("tile", "resolve", "generic"))}
 
 
 def border_finder_device(seq: bytes, read: bytes, mismatch: int, start_place: int = 0, device: int = 0):

@@ -55,8 +55,12 @@ struct f2q_ctx {
     uint32_t* d_tickets = nullptr;
     // streaming
     uint64_t carry_cap = 4ull << 20;
-    DevBuf carry, status, status_stitch, queue, gqueue;
-    uint32_t q_cap = 0, g_cap = 0;
+    DevBuf carry, status, status_stitch, queue, gqueue, seg_count;
+    uint32_t q_cap = 0, g_cap = 0;     // q_cap = total queue entries (n_segs * seg_cap)
+    uint32_t seg_cap = 0, n_segs = 0;
+    int force_ch = 0;
+    int ch = 7;                        // row chunks of the tile kernel (row = 16*ch bytes), picked per sample from the record length
+    bool ch_decided = false;
     int64_t opt_queue_entries = 0;
     // staging for host submits
     uint64_t stage_bytes = 64ull << 20;
@@ -74,7 +78,14 @@ struct f2q_ctx {
     int sticky = F2Q_OK;
     std::string err;
     uint64_t launches = 0;
-    int tile_blocks[2] = {0, 0};
+    int tile_blocks[2][8] = {{0}};
+    // optional per-kernel timing (option "time_kernels"): event pairs around the tile / resolver / generic launches
+    bool time_kernels = false;
+    struct Timed { cudaEvent_t a, b; int kind; };
+    std::vector<Timed> timed;
+    std::vector<cudaEvent_t> event_pool;
+    double kernel_ms[3] = {0, 0, 0};
+    uint64_t kernel_launches[3] = {0, 0, 0};
 };
 
 namespace {
@@ -165,23 +176,91 @@ void decide_policy(f2q_ctx* c) {
     if (g.mode == F2Q_MODE_COUNT && !g.has_up && !g.has_down && g.n_iter == 1 && g.length >= 0 && g.length <= 32) c->policy = POLICY_FAST1;
 }
 
-template <int POLICY>
-int launch_tile(f2q_ctx* c, const TileParams& P, Outputs O, uint64_t n_tiles_upper) {
-    const bool hist = (POLICY == POLICY_FAST1) && c->n_keys > 0 && c->n_keys <= 8192;
-    TileParams p = P; p.hist_smem = hist;
-    const size_t smem = tile_smem_bytes(hist ? c->n_keys : 0);
-    int& blocks_per_sm = c->tile_blocks[POLICY];
+constexpr uint32_t HIST_MAX_KEYS = 8192;     // shared-memory histogram up to this many features (32 KB of u32)
+
+// persistent grid of the tile kernel for (policy, ch): SM count x resident CTAs per SM
+template <int POLICY, int CH>
+int tile_grid(f2q_ctx* c, unsigned* grid) {
+    const bool hist = (POLICY == POLICY_FAST1) && c->n_keys > 0 && c->n_keys <= HIST_MAX_KEYS;
+    const size_t smem = tile_smem_bytes<CH>(hist ? c->n_keys : 0);
+    int& blocks_per_sm = c->tile_blocks[POLICY][CH];
     if (blocks_per_sm == 0) {
-        CU(c, cudaFuncSetAttribute(k_tile<POLICY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tile_smem_bytes(8192))));
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_tile<POLICY>, TILE_THREADS, smem));
+        CU(c, cudaFuncSetAttribute(k_tile<POLICY, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tile_smem_bytes<CH>(HIST_MAX_KEYS))));
+        CU(c, cudaFuncSetAttribute(k_tile<POLICY, CH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_tile<POLICY, CH>, TILE_THREADS, smem));
         if (blocks_per_sm < 1) return fail(c, F2Q_EINTERNAL, "tile kernel does not fit on an SM");
     }
-    uint64_t grid = (uint64_t)c->sm_count * blocks_per_sm;
-    grid = std::max<uint64_t>(1, std::min<uint64_t>(grid, n_tiles_upper));
-    k_tile<POLICY><<<(unsigned)grid, TILE_THREADS, smem, c->stream>>>(p, c->dG, c->T, c->E, O);
+    *grid = (unsigned)c->sm_count * (unsigned)blocks_per_sm;
+    return F2Q_OK;
+}
+
+template <int POLICY, int CH>
+int launch_tile(f2q_ctx* c, const TileParams& P, Outputs O, uint64_t n_tiles_upper) {
+    const bool hist = (POLICY == POLICY_FAST1) && c->n_keys > 0 && c->n_keys <= HIST_MAX_KEYS;
+    TileParams p = P; p.hist_smem = hist;
+    const size_t smem = tile_smem_bytes<CH>(hist ? c->n_keys : 0);
+    unsigned grid = 0;
+    int rc = tile_grid<POLICY, CH>(c, &grid); if (rc) return rc;
+    if (p.seg_cap == 0) grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(grid, n_tiles_upper));   // main launches keep one segment per CTA
+    k_tile<POLICY, CH><<<grid, TILE_THREADS, smem, c->stream>>>(p, c->dG, c->T, c->E, O);
     c->launches++;
     CU(c, cudaGetLastError());
     return F2Q_OK;
+}
+
+int tile_grid_dyn(f2q_ctx* c, unsigned* grid) {
+    const bool f = c->policy == POLICY_FAST1;
+    switch (c->ch) {
+        case 3: return f ? tile_grid<POLICY_FAST1, 3>(c, grid) : tile_grid<POLICY_GENERIC, 3>(c, grid);
+        case 5: return f ? tile_grid<POLICY_FAST1, 5>(c, grid) : tile_grid<POLICY_GENERIC, 5>(c, grid);
+        default: return f ? tile_grid<POLICY_FAST1, 7>(c, grid) : tile_grid<POLICY_GENERIC, 7>(c, grid);
+    }
+}
+
+int launch_tile_dyn(f2q_ctx* c, const TileParams& P, Outputs O, uint64_t n_tiles_upper) {
+    const bool f = c->policy == POLICY_FAST1;
+    switch (c->ch) {
+        case 3: return f ? launch_tile<POLICY_FAST1, 3>(c, P, O, n_tiles_upper) : launch_tile<POLICY_GENERIC, 3>(c, P, O, n_tiles_upper);
+        case 5: return f ? launch_tile<POLICY_FAST1, 5>(c, P, O, n_tiles_upper) : launch_tile<POLICY_GENERIC, 5>(c, P, O, n_tiles_upper);
+        default: return f ? launch_tile<POLICY_FAST1, 7>(c, P, O, n_tiles_upper) : launch_tile<POLICY_GENERIC, 7>(c, P, O, n_tiles_upper);
+    }
+}
+
+// record length of ordinary FASTQ from the first bytes of a sample -> row size of the tile kernel (16*ch just below it)
+void decide_ch(f2q_ctx* c, const uint8_t* head, size_t n) {
+    size_t nl = 0, pos = 0;
+    for (size_t i = 0; i < n && nl < 8; i++) if (head[i] == '\n') { nl++; pos = i + 1; }
+    c->ch = 7;
+    if (nl == 8) { const size_t rec = pos / 2; c->ch = rec >= 112 ? 7 : rec >= 80 ? 5 : 3; }
+    if (c->force_ch) c->ch = c->force_ch;
+    c->ch_decided = true;
+}
+
+cudaEvent_t timing_begin(f2q_ctx* c) {
+    if (!c->time_kernels) return nullptr;
+    cudaEvent_t e;
+    if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+    cudaEventRecord(e, c->stream);
+    return e;
+}
+void timing_end(f2q_ctx* c, cudaEvent_t a, int kind) {
+    if (!a) return;
+    cudaEvent_t e;
+    if (!c->event_pool.empty()) { e = c->event_pool.back(); c->event_pool.pop_back(); }
+    else if (cudaEventCreate(&e) != cudaSuccess) { c->event_pool.push_back(a); return; }
+    cudaEventRecord(e, c->stream);
+    c->timed.push_back({a, e, kind});
+}
+void timing_collect(f2q_ctx* c) {
+    for (int k = 0; k < 3; k++) { c->kernel_ms[k] = 0; c->kernel_launches[k] = 0; }
+    for (auto& t : c->timed) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { c->kernel_ms[t.kind] += ms; c->kernel_launches[t.kind]++; }
+        c->event_pool.push_back(t.a); c->event_pool.push_back(t.b);
+    }
+    c->timed.clear();
+    cudaGetLastError();
 }
 
 Outputs outputs_of(f2q_ctx* c) {
@@ -257,16 +336,31 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     const uint64_t addr = reinterpret_cast<uint64_t>(dptr);
     const uint64_t delta = n ? (addr & 127ull) : 0;
     const uint8_t* base = n ? reinterpret_cast<const uint8_t*>(addr - delta) : reinterpret_cast<const uint8_t*>(c->carry.p);
-    const uint64_t n_tiles = (delta + n) / OWN_BYTES + 2;
-    const uint64_t stitch_tiles = c->carry_cap / OWN_BYTES + 2;
     int rc;
+    if (!c->ch_decided) {
+        // sniff the record length once per sample (4 KiB of the first chunk) to size the tile rows
+        uint8_t head[4096];
+        const size_t hn = (size_t)std::min<uint64_t>(n, sizeof(head));
+        if (hn) { CU(c, cudaMemcpyAsync(head, dptr, hn, cudaMemcpyDeviceToHost, c->stream)); CU(c, cudaStreamSynchronize(c->stream)); }
+        decide_ch(c, head, hn);
+    }
+    const uint64_t own_bytes = (uint64_t)TILE_THREADS * 16 * c->ch;
+    const uint64_t n_tiles = (delta + n) / own_bytes + 2;
+    const uint64_t stitch_tiles = c->carry_cap / (TILE_THREADS * 16 * 3) + 2;
     if ((rc = dev_alloc(c, c->status, n_tiles * 4))) return rc;
+    unsigned grid = 0;
+    if ((rc = tile_grid_dyn(c, &grid))) return rc;
     // queues sized for the chunk: one entry per 64 bytes covers every non-exact read of ordinary FASTQ; anything
     // beyond that is resolved in place by the tile kernel, so capacity never changes results
     uint64_t want_q = c->opt_queue_entries > 0 ? (uint64_t)c->opt_queue_entries : std::max<uint64_t>(1 << 16, n / 64 + 1024);
     want_q = std::min<uint64_t>(want_q, 0x7FFFFFFFull);
-    if (c->policy == POLICY_GENERIC) want_q = 16;
-    if (want_q > c->q_cap) { if ((rc = dev_alloc(c, c->queue, want_q * sizeof(QEntry)))) return rc; c->q_cap = (uint32_t)want_q; }
+    if (c->policy == POLICY_GENERIC) want_q = grid;
+    if (want_q > c->q_cap || grid != c->n_segs) {
+        want_q = std::max<uint64_t>(want_q, c->q_cap);
+        if ((rc = dev_alloc(c, c->queue, want_q * sizeof(QEntry)))) return rc;
+        if ((rc = dev_alloc(c, c->seg_count, (size_t)grid * 4))) return rc;
+        c->q_cap = (uint32_t)want_q; c->n_segs = grid; c->seg_cap = (uint32_t)(want_q / grid);
+    }
     uint64_t want_g = c->policy == POLICY_GENERIC ? 16 : std::max<uint64_t>(1 << 14, want_q / 8);
     if (want_g > c->g_cap) { if ((rc = dev_alloc(c, c->gqueue, want_g * sizeof(GEntry)))) return rc; c->g_cap = (uint32_t)want_g; }
     if (c->cfg.mode == F2Q_MODE_EXTRACT_COUNT) {
@@ -276,6 +370,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
 
     CU(c, cudaMemsetAsync(c->status.p, 0, n_tiles * 4, c->stream));
     CU(c, cudaMemsetAsync(c->status_stitch.p, 0, stitch_tiles * 4, c->stream));
+    CU(c, cudaMemsetAsync(c->seg_count.p, 0, (size_t)c->n_segs * 4, c->stream));
     k_prepare<<<1, PREP_THREADS, 0, c->stream>>>(c->dS, base, delta, n, is_last ? 1u : 0u, reinterpret_cast<uint8_t*>(c->carry.p),
                                                  c->carry_cap, c->d_tickets, c->q_cap, c->g_cap);
     c->launches++;
@@ -284,13 +379,15 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     P.S = c->dS; P.queue = reinterpret_cast<QEntry*>(c->queue.p); P.gqueue = reinterpret_cast<GEntry*>(c->gqueue.p);
     // 1. the record stitched from the carried tail and the head of this chunk (lives in the carry buffer)
     P.buf = reinterpret_cast<const uint8_t*>(c->carry.p); P.status = reinterpret_cast<uint32_t*>(c->status_stitch.p);
-    P.ticket = c->d_tickets; P.stitch = 1;
-    rc = c->policy == POLICY_FAST1 ? launch_tile<POLICY_FAST1>(c, P, O, 4) : launch_tile<POLICY_GENERIC>(c, P, O, 4);
-    if (rc) return rc;
+    P.ticket = c->d_tickets; P.stitch = 1; P.seg_count = reinterpret_cast<uint32_t*>(c->seg_count.p); P.seg_cap = 0;
+    if ((rc = launch_tile_dyn(c, P, O, 4))) return rc;
     // 2. the chunk itself
     if (n) {
         P.buf = base; P.status = reinterpret_cast<uint32_t*>(c->status.p); P.ticket = c->d_tickets + 1; P.stitch = 0;
-        rc = c->policy == POLICY_FAST1 ? launch_tile<POLICY_FAST1>(c, P, O, n_tiles) : launch_tile<POLICY_GENERIC>(c, P, O, n_tiles);
+        P.seg_cap = c->policy == POLICY_FAST1 ? c->seg_cap : 0;
+        cudaEvent_t t0 = timing_begin(c);
+        rc = launch_tile_dyn(c, P, O, n_tiles);
+        timing_end(c, t0, 0);
         if (rc) return rc;
     }
     // 3. deferred work
@@ -299,12 +396,15 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
             int res = c->resolver ? c->resolver : (c->cfg.miss == 1 ? 1 : 3);
             if (res == 1 && c->cfg.miss != 1) res = 3;
             if (res == 2) res = 3;    // TODO(seed index): falls back to the exact tile scan
-            const unsigned grid = (unsigned)c->sm_count * 4;
-            if (res == 1) k_resolve_probe<<<grid, 256, 0, c->stream>>>(c->T, P.queue, c->dS, O.counts, O.stats);
-            else k_resolve_scan<<<grid, SCAN_THREADS, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, c->dS, O.counts, O.stats);
+            cudaEvent_t t1 = timing_begin(c);
+            if (res == 1) k_resolve_probe<<<c->n_segs, 256, 0, c->stream>>>(c->T, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
+            else k_resolve_scan<<<c->n_segs, SCAN_THREADS, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
+            timing_end(c, t1, 1);
             c->launches++;
         }
+        cudaEvent_t t2 = timing_begin(c);
         k_generic_queue<<<(unsigned)c->sm_count, 128, 0, c->stream>>>(c->dG, c->T, c->E, O, P.gqueue, c->dS);
+        timing_end(c, t2, 2);
         c->launches++;
     }
     // 4. carry the new partial record
@@ -407,10 +507,13 @@ F2Q_EXPORT void f2q_destroy(f2q_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& b : c->lib_bufs) b.release();
     c->result.release(); c->carry.release(); c->status.release(); c->status_stitch.release(); c->queue.release(); c->gqueue.release();
+    c->seg_count.release();
     c->ec_slots.release(); c->ec_counts.release(); c->ec_arena.release(); c->ec_meta.release();
     for (auto p : c->d_stage) cudaFree(p);
     for (auto e : c->ev_copied) cudaEventDestroy(e);
     for (auto e : c->ev_free) cudaEventDestroy(e);
+    for (auto& t : c->timed) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (auto e : c->event_pool) cudaEventDestroy(e);
     if (c->dG) cudaFree(c->dG);
     if (c->d_error) cudaFree(c->d_error);
     if (c->dS) cudaFree(c->dS);
@@ -430,7 +533,9 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "stage_bytes") { if (value < 4096 || !c->d_stage.empty()) return fail(c, F2Q_EINVAL, "stage_bytes invalid or staging already allocated"); c->stage_bytes = (uint64_t)value; }
     else if (n == "stage_slots") { if (value < 1 || value > 16 || !c->d_stage.empty()) return fail(c, F2Q_EINVAL, "stage_slots invalid or staging already allocated"); c->stage_slots = (int)value; }
     else if (n == "resolver") { if (value < 0 || value > 3) return fail(c, F2Q_EINVAL, "resolver must be 0..3"); c->resolver = (int)value; }
-    else if (n == "queue_entries") { if (value < 0) return fail(c, F2Q_EINVAL, "queue_entries < 0"); c->opt_queue_entries = value; c->q_cap = 0; c->g_cap = 0; c->queue.release(); c->gqueue.release(); }
+    else if (n == "queue_entries") { if (value < 0) return fail(c, F2Q_EINVAL, "queue_entries < 0"); c->opt_queue_entries = value; c->q_cap = 0; c->g_cap = 0; c->n_segs = 0; c->queue.release(); c->gqueue.release(); }
+    else if (n == "row_chunks") { if (value != 0 && value != 3 && value != 5 && value != 7) return fail(c, F2Q_EINVAL, "row_chunks must be 0 (auto), 3, 5 or 7"); c->force_ch = (int)value; }
+    else if (n == "time_kernels") c->time_kernels = value != 0;
     else if (n == "force_generic") { if (value) c->policy = POLICY_GENERIC; else decide_policy(c); }
     else return fail(c, F2Q_EINVAL, "unknown option " + n);
     return F2Q_OK;
@@ -443,7 +548,7 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
     if (n_keys && (!key_bytes || !key_offsets)) return fail(c, F2Q_EINVAL, "null library arrays");
     for (auto& b : c->lib_bufs) b.release();
     c->lib_bufs.clear(); c->T = LibTables{}; c->lib_set = false;
-    c->tile_blocks[0] = c->tile_blocks[1] = 0;
+    memset(c->tile_blocks, 0, sizeof(c->tile_blocks));
 
     std::vector<uint64_t> off(n_keys + 1, 0);
     for (uint32_t i = 0; i <= n_keys && n_keys; i++) off[i] = key_offsets[i] - key_offsets[0];
@@ -501,7 +606,8 @@ F2Q_EXPORT int f2q_begin_sample(f2q_ctx* c) {
     int rc = check_ctx(c); if (rc) return rc;
     if (!c->lib_set) return fail(c, F2Q_ESTATE, "f2q_set_library must be called first in Counter mode");
     if ((rc = dev_alloc(c, c->carry, c->carry_cap + 256))) return rc;
-    if ((rc = dev_alloc(c, c->status_stitch, (c->carry_cap / OWN_BYTES + 2) * 4))) return rc;
+    if ((rc = dev_alloc(c, c->status_stitch, (c->carry_cap / (TILE_THREADS * 16 * 3) + 2) * 4))) return rc;
+    c->ch_decided = false;
     CU(c, cudaMemsetAsync(c->result.p, 0, ((size_t)c->n_keys + 5) * 8, c->stream));
     CU(c, cudaMemsetAsync(c->d_error, 0, 4, c->stream));
     CU(c, cudaMemsetAsync(c->dS, 0, sizeof(DevState), c->stream));
@@ -565,6 +671,7 @@ F2Q_EXPORT int f2q_end_sample(f2q_ctx* c, uint64_t* counts, uint64_t* stats) {
     if (!c->closed && (rc = process_device_chunk(c, nullptr, 0, 1))) return rc;     // flush a carried final record
     if ((rc = f2q_sync(c))) return rc;
     c->in_sample = false;
+    timing_collect(c);
     uint32_t err = 0;
     CU(c, cudaMemcpy(&err, c->d_error, 4, cudaMemcpyDeviceToHost));
     DevState hs;
@@ -658,6 +765,12 @@ F2Q_EXPORT int f2q_memcpy_h2d(f2q_ctx* c, void* dptr, const void* host, uint64_t
 }
 
 F2Q_EXPORT uint64_t f2q_launch_count(const f2q_ctx* c) { return c ? c->launches : 0; }
+
+F2Q_EXPORT int f2q_kernel_times(f2q_ctx* c, double* ms, uint64_t* launches) {
+    if (!c || !ms || !launches) return F2Q_EINVAL;
+    for (int k = 0; k < 3; k++) { ms[k] = c->kernel_ms[k]; launches[k] = c->kernel_launches[k]; }
+    return F2Q_OK;
+}
 
 // ---- K0 synthetic generator ------------------------------------------------------------------------------
 F2Q_EXPORT int f2q_synth_fastq(f2q_ctx* c, const f2q_synth_spec* spec, const uint8_t* guides, void* dptr) {

@@ -12,20 +12,9 @@
 namespace f2q {
 
 // ------------------------------------------------------------------------------------------------
-// geometry of one tile of the FASTQ byte stream in shared memory
-//   a tile = TILE_ROWS rows of 128 bytes; rows [0, OWN_ROWS) are owned, the rest is read-ahead (halo) so that
-//   a record that starts in the owned part can be finished without leaving shared memory.
-//   Rows are stored with the 128-byte XOR swizzle (16-byte chunk c of row r lives at chunk c ^ (r & 7)), the same
-//   pattern as CU_TENSOR_MAP_SWIZZLE_128B, so that "thread t scans row t" is bank-conflict free.
+// geometry of the tile kernel: see TileGeom<CH> in tile.cuh (256 owned rows of 16*CH bytes + read-ahead rows)
 // ------------------------------------------------------------------------------------------------
-constexpr int ROW_BYTES = 128;
-constexpr int TILE_ROWS = 256;
-constexpr int HALO_ROWS = 8;
-constexpr int OWN_ROWS = TILE_ROWS - HALO_ROWS;            // 248
-constexpr int TILE_BYTES = TILE_ROWS * ROW_BYTES;          // 32768 bytes resident per tile
-constexpr int OWN_BYTES = OWN_ROWS * ROW_BYTES;            // 31744 bytes advanced per tile
-constexpr int TILE_THREADS = 256;                          // one thread per row
-constexpr int NL_CAP = 4096;                               // newline positions kept per pass (u16 each)
+constexpr int TILE_THREADS = 256;                          // one thread per owned row
 
 // status word of the decoupled look-back over tiles: [31:30] flag, [29:0] newline count (mod 2^30; only mod 4 is used)
 constexpr uint32_t LB_FLAG_AGG = 1u << 30;
@@ -112,7 +101,7 @@ struct DevState {
     uint32_t nl_total;             // newlines in [beg, end) (mod 2^30)
     uint32_t ticket;
     uint32_t error;
-    uint32_t q_count, q_cap;       // non-exact key queue
+    uint32_t q_count, q_cap;       // (unused; the non-exact key queue is segmented per CTA, see TileParams)
     uint32_t g_count, g_cap;       // generic read queue
     uint32_t pad;
 };

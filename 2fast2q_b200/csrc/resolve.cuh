@@ -83,13 +83,16 @@ __device__ inline uint32_t resolve_thread(const LibTables& T, int m, uint64_t ke
 }
 
 // ---- Hamming-1 neighbour probing: one warp per queued key, lane p owns position p -----------------
-__global__ void __launch_bounds__(256) k_resolve_probe(LibTables T, const QEntry* __restrict__ q, const DevState* S,
-                                                       unsigned long long* counts, unsigned long long* stats) {
-    const uint32_t n = S->q_count < S->q_cap ? S->q_count : S->q_cap;
-    const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+// the queue is cut into n_segs segments of seg_cap entries, one per tile-kernel CTA; seg_count[s] = entries in use
+__global__ void __launch_bounds__(256) k_resolve_probe(LibTables T, const QEntry* __restrict__ queue, const uint32_t* __restrict__ seg_count,
+                                                       uint32_t seg_cap, uint32_t n_segs, unsigned long long* counts,
+                                                       unsigned long long* stats) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     uint32_t imperfect = 0, nonal = 0;
-    for (uint32_t i = warp; i < n; i += nwarps) {
+    for (uint32_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
+      const uint32_t n = min(seg_count[seg], seg_cap);
+      const QEntry* __restrict__ q = queue + (size_t)seg * seg_cap;
+      for (uint32_t i = warp; i < n; i += nwarps) {
         const QEntry e = q[i];
         const int nbad = __popc(e.bad);
         uint32_t hits = 0, idx = 0;
@@ -114,6 +117,7 @@ __global__ void __launch_bounds__(256) k_resolve_probe(LibTables T, const QEntry
             if (lane == (uint32_t)(__ffs(who) - 1)) atomicAdd(counts + idx, 1ull);
             imperfect++;
         } else nonal++;
+      }
     }
     if (lane == 0) {
         if (imperfect) atomicAdd(stats + F2Q_STAT_IMPERFECT, (unsigned long long)imperfect);
@@ -125,14 +129,17 @@ __global__ void __launch_bounds__(256) k_resolve_probe(LibTables T, const QEntry
 constexpr int SCAN_TILE = 2048;     // library entries per shared-memory tile (16 KB keys + 8 KB lens + 8 KB idx)
 constexpr int SCAN_THREADS = 256;
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_resolve_scan(LibTables T, int m, const QEntry* __restrict__ q, const DevState* S,
+__global__ void __launch_bounds__(SCAN_THREADS) k_resolve_scan(LibTables T, int m, const QEntry* __restrict__ queue,
+                                                               const uint32_t* __restrict__ seg_count, uint32_t seg_cap, uint32_t n_segs,
                                                                unsigned long long* counts, unsigned long long* stats) {
     __shared__ __align__(16) uint64_t s_key[SCAN_TILE];
     __shared__ uint32_t s_len[SCAN_TILE];
     __shared__ uint32_t s_idx[SCAN_TILE];
-    const uint32_t n = S->q_count < S->q_cap ? S->q_count : S->q_cap;
     uint32_t imperfect = 0, nonal = 0;
-    for (uint32_t base = blockIdx.x * SCAN_THREADS; base < n; base += gridDim.x * SCAN_THREADS) {
+    for (uint32_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
+      const uint32_t n = min(seg_count[seg], seg_cap);
+      const QEntry* __restrict__ q = queue + (size_t)seg * seg_cap;
+      for (uint32_t base = 0; base < n; base += SCAN_THREADS) {
         const uint32_t i = base + threadIdx.x;
         const bool live = i < n;
         QEntry e{0, 0, 0};
@@ -161,6 +168,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_resolve_scan(LibTables T, int 
             if (b.d <= m && b.n == 1) { atomicAdd(counts + b.idx, 1ull); imperfect++; }
             else nonal++;
         }
+      }
     }
     imperfect = __reduce_add_sync(0xffffffffu, imperfect);
     nonal = __reduce_add_sync(0xffffffffu, nonal);

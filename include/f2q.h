@@ -107,6 +107,7 @@ const char* f2q_last_error(const f2q_ctx* ctx);   /* ctx may be NULL: last creat
  *   "queue_entries"   capacity of the deferred non-exact key queue (default: derived from the chunk size;
  *                     capacity never changes results — overflow is resolved in place)
  *   "force_generic"   1: run every read through the byte-wise generic kernels (cross-check of the packed path)
+ *   "time_kernels"    1: bracket the tile / resolver / generic launches with CUDA events (see f2q_kernel_times)
  */
 int f2q_set_option(f2q_ctx* ctx, const char* name, int64_t value);
 
@@ -199,6 +200,11 @@ int f2q_memcpy_h2d(f2q_ctx* ctx, void* dptr, const void* host, uint64_t nbytes);
 
 /* number of kernel launches issued by this context so far (bench.py reports it as gpu_launches) */
 uint64_t f2q_launch_count(const f2q_ctx* ctx);
+
+/* device time of the last finished sample per kernel class, measured with CUDA events on the context's stream
+ * (needs option "time_kernels" = 1): [0] fused tile kernel over the chunk, [1] mismatch resolver, [2] generic queue.
+ * launches[k] = number of launches ms[k] sums over. */
+int f2q_kernel_times(f2q_ctx* ctx, double ms[3], uint64_t launches[3]);
 
 #ifdef __cplusplus
 }

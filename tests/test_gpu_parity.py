@@ -48,6 +48,20 @@ def test_fuzz_cases_chunked(gu, chunk):
         gu.check_case(c, c["fastq"], chunk)
 
 
+@pytest.mark.parametrize("ch", [3, 5, 7])
+def test_row_sizes(gu, ch):
+    """every row size of the tile kernel (16*ch bytes per thread) on inputs whose records are shorter and longer than it"""
+    for c in G.kat():
+        gu.check_case(c, c["fastq"], row_chunks=ch)
+    for c in G.fuzz()[::4]:
+        gu.check_case(c, c["fastq"], row_chunks=ch)
+    for name in ("config2_slice", "config3_m3", "config4_barseq"):
+        c = [x for x in G.shaped() if x["name"] == name][0]
+        params, lib, data = cases.shaped_inputs(name)
+        gu.check_case(dict(c, library=lib), data, row_chunks=ch)
+        gu.check_case(dict(c, library=lib), data, 250007, row_chunks=ch)
+
+
 def test_fuzz_cases_generic_kernels(gu):
     for c in G.fuzz()[::2]:
         gu.check_case(c, c["fastq"], force_generic=1)
