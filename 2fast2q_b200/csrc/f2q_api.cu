@@ -59,6 +59,7 @@ struct f2q_ctx {
     uint32_t q_cap = 0, g_cap = 0;     // q_cap = total queue entries (n_segs * seg_cap)
     uint32_t seg_cap = 0, n_segs = 0;
     int force_ch = 0;
+    int halo_rows = 6;
     int ch = 7;                        // row chunks of the tile kernel (row = 16*ch bytes), picked per sample from the record length
     bool ch_decided = false;
     int64_t opt_queue_entries = 0;
@@ -78,7 +79,8 @@ struct f2q_ctx {
     int sticky = F2Q_OK;
     std::string err;
     uint64_t launches = 0;
-    int tile_blocks[2][8] = {{0}};
+    int tile_blocks[2][8][2] = {{{0}}};
+    int nt = 128;                      // threads (= owned rows) per tile-kernel CTA: 128 or 256
     // optional per-kernel timing (option "time_kernels"): event pairs around the tile / resolver / generic launches
     bool time_kernels = false;
     struct Timed { cudaEvent_t a, b; int kind; };
@@ -178,61 +180,67 @@ void decide_policy(f2q_ctx* c) {
 
 constexpr uint32_t HIST_MAX_KEYS = 8192;     // shared-memory histogram up to this many features (32 KB of u32)
 
-// persistent grid of the tile kernel for (policy, ch): SM count x resident CTAs per SM
-template <int POLICY, int CH>
+// persistent grid of the tile kernel for (policy, ch, nt): SM count x resident CTAs per SM
+template <int POLICY, int CH, int NT>
 int tile_grid(f2q_ctx* c, unsigned* grid) {
     const bool hist = (POLICY == POLICY_FAST1) && c->n_keys > 0 && c->n_keys <= HIST_MAX_KEYS;
-    const size_t smem = tile_smem_bytes<CH>(hist ? c->n_keys : 0);
-    int& blocks_per_sm = c->tile_blocks[POLICY][CH];
+    const size_t smem = tile_smem_bytes<CH, NT>(hist ? c->n_keys : 0);
+    int& blocks_per_sm = c->tile_blocks[POLICY][CH][NT == 256];
     if (blocks_per_sm == 0) {
-        CU(c, cudaFuncSetAttribute(k_tile<POLICY, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tile_smem_bytes<CH>(HIST_MAX_KEYS))));
-        CU(c, cudaFuncSetAttribute(k_tile<POLICY, CH>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_tile<POLICY, CH>, TILE_THREADS, smem));
+        CU(c, cudaFuncSetAttribute(k_tile<POLICY, CH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tile_smem_bytes<CH, NT>(HIST_MAX_KEYS))));
+        CU(c, cudaFuncSetAttribute(k_tile<POLICY, CH, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_tile<POLICY, CH, NT>, NT, smem));
         if (blocks_per_sm < 1) return fail(c, F2Q_EINTERNAL, "tile kernel does not fit on an SM");
     }
     *grid = (unsigned)c->sm_count * (unsigned)blocks_per_sm;
     return F2Q_OK;
 }
 
-template <int POLICY, int CH>
+template <int POLICY, int CH, int NT>
 int launch_tile(f2q_ctx* c, const TileParams& P, Outputs O, uint64_t n_tiles_upper) {
     const bool hist = (POLICY == POLICY_FAST1) && c->n_keys > 0 && c->n_keys <= HIST_MAX_KEYS;
     TileParams p = P; p.hist_smem = hist;
-    const size_t smem = tile_smem_bytes<CH>(hist ? c->n_keys : 0);
+    const size_t smem = tile_smem_bytes<CH, NT>(hist ? c->n_keys : 0);
     unsigned grid = 0;
-    int rc = tile_grid<POLICY, CH>(c, &grid); if (rc) return rc;
+    int rc = tile_grid<POLICY, CH, NT>(c, &grid); if (rc) return rc;
     if (p.seg_cap == 0) grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(grid, n_tiles_upper));   // main launches keep one segment per CTA
-    k_tile<POLICY, CH><<<grid, TILE_THREADS, smem, c->stream>>>(p, c->dG, c->T, c->E, O);
+    k_tile<POLICY, CH, NT><<<grid, NT, smem, c->stream>>>(p, c->dG, c->T, c->E, O);
     c->launches++;
     CU(c, cudaGetLastError());
     return F2Q_OK;
 }
 
-int tile_grid_dyn(f2q_ctx* c, unsigned* grid) {
-    const bool f = c->policy == POLICY_FAST1;
-    switch (c->ch) {
-        case 3: return f ? tile_grid<POLICY_FAST1, 3>(c, grid) : tile_grid<POLICY_GENERIC, 3>(c, grid);
-        case 5: return f ? tile_grid<POLICY_FAST1, 5>(c, grid) : tile_grid<POLICY_GENERIC, 5>(c, grid);
-        default: return f ? tile_grid<POLICY_FAST1, 7>(c, grid) : tile_grid<POLICY_GENERIC, 7>(c, grid);
-    }
-}
+#define F2Q_DISPATCH(FN, ...)                                                                                     \
+    do {                                                                                                          \
+        const bool f = c->policy == POLICY_FAST1;                                                                 \
+        if (c->nt == 256) {                                                                                       \
+            switch (c->ch) {                                                                                      \
+                case 3: return f ? FN<POLICY_FAST1, 3, 256>(__VA_ARGS__) : FN<POLICY_GENERIC, 3, 256>(__VA_ARGS__); \
+                case 5: return f ? FN<POLICY_FAST1, 5, 256>(__VA_ARGS__) : FN<POLICY_GENERIC, 5, 256>(__VA_ARGS__); \
+                default: return f ? FN<POLICY_FAST1, 7, 256>(__VA_ARGS__) : FN<POLICY_GENERIC, 7, 256>(__VA_ARGS__); \
+            }                                                                                                     \
+        }                                                                                                         \
+        switch (c->ch) {                                                                                          \
+            case 3: return f ? FN<POLICY_FAST1, 3, 128>(__VA_ARGS__) : FN<POLICY_GENERIC, 3, 128>(__VA_ARGS__);   \
+            case 5: return f ? FN<POLICY_FAST1, 5, 128>(__VA_ARGS__) : FN<POLICY_GENERIC, 5, 128>(__VA_ARGS__);   \
+            default: return f ? FN<POLICY_FAST1, 7, 128>(__VA_ARGS__) : FN<POLICY_GENERIC, 7, 128>(__VA_ARGS__);  \
+        }                                                                                                         \
+    } while (0)
 
-int launch_tile_dyn(f2q_ctx* c, const TileParams& P, Outputs O, uint64_t n_tiles_upper) {
-    const bool f = c->policy == POLICY_FAST1;
-    switch (c->ch) {
-        case 3: return f ? launch_tile<POLICY_FAST1, 3>(c, P, O, n_tiles_upper) : launch_tile<POLICY_GENERIC, 3>(c, P, O, n_tiles_upper);
-        case 5: return f ? launch_tile<POLICY_FAST1, 5>(c, P, O, n_tiles_upper) : launch_tile<POLICY_GENERIC, 5>(c, P, O, n_tiles_upper);
-        default: return f ? launch_tile<POLICY_FAST1, 7>(c, P, O, n_tiles_upper) : launch_tile<POLICY_GENERIC, 7>(c, P, O, n_tiles_upper);
-    }
-}
+int tile_grid_dyn(f2q_ctx* c, unsigned* grid) { F2Q_DISPATCH(tile_grid, c, grid); }
+int launch_tile_dyn(f2q_ctx* c, const TileParams& P, Outputs O, uint64_t n_tiles_upper) { F2Q_DISPATCH(launch_tile, c, P, O, n_tiles_upper); }
 
 // record length of ordinary FASTQ from the first bytes of a sample -> row size of the tile kernel (16*ch just below it)
 void decide_ch(f2q_ctx* c, const uint8_t* head, size_t n) {
     size_t nl = 0, pos = 0;
     for (size_t i = 0; i < n && nl < 8; i++) if (head[i] == '\n') { nl++; pos = i + 1; }
     c->ch = 7;
-    if (nl == 8) { const size_t rec = pos / 2; c->ch = rec >= 112 ? 7 : rec >= 80 ? 5 : 3; }
+    size_t rec = 0;
+    if (nl == 8) { rec = pos / 2; c->ch = rec >= 112 ? 7 : rec >= 80 ? 5 : 3; }
     if (c->force_ch) c->ch = c->force_ch;
+    // read-ahead rows behind each tile: two records' worth (reads that need more take the global-memory path)
+    const int S = 16 * c->ch, halo_max = (1024 + S - 1) / S + 1;
+    c->halo_rows = rec ? (int)std::min<size_t>(halo_max, std::max<size_t>(2, (2 * rec + S - 1) / S + 1)) : halo_max;
     c->ch_decided = true;
 }
 
@@ -344,9 +352,9 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         if (hn) { CU(c, cudaMemcpyAsync(head, dptr, hn, cudaMemcpyDeviceToHost, c->stream)); CU(c, cudaStreamSynchronize(c->stream)); }
         decide_ch(c, head, hn);
     }
-    const uint64_t own_bytes = (uint64_t)TILE_THREADS * 16 * c->ch;
+    const uint64_t own_bytes = (uint64_t)c->nt * 16 * c->ch;
     const uint64_t n_tiles = (delta + n) / own_bytes + 2;
-    const uint64_t stitch_tiles = c->carry_cap / (TILE_THREADS * 16 * 3) + 2;
+    const uint64_t stitch_tiles = c->carry_cap / (128 * 16 * 3) + 2;
     if ((rc = dev_alloc(c, c->status, n_tiles * 4))) return rc;
     unsigned grid = 0;
     if ((rc = tile_grid_dyn(c, &grid))) return rc;
@@ -377,6 +385,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     Outputs O = outputs_of(c);
     TileParams P{};
     P.S = c->dS; P.queue = reinterpret_cast<QEntry*>(c->queue.p); P.gqueue = reinterpret_cast<GEntry*>(c->gqueue.p);
+    P.halo_rows = (uint32_t)c->halo_rows;
     // 1. the record stitched from the carried tail and the head of this chunk (lives in the carry buffer)
     P.buf = reinterpret_cast<const uint8_t*>(c->carry.p); P.status = reinterpret_cast<uint32_t*>(c->status_stitch.p);
     P.ticket = c->d_tickets; P.stitch = 1; P.seg_count = reinterpret_cast<uint32_t*>(c->seg_count.p); P.seg_cap = 0;
@@ -393,11 +402,12 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     // 3. deferred work
     if (c->policy == POLICY_FAST1) {
         if (c->cfg.miss > 0) {
-            int res = c->resolver ? c->resolver : (c->cfg.miss == 1 ? 1 : 3);
-            if (res == 1 && c->cfg.miss != 1) res = 3;
-            if (res == 2) res = 3;    // TODO(seed index): falls back to the exact tile scan
+            int res = c->resolver ? c->resolver : 2;          // auto: the pigeonhole seed index is the cheapest exact method
+            if (res == 1 && c->cfg.miss != 1) res = 2;
+            if (res == 2 && c->cfg.miss > 32) res = 3;
             cudaEvent_t t1 = timing_begin(c);
             if (res == 1) k_resolve_probe<<<c->n_segs, 256, 0, c->stream>>>(c->T, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
+            else if (res == 2) k_resolve_seed<<<c->n_segs, 256, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
             else k_resolve_scan<<<c->n_segs, SCAN_THREADS, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
             timing_end(c, t1, 1);
             c->launches++;
@@ -534,6 +544,7 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "stage_slots") { if (value < 1 || value > 16 || !c->d_stage.empty()) return fail(c, F2Q_EINVAL, "stage_slots invalid or staging already allocated"); c->stage_slots = (int)value; }
     else if (n == "resolver") { if (value < 0 || value > 3) return fail(c, F2Q_EINVAL, "resolver must be 0..3"); c->resolver = (int)value; }
     else if (n == "queue_entries") { if (value < 0) return fail(c, F2Q_EINVAL, "queue_entries < 0"); c->opt_queue_entries = value; c->q_cap = 0; c->g_cap = 0; c->n_segs = 0; c->queue.release(); c->gqueue.release(); }
+    else if (n == "tile_threads") { if (value != 128 && value != 256) return fail(c, F2Q_EINVAL, "tile_threads must be 128 or 256"); c->nt = (int)value; c->n_segs = 0; }
     else if (n == "row_chunks") { if (value != 0 && value != 3 && value != 5 && value != 7) return fail(c, F2Q_EINVAL, "row_chunks must be 0 (auto), 3, 5 or 7"); c->force_ch = (int)value; }
     else if (n == "time_kernels") c->time_kernels = value != 0;
     else if (n == "force_generic") { if (value) c->policy = POLICY_GENERIC; else decide_policy(c); }
@@ -589,6 +600,37 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
         while (gh[j]) j = (j + 1) & (gcap - 1);
         gh[j] = i + 1;
     }
+    // pigeonhole seed index for <= miss mismatches (resolve.cuh)
+    std::vector<uint4> seed_slots(16, make_uint4(0, 0, 0, 0));
+    std::vector<uint32_t> seed_items;
+    const uint32_t parts = (uint32_t)std::max(1, std::min(c->cfg.miss, 32) + 1);
+    if (c->cfg.miss > 0 && !fk.empty()) {
+        std::vector<std::pair<uint64_t, uint32_t>> ent;
+        ent.reserve(fk.size() * parts);
+        for (uint32_t j = 0; j < fk.size(); j++)
+            for (uint32_t sgm = 0; sgm < parts; sgm++) {
+                const uint32_t b0 = sgm * fl[j] / parts, b1 = (sgm + 1) * fl[j] / parts;
+                const uint64_t rng = even_range(b0, b1);
+                const uint64_t v = (fk[j] >> (2 * b0)) & ((rng | (rng << 1)) >> (2 * b0));
+                ent.emplace_back(seed_tag(fl[j], sgm, v), j);
+            }
+        std::sort(ent.begin(), ent.end());
+        size_t uniq = 0;
+        for (size_t i = 0; i < ent.size(); i++) if (i == 0 || ent[i].first != ent[i - 1].first) uniq++;
+        const uint32_t scap = pow2_at_least(2 * (uint64_t)uniq + 2);
+        seed_slots.assign(scap, make_uint4(0, 0, 0, 0));
+        seed_items.resize(ent.size());
+        for (size_t i = 0; i < ent.size();) {
+            size_t e = i;
+            while (e < ent.size() && ent[e].first == ent[i].first) { seed_items[e] = ent[e].second; e++; }
+            uint32_t h = seed_hash(ent[i].first) & (scap - 1);
+            while (seed_slots[h].x | seed_slots[h].y) h = (h + 1) & (scap - 1);
+            seed_slots[h] = make_uint4((uint32_t)ent[i].first, (uint32_t)(ent[i].first >> 32), (uint32_t)i, (uint32_t)(e - i));
+            i = e;
+        }
+    }
+    if ((rc = upload(c, seed_slots, &c->T.seed_slots)) || (rc = upload(c, seed_items, &c->T.seed_items))) return rc;
+    c->T.seed_mask = (uint32_t)seed_slots.size() - 1; c->T.seed_parts = parts;
     if ((rc = upload(c, slots, &c->T.slots)) || (rc = upload(c, fk, &c->T.fast_keys)) || (rc = upload(c, fl, &c->T.fast_lens)) ||
         (rc = upload(c, fi, &c->T.fast_idx)) || (rc = upload(c, bytes, &c->T.key_bytes)) || (rc = upload(c, off, &c->T.key_off)) ||
         (rc = upload(c, gh, &c->T.ghash)))
@@ -606,7 +648,7 @@ F2Q_EXPORT int f2q_begin_sample(f2q_ctx* c) {
     int rc = check_ctx(c); if (rc) return rc;
     if (!c->lib_set) return fail(c, F2Q_ESTATE, "f2q_set_library must be called first in Counter mode");
     if ((rc = dev_alloc(c, c->carry, c->carry_cap + 256))) return rc;
-    if ((rc = dev_alloc(c, c->status_stitch, (c->carry_cap / (TILE_THREADS * 16 * 3) + 2) * 4))) return rc;
+    if ((rc = dev_alloc(c, c->status_stitch, (c->carry_cap / (128 * 16 * 3) + 2) * 4))) return rc;
     c->ch_decided = false;
     CU(c, cudaMemsetAsync(c->result.p, 0, ((size_t)c->n_keys + 5) * 8, c->stream));
     CU(c, cudaMemsetAsync(c->d_error, 0, 4, c->stream));

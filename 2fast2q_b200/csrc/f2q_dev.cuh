@@ -12,10 +12,8 @@
 namespace f2q {
 
 // ------------------------------------------------------------------------------------------------
-// geometry of the tile kernel: see TileGeom<CH> in tile.cuh (256 owned rows of 16*CH bytes + read-ahead rows)
+// geometry of the tile kernel: see TileGeom<CH, NT> in tile.cuh (NT owned rows of 16*CH bytes + read-ahead rows)
 // ------------------------------------------------------------------------------------------------
-constexpr int TILE_THREADS = 256;                          // one thread per owned row
-
 // status word of the decoupled look-back over tiles: [31:30] flag, [29:0] newline count (mod 2^30; only mod 4 is used)
 constexpr uint32_t LB_FLAG_AGG = 1u << 30;
 constexpr uint32_t LB_FLAG_PREFIX = 2u << 30;
@@ -64,7 +62,7 @@ struct LibTables {
     uint32_t n_generic;        // keys that are NOT in the packed table
     uint64_t generic_len_mask; // bit L set: some non-packed key has length L (L < 64); bit 63: some length >= 63
     // pigeonhole seed index over the packed keys (resolver 2)
-    const uint2* seed_slots;   // {tag, start|count} hash of (len, segment, value) -> range in seed_items
+    const uint4* seed_slots;   // {tag lo, tag hi, start, count}: hash of (len, segment, value) -> range in seed_items; tag 0 = empty
     uint32_t seed_mask;
     const uint32_t* seed_items;   // indices into fast_keys
     uint32_t seed_parts;       // miss + 1

@@ -177,6 +177,74 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_resolve_scan(LibTables T, int 
         if (nonal) atomicAdd(stats + F2Q_STAT_NON_ALIGNED, (unsigned long long)nonal);
     }
 }
+// ---- pigeonhole seed index: a key within m mismatches of a library entry agrees exactly with it on at least one
+// of m+1 segments.  seed_slots hashes (length, segment, segment value) -> range of seed_items (indices into fast_keys).
+__host__ __device__ __forceinline__ uint64_t seed_tag(uint32_t len, uint32_t seg, uint64_t v) {
+    return (1ull << 63) | ((uint64_t)len << 40) | ((uint64_t)seg << 32) | v;
+}
+__host__ __device__ __forceinline__ uint32_t seed_hash(uint64_t tag) {
+    uint64_t h = tag * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 31; h *= 0xD6E8FEB86659FD93ull;
+    return (uint32_t)(h >> 32);
+}
+__host__ __device__ __forceinline__ uint64_t even_range(uint32_t b0, uint32_t b1) {     // even bits of symbols [b0, b1)
+    const uint64_t hi = b1 >= 32 ? ~0ull : ((1ull << (2 * b1)) - 1), lo = b0 >= 32 ? ~0ull : ((1ull << (2 * b0)) - 1);
+    return (hi & ~lo) & 0x5555555555555555ull;
+}
+
+__device__ inline uint32_t resolve_seed_thread(const LibTables& T, int m, uint64_t key, uint32_t bad, uint32_t len) {
+    const int nbad = __popc(bad);
+    if (m <= 0 || nbad > m) return RES_NONE;
+    const uint32_t parts = T.seed_parts;
+    const uint64_t lenmask = even_range(0, len), badeven = spread_even(bad) & lenmask;
+    Best b{m + 1, 0, 0};
+    for (uint32_t s = 0; s < parts; s++) {
+        const uint32_t b0 = s * len / parts, b1 = (s + 1) * len / parts;
+        const uint64_t seg = even_range(b0, b1);
+        if (badeven & seg) continue;                                   // a non-ACGT symbol can never agree exactly
+        const uint64_t v = (key >> (2 * b0)) & ((seg | (seg << 1)) >> (2 * b0));
+        const uint64_t tag = seed_tag(len, s, v);
+        uint32_t h = seed_hash(tag) & T.seed_mask, start = 0, count = 0;
+        for (;;) {
+            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(T.seed_slots) + h);
+            const uint64_t t = ((uint64_t)raw.y << 32) | raw.x;
+            if (t == 0) break;
+            if (t == tag) { start = raw.z; count = raw.w; break; }
+            h = (h + 1) & T.seed_mask;
+        }
+        for (uint32_t c = 0; c < count; c++) {
+            const uint32_t j = __ldg(T.seed_items + start + c);
+            const uint64_t x = key ^ __ldg(T.fast_keys + j);
+            const uint64_t diff = (((x | (x >> 1)) & lenmask) | badeven);     // even bit 2p: symbol p differs (or is bad)
+            bool dup = false;                                          // already seen through an earlier agreeing segment?
+            for (uint32_t s2 = 0; s2 < s; s2++)
+                if ((diff & even_range(s2 * len / parts, (s2 + 1) * len / parts)) == 0) { dup = true; break; }
+            if (dup) continue;
+            b.add(__popcll(diff), __ldg(T.fast_idx + j), m);
+        }
+    }
+    return (b.d <= m && b.n == 1) ? b.idx : RES_NONE;
+}
+
+__global__ void __launch_bounds__(256) k_resolve_seed(LibTables T, int m, const QEntry* __restrict__ queue, const uint32_t* __restrict__ seg_count,
+                                                      uint32_t seg_cap, uint32_t n_segs, unsigned long long* counts, unsigned long long* stats) {
+    uint32_t imperfect = 0, nonal = 0;
+    for (uint32_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
+        const uint32_t n = min(seg_count[seg], seg_cap);
+        const QEntry* __restrict__ q = queue + (size_t)seg * seg_cap;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const QEntry e = q[i];
+            const uint32_t r = resolve_seed_thread(T, m, e.key, e.bad, e.len);
+            if (r != RES_NONE) { atomicAdd(counts + r, 1ull); imperfect++; } else nonal++;
+        }
+    }
+    imperfect = __reduce_add_sync(0xffffffffu, imperfect);
+    nonal = __reduce_add_sync(0xffffffffu, nonal);
+    if ((threadIdx.x & 31) == 0) {
+        if (imperfect) atomicAdd(stats + F2Q_STAT_IMPERFECT, (unsigned long long)imperfect);
+        if (nonal) atomicAdd(stats + F2Q_STAT_NON_ALIGNED, (unsigned long long)nonal);
+    }
+}
 #endif  // __CUDACC__
 
 }  // namespace f2q

@@ -7,8 +7,10 @@
 //   K4 lookup/count   2-bit pack, exact probe of the packed-key table, shared-memory histogram (fast2q.py:365-367)
 //   -> non-exact keys go to this CTA's segment of the resolver queue (K5), undecidable reads to the generic queue.
 //
-// Work decomposition: persistent CTAs take tiles by atomic ticket (a tile's predecessors are always running or done,
-// so the look-back cannot deadlock).  A tile is (256 + halo) rows of S = 16*CH bytes in shared memory, CH odd so that
+// Work decomposition: persistent CTAs take tiles by atomic ticket WHEN THEY ARE READY for them and publish the tile's
+// newline count as soon as it is scanned (a tile's predecessors are always running or done, so the look-back cannot
+// deadlock and rarely waits); latency is hidden by several small CTAs per SM rather than by pipelining inside a CTA.
+// A tile is (NT + halo) rows of S = 16*CH bytes in shared memory, NT = threads per CTA, CH odd so that
 // "thread t scans row t with 16-byte loads" is bank-conflict free without a swizzle; CH is chosen by the host so that
 // S is just below the record length (about one read start per row).  Interior tiles are fetched by one TMA bulk copy
 // (cp.async.bulk + mbarrier); the first/last tile of a range, which needs byte masking, is loaded by the threads.
@@ -34,25 +36,26 @@ struct TileParams {
     uint32_t seg_cap;          // 0: resolve every non-exact key in place
     GEntry* gqueue;
     uint32_t hist_smem;        // 1: per-CTA shared-memory histogram of n_keys u32
+    uint32_t halo_rows;        // read-ahead rows loaded and scanned behind the NT owned rows (2 .. TileGeom::HALO)
 };
 
 constexpr uint32_t LB_SPIN_LIMIT = 1u << 24;
 
-template <int CH>
+template <int CH, int NT_>
 struct TileGeom {
     static constexpr int S = CH * 16;                          // bytes per row
-    static constexpr int NT = TILE_THREADS;                    // owned rows = threads
-    static constexpr int HALO = (1024 + S - 1) / S + 1;        // read-ahead rows (>= 1 KiB)
+    static constexpr int NT = NT_;                             // owned rows = threads per CTA
+    static constexpr int HALO = (1024 + S - 1) / S + 1;        // max read-ahead rows (>= 1 KiB); P.halo_rows of them are used
     static constexpr int ROWS = NT + HALO;
     static constexpr int OWN_BYTES = NT * S;
-    static constexpr int LOAD_BYTES = ROWS * S;                // multiple of 16
-    static constexpr int MASK_OFF = LOAD_BYTES + 16;           // uint4 row masks (16-byte aligned since S % 16 == 0)
+    static constexpr int BUF_BYTES = ROWS * S + 16;            // tile buffer (+16 so that word reads may run past the end)
+    static constexpr int MASK_OFF = BUF_BYTES;                 // ROWS uint4 row masks
     static constexpr int HIST_OFF = MASK_OFF + ROWS * 16;
 };
 
-template <int CH>
+template <int CH, int NT>
 __host__ __device__ inline size_t tile_smem_bytes(uint32_t hist_entries) {
-    return (size_t)TileGeom<CH>::HIST_OFF + (size_t)hist_entries * 4;
+    return (size_t)TileGeom<CH, NT>::HIST_OFF + (size_t)hist_entries * 4;
 }
 
 // ---- mbarrier / TMA bulk copy (sm_90+ PTX) ------------------------------------------------------------
@@ -103,14 +106,15 @@ __device__ __forceinline__ bool qual_fails_tile(const uint8_t* tile, uint32_t o,
     const uint32_t add_ge = (0x80u - 33u) * 0x01010101u, add_gt = (0x80u - (uint32_t)(fmax + 1)) * 0x01010101u;
     WordReader rd(tile, o);
     uint32_t acc = 0;
-    for (int k = 0; k < n; k += 4) {
-        uint32_t w = rd.next();
-        if (n - k < 4) w &= (1u << (8 * (n - k))) - 1u;               // bytes past the slice become 0 (never fail)
-        uint32_t lo7 = w & 0x7F7F7F7Fu;
-        uint32_t ge33 = ((lo7 + add_ge) | w);                          // bit 7: byte >= 33
-        uint32_t gtmax = ((lo7 + add_gt) | w);                         // bit 7: byte >  fmax
+    auto test = [&](uint32_t w) {
+        const uint32_t lo7 = w & 0x7F7F7F7Fu;
+        const uint32_t ge33 = ((lo7 + add_ge) | w);                    // bit 7: byte >= 33
+        const uint32_t gtmax = ((lo7 + add_gt) | w);                   // bit 7: byte >  fmax
         acc |= ge33 & ~gtmax;
-    }
+    };
+    const int full = n >> 2;
+    for (int k = 0; k < full; k++) test(rd.next());
+    if (n & 3) test(rd.next() & ((1u << (8 * (n & 3))) - 1u));         // bytes past the slice become 0 (never fail)
     return (acc & 0x80808080u) != 0;
 }
 
@@ -119,9 +123,11 @@ __device__ __forceinline__ void pack_tile(const uint8_t* tile, uint32_t o, int n
     key = 0; bad = 0;
     if (n <= 0) return;
     WordReader rd(tile, o);
-    for (int k = 0; k < n; k += 4) {
+    const int words = (n + 3) >> 2;
+    for (int kw = 0; kw < words; kw++) {
+        const int k = kw * 4;
         uint32_t w = rd.next();
-        if (n - k < 4) { uint32_t keep = (1u << (8 * (n - k))) - 1u; w = (w & keep) | (0x41414141u & ~keep); }   // pad with 'A' (code 0)
+        if (kw == words - 1 && (n & 3)) { const uint32_t keep = (1u << (8 * (n & 3))) - 1u; w = (w & keep) | (0x41414141u & ~keep); }   // pad with 'A' (code 0)
         uint32_t codes = (w >> 1) & 0x03030303u;
         uint32_t t = (codes | (codes >> 4)) & 0x00330033u;
         t = (t | (t >> 8)) & 0x3333u;                                  // nibble i = code of byte i
@@ -161,11 +167,11 @@ struct Acc {
     unsigned long long reads, perfect, imperfect, nonal, qfail, last_end;
 };
 
-template <int POLICY, int CH>
-__global__ void __launch_bounds__(TILE_THREADS, POLICY == POLICY_FAST1 ? 3 : 2)
+template <int POLICY, int CH, int NT>
+__global__ void __launch_bounds__(NT, POLICY == POLICY_FAST1 ? (768 / NT) : (512 / NT))
 k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, Outputs O) {
-    using G_ = TileGeom<CH>;
-    constexpr int S = G_::S, NT = G_::NT, ROWS = G_::ROWS;
+    using G_ = TileGeom<CH, NT>;
+    constexpr int S = G_::S;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* tile = smem;
     uint4* rowmask = reinterpret_cast<uint4*>(smem + G_::MASK_OFF);
@@ -185,10 +191,12 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     for (uint32_t i = tid; i < sizeof(GenericCfg) / 4; i += NT)
         reinterpret_cast<uint32_t*>(&s_G)[i] = reinterpret_cast<const uint32_t*>(Gp)[i];
     if (P.hist_smem) for (uint32_t i = tid; i < T.n_keys; i += NT) hist[i] = 0;
+    for (uint32_t i = tid; i < G_::ROWS; i += NT) rowmask[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) { mbar_init(&s_bar, 1); s_qn = 0; }
-    __syncthreads();
     const DevCfg& C = s_G.c;
 
+    const uint32_t rows_loaded = NT + P.halo_rows;                     // owned + read-ahead rows of every tile
+    const uint32_t load_bytes = rows_loaded * S;
     const uint64_t first_tile = beg / G_::OWN_BYTES;
     const uint64_t n_tiles = (end - 1) / G_::OWN_BYTES + 1;
     const uint8_t* __restrict__ buf = P.buf;
@@ -197,26 +205,39 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     unsigned long long gst[F2Q_N_STATS] = {0, 0, 0, 0, 0};            // stats of reads handled in place by the generic code
     uint32_t bar_phase = 0;
 
+    // newline flags of one 16-byte chunk, bit i = byte i
+    auto chunk_mask = [&](const uint8_t* p16) -> uint32_t {
+        const uint4 v = *reinterpret_cast<const uint4*>(p16);
+        const uint32_t z0 = eq_bytes(v.x, 0x0A0A0A0Au), z1 = eq_bytes(v.y, 0x0A0A0A0Au);
+        const uint32_t z2 = eq_bytes(v.z, 0x0A0A0A0Au), z3 = eq_bytes(v.w, 0x0A0A0A0Au);
+        const uint32_t lo = __dp4a(z0, 0x08040201u, __dp4a(z1, 0x80402010u, 0u));     // 128 * (flags of bytes 0..7)
+        const uint32_t hi = __dp4a(z2, 0x08040201u, __dp4a(z3, 0x80402010u, 0u));     // 128 * (flags of bytes 8..15)
+        return (lo >> 7) | (hi << 1);
+    };
+
     for (;;) {
         __syncthreads();                                               // everyone is done with the previous tile
-        if (tid == 0) s_tile = atomicAdd(P.ticket, 1u);
+        // ---- ticket + load.  Thread 0 takes the ticket only now, so the tile's count is published ~one load later ----
+        if (tid == 0) {
+            const uint32_t tk = atomicAdd(P.ticket, 1u);
+            s_tile = tk;
+            const uint64_t b0 = (first_tile + tk) * G_::OWN_BYTES;
+            if (first_tile + tk < n_tiles && b0 >= beg && b0 + load_bytes <= end) {       // interior tile: one TMA bulk copy
+                mbar_expect_tx(&s_bar, load_bytes);
+                tma_load_1d(tile, buf + b0, load_bytes, &s_bar);
+            }
+        }
         __syncthreads();
         const uint64_t t = first_tile + s_tile;
         if (t >= n_tiles) break;
         const uint64_t base = t * G_::OWN_BYTES;
-
-        // ---- load ----
-        const bool interior = (base >= beg) && (base + G_::LOAD_BYTES <= end);
+        const bool interior = (base >= beg) && (base + load_bytes <= end);
         if (interior) {
-            if (tid == 0) {
-                mbar_expect_tx(&s_bar, G_::LOAD_BYTES);
-                tma_load_1d(tile, buf + base, G_::LOAD_BYTES, &s_bar);
-            }
             mbar_wait(&s_bar, bar_phase);
             bar_phase ^= 1;
         } else {
-            // first / last tile of the range: bytes outside [beg, end) become 0
-            for (uint32_t c = tid; c < G_::LOAD_BYTES / 16; c += NT) {
+            // first / last tile of the range: loaded by the threads, bytes outside [beg, end) become 0
+            for (uint32_t c = tid; c < load_bytes / 16; c += NT) {
                 const uint64_t g = base + (uint64_t)c * 16;
                 uint4 v = make_uint4(0, 0, 0, 0);
                 if (g + 16 > beg && g < end) {
@@ -236,32 +257,24 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             __syncthreads();
         }
 
-        // ---- K1: newline mask of row tid (and of one halo row for the first HALO threads) ----
-        auto scan_row = [&](uint32_t row) -> Mask128 {
-            uint32_t m16[8];
-            #pragma unroll
-            for (int j = 0; j < 8; j++) m16[j] = 0;
-            #pragma unroll
-            for (int j = 0; j < CH; j++) {
-                const uint4 v = *reinterpret_cast<const uint4*>(tile + row * S + j * 16);
-                const uint32_t z0 = eq_bytes(v.x, 0x0A0A0A0Au), z1 = eq_bytes(v.y, 0x0A0A0A0Au);
-                const uint32_t z2 = eq_bytes(v.z, 0x0A0A0A0Au), z3 = eq_bytes(v.w, 0x0A0A0A0Au);
-                const uint32_t lo = __dp4a(z0, 0x08040201u, __dp4a(z1, 0x80402010u, 0u));     // 128 * (flags of bytes 0..7)
-                const uint32_t hi = __dp4a(z2, 0x08040201u, __dp4a(z3, 0x80402010u, 0u));     // 128 * (flags of bytes 8..15)
-                m16[j] = (lo >> 7) | (hi << 1);
+        // ---- K1: newline mask of row tid; the read-ahead rows are scanned chunk-wise by the lanes of the last warp ----
+        uint32_t m16[8];
+        #pragma unroll
+        for (int j = 0; j < 8; j++) m16[j] = 0;
+        #pragma unroll
+        for (int j = 0; j < CH; j++) m16[j] = chunk_mask(tile + tid * S + j * 16);
+        const uint4 mv = make_uint4(m16[0] | (m16[1] << 16), m16[2] | (m16[3] << 16), m16[4] | (m16[5] << 16), m16[6] | (m16[7] << 16));
+        rowmask[tid] = mv;
+        Mask128 own;
+        own.lo = (uint64_t)mv.x | ((uint64_t)mv.y << 32); own.hi = (uint64_t)mv.z | ((uint64_t)mv.w << 32);
+        if (warp == NT / 32 - 1) {
+            uint16_t* hm = reinterpret_cast<uint16_t*>(rowmask + NT);     // 8 u16 per row; slots >= CH stay 0
+            for (uint32_t c = lane; c < P.halo_rows * CH; c += 32) {
+                const uint32_t r = c / CH, j = c - r * CH;
+                hm[r * 8 + j] = (uint16_t)chunk_mask(tile + (NT + r) * S + j * 16);
             }
-            Mask128 m;
-            m.lo = (uint64_t)(m16[0] | (m16[1] << 16)) | ((uint64_t)(m16[2] | (m16[3] << 16)) << 32);
-            m.hi = (uint64_t)(m16[4] | (m16[5] << 16)) | ((uint64_t)(m16[6] | (m16[7] << 16)) << 32);
-            return m;
-        };
-        const Mask128 own = scan_row(tid);
-        rowmask[tid] = make_uint4((uint32_t)own.lo, (uint32_t)(own.lo >> 32), (uint32_t)own.hi, (uint32_t)(own.hi >> 32));
-        if (tid < G_::HALO) {
-            const Mask128 h = scan_row(NT + tid);
-            rowmask[NT + tid] = make_uint4((uint32_t)h.lo, (uint32_t)(h.lo >> 32), (uint32_t)h.hi, (uint32_t)(h.hi >> 32));
         }
-        const uint32_t cnt = __popcll(own.lo) + __popcll(own.hi);
+        const uint32_t cnt = __popc(mv.x) + __popc(mv.y) + __popc(mv.z) + __popc(mv.w);
         uint32_t incl = cnt;
         #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
@@ -304,10 +317,9 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         }
         __syncthreads();
         const uint32_t p0 = s_p0;
-
         // ---- reads whose header line ends in this row ----
-        const uint32_t region_end = (uint32_t)min((uint64_t)G_::LOAD_BYTES, end - base);   // valid bytes of the loaded region
-        const bool region_has_eof = (base + G_::LOAD_BYTES >= end);
+        const uint32_t region_end = (uint32_t)min((uint64_t)load_bytes, end - base);       // valid bytes of the loaded region
+        const bool region_has_eof = (base + load_bytes >= end);
         Mask128 m = own;
         uint32_t remaining = cnt;
         uint32_t skip = (4u - ((p0 + excl) & 3u)) & 3u;                // newlines of this row before the next header end
@@ -321,7 +333,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             uint32_t nl[3]; int have = 0;
             #pragma unroll
             for (int k = 0; k < 3; k++) {
-                while (cm.empty() && crow + 1 < (uint32_t)ROWS) {
+                while (cm.empty() && crow + 1 < rows_loaded) {
                     crow++;
                     const uint4 r = rowmask[crow];
                     cm.lo = (uint64_t)r.x | ((uint64_t)r.y << 32); cm.hi = (uint64_t)r.z | ((uint64_t)r.w << 32);
@@ -333,7 +345,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             uint32_t e0 = 0, s3 = 0, e3 = 0;
             bool complete = false, spill = false;
             if (have == 3) {
-                e0 = nl[0]; s3 = nl[2 - 1] + 1u; e3 = nl[2];
+                e0 = nl[0]; s3 = nl[1] + 1u; e3 = nl[2];
                 complete = true;
                 acc.last_end = max(acc.last_end, (unsigned long long)(base + e3 + 1));
             } else if (region_has_eof) {
@@ -349,7 +361,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 uint64_t pos[4];
                 pos[0] = base + s0 - 1;
                 for (int k = 0; k < 3; k++) pos[k + 1] = (k < have) ? base + nl[k] : 0;
-                uint64_t from = base + G_::LOAD_BYTES;
+                uint64_t from = base + load_bytes;
                 bool ok = true;
                 for (int k = have + 1; k < 4; k++) {
                     uint64_t p = find_newline_global(buf, from, end);
@@ -416,6 +428,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 }
             }
         }
+
     }
 
     // ---- CTA epilogue: queue segment length, histogram, statistics ----

@@ -175,7 +175,10 @@ def run_gpu(args, rank, local_rank, world):
     nbytes = n_reads * REC
     stream = torch.cuda.Stream(device=dev)
     cfg = lib.make_config(mode="C", miss=1, phred=30, length=FEAT_LEN, start="0")
-    eng = lib.Engine(cfg, local_rank, stream.cuda_stream, time_kernels=1)
+    opts = {"time_kernels": 1}
+    if args.tile_threads:
+        opts["tile_threads"] = args.tile_threads
+    eng = lib.Engine(cfg, local_rank, stream.cuda_stream, **opts)
     eng.set_library(keys)
     data = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     eng.synth(data.data_ptr(), keys, rank * n_reads, n_reads, **spec)      # every rank owns its own contiguous read range
@@ -314,6 +317,7 @@ def main():
     ap.add_argument("--reads", type=int, default=100_000_000, help="reads per GPU (configs[1] = 100 M)")
     ap.add_argument("--cpu-reads", type=int, default=2_000_000)
     ap.add_argument("--ref-reads-per-thread", type=int, default=400_000)
+    ap.add_argument("--tile-threads", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -77,11 +77,23 @@ def test_shaped_cases(gu, name):
     gu.check_case(c, data, 100003)        # odd chunk size: every submit cuts a record
 
 
-@pytest.mark.parametrize("name,resolver", [("config2_slice", 1), ("config2_slice", 3), ("config3_slice", 3), ("config3_m3", 3)])
+@pytest.mark.parametrize("name,resolver", [("config2_slice", 1), ("config2_slice", 2), ("config2_slice", 3), ("config3_slice", 2),
+                                           ("config3_slice", 3), ("config3_m3", 2), ("config3_m3", 3)])
 def test_resolvers_agree(gu, name, resolver):
     c = [x for x in G.shaped() if x["name"] == name][0]
     params, lib, data = cases.shaped_inputs(name)
     gu.check_case(dict(c, library=lib), data, resolver=resolver)
+
+
+@pytest.mark.parametrize("resolver", [1, 2, 3])
+def test_resolvers_on_fuzz(gu, resolver):
+    """ties, N symbols, mixed key lengths, m up to 3: every resolver must reproduce the reference's answers"""
+    for c in G.fuzz()[::2]:
+        if c["params"]["mode"] == "C":
+            gu.check_case(c, c["fastq"], resolver=resolver)
+    for c in G.kat():
+        if c["params"]["mode"] == "C":
+            gu.check_case(c, c["fastq"], resolver=resolver)
 
 
 def test_queue_overflow_resolves_in_place(gu):
