@@ -63,6 +63,7 @@ SYMBOLS = {
     "f2q_submit": (C.c_int, [_VP, _VP, C.c_uint64, C.c_int]),
     "f2q_submit_device": (C.c_int, [_VP, _VP, C.c_uint64, C.c_int]),
     "f2q_sync": (C.c_int, [_VP]),
+    "f2q_sync_copies": (C.c_int, [_VP]),
     "f2q_end_sample": (C.c_int, [_VP, _VP, _VP]),
     "f2q_result_device": (C.c_int, [_VP, C.POINTER(_VP), _U64P]),
     "f2q_ec_size": (C.c_int, [_VP, _U64P, _U64P]),
@@ -246,6 +247,10 @@ class Engine:
 
     def sync(self):
         self._ck(self.L.f2q_sync(self.h))
+
+    def sync_copies(self):
+        """pinned host buffers passed to submit_ptr may be refilled after this returns"""
+        self._ck(self.L.f2q_sync_copies(self.h))
 
     def end(self):
         """returns (counts uint64[n_keys], stats dict)"""

@@ -699,6 +699,12 @@ F2Q_EXPORT int f2q_sync(f2q_ctx* c) {
     return F2Q_OK;
 }
 
+F2Q_EXPORT int f2q_sync_copies(f2q_ctx* c) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (c->copy_stream) CU(c, cudaStreamSynchronize(c->copy_stream));
+    return F2Q_OK;
+}
+
 F2Q_EXPORT int f2q_result_device(f2q_ctx* c, void** dptr, uint64_t* n_words) {
     int rc = check_ctx(c); if (rc) return rc;
     if (!dptr || !n_words) return fail(c, F2Q_EINVAL, "null argument");

@@ -141,6 +141,10 @@ int f2q_submit_device(f2q_ctx* ctx, const void* dptr, uint64_t nbytes, int is_la
 /* block until everything submitted so far has been consumed (device buffers may be reused after) */
 int f2q_sync(f2q_ctx* ctx);
 
+/* block until every host chunk handed to f2q_submit so far has been copied off the host: pinned buffers
+ * (f2q_host_alloc) may be refilled after this returns, while the kernels that parse the copies still run */
+int f2q_sync_copies(f2q_ctx* ctx);
+
 /*
  * Finish the sample: waits, then writes counts[n_keys] (Counter mode; may be NULL in EC mode) and the
  * five statistics.  Replaces the return value of fastq_parser (fast2q.py:409).

@@ -1,0 +1,222 @@
+"""
+CPU tests of the host-side mirror (2fast2q_b200/fast2q.py) against fixtures produced by the UNMODIFIED reference
+(tests/golden/make_cli_golden.py): features .csv loader, command-line parser, per-sample csv, compiled.csv and
+compiled_stats.csv writers, gzip streaming, record-aligned sharding.  No kernel is called here.
+"""
+import base64
+import gzip
+import importlib
+import io
+import os
+import random
+import re
+import zlib
+
+import pytest
+
+import cli_golden as CG
+
+fq = importlib.import_module("2fast2q_b200.fast2q")
+
+
+@pytest.mark.parametrize("name", sorted(CG.load()["loader"]))
+def test_features_loader_matches_reference(name, tmp_path, capsys):
+    c = CG.load()["loader"][name]
+    p = tmp_path / "lib.csv"
+    p.write_text(c["text"], newline="")
+    if c["expect"] == "FATAL":
+        with pytest.raises(SystemExit):
+            fq.features_loader(str(p))
+        return
+    feats = fq.features_loader(str(p))
+    assert [[seq, f.name] for seq, f in feats.items()] == c["expect"]
+    assert all(f.counts == 0 for f in feats.values())
+
+
+def test_features_loader_missing_file_is_fatal(tmp_path):
+    with pytest.raises(SystemExit):
+        fq.features_loader(str(tmp_path / "nope.csv"))
+
+
+@pytest.mark.parametrize("k", range(len(CG.load()["parser"])))
+def test_input_parser_matches_reference(k, tmp_path, monkeypatch):
+    c = CG.load()["parser"][k]
+    monkeypatch.chdir(tmp_path)
+    got = fq.input_parser(c["argv"])
+    for key, want in c["expect"].items():
+        if isinstance(want, str):
+            want = want.replace("<CWD>", str(tmp_path))
+        assert got[key] == want, key
+    assert set(got) - set(c["expect"]) == {"gpus"}          # the one documented addition
+
+
+def test_input_parser_gui_mode_and_version(capsys):
+    assert fq.input_parser([]) is None                       # no -c: the reference opens its GUI (out of scope here)
+    with pytest.raises(SystemExit):
+        fq.initializer(None)
+    with pytest.raises(SystemExit):
+        fq.input_parser(["-v"])
+    assert "Version: 2.8.1" in capsys.readouterr().out
+
+
+def test_initializer_clamps_and_sets(tmp_path):
+    p = fq.input_parser(["-c", "--s", "/d", "--g", "/l.csv", "--o", str(tmp_path), "--ph", "0", "--qsu", "-3", "--qsd", "31", "--cp", "1"])
+    p = fq.initializer(p)
+    assert p["phred"] == 1 and p["qual_up"] == 1 and p["quality_set"] == set() and p["quality_set_up"] == set()
+    assert p["quality_set_down"] == {chr(33 + i) for i in range(30)}          # Q0..Q29 fail at 31
+    assert re.fullmatch(r"2FAST2Q_output_\d{4}(_\d\d){5}", os.path.basename(p["directory"]))
+    assert p["cpu"] == 1
+
+
+def _param_for(case, tmp_path, directory):
+    args = ["-c", "--s", str(tmp_path / "in"), "--o", str(tmp_path / "out")] + case["args"]
+    if case["library"] is not None:
+        args += ["--g", str(tmp_path / "library.csv")]
+    p = fq.initializer(fq.input_parser(args))
+    p["directory"] = str(directory)
+    p["used_cmd"] = p["used_cmd"].replace(str(tmp_path), "<TMP>")
+    return p
+
+
+@pytest.mark.parametrize("name", [c["name"] for c in CG.load()["cli"] if "--k" in c["args"]])
+def test_compiling_reproduces_reference_bytes(name, tmp_path):
+    """golden *_reads.csv in -> compiled.csv and compiled_stats.csv out, byte for byte"""
+    c = CG.case(name)
+    d = tmp_path / "res"
+    d.mkdir()
+    for fn, text in c["outputs"].items():
+        if fn.endswith("_reads.csv"):
+            (d / fn).write_text(text, newline="")
+    p = _param_for(c, tmp_path, d)
+    p["delete"] = True
+    fq.compiling(p)
+    assert (d / "compiled.csv").read_bytes().decode() == c["outputs"]["compiled.csv"]
+    assert (d / "compiled_stats.csv").read_bytes().decode() == c["outputs"]["compiled_stats.csv"]
+    assert sorted(os.listdir(d)) == ["compiled.csv", "compiled_stats.csv"]    # intermediates removed (fast2q.py:1375-1377)
+
+
+@pytest.mark.parametrize("name", ["cli_counter", "cli_single_split", "cli_dual_delim"])
+def test_write_sample_reproduces_reference_bytes(name, tmp_path):
+    c = CG.case(name)
+    (tmp_path / "library.csv").write_text(c["library"], newline="")
+    feats = fq.features_loader(str(tmp_path / "library.csv"))
+    d = tmp_path / "res"
+    d.mkdir()
+    p = _param_for(c, tmp_path, d)
+    for fn, text in c["outputs"].items():
+        if not fn.endswith("_reads.csv"):
+            continue
+        lines = text.split("\r\n")
+        t = lines[0].split()
+        secs = float(t[3])
+        stats = dict(reads=int(t[12]), perfect_counter=int(t[15]), imperfect_counter=int(t[19]), non_aligned_counter=int(t[24]),
+                     quality_failed=int(t[32]))
+        by_name = dict(l.split(",") for l in lines[2:] if l)
+        sample = {seq: fq.Features(f.name, int(by_name[f.name])) for seq, f in feats.items()}
+        raw = [k for k in c["files"] if fq.sample_name(k) == fn[:-len("_reads.csv")]][0]
+        fq.write_sample(str(tmp_path / "in" / raw), sample, stats, p, secs)
+        assert (d / fn).read_bytes().decode() == text
+
+
+def test_sample_name_rules():
+    assert fq.sample_name("/x/a.fastq.gz") == "a"
+    assert fq.sample_name("/x/a.fastq") == "a"
+    assert fq.sample_name("/x/a.fq.gz") == "a.fq"
+    assert fq.sample_name("/x/a.b.fastq.gz") == "a.b"
+    assert fq._timing_text(3.14159) == "3.14 seconds" and fq._timing_text(61) == "1.02 minutes" and fq._timing_text(7200) == "2.0 hours"
+
+
+def _py_gzip_lines(path):
+    """what the reference's `for line in gzip.open(raw, 'rb')` delivers before it ends or raises EOFError"""
+    out, ok = [], True
+    try:
+        with gzip.open(path, "rb") as f:
+            for line in f:
+                out.append(line)
+    except EOFError:
+        ok = False
+    return b"".join(out), ok
+
+
+def _gz(data, level=6):
+    b = io.BytesIO()
+    with gzip.GzipFile(fileobj=b, mode="wb", compresslevel=level, mtime=0) as f:
+        f.write(data)
+    return b.getvalue()
+
+
+def test_inflate_blocks_equals_gzip_module(tmp_path):
+    rnd = random.Random(5)
+    body = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, bytes(rnd.choice(b"ACGT") for _ in range(50)), b"I" * 50) for i in range(4000))
+    variants = {
+        "plain": _gz(body),
+        "multi_member": _gz(body[:100000]) + _gz(body[100000:300000], 1) + _gz(body[300000:], 9),
+        "zero_padded": _gz(body[:5000]) + b"\0" * 37 + _gz(body[5000:]) + b"\0" * 5,
+        "empty_member": _gz(b"") + _gz(body[:999]),
+        "empty_file": b"",
+        "unterminated": _gz(body + b"@last\nACGT"),
+    }
+    for name, blob in variants.items():
+        p = tmp_path / (name + ".fastq.gz")
+        p.write_bytes(blob)
+        want, ok = _py_gzip_lines(p)
+        assert ok
+        assert b"".join(fq._inflate_blocks(str(p), want=70001)) == want, name
+    # truncation anywhere: every decodable byte is delivered, then TruncatedGzip
+    whole = variants["multi_member"]
+    for cut in [9, 10, 500, len(whole) // 3, len(whole) // 2, len(whole) - 9, len(whole) - 1]:
+        p = tmp_path / "cut.fastq.gz"
+        p.write_bytes(whole[:cut])
+        want, ok = _py_gzip_lines(p)
+        got, trunc = [], False
+        try:
+            for b in fq._inflate_blocks(str(p), want=4096):
+                got.append(b)
+        except fq.TruncatedGzip:
+            trunc = True
+        got = b"".join(got)
+        assert trunc == (not ok), cut
+        assert got[:got.rfind(b"\n") + 1] == want, cut      # the reference's iterator never yields the unfinished line
+    p = tmp_path / "garbage.fastq.gz"
+    p.write_bytes(b"this is not gzip")
+    with pytest.raises(zlib.error):
+        list(fq._inflate_blocks(str(p)))
+
+
+def test_record_aligned_shards():
+    rnd = random.Random(11)
+    data = b"".join(b"@r%d\n" % i + bytes(rnd.choice(b"ACGT") for _ in range(rnd.randint(0, 30))) + b"\n+\n" +
+                    b"I" * rnd.randint(0, 30) + b"\n" for i in range(3000)) + b"@x\nAC"
+
+    def blocks(n):
+        for o in range(0, len(data), n):
+            yield data[o:o + n]
+    for bs in (7, 100, 1000, 4096, 1 << 20):
+        for sb in (1, 50, 1000, 5000, 1 << 22):
+            out = list(fq.record_aligned_shards(blocks(bs), sb))
+            assert b"".join(x for x, _ in out) == data
+            assert [f for _, f in out] == [False] * (len(out) - 1) + [True]
+            for x, _ in out[:-1]:
+                assert x and x.endswith(b"\n") and x.count(b"\n") % 4 == 0
+    assert list(fq.record_aligned_shards(iter([]))) == [(b"", True)]
+    assert list(fq.record_aligned_shards(iter([b"\n\n\n"]), 1)) == [(b"\n\n\n", True)]
+
+
+def test_merge_sample_adds_counts_and_stats():
+    lib = {"AAAA": fq.Features("a", 0), "CCCC": fq.Features("b", 0)}
+    s1 = dict(reads=5, perfect_counter=3, imperfect_counter=1, non_aligned_counter=1, quality_failed=0)
+    s2 = dict(reads=2, perfect_counter=1, imperfect_counter=0, non_aligned_counter=0, quality_failed=1)
+    r1 = ({"AAAA": fq.Features("a", 3), "CCCC": fq.Features("b", 1)}, s1)
+    r2 = ({"AAAA": fq.Features("a", 0), "CCCC": fq.Features("b", 1)}, s2)
+    m, s = fq._merge_sample({"Running Mode": "C"}, lib, [r1, r2])
+    assert [(k, v.name, v.counts) for k, v in m.items()] == [("AAAA", "a", 3), ("CCCC", "b", 2)]
+    assert s == dict(reads=7, perfect_counter=4, imperfect_counter=1, non_aligned_counter=1, quality_failed=1)
+    e1 = ({"GG": fq.Features("GG", 2)}, s1)
+    e2 = ({"TT": fq.Features("TT", 1), "GG": fq.Features("GG", 5)}, s2)
+    m, s = fq._merge_sample({"Running Mode": "EC"}, {}, [e1, e2])
+    assert {k: v.counts for k, v in m.items()} == {"GG": 7, "TT": 1}
+
+
+def test_seq2bin_known_answer():
+    assert fq.seq2bin("GATTACA").tolist() == [71, 65, 84, 84, 65, 67, 65]      # tests/test_mainfunctions.py:4-8
+    assert fq.seq2bin("GATTACA").dtype.name == "int8"
