@@ -58,7 +58,7 @@ struct f2q_ctx {
     DevBuf carry, status, status_stitch, queue, gqueue, seg_count;
     uint32_t q_cap = 0, g_cap = 0;     // q_cap = total queue entries (n_segs * seg_cap)
     uint32_t seg_cap = 0, n_segs = 0;
-    int force_ch = 0;
+    int force_ch = 0, force_halo = 0;
     int halo_rows = 6;
     int ch = 7;                        // row chunks of the tile kernel (row = 16*ch bytes), picked per sample from the record length
     bool ch_decided = false;
@@ -238,9 +238,10 @@ void decide_ch(f2q_ctx* c, const uint8_t* head, size_t n) {
     size_t rec = 0;
     if (nl == 8) { rec = pos / 2; c->ch = rec >= 112 ? 7 : rec >= 80 ? 5 : 3; }
     if (c->force_ch) c->ch = c->force_ch;
-    // read-ahead rows behind each tile: two records' worth (reads that need more take the global-memory path)
-    const int S = 16 * c->ch, halo_max = (1024 + S - 1) / S + 1;
-    c->halo_rows = rec ? (int)std::min<size_t>(halo_max, std::max<size_t>(2, (2 * rec + S - 1) / S + 1)) : halo_max;
+    // read-ahead rows at the end of each tile: one and a half records' worth (reads that need more finish in global memory)
+    const int S = 16 * c->ch, halo_max = c->nt / 2;
+    c->halo_rows = rec ? (int)std::min<size_t>(halo_max, std::max<size_t>(2, (rec + rec / 2 + S - 1) / S + 1)) : std::min(halo_max, (1024 + S - 1) / S + 1);
+    if (c->force_halo) c->halo_rows = std::min(halo_max, c->force_halo);
     c->ch_decided = true;
 }
 
@@ -352,9 +353,9 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         if (hn) { CU(c, cudaMemcpyAsync(head, dptr, hn, cudaMemcpyDeviceToHost, c->stream)); CU(c, cudaStreamSynchronize(c->stream)); }
         decide_ch(c, head, hn);
     }
-    const uint64_t own_bytes = (uint64_t)c->nt * 16 * c->ch;
+    const uint64_t own_bytes = (uint64_t)(c->nt - c->halo_rows) * 16 * c->ch;
     const uint64_t n_tiles = (delta + n) / own_bytes + 2;
-    const uint64_t stitch_tiles = c->carry_cap / (128 * 16 * 3) + 2;
+    const uint64_t stitch_tiles = c->carry_cap / (64 * 16 * 3) + 2;
     if ((rc = dev_alloc(c, c->status, n_tiles * 4))) return rc;
     unsigned grid = 0;
     if ((rc = tile_grid_dyn(c, &grid))) return rc;
@@ -545,6 +546,7 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "resolver") { if (value < 0 || value > 3) return fail(c, F2Q_EINVAL, "resolver must be 0..3"); c->resolver = (int)value; }
     else if (n == "queue_entries") { if (value < 0) return fail(c, F2Q_EINVAL, "queue_entries < 0"); c->opt_queue_entries = value; c->q_cap = 0; c->g_cap = 0; c->n_segs = 0; c->queue.release(); c->gqueue.release(); }
     else if (n == "tile_threads") { if (value != 128 && value != 256) return fail(c, F2Q_EINVAL, "tile_threads must be 128 or 256"); c->nt = (int)value; c->n_segs = 0; }
+    else if (n == "halo_rows") { if (value < 0 || value > 128) return fail(c, F2Q_EINVAL, "halo_rows must be 0 (auto) .. 128"); c->force_halo = (int)value; }
     else if (n == "row_chunks") { if (value != 0 && value != 3 && value != 5 && value != 7) return fail(c, F2Q_EINVAL, "row_chunks must be 0 (auto), 3, 5 or 7"); c->force_ch = (int)value; }
     else if (n == "time_kernels") c->time_kernels = value != 0;
     else if (n == "force_generic") { if (value) c->policy = POLICY_GENERIC; else decide_policy(c); }
@@ -648,7 +650,7 @@ F2Q_EXPORT int f2q_begin_sample(f2q_ctx* c) {
     int rc = check_ctx(c); if (rc) return rc;
     if (!c->lib_set) return fail(c, F2Q_ESTATE, "f2q_set_library must be called first in Counter mode");
     if ((rc = dev_alloc(c, c->carry, c->carry_cap + 256))) return rc;
-    if ((rc = dev_alloc(c, c->status_stitch, (c->carry_cap / (128 * 16 * 3) + 2) * 4))) return rc;
+    if ((rc = dev_alloc(c, c->status_stitch, (c->carry_cap / (64 * 16 * 3) + 2) * 4))) return rc;
     c->ch_decided = false;
     CU(c, cudaMemsetAsync(c->result.p, 0, ((size_t)c->n_keys + 5) * 8, c->stream));
     CU(c, cudaMemsetAsync(c->d_error, 0, 4, c->stream));

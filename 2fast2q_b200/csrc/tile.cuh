@@ -1,20 +1,26 @@
 // tile.cuh — the fused hot kernel: ONE pass over the FASTQ bytes.
 //
-//   K1 line scan      per-row newline bitmasks (SWAR compare + dp4a gather), block scan of the counts, decoupled
-//                     look-back across tiles for the line phase (records are "every 4 lines from byte 0",
-//                     fast2q.py:324-328); rows exchange their masks through shared memory
+//   K1 line scan      per-row newline bitmasks (SWAR compare + dp4a gather) -> block scan of the counts -> a list of the
+//                     tile's newline positions in shared memory; decoupled look-back across tiles for the line phase
+//                     (records are "every 4 lines from byte 0", fast2q.py:324-328)
 //   K2 extract        fixed-position window with Python slice clamping, rstrip, Phred fail-set test (fast2q.py:349-360)
 //   K4 lookup/count   2-bit pack, exact probe of the packed-key table, shared-memory histogram (fast2q.py:365-367)
 //   -> non-exact keys go to this CTA's segment of the resolver queue (K5), undecidable reads to the generic queue.
 //
-// Work decomposition: persistent CTAs take tiles by atomic ticket WHEN THEY ARE READY for them and publish the tile's
-// newline count as soon as it is scanned (a tile's predecessors are always running or done, so the look-back cannot
-// deadlock and rarely waits); latency is hidden by several small CTAs per SM rather than by pipelining inside a CTA.
-// A tile is (NT + halo) rows of S = 16*CH bytes in shared memory, NT = threads per CTA, CH odd so that
-// "thread t scans row t with 16-byte loads" is bank-conflict free without a swizzle; CH is chosen by the host so that
-// S is just below the record length (about one read start per row).  Interior tiles are fetched by one TMA bulk copy
-// (cp.async.bulk + mbarrier); the first/last tile of a range, which needs byte masking, is loaded by the threads.
-// A read belongs to the row (thread) that holds the newline ending its header line.
+// Work decomposition.  A tile is NT rows of S = 16*CH bytes (CH odd: "thread t scans row t with 16-byte loads" is then
+// bank-conflict free without a swizzle; the host picks CH so that S is just below the record length).  The first
+// NT-H rows are OWNED by the tile, the last H rows are read-ahead (they are the first rows of the next tile): a read
+// belongs to the tile that owns the newline ending its header line, and finds its other three newlines in the rows
+// behind it.  Persistent CTAs take tiles by atomic ticket and run a 3-stage software pipeline per CTA:
+//     iteration k:   issue the TMA bulk copy (cp.async.bulk + mbarrier) of tile k+2
+//                    issue the look-back loads for tile k            (warp 0; consumed after the scan below)
+//                    scan tile k+1: row masks, counts, position list; publish its newline count (aggregate)
+//                    finish the look-back of tile k -> line phase p0; publish the inclusive prefix
+//                    parse the reads of tile k: thread q takes the q-th read of the tile (dense lanes, no row walk)
+// so HBM latency is hidden by the TMA prefetch, the look-back latency by the scan, and a tile's aggregate is public one
+// whole parse phase before its successors need it.  Tickets are taken in increasing order by every CTA, so the smallest
+// unfinished tile can always make progress: the look-back cannot deadlock even if not all CTAs are resident.
+// The first / last tile of a range (bytes outside [beg, end) must read as 0) is loaded by the threads instead of TMA.
 #pragma once
 
 #include "f2q_dev.cuh"
@@ -36,21 +42,24 @@ struct TileParams {
     uint32_t seg_cap;          // 0: resolve every non-exact key in place
     GEntry* gqueue;
     uint32_t hist_smem;        // 1: per-CTA shared-memory histogram of n_keys u32
-    uint32_t halo_rows;        // read-ahead rows loaded and scanned behind the NT owned rows (2 .. TileGeom::HALO)
+    uint32_t halo_rows;        // H: read-ahead rows at the end of every tile (1 .. NT/2)
 };
 
 constexpr uint32_t LB_SPIN_LIMIT = 1u << 24;
+constexpr int TILE_STAGES = 3;
 
 template <int CH, int NT_>
 struct TileGeom {
-    static constexpr int S = CH * 16;                          // bytes per row
-    static constexpr int NT = NT_;                             // owned rows = threads per CTA
-    static constexpr int HALO = (1024 + S - 1) / S + 1;        // max read-ahead rows (>= 1 KiB); P.halo_rows of them are used
-    static constexpr int ROWS = NT + HALO;
-    static constexpr int OWN_BYTES = NT * S;
-    static constexpr int BUF_BYTES = ROWS * S + 16;            // tile buffer (+16 so that word reads may run past the end)
-    static constexpr int MASK_OFF = BUF_BYTES;                 // ROWS uint4 row masks
-    static constexpr int HIST_OFF = MASK_OFF + ROWS * 16;
+    static constexpr int S = CH * 16;                                   // bytes per row
+    static constexpr int NT = NT_;                                      // rows per tile = threads per CTA
+    static constexpr int NS = TILE_STAGES;
+    static constexpr int LOAD_BYTES = NT * S;
+    static constexpr int STAGE_BYTES = ((LOAD_BYTES + 16 + 127) / 128) * 128;   // +16: word reads may run past the end
+    static constexpr int CAP = 8 * NT;                                  // newline positions kept per tile
+    static constexpr int NL_OFF = NS * STAGE_BYTES;                     // two u16[CAP + 8] position lists
+    static constexpr int NL_STRIDE = (CAP + 8) * 2;
+    static constexpr int EXCL_OFF = NL_OFF + 2 * NL_STRIDE;             // two u16[NT]: newlines of the tile before each row
+    static constexpr int HIST_OFF = ((EXCL_OFF + 2 * NT * 2 + 15) / 16) * 16;
 };
 
 template <int CH, int NT>
@@ -62,8 +71,8 @@ __host__ __device__ inline size_t tile_smem_bytes(uint32_t hist_entries) {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -85,7 +94,14 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-// ---- byte access to the (unswizzled) tile ---------------------------------------------------------------
+// a constant the compiler must keep in a register (so that LOP3 can combine it with two other register operands)
+__device__ __forceinline__ uint32_t reg_const(uint32_t v) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+
+// ---- byte access to the tile ---------------------------------------------------------------------------
 struct WordReader {                 // 4 bytes at an arbitrary tile offset, little endian
     const uint8_t* tile; uint32_t a, sh, prev;
     __device__ __forceinline__ WordReader(const uint8_t* t, uint32_t o) : tile(t), a(o & ~3u), sh((o & 3u) * 8u) {
@@ -108,9 +124,9 @@ __device__ __forceinline__ bool qual_fails_tile(const uint8_t* tile, uint32_t o,
     uint32_t acc = 0;
     auto test = [&](uint32_t w) {
         const uint32_t lo7 = w & 0x7F7F7F7Fu;
-        const uint32_t ge33 = ((lo7 + add_ge) | w);                    // bit 7: byte >= 33
-        const uint32_t gtmax = ((lo7 + add_gt) | w);                   // bit 7: byte >  fmax
-        acc |= ge33 & ~gtmax;
+        const uint32_t ge33 = lo7 + add_ge;                            // bit 7: low 7 bits >= 33
+        const uint32_t gtmax = lo7 + add_gt;                           // bit 7: low 7 bits >  fmax
+        acc |= ge33 & ~gtmax & ~w;                                     // bytes >= 0x80 never fail
     };
     const int full = n >> 2;
     for (int k = 0; k < full; k++) test(rd.next());
@@ -124,27 +140,25 @@ __device__ __forceinline__ void pack_tile(const uint8_t* tile, uint32_t o, int n
     if (n <= 0) return;
     WordReader rd(tile, o);
     const int words = (n + 3) >> 2;
+    uint32_t klo = 0, khi = 0;
     for (int kw = 0; kw < words; kw++) {
-        const int k = kw * 4;
         uint32_t w = rd.next();
         if (kw == words - 1 && (n & 3)) { const uint32_t keep = (1u << (8 * (n & 3))) - 1u; w = (w & keep) | (0x41414141u & ~keep); }   // pad with 'A' (code 0)
         uint32_t codes = (w >> 1) & 0x03030303u;
         uint32_t t = (codes | (codes >> 4)) & 0x00330033u;
         t = (t | (t >> 8)) & 0x3333u;                                  // nibble i = code of byte i
         const uint32_t expect = __byte_perm(0x47544341u, 0u, t);        // code -> 'A','C','T','G'
-        const uint32_t ok = eq_bytes(w & 0xDFDFDFDFu, expect);          // 0x80 per valid byte
-        if (ok != 0x80808080u) {                                        // some symbol is not A/C/G/T: flag it, zero its bits
-            const uint32_t nb = (ok ^ 0x80808080u);
-            bad |= ((nb * 0x00204081u) >> 28) << k;
-            const uint32_t keep2 = (ok >> 7) * 3u;                      // 0x03 per valid byte
-            codes &= keep2;
-            t = (codes | (codes >> 4)) & 0x00330033u;
-            t = (t | (t >> 8)) & 0x3333u;
+        const uint32_t diff = (w & 0xDFDFDFDFu) ^ expect;               // 0 where the upper-cased byte is that base
+        if (diff) {                                                     // some symbol is not A/C/G/T: flag it, zero its bits
+            const uint32_t nz = ((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff;     // bit 7 of every non-zero byte
+            const uint32_t nb = nz & 0x80808080u;
+            bad |= ((nb * 0x00204081u) >> 28) << (4 * kw);
+            codes &= ~((nb >> 7) * 3u);
         }
-        uint32_t p = (t | (t >> 2)) & 0x0F0Fu;
-        p = (p | (p >> 4)) & 0xFFu;                                    // 4 symbols -> 8 bits
-        key |= (uint64_t)p << (2 * k);
+        const uint32_t p = (codes * 0x01041040u) >> 24;                 // 4 symbols -> 8 bits (one multiply, no carries)
+        if (kw < 4) klo |= p << (8 * kw); else khi |= p << (8 * (kw - 4));
     }
+    key = ((uint64_t)khi << 32) | klo;
 }
 
 __device__ __noinline__ uint64_t find_newline_global(const uint8_t* buf, uint64_t from, uint64_t end) {
@@ -152,33 +166,46 @@ __device__ __noinline__ uint64_t find_newline_global(const uint8_t* buf, uint64_
     return end;
 }
 
-// 128-bit row mask helpers (bit b = byte b of the row is '\n')
-struct Mask128 {
-    uint64_t lo, hi;
-    __device__ __forceinline__ bool empty() const { return (lo | hi) == 0; }
-    __device__ __forceinline__ int pop_lowest() {               // index of the lowest set bit, which is cleared
-        if (lo) { int b = __ffsll((long long)lo) - 1; lo &= lo - 1; return b; }
-        int b = 64 + __ffsll((long long)hi) - 1; hi &= hi - 1; return b;
-    }
-};
-
 // per-thread accumulators, reduced once per CTA
 struct Acc {
     unsigned long long reads, perfect, imperfect, nonal, qfail, last_end;
 };
 
+// a read whose four lines do not all lie inside the loaded tile (or a tile with more newlines than the position list
+// holds): finish the geometry in global memory and run the byte-wise generic code on it.  hdr_end = absolute buffer
+// offset of the newline that ends the header line.  Rare by construction; exactness matters here, speed does not.
+__device__ __noinline__ void slow_record(const uint8_t* buf, uint64_t hdr_end, uint64_t end, bool eof, const GenericCfg& G,
+                                         const LibTables& T, const EcTable& E, const Outputs& O, Acc& acc, unsigned long long* gst) {
+    uint64_t pos[4];
+    pos[0] = hdr_end;
+    uint64_t from = hdr_end + 1;
+    for (int k = 1; k < 4; k++) {
+        const uint64_t p = find_newline_global(buf, from, end);
+        if (p >= end) {
+            if (k == 3 && eof && from < end) { pos[3] = end; break; }      // unterminated final quality line (fast2q.py:324-328)
+            return;                                                        // incomplete record: carried or dropped
+        }
+        pos[k] = p; from = p + 1;
+    }
+    acc.reads++;
+    const unsigned long long le = (unsigned long long)(pos[3] + 1 < end ? pos[3] + 1 : end);
+    acc.last_end = acc.last_end > le ? acc.last_end : le;
+    const uint8_t* Rp = buf + pos[0] + 1; const uint8_t* Qp = buf + pos[2] + 1;
+    g_process_read(G, T, E, O, Rp, g_rstrip(Rp, (int)(pos[1] - pos[0] - 1)), Qp, g_rstrip(Qp, (int)(pos[3] - pos[2] - 1)), gst);
+}
+
 template <int POLICY, int CH, int NT>
-__global__ void __launch_bounds__(NT, POLICY == POLICY_FAST1 ? (768 / NT) : (512 / NT))
+__global__ void __launch_bounds__(NT, POLICY == POLICY_FAST1 ? (512 / NT) : (256 / NT))
 k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, Outputs O) {
     using G_ = TileGeom<CH, NT>;
-    constexpr int S = G_::S;
+    constexpr int S = G_::S, NS = G_::NS, CAP = G_::CAP;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* tile = smem;
-    uint4* rowmask = reinterpret_cast<uint4*>(smem + G_::MASK_OFF);
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem + G_::HIST_OFF);
     __shared__ uint32_t s_wsum[NT / 32];
-    __shared__ uint32_t s_tile, s_p0, s_qn;
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_ticket[NS], s_mode[NS];                      // per stage: tile ticket, 0 none / 1 TMA / 2 loaded by threads
+    __shared__ uint32_t s_total_own[2], s_total_all[2];
+    __shared__ uint32_t s_p0, s_qn;
+    __shared__ __align__(8) uint64_t s_bar[NS];
     __shared__ GenericCfg s_G;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -188,56 +215,70 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     const bool eof = P.stitch ? (St->stitch_eof != 0) : (St->is_last != 0);
     if (end <= beg) { if (tid == 0 && P.seg_cap) P.seg_count[blockIdx.x] = 0; return; }
 
-    for (uint32_t i = tid; i < sizeof(GenericCfg) / 4; i += NT)
-        reinterpret_cast<uint32_t*>(&s_G)[i] = reinterpret_cast<const uint32_t*>(Gp)[i];
+    if (POLICY == POLICY_GENERIC)                                      // the packed policy keeps its few scalars in registers
+        for (uint32_t i = tid; i < sizeof(GenericCfg) / 4; i += NT)
+            reinterpret_cast<uint32_t*>(&s_G)[i] = reinterpret_cast<const uint32_t*>(Gp)[i];
     if (P.hist_smem) for (uint32_t i = tid; i < T.n_keys; i += NT) hist[i] = 0;
-    for (uint32_t i = tid; i < G_::ROWS; i += NT) rowmask[i] = make_uint4(0, 0, 0, 0);
-    if (tid == 0) { mbar_init(&s_bar, 1); s_qn = 0; }
-    const DevCfg& C = s_G.c;
+    if (tid == 0) {
+        for (int s = 0; s < NS; s++) { mbar_init(&s_bar[s], 1); s_mode[s] = 0; }
+        mbar_fence_init();
+        s_qn = 0;
+    }
+    const GenericCfg& G = (POLICY == POLICY_GENERIC) ? s_G : *Gp;
+    const int c_start = Gp->c.starts[0], c_length = Gp->c.length, c_fmax = Gp->c.fmax_ph, c_miss = Gp->c.miss;
 
-    const uint32_t rows_loaded = NT + P.halo_rows;                     // owned + read-ahead rows of every tile
-    const uint32_t load_bytes = rows_loaded * S;
-    const uint64_t first_tile = beg / G_::OWN_BYTES;
-    const uint64_t n_tiles = (end - 1) / G_::OWN_BYTES + 1;
+    const uint32_t own_rows = NT - P.halo_rows;
+    const uint32_t own_bytes = own_rows * S;
+    const uint64_t first_tile = beg / own_bytes;
+    const uint64_t n_tiles = (end - 1) / own_bytes + 1;
     const uint8_t* __restrict__ buf = P.buf;
     QEntry* const myq = P.queue + (size_t)blockIdx.x * P.seg_cap;
     Acc acc{0, 0, 0, 0, 0, 0};
-    unsigned long long gst[F2Q_N_STATS] = {0, 0, 0, 0, 0};            // stats of reads handled in place by the generic code
-    uint32_t bar_phase = 0;
+    unsigned long long gst[F2Q_N_STATS] = {0, 0, 0, 0, 0};            // stats of reads handled by the generic code
+    uint32_t bar_phase = 0;                                            // bit s: parity the next wait on stage s uses
 
-    // newline flags of one 16-byte chunk, bit i = byte i
+    const uint32_t c0A = reg_const(0x0A0A0A0Au), c7F = reg_const(0x7F7F7F7Fu), c80 = reg_const(0x80808080u);
+    // newline flags of one 16-byte chunk, bit i = byte i.  Exact per-byte compare in 3 operations per word:
+    //   a = (w ^ 0x0A..) & 0x7F..; b = a + 0x7F..  (bit 7: low 7 bits differ); z = ~(b | w) & 0x80..  (w's own bit 7 must be 0)
     auto chunk_mask = [&](const uint8_t* p16) -> uint32_t {
         const uint4 v = *reinterpret_cast<const uint4*>(p16);
-        const uint32_t z0 = eq_bytes(v.x, 0x0A0A0A0Au), z1 = eq_bytes(v.y, 0x0A0A0A0Au);
-        const uint32_t z2 = eq_bytes(v.z, 0x0A0A0A0Au), z3 = eq_bytes(v.w, 0x0A0A0A0Au);
+        const uint32_t z0 = ~(((v.x ^ c0A) & c7F) + c7F | v.x) & c80, z1 = ~(((v.y ^ c0A) & c7F) + c7F | v.y) & c80;
+        const uint32_t z2 = ~(((v.z ^ c0A) & c7F) + c7F | v.z) & c80, z3 = ~(((v.w ^ c0A) & c7F) + c7F | v.w) & c80;
         const uint32_t lo = __dp4a(z0, 0x08040201u, __dp4a(z1, 0x80402010u, 0u));     // 128 * (flags of bytes 0..7)
         const uint32_t hi = __dp4a(z2, 0x08040201u, __dp4a(z3, 0x80402010u, 0u));     // 128 * (flags of bytes 8..15)
         return (lo >> 7) | (hi << 1);
     };
 
-    for (;;) {
-        __syncthreads();                                               // everyone is done with the previous tile
-        // ---- ticket + load.  Thread 0 takes the ticket only now, so the tile's count is published ~one load later ----
-        if (tid == 0) {
-            const uint32_t tk = atomicAdd(P.ticket, 1u);
-            s_tile = tk;
-            const uint64_t b0 = (first_tile + tk) * G_::OWN_BYTES;
-            if (first_tile + tk < n_tiles && b0 >= beg && b0 + load_bytes <= end) {       // interior tile: one TMA bulk copy
-                mbar_expect_tx(&s_bar, load_bytes);
-                tma_load_1d(tile, buf + b0, load_bytes, &s_bar);
-            }
+    // thread 0: take the ticket of local iteration i and start its load into stage i % NS
+    auto issue = [&](uint32_t i) {
+        const uint32_t s = i % NS;
+        const uint32_t tk = atomicAdd(P.ticket, 1u);
+        s_ticket[s] = tk;
+        const uint64_t t = first_tile + tk;
+        uint32_t mode = 0;
+        if (t < n_tiles) {
+            const uint64_t b0 = t * own_bytes;
+            if (b0 >= beg && b0 + G_::LOAD_BYTES <= end) {               // interior tile: one TMA bulk copy
+                mode = 1;
+                mbar_expect_tx(&s_bar[s], G_::LOAD_BYTES);
+                tma_load_1d(smem + s * G_::STAGE_BYTES, buf + b0, G_::LOAD_BYTES, &s_bar[s]);
+            } else mode = 2;
         }
-        __syncthreads();
-        const uint64_t t = first_tile + s_tile;
-        if (t >= n_tiles) break;
-        const uint64_t base = t * G_::OWN_BYTES;
-        const bool interior = (base >= beg) && (base + load_bytes <= end);
-        if (interior) {
-            mbar_wait(&s_bar, bar_phase);
-            bar_phase ^= 1;
+        s_mode[s] = mode;
+    };
+
+    // all threads: newline masks, counts and position list of local iteration i (its stage is loaded or gets loaded here)
+    auto scan = [&](uint32_t i) {
+        const uint32_t s = i % NS, par = i & 1u;
+        uint8_t* tile = smem + s * G_::STAGE_BYTES;
+        const uint64_t t = first_tile + s_ticket[s];
+        const uint64_t base = t * own_bytes;
+        if (s_mode[s] == 1) {
+            mbar_wait(&s_bar[s], (bar_phase >> s) & 1u);
+            bar_phase ^= 1u << s;
         } else {
             // first / last tile of the range: loaded by the threads, bytes outside [beg, end) become 0
-            for (uint32_t c = tid; c < load_bytes / 16; c += NT) {
+            for (uint32_t c = tid; c < G_::LOAD_BYTES / 16; c += NT) {
                 const uint64_t g = base + (uint64_t)c * 16;
                 uint4 v = make_uint4(0, 0, 0, 0);
                 if (g + 16 > beg && g < end) {
@@ -256,54 +297,88 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             }
             __syncthreads();
         }
-
-        // ---- K1: newline mask of row tid; the read-ahead rows are scanned chunk-wise by the lanes of the last warp ----
         uint32_t m16[8];
         #pragma unroll
         for (int j = 0; j < 8; j++) m16[j] = 0;
         #pragma unroll
         for (int j = 0; j < CH; j++) m16[j] = chunk_mask(tile + tid * S + j * 16);
-        const uint4 mv = make_uint4(m16[0] | (m16[1] << 16), m16[2] | (m16[3] << 16), m16[4] | (m16[5] << 16), m16[6] | (m16[7] << 16));
-        rowmask[tid] = mv;
-        Mask128 own;
-        own.lo = (uint64_t)mv.x | ((uint64_t)mv.y << 32); own.hi = (uint64_t)mv.z | ((uint64_t)mv.w << 32);
-        if (warp == NT / 32 - 1) {
-            uint16_t* hm = reinterpret_cast<uint16_t*>(rowmask + NT);     // 8 u16 per row; slots >= CH stay 0
-            for (uint32_t c = lane; c < P.halo_rows * CH; c += 32) {
-                const uint32_t r = c / CH, j = c - r * CH;
-                hm[r * 8 + j] = (uint16_t)chunk_mask(tile + (NT + r) * S + j * 16);
-            }
-        }
-        const uint32_t cnt = __popc(mv.x) + __popc(mv.y) + __popc(mv.z) + __popc(mv.w);
+        uint32_t mw[4] = {m16[0] | (m16[1] << 16), m16[2] | (m16[3] << 16), m16[4] | (m16[5] << 16), m16[6] | (m16[7] << 16)};
+        const uint32_t cnt = __popc(mw[0]) + __popc(mw[1]) + __popc(mw[2]) + __popc(mw[3]);
         uint32_t incl = cnt;
         #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
         if (lane == 31) s_wsum[warp] = incl;
         __syncthreads();
-        uint32_t wbase = 0, total = 0;
+        uint32_t wbase = 0;
         #pragma unroll
-        for (int w = 0; w < NT / 32; w++) { uint32_t x = s_wsum[w]; if (w < (int)warp) wbase += x; total += x; }
+        for (int w = 0; w < NT / 32; w++) { const uint32_t x = s_wsum[w]; if (w < (int)warp) wbase += x; }
         const uint32_t excl = wbase + incl - cnt;                      // newlines of the tile before this row
-
-        // ---- decoupled look-back for the line phase of the tile (warp 0) ----
-        if (warp == 0) {
-            const uint32_t A = total;
+        reinterpret_cast<uint16_t*>(smem + G_::EXCL_OFF)[par * NT + tid] = (uint16_t)min(excl, 0xFFFFu);
+        if (tid == own_rows) {                                         // excl of the first read-ahead row = newlines of the owned rows
+            s_total_own[par] = excl;
             const uint64_t rel = t - first_tile;
+            if (rel != 0) st_volatile_u32(P.status + rel, LB_FLAG_AGG | (excl & LB_VALUE_MASK));
+        }
+        if (tid == NT - 1) s_total_all[par] = excl + cnt;
+        uint16_t* nl = reinterpret_cast<uint16_t*>(smem + G_::NL_OFF + par * G_::NL_STRIDE);
+        uint32_t o = excl;
+        #pragma unroll
+        for (int w = 0; w < (CH + 1) / 2; w++) {
+            uint32_t m = mw[w];
+            while (m) {
+                const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+                m &= m - 1u;
+                if (o < (uint32_t)CAP) nl[o] = (uint16_t)(tid * S + 32u * w + b);
+                o++;
+            }
+        }
+    };
+
+    // ---- prologue: tickets + loads of the first NS-1 local iterations, scan of the first ----
+    __syncthreads();
+    if (tid == 0) for (uint32_t i = 0; i + 1 < (uint32_t)NS; i++) issue(i);
+    __syncthreads();
+    if (s_mode[0] != 0) scan(0);
+
+    for (uint32_t k = 0;; k++) {
+        __syncthreads();                                               // tile k-1 is parsed: its stage and lists are free
+        const uint32_t s = k % NS, par = k & 1u;
+        if (s_mode[s] == 0) break;                                     // tickets are monotone: nothing further for this CTA
+        const uint64_t t = first_tile + s_ticket[s];
+        const uint64_t rel = t - first_tile;
+        if (tid == 0) issue(k + NS - 1);
+        // ---- look-back, part 1 (warp 0): request the status of the 128 tiles before this one ----
+        uint32_t lbw[4] = {0, 0, 0, 0};
+        if (warp == 0 && rel != 0) {
+            #pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const int64_t idx = (int64_t)rel - 1 - lane - 32 * g;
+                lbw[g] = idx >= 0 ? ld_volatile_u32(P.status + idx) : LB_FLAG_PREFIX;
+            }
+        }
+        if (s_mode[(k + 1) % NS] != 0) scan(k + 1);                    // (its ticket was taken one iteration ago)
+        // ---- look-back, part 2 (warp 0): line phase of tile k ----
+        if (warp == 0) {
+            const uint32_t A = s_total_own[par];
             uint32_t p0 = 0;
             if (rel != 0) {
-                if (lane == 0) st_volatile_u32(P.status + rel, LB_FLAG_AGG | (A & LB_VALUE_MASK));
                 int64_t look = (int64_t)rel - 1;
-                for (;;) {
+                for (int g = 0;; g++) {
                     const int64_t idx = look - lane;
-                    uint32_t sw = LB_FLAG_PREFIX;                       // before the first tile: prefix 0
-                    if (idx >= 0) {
-                        uint32_t spins = 0;
-                        do { sw = ld_volatile_u32(P.status + idx); } while ((sw >> 30) == 0 && ++spins < LB_SPIN_LIMIT);
-                        if ((sw >> 30) == 0) { atomicOr(O.error, ERR_LOOKBACK_TIMEOUT); sw = LB_FLAG_PREFIX; }
+                    uint32_t sw = lbw[0];                               // groups 0..3 were requested before the scan
+                    lbw[0] = lbw[1]; lbw[1] = lbw[2]; lbw[2] = lbw[3];
+                    if (g >= 4) sw = idx >= 0 ? ld_volatile_u32(P.status + idx) : LB_FLAG_PREFIX;
+                    uint32_t is_prefix, spins = 0;
+                    for (;;) {
+                        is_prefix = __ballot_sync(0xffffffffu, (sw >> 30) == 2);
+                        const uint32_t first = is_prefix ? (uint32_t)__ffs((int)is_prefix) - 1u : 32u;
+                        const bool wait = (sw >> 30) == 0 && lane <= first;
+                        if (!__any_sync(0xffffffffu, wait)) break;
+                        if (wait) sw = ld_volatile_u32(P.status + idx);     // idx >= 0 here: negative indices read as PREFIX
+                        if (++spins > LB_SPIN_LIMIT) { if (lane == 0) atomicOr(O.error, ERR_LOOKBACK_TIMEOUT); if ((sw >> 30) == 0) sw = LB_FLAG_PREFIX; }
                     }
-                    const uint32_t is_prefix = __ballot_sync(0xffffffffu, (sw >> 30) == 2);
-                    const int first = is_prefix ? __ffs(is_prefix) - 1 : 32;
-                    const uint32_t contrib = ((int)lane <= first) ? (sw & LB_VALUE_MASK) : 0u;
+                    const uint32_t first = is_prefix ? (uint32_t)__ffs((int)is_prefix) - 1u : 32u;
+                    const uint32_t contrib = (lane <= first) ? (sw & LB_VALUE_MASK) : 0u;
                     p0 += __reduce_add_sync(0xffffffffu, contrib);
                     if (is_prefix) break;
                     look -= 32;
@@ -316,119 +391,85 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             }
         }
         __syncthreads();
-        const uint32_t p0 = s_p0;
-        // ---- reads whose header line ends in this row ----
-        const uint32_t region_end = (uint32_t)min((uint64_t)load_bytes, end - base);       // valid bytes of the loaded region
-        const bool region_has_eof = (base + load_bytes >= end);
-        Mask128 m = own;
-        uint32_t remaining = cnt;
-        uint32_t skip = (4u - ((p0 + excl) & 3u)) & 3u;                // newlines of this row before the next header end
-        while (skip < remaining) {
-            for (uint32_t k = 0; k < skip; k++) m.pop_lowest();
-            remaining -= skip + 1;
-            skip = 3;
-            const uint32_t s0 = tid * S + (uint32_t)m.pop_lowest() + 1u;          // first byte of the sequence line
-            // the next three newlines, walking into the following rows if needed
-            Mask128 cm = m; uint32_t crow = tid;
-            uint32_t nl[3]; int have = 0;
-            #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                while (cm.empty() && crow + 1 < rows_loaded) {
-                    crow++;
-                    const uint4 r = rowmask[crow];
-                    cm.lo = (uint64_t)r.x | ((uint64_t)r.y << 32); cm.hi = (uint64_t)r.z | ((uint64_t)r.w << 32);
-                }
-                if (cm.empty()) break;
-                nl[k] = crow * S + (uint32_t)cm.pop_lowest();
-                have = k + 1;
-            }
-            uint32_t e0 = 0, s3 = 0, e3 = 0;
-            bool complete = false, spill = false;
-            if (have == 3) {
-                e0 = nl[0]; s3 = nl[1] + 1u; e3 = nl[2];
-                complete = true;
-                acc.last_end = max(acc.last_end, (unsigned long long)(base + e3 + 1));
-            } else if (region_has_eof) {
-                // no further newline exists: only an unterminated final quality line can complete the record
-                if (eof && have == 2) {
-                    e0 = nl[0]; s3 = nl[1] + 1u; e3 = region_end;
-                    if (s3 < region_end) { complete = true; acc.last_end = max(acc.last_end, (unsigned long long)end); }
-                }
-            } else spill = true;
 
-            if (spill) {
-                // finish the geometry in global memory, then hand the read to the generic code
-                uint64_t pos[4];
-                pos[0] = base + s0 - 1;
-                for (int k = 0; k < 3; k++) pos[k + 1] = (k < have) ? base + nl[k] : 0;
-                uint64_t from = base + load_bytes;
-                bool ok = true;
-                for (int k = have + 1; k < 4; k++) {
-                    uint64_t p = find_newline_global(buf, from, end);
-                    if (p >= end) {
-                        if (k == 3 && eof && from < end) pos[3] = end;             // unterminated final line
-                        else ok = false;
-                        break;
-                    }
-                    pos[k] = p; from = p + 1;
+        // ---- reads of tile k: thread q takes the q-th read whose header line ends in the owned rows ----
+        const uint8_t* tile = smem + s * G_::STAGE_BYTES;
+        const uint16_t* nl = reinterpret_cast<const uint16_t*>(smem + G_::NL_OFF + par * G_::NL_STRIDE);
+        const uint64_t base = t * own_bytes;
+        const uint32_t p0 = s_p0;
+        const uint32_t total_own = s_total_own[par], total_all = s_total_all[par];
+        const uint32_t region_end = (uint32_t)min((uint64_t)G_::LOAD_BYTES, end - base);   // valid bytes of the loaded region
+        const bool region_has_eof = (base + G_::LOAD_BYTES >= end);
+        const uint32_t jf = (4u - (p0 & 3u)) & 3u;                     // first newline of the tile that ends a header line
+
+        if (total_all > (uint32_t)CAP) {
+            // more newlines than the position list holds (a tile of very short lines): every owned row walks its own
+            // header ends and finishes each read in global memory
+            if (tid < own_rows) {
+                const uint32_t excl = reinterpret_cast<const uint16_t*>(smem + G_::EXCL_OFF)[par * NT + tid];
+                uint32_t idx = excl;                                   // (excl is exact: total_all <= NT*S < 65536)
+                for (uint32_t b = 0; b < (uint32_t)S; b++) {
+                    if (tile[tid * S + b] != '\n') continue;
+                    if (((p0 + idx) & 3u) == 0) slow_record(buf, base + tid * S + b, end, eof, G, T, E, O, acc, gst);
+                    idx++;
                 }
-                if (ok) {
-                    acc.reads++;
-                    acc.last_end = max(acc.last_end, (unsigned long long)min(pos[3] + 1, end));
-                    GEntry ge; ge.seq_addr = (uint64_t)(buf + pos[0] + 1); ge.seq_len = (uint32_t)(pos[1] - pos[0] - 1);
-                    ge.qual_addr = (uint64_t)(buf + pos[2] + 1); ge.qual_len = (uint32_t)(pos[3] - pos[2] - 1);
-                    uint32_t slot = (POLICY == POLICY_GENERIC) ? 0xFFFFFFFFu : atomicAdd(&St->g_count, 1u);
-                    if (slot < St->g_cap) P.gqueue[slot] = ge;
-                    else {
-                        const uint8_t* Rp = (const uint8_t*)ge.seq_addr; const uint8_t* Qp = (const uint8_t*)ge.qual_addr;
-                        g_process_read(s_G, T, E, O, Rp, g_rstrip(Rp, (int)ge.seq_len), Qp, g_rstrip(Qp, (int)ge.qual_len), gst);
-                    }
-                }
-            } else if (complete) {
-                acc.reads++;
-                if (POLICY == POLICY_GENERIC) {
-                    const uint8_t* Rp = buf + base + s0; const uint8_t* Qp = buf + base + s3;
-                    g_process_read(s_G, T, E, O, Rp, g_rstrip(Rp, (int)(e0 - s0)), Qp, g_rstrip(Qp, (int)(e3 - s3)), gst);
-                } else {
-                    // ---- K2: rstrip, window, Phred test ----
-                    while (e0 > s0 && is_py_space(tile[e0 - 1])) e0--;
-                    while (e3 > s3 && is_py_space(tile[e3 - 1])) e3--;
-                    int lo, hi, qlo, qhi;
-                    py_slice((int)(e0 - s0), C.starts[0], C.starts[0] + C.length, lo, hi);
-                    py_slice((int)(e3 - s3), C.starts[0], C.starts[0] + C.length, qlo, qhi);
-                    if (qual_fails_tile(tile, s3 + qlo, qhi - qlo, C.fmax_ph)) acc.qfail++;
-                    else {
-                        // ---- K4: pack, exact lookup, count ----
-                        uint64_t key; uint32_t bad; const uint32_t klen = (uint32_t)(hi - lo);
-                        pack_tile(tile, s0 + lo, (int)klen, key, bad);
-                        const bool generic_len = (T.generic_len_mask >> min(klen, 63u)) & 1ull;
-                        uint32_t idx = SLOT_EMPTY;
-                        if (!generic_len && bad == 0) idx = fast_lookup(T, key, klen);
-                        if (idx != SLOT_EMPTY) {
-                            acc.perfect++;
-                            if (P.hist_smem) atomicAdd(hist + idx, 1u);
-                            else atomicAdd(O.counts + idx, 1ull);
-                        } else if (generic_len) {
-                            // library keys of this length exist that the packed tables cannot hold
-                            GEntry ge; ge.seq_addr = (uint64_t)(buf + base + s0); ge.seq_len = e0 - s0;
-                            ge.qual_addr = (uint64_t)(buf + base + s3); ge.qual_len = e3 - s3;
-                            uint32_t slot = atomicAdd(&St->g_count, 1u);
-                            if (slot < St->g_cap) P.gqueue[slot] = ge;
-                            else g_process_read(s_G, T, E, O, (const uint8_t*)ge.seq_addr, (int)ge.seq_len, (const uint8_t*)ge.qual_addr, (int)ge.qual_len, gst);
-                        } else if (C.miss <= 0) acc.nonal++;
-                        else {
-                            const uint32_t sl = atomicAdd(&s_qn, 1u);              // this CTA's private queue segment
-                            if (sl < P.seg_cap) { QEntry e; e.key = key; e.bad = bad; e.len = klen; myq[sl] = e; }
-                            else {                                                 // segment full: resolve right here
-                                const uint32_t r = resolve_thread(T, C.miss, key, bad, klen);
-                                if (r != RES_NONE) { atomicAdd(O.counts + r, 1ull); acc.imperfect++; } else acc.nonal++;
-                            }
-                        }
-                    }
+            }
+            continue;
+        }
+
+        for (uint32_t j = jf + 4u * tid; j < total_own; j += 4u * NT) {
+            const uint32_t h0 = nl[j];
+            if (j + 3 >= total_all) {
+                // the read's last newline is not in the loaded rows (a long record, or the end of the range where only
+                // an unterminated final quality line can still complete it): finish it in global memory
+                slow_record(buf, base + h0, end, eof, G, T, E, O, acc, gst);
+                continue;
+            }
+            const uint32_t s0 = h0 + 1u;
+            uint32_t e0 = nl[j + 1];
+            const uint32_t s3 = (uint32_t)nl[j + 2] + 1u;
+            uint32_t e3 = nl[j + 3];
+            acc.reads++;
+            acc.last_end = max(acc.last_end, (unsigned long long)(base + e3 + 1));
+            if (POLICY == POLICY_GENERIC) {
+                const uint8_t* Rp = tile + s0; const uint8_t* Qp = tile + s3;
+                g_process_read(G, T, E, O, Rp, g_rstrip(Rp, (int)(e0 - s0)), Qp, g_rstrip(Qp, (int)(e3 - s3)), gst);
+                continue;
+            }
+            // ---- K2: rstrip, window, Phred test ----
+            while (e0 > s0 && is_py_space(tile[e0 - 1])) e0--;
+            while (e3 > s3 && is_py_space(tile[e3 - 1])) e3--;
+            int lo, hi, qlo, qhi;
+            py_slice((int)(e0 - s0), c_start, c_start + c_length, lo, hi);
+            py_slice((int)(e3 - s3), c_start, c_start + c_length, qlo, qhi);
+            if (qual_fails_tile(tile, s3 + qlo, qhi - qlo, c_fmax)) { acc.qfail++; continue; }
+            // ---- K4: pack, exact lookup, count ----
+            uint64_t key; uint32_t bad; const uint32_t klen = (uint32_t)(hi - lo);
+            pack_tile(tile, s0 + lo, (int)klen, key, bad);
+            const bool generic_len = (T.generic_len_mask >> min(klen, 63u)) & 1ull;
+            uint32_t idx = SLOT_EMPTY;
+            if (!generic_len && bad == 0) idx = fast_lookup(T, key, klen);
+            if (idx != SLOT_EMPTY) {
+                acc.perfect++;
+                if (P.hist_smem) atomicAdd(hist + idx, 1u);
+                else atomicAdd(O.counts + idx, 1ull);
+            } else if (generic_len) {
+                // library keys of this length exist that the packed tables cannot hold
+                GEntry ge; ge.seq_addr = (uint64_t)(buf + base + s0); ge.seq_len = e0 - s0;
+                ge.qual_addr = (uint64_t)(buf + base + s3); ge.qual_len = e3 - s3;
+                const uint32_t slot = atomicAdd(&St->g_count, 1u);
+                if (slot < St->g_cap) P.gqueue[slot] = ge;
+                else g_process_read(G, T, E, O, (const uint8_t*)ge.seq_addr, (int)ge.seq_len, (const uint8_t*)ge.qual_addr, (int)ge.qual_len, gst);
+            } else if (c_miss <= 0) acc.nonal++;
+            else {
+                const uint32_t sl = atomicAdd(&s_qn, 1u);              // this CTA's private queue segment
+                if (sl < P.seg_cap) { QEntry e; e.key = key; e.bad = bad; e.len = klen; myq[sl] = e; }
+                else {                                                 // segment full: resolve right here
+                    const uint32_t r = resolve_seed_thread(T, c_miss, key, bad, klen);
+                    if (r != RES_NONE) { atomicAdd(O.counts + r, 1ull); acc.imperfect++; } else acc.nonal++;
                 }
             }
         }
-
     }
 
     // ---- CTA epilogue: queue segment length, histogram, statistics ----
