@@ -593,6 +593,25 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
         while (slots[h].idx != SLOT_EMPTY) h = (h + 1) & (cap - 1);
         slots[h] = FastSlot{fk[k], fl[k], fi[k]};
     }
+    // compact 8-byte table for the tile kernel (one key length, index fits above the key bits)
+    std::vector<uint64_t> cslots(1, ~0ull);
+    uint32_t c_len = 0, c_mask = 0; bool compact = !fk.empty();
+    for (size_t k = 0; k < fl.size() && compact; k++) compact = fl[k] == fl[0];
+    if (compact) {
+        c_len = fl[0];
+        const uint32_t idx_bits = 64 - 2 * c_len;
+        compact = c_len >= 1 && c_len < 32 && (idx_bits >= 32 || (uint64_t)n_keys < (1ull << idx_bits) - 1);
+    }
+    if (compact) {
+        const uint32_t ccap = pow2_at_least(4 * (uint64_t)fk.size());
+        cslots.assign(ccap, ~0ull);
+        c_mask = ccap - 1;
+        for (size_t k = 0; k < fk.size(); k++) {
+            uint32_t h = mix_compact((uint32_t)fk[k], (uint32_t)(fk[k] >> 32)) & c_mask;
+            while (cslots[h] != ~0ull) h = (h + 1) & c_mask;
+            cslots[h] = fk[k] | ((uint64_t)fi[k] << (2 * c_len));
+        }
+    }
     const uint32_t gcap = pow2_at_least(2 * (uint64_t)n_keys + 2);
     std::vector<uint32_t> gh(gcap, 0);
     for (uint32_t i = 0; i < n_keys; i++) {
@@ -637,6 +656,10 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
         (rc = upload(c, fi, &c->T.fast_idx)) || (rc = upload(c, bytes, &c->T.key_bytes)) || (rc = upload(c, off, &c->T.key_off)) ||
         (rc = upload(c, gh, &c->T.ghash)))
         return rc;
+    if (compact) {
+        if ((rc = upload(c, cslots, &c->T.cslots))) return rc;
+        c->T.c_mask = c_mask; c->T.c_len = c_len; c->T.c_keybits = 2 * c_len;
+    }
     c->T.slot_mask = cap - 1; c->T.n_fast = (uint32_t)fk.size(); c->T.n_keys = n_keys; c->T.ghash_mask = gcap - 1;
     c->T.n_generic = n_generic; c->T.generic_len_mask = gmask;
     c->n_keys = n_keys;

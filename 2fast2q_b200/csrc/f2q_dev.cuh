@@ -50,6 +50,13 @@ struct LibTables {
     const FastSlot* slots;
     uint32_t slot_mask;        // capacity - 1 (power of two)
     uint32_t n_fast;
+    // compact 8-byte form of the same table for the fused tile kernel, present when every packed key has ONE length c_len and
+    // 2*c_len + bits(index) <= 64:  slot = packed key | feature index << 2*c_len;  ~0 = empty.  Load factor <= 1/4, so a probe
+    // sequence is short for every lane of a warp and small libraries stay L1-resident (2 000 guides: 64 KB)
+    const uint64_t* cslots;
+    uint32_t c_mask;           // capacity - 1
+    uint32_t c_len;
+    uint32_t c_keybits;        // 2 * c_len
     const uint64_t* fast_keys; // n_fast packed keys grouped by length (for the tile-scan resolver)
     const uint32_t* fast_lens;
     const uint32_t* fast_idx;
@@ -114,6 +121,16 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint64_t key, uint32_t len) {
     return (uint32_t)(h >> 32);
 }
 
+// hash of a packed key for the compact table (32-bit multiplies only; the table mask takes the HIGH bits' mix)
+__host__ __device__ __forceinline__ uint32_t mix_compact(uint32_t klo, uint32_t khi) {
+    uint32_t x = klo ^ (khi * 0x9E3779B1u);
+    x *= 0x85EBCA6Bu;
+    x ^= x >> 15;
+    x *= 0xC2B2AE35u;
+    x ^= x >> 13;
+    return x;
+}
+
 // Python slice bounds seq[a:b] for a sequence of length n (fast2q.py:354-355)
 __host__ __device__ __forceinline__ void py_slice(int n, int a, int b, int& lo, int& hi) {
     if (a < 0) { a += n; if (a < 0) a = 0; } else if (a > n) a = n;
@@ -172,6 +189,21 @@ __device__ __forceinline__ uint32_t fast_lookup(const LibTables& T, uint64_t key
         if (raw.w == SLOT_EMPTY) return SLOT_EMPTY;
         if (k == key && raw.z == len) return raw.w;
         h = (h + 1) & T.slot_mask;
+    }
+}
+
+// probe the compact table (all keys have T.c_len symbols; the caller checked len == T.c_len); feature index or SLOT_EMPTY
+__device__ __forceinline__ uint32_t compact_lookup(const LibTables& T, uint32_t klo, uint32_t khi) {
+    uint32_t h = mix_compact(klo, khi) & T.c_mask;
+    const uint64_t key = ((uint64_t)khi << 32) | klo;
+    const uint64_t keymask = T.c_keybits >= 64 ? ~0ull : ((1ull << T.c_keybits) - 1ull);
+    #pragma unroll 1
+    for (;;) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(T.cslots) + h);
+        const uint64_t sl = ((uint64_t)raw.y << 32) | raw.x;
+        if ((sl & keymask) == key && sl != ~0ull) return (uint32_t)(sl >> T.c_keybits);
+        if (sl == ~0ull) return SLOT_EMPTY;
+        h = (h + 1) & T.c_mask;
     }
 }
 #endif  // __CUDACC__

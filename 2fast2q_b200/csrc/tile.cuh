@@ -102,6 +102,7 @@ __device__ __forceinline__ uint32_t reg_const(uint32_t v) {
 }
 
 // ---- byte access to the tile ---------------------------------------------------------------------------
+// @region WordReader
 struct WordReader {                 // 4 bytes at an arbitrary tile offset, little endian
     const uint8_t* tile; uint32_t a, sh, prev;
     __device__ __forceinline__ WordReader(const uint8_t* t, uint32_t o) : tile(t), a(o & ~3u), sh((o & 3u) * 8u) {
@@ -116,6 +117,7 @@ struct WordReader {                 // 4 bytes at an arbitrary tile offset, litt
     }
 };
 
+// @region qual_fails
 // any byte b of tile[o, o+n) with 33 <= b <= fmax ?   (fast2q.py:357 with the fail set of :1127)
 __device__ __forceinline__ bool qual_fails_tile(const uint8_t* tile, uint32_t o, int n, int fmax) {
     if (fmax == 0 || n <= 0) return false;
@@ -134,6 +136,7 @@ __device__ __forceinline__ bool qual_fails_tile(const uint8_t* tile, uint32_t o,
     return (acc & 0x80808080u) != 0;
 }
 
+// @region pack
 // 2-bit pack of tile[o, o+n), n <= 32.  bad = mask of symbols outside ACGT (after upper()); their key bits are 0
 __device__ __forceinline__ void pack_tile(const uint8_t* tile, uint32_t o, int n, uint64_t& key, uint32_t& bad) {
     key = 0; bad = 0;
@@ -161,6 +164,62 @@ __device__ __forceinline__ void pack_tile(const uint8_t* tile, uint32_t o, int n
     key = ((uint64_t)khi << 32) | klo;
 }
 
+
+// @region window_words
+// W words starting at an arbitrary tile offset: W+1 aligned loads, W funnel shifts, everything unrolled so the
+// independent words overlap in the pipeline
+template <int W>
+__device__ __forceinline__ void load_words(const uint8_t* tile, uint32_t o, uint32_t (&w)[W]) {
+    const uint32_t a = o & ~3u, sh = (o & 3u) * 8u;
+    uint32_t r[W + 1];
+    #pragma unroll
+    for (int i = 0; i <= W; i++) r[i] = *reinterpret_cast<const uint32_t*>(tile + a + 4 * i);
+    #pragma unroll
+    for (int i = 0; i < W; i++) w[i] = __funnelshift_r(r[i], r[i + 1], sh);
+}
+
+// quality test of a window of W words (n bytes, 4W-3 <= n <= 4W)
+template <int W>
+__device__ __forceinline__ bool qual_fails_w(const uint8_t* tile, uint32_t o, int n, uint32_t add_ge, uint32_t add_gt) {
+    uint32_t w[W];
+    load_words<W>(tile, o, w);
+    if (n & 3) w[W - 1] &= (1u << (8 * (n & 3))) - 1u;                 // bytes past the slice become 0 (never fail)
+    uint32_t acc = 0;
+    #pragma unroll
+    for (int i = 0; i < W; i++) {
+        const uint32_t lo7 = w[i] & 0x7F7F7F7Fu;
+        acc |= (lo7 + add_ge) & ~(lo7 + add_gt) & ~w[i];
+    }
+    return (acc & 0x80808080u) != 0;
+}
+
+// 2-bit pack of a window of W words; returns non-zero when some symbol is not A/C/G/T (the caller then takes pack_tile)
+template <int W>
+__device__ __forceinline__ uint32_t pack_w(const uint8_t* tile, uint32_t o, int n, uint32_t& klo, uint32_t& khi) {
+    uint32_t w[W];
+    load_words<W>(tile, o, w);
+    if (n & 3) { const uint32_t keep = (1u << (8 * (n & 3))) - 1u; w[W - 1] = (w[W - 1] & keep) | (0x41414141u & ~keep); }   // pad with 'A'
+    uint32_t lo = 0, hi = 0, any = 0;
+    #pragma unroll
+    for (int i = 0; i < W; i++) {
+        const uint32_t codes = (w[i] >> 1) & 0x03030303u;
+        uint32_t t = (codes | (codes >> 4)) & 0x00330033u;
+        t = (t | (t >> 8)) & 0x3333u;                                  // nibble k = code of byte k
+        any |= (w[i] & 0xDFDFDFDFu) ^ __byte_perm(0x47544341u, 0u, t);  // upper-cased byte vs the base its code stands for
+        const uint32_t p = (codes * 0x01041040u) >> 24;                 // 4 symbols -> 8 bits (one multiply, no carries)
+        if (i < 4) lo |= p << (8 * (i & 3)); else hi |= p << (8 * (i & 3));
+    }
+    klo = lo; khi = hi;
+    return any;
+}
+
+#define F2Q_WORDS_SWITCH(words, CALL)                                                                   \
+    switch (words) {                                                                                    \
+        case 1: CALL(1); break; case 2: CALL(2); break; case 3: CALL(3); break; case 4: CALL(4); break; \
+        case 5: CALL(5); break; case 6: CALL(6); break; case 7: CALL(7); break; default: CALL(8); break; \
+    }
+
+// @region slow_path
 __device__ __noinline__ uint64_t find_newline_global(const uint8_t* buf, uint64_t from, uint64_t end) {
     for (uint64_t p = from; p < end; p++) if (buf[p] == '\n') return p;
     return end;
@@ -194,6 +253,7 @@ __device__ __noinline__ void slow_record(const uint8_t* buf, uint64_t hdr_end, u
     g_process_read(G, T, E, O, Rp, g_rstrip(Rp, (int)(pos[1] - pos[0] - 1)), Qp, g_rstrip(Qp, (int)(pos[3] - pos[2] - 1)), gst);
 }
 
+// @region kernel_prologue
 template <int POLICY, int CH, int NT>
 __global__ void __launch_bounds__(NT, POLICY == POLICY_FAST1 ? (512 / NT) : (256 / NT))
 k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, Outputs O) {
@@ -236,8 +296,13 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     Acc acc{0, 0, 0, 0, 0, 0};
     unsigned long long gst[F2Q_N_STATS] = {0, 0, 0, 0, 0};            // stats of reads handled by the generic code
     uint32_t bar_phase = 0;                                            // bit s: parity the next wait on stage s uses
+    uint32_t reads = 0, perfect = 0, nonal = 0, qfail = 0;            // per-thread counts of this launch (a chunk is < 2^32 bytes per thread)
+    const int c_end = c_start + c_length;
+    const bool simple_slice = c_start >= 0 && c_length >= 0;
+    const uint32_t add_ge = (0x80u - 33u) * 0x01010101u, add_gt = (0x80u - (uint32_t)(c_fmax + 1)) * 0x01010101u;
 
     const uint32_t c0A = reg_const(0x0A0A0A0Au), c7F = reg_const(0x7F7F7F7Fu), c80 = reg_const(0x80808080u);
+    // @region scan_chunk_mask
     // newline flags of one 16-byte chunk, bit i = byte i.  Exact per-byte compare in 3 operations per word:
     //   a = (w ^ 0x0A..) & 0x7F..; b = a + 0x7F..  (bit 7: low 7 bits differ); z = ~(b | w) & 0x80..  (w's own bit 7 must be 0)
     auto chunk_mask = [&](const uint8_t* p16) -> uint32_t {
@@ -249,6 +314,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         return (lo >> 7) | (hi << 1);
     };
 
+    // @region issue
     // thread 0: take the ticket of local iteration i and start its load into stage i % NS
     auto issue = [&](uint32_t i) {
         const uint32_t s = i % NS;
@@ -267,6 +333,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         s_mode[s] = mode;
     };
 
+    // @region scan_wait_load
     // all threads: newline masks, counts and position list of local iteration i (its stage is loaded or gets loaded here)
     auto scan = [&](uint32_t i) {
         const uint32_t s = i % NS, par = i & 1u;
@@ -297,6 +364,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             }
             __syncthreads();
         }
+        // @region scan_masks_blockscan
         uint32_t m16[8];
         #pragma unroll
         for (int j = 0; j < 8; j++) m16[j] = 0;
@@ -309,9 +377,10 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
         if (lane == 31) s_wsum[warp] = incl;
         __syncthreads();
-        uint32_t wbase = 0;
+        uint32_t wv = lane < NT / 32 ? s_wsum[lane] : 0u, wi = wv;        // warp totals, scanned again inside every warp
         #pragma unroll
-        for (int w = 0; w < NT / 32; w++) { const uint32_t x = s_wsum[w]; if (w < (int)warp) wbase += x; }
+        for (int d = 1; d < NT / 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += y; }
+        const uint32_t wbase = __shfl_sync(0xffffffffu, wi - wv, warp);
         const uint32_t excl = wbase + incl - cnt;                      // newlines of the tile before this row
         reinterpret_cast<uint16_t*>(smem + G_::EXCL_OFF)[par * NT + tid] = (uint16_t)min(excl, 0xFFFFu);
         if (tid == own_rows) {                                         // excl of the first read-ahead row = newlines of the owned rows
@@ -320,20 +389,31 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             if (rel != 0) st_volatile_u32(P.status + rel, LB_FLAG_AGG | (excl & LB_VALUE_MASK));
         }
         if (tid == NT - 1) s_total_all[par] = excl + cnt;
+        // @region scan_nlpos
         uint16_t* nl = reinterpret_cast<uint16_t*>(smem + G_::NL_OFF + par * G_::NL_STRIDE);
         uint32_t o = excl;
+        const uint32_t rowbase = tid * S;
         #pragma unroll
         for (int w = 0; w < (CH + 1) / 2; w++) {
             uint32_t m = mw[w];
-            while (m) {
+            #pragma unroll
+            for (int step = 0; step < 2; step++) {                     // two predicated steps: no divergence for ordinary FASTQ
+                const bool has = m != 0;
+                const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+                if (has && o < (uint32_t)CAP) nl[o] = (uint16_t)(rowbase + 32u * w + b);
+                o += has ? 1u : 0u;
+                m &= m - 1u;
+            }
+            while (m) {                                                // three or more newlines within 32 bytes
                 const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
                 m &= m - 1u;
-                if (o < (uint32_t)CAP) nl[o] = (uint16_t)(tid * S + 32u * w + b);
+                if (o < (uint32_t)CAP) nl[o] = (uint16_t)(rowbase + 32u * w + b);
                 o++;
             }
         }
     };
 
+    // @region loop_top
     // ---- prologue: tickets + loads of the first NS-1 local iterations, scan of the first ----
     __syncthreads();
     if (tid == 0) for (uint32_t i = 0; i + 1 < (uint32_t)NS; i++) issue(i);
@@ -357,6 +437,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             }
         }
         if (s_mode[(k + 1) % NS] != 0) scan(k + 1);                    // (its ticket was taken one iteration ago)
+        // @region lookback2
         // ---- look-back, part 2 (warp 0): line phase of tile k ----
         if (warp == 0) {
             const uint32_t A = s_total_own[par];
@@ -392,6 +473,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         }
         __syncthreads();
 
+        // @region parse_setup
         // ---- reads of tile k: thread q takes the q-th read whose header line ends in the owned rows ----
         const uint8_t* tile = smem + s * G_::STAGE_BYTES;
         const uint16_t* nl = reinterpret_cast<const uint16_t*>(smem + G_::NL_OFF + par * G_::NL_STRIDE);
@@ -429,28 +511,52 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             uint32_t e0 = nl[j + 1];
             const uint32_t s3 = (uint32_t)nl[j + 2] + 1u;
             uint32_t e3 = nl[j + 3];
-            acc.reads++;
-            acc.last_end = max(acc.last_end, (unsigned long long)(base + e3 + 1));
+            reads++;
+            acc.last_end = (unsigned long long)(base + e3 + 1);         // (a thread meets its reads in stream order)
             if (POLICY == POLICY_GENERIC) {
                 const uint8_t* Rp = tile + s0; const uint8_t* Qp = tile + s3;
                 g_process_read(G, T, E, O, Rp, g_rstrip(Rp, (int)(e0 - s0)), Qp, g_rstrip(Qp, (int)(e3 - s3)), gst);
                 continue;
             }
+            // @region parse_k2
             // ---- K2: rstrip, window, Phred test ----
-            while (e0 > s0 && is_py_space(tile[e0 - 1])) e0--;
-            while (e3 > s3 && is_py_space(tile[e3 - 1])) e3--;
+            if (is_py_space(tile[e0 - 1])) while (e0 > s0 && is_py_space(tile[e0 - 1])) e0--;     // (tile[s0 - 1] is the '\n' before the line)
+            if (is_py_space(tile[e3 - 1])) while (e3 > s3 && is_py_space(tile[e3 - 1])) e3--;
             int lo, hi, qlo, qhi;
-            py_slice((int)(e0 - s0), c_start, c_start + c_length, lo, hi);
-            py_slice((int)(e3 - s3), c_start, c_start + c_length, qlo, qhi);
-            if (qual_fails_tile(tile, s3 + qlo, qhi - qlo, c_fmax)) { acc.qfail++; continue; }
+            if (simple_slice) {
+                const int ls = (int)(e0 - s0), lq = (int)(e3 - s3);
+                lo = min(c_start, ls); hi = min(c_end, ls); qlo = min(c_start, lq); qhi = min(c_end, lq);
+            } else {
+                py_slice((int)(e0 - s0), c_start, c_end, lo, hi);
+                py_slice((int)(e3 - s3), c_start, c_end, qlo, qhi);
+            }
+            const int qn = qhi - qlo;
+            if (c_fmax != 0 && qn > 0) {
+                bool fails;
+                #define F2Q_QCALL(W) fails = qual_fails_w<W>(tile, s3 + qlo, qn, add_ge, add_gt)
+                F2Q_WORDS_SWITCH((qn + 3) >> 2, F2Q_QCALL)
+                #undef F2Q_QCALL
+                if (fails) { qfail++; continue; }
+            }
+            // @region parse_k4
             // ---- K4: pack, exact lookup, count ----
-            uint64_t key; uint32_t bad; const uint32_t klen = (uint32_t)(hi - lo);
-            pack_tile(tile, s0 + lo, (int)klen, key, bad);
+            const uint32_t klen = (uint32_t)(hi - lo);
+            uint32_t klo = 0, khi = 0, bad = 0, any = 0;
+            if (klen) {
+                #define F2Q_PCALL(W) any = pack_w<W>(tile, s0 + lo, (int)klen, klo, khi)
+                F2Q_WORDS_SWITCH((klen + 3) >> 2, F2Q_PCALL)
+                #undef F2Q_PCALL
+            }
+            uint64_t key = ((uint64_t)khi << 32) | klo;
+            if (any) pack_tile(tile, s0 + lo, (int)klen, key, bad);     // a symbol outside ACGT: the exact (slower) packer flags it
             const bool generic_len = (T.generic_len_mask >> min(klen, 63u)) & 1ull;
             uint32_t idx = SLOT_EMPTY;
-            if (!generic_len && bad == 0) idx = fast_lookup(T, key, klen);
+            if (!generic_len && bad == 0) {
+                if (T.cslots) { if (klen == T.c_len) idx = compact_lookup(T, klo, khi); }
+                else idx = fast_lookup(T, key, klen);
+            }
             if (idx != SLOT_EMPTY) {
-                acc.perfect++;
+                perfect++;
                 if (P.hist_smem) atomicAdd(hist + idx, 1u);
                 else atomicAdd(O.counts + idx, 1ull);
             } else if (generic_len) {
@@ -460,23 +566,25 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 const uint32_t slot = atomicAdd(&St->g_count, 1u);
                 if (slot < St->g_cap) P.gqueue[slot] = ge;
                 else g_process_read(G, T, E, O, (const uint8_t*)ge.seq_addr, (int)ge.seq_len, (const uint8_t*)ge.qual_addr, (int)ge.qual_len, gst);
-            } else if (c_miss <= 0) acc.nonal++;
+            } else if (c_miss <= 0) nonal++;
             else {
                 const uint32_t sl = atomicAdd(&s_qn, 1u);              // this CTA's private queue segment
                 if (sl < P.seg_cap) { QEntry e; e.key = key; e.bad = bad; e.len = klen; myq[sl] = e; }
                 else {                                                 // segment full: resolve right here
                     const uint32_t r = resolve_seed_thread(T, c_miss, key, bad, klen);
-                    if (r != RES_NONE) { atomicAdd(O.counts + r, 1ull); acc.imperfect++; } else acc.nonal++;
+                    if (r != RES_NONE) { atomicAdd(O.counts + r, 1ull); acc.imperfect++; } else nonal++;
                 }
             }
         }
     }
 
+    // @region epilogue
     // ---- CTA epilogue: queue segment length, histogram, statistics ----
     __syncthreads();
     if (tid == 0 && P.seg_cap) P.seg_count[blockIdx.x] = min(s_qn, P.seg_cap);
     if (P.hist_smem)
         for (uint32_t i = tid; i < T.n_keys; i += NT) { uint32_t v = hist[i]; if (v) atomicAdd(O.counts + i, (unsigned long long)v); }
+    acc.reads += reads; acc.perfect += perfect; acc.nonal += nonal; acc.qfail += qfail;
     acc.perfect += gst[F2Q_STAT_PERFECT]; acc.imperfect += gst[F2Q_STAT_IMPERFECT];
     acc.nonal += gst[F2Q_STAT_NON_ALIGNED]; acc.qfail += gst[F2Q_STAT_QUALITY_FAILED];
     unsigned long long v[5] = {acc.reads, acc.perfect, acc.imperfect, acc.nonal, acc.qfail};
