@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -189,8 +190,14 @@ int tile_grid(f2q_ctx* c, unsigned* grid) {
     if (blocks_per_sm == 0) {
         CU(c, cudaFuncSetAttribute(k_tile<POLICY, CH, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(tile_smem_bytes<CH, NT>(HIST_MAX_KEYS))));
         CU(c, cudaFuncSetAttribute(k_tile<POLICY, CH, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_tile<POLICY, CH, NT>, NT, smem));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_tile<POLICY, CH, NT>, NT + TILE_CTRL_THREADS, smem));
         if (blocks_per_sm < 1) return fail(c, F2Q_EINTERNAL, "tile kernel does not fit on an SM");
+        // leave the rest of the 228 KB to L1: the lookup table of a small library then stays L1-resident
+        cudaFuncAttributes fa;
+        CU(c, cudaFuncGetAttributes(&fa, k_tile<POLICY, CH, NT>));
+        const size_t need = (size_t)blocks_per_sm * (smem + fa.sharedSizeBytes + 1024);
+        const int pct = (int)std::min<size_t>(100, (need * 100 + 233472 - 1) / 233472);
+        CU(c, cudaFuncSetAttribute(k_tile<POLICY, CH, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     }
     *grid = (unsigned)c->sm_count * (unsigned)blocks_per_sm;
     return F2Q_OK;
@@ -204,7 +211,7 @@ int launch_tile(f2q_ctx* c, const TileParams& P, Outputs O, uint64_t n_tiles_upp
     unsigned grid = 0;
     int rc = tile_grid<POLICY, CH, NT>(c, &grid); if (rc) return rc;
     if (p.seg_cap == 0) grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(grid, n_tiles_upper));   // main launches keep one segment per CTA
-    k_tile<POLICY, CH, NT><<<grid, NT, smem, c->stream>>>(p, c->dG, c->T, c->E, O);
+    k_tile<POLICY, CH, NT><<<grid, NT + TILE_CTRL_THREADS, smem, c->stream>>>(p, c->dG, c->T, c->E, O);
     c->launches++;
     CU(c, cudaGetLastError());
     return F2Q_OK;
@@ -356,7 +363,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     const uint64_t own_bytes = (uint64_t)(c->nt - c->halo_rows) * 16 * c->ch;
     const uint64_t n_tiles = (delta + n) / own_bytes + 2;
     const uint64_t stitch_tiles = c->carry_cap / (64 * 16 * 3) + 2;
-    if ((rc = dev_alloc(c, c->status, n_tiles * 4))) return rc;
+    if ((rc = dev_alloc(c, c->status, n_tiles + 64))) return rc;
     unsigned grid = 0;
     if ((rc = tile_grid_dyn(c, &grid))) return rc;
     // queues sized for the chunk: one entry per 64 bytes covers every non-exact read of ordinary FASTQ; anything
@@ -377,8 +384,8 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         if ((rc = ec_reserve(c, (n + c->carry_cap) / 4 + 16, (uint64_t)c->cfg.n_iter * (n + c->carry_cap) + 64))) return rc;
     }
 
-    CU(c, cudaMemsetAsync(c->status.p, 0, n_tiles * 4, c->stream));
-    CU(c, cudaMemsetAsync(c->status_stitch.p, 0, stitch_tiles * 4, c->stream));
+    CU(c, cudaMemsetAsync(c->status.p, 0, n_tiles + 64, c->stream));
+    CU(c, cudaMemsetAsync(c->status_stitch.p, 0, stitch_tiles + 64, c->stream));
     CU(c, cudaMemsetAsync(c->seg_count.p, 0, (size_t)c->n_segs * 4, c->stream));
     k_prepare<<<1, PREP_THREADS, 0, c->stream>>>(c->dS, base, delta, n, is_last ? 1u : 0u, reinterpret_cast<uint8_t*>(c->carry.p),
                                                  c->carry_cap, c->d_tickets, c->q_cap, c->g_cap);
@@ -387,18 +394,32 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     TileParams P{};
     P.S = c->dS; P.queue = reinterpret_cast<QEntry*>(c->queue.p); P.gqueue = reinterpret_cast<GEntry*>(c->gqueue.p);
     P.halo_rows = (uint32_t)c->halo_rows;
+    P.debug = getenv("F2Q_DEBUG") ? (uint32_t)atoi(getenv("F2Q_DEBUG")) : 0u;
+    static unsigned long long* g_trace = nullptr; static uint64_t g_trace_tiles = 0;
+    if (getenv("F2Q_TRACE")) {
+        if (!g_trace) { g_trace_tiles = n_tiles + 16; cudaMalloc(&g_trace, g_trace_tiles * 48); }
+        cudaMemsetAsync(g_trace, 0, g_trace_tiles * 48, c->stream);
+    }
     // 1. the record stitched from the carried tail and the head of this chunk (lives in the carry buffer)
-    P.buf = reinterpret_cast<const uint8_t*>(c->carry.p); P.status = reinterpret_cast<uint32_t*>(c->status_stitch.p);
+    P.buf = reinterpret_cast<const uint8_t*>(c->carry.p); P.status = reinterpret_cast<uint8_t*>(c->status_stitch.p);
     P.ticket = c->d_tickets; P.stitch = 1; P.seg_count = reinterpret_cast<uint32_t*>(c->seg_count.p); P.seg_cap = 0;
     if ((rc = launch_tile_dyn(c, P, O, 4))) return rc;
     // 2. the chunk itself
     if (n) {
-        P.buf = base; P.status = reinterpret_cast<uint32_t*>(c->status.p); P.ticket = c->d_tickets + 1; P.stitch = 0;
+        P.buf = base; P.status = reinterpret_cast<uint8_t*>(c->status.p); P.ticket = c->d_tickets + 1; P.stitch = 0;
+        P.trace = (getenv("F2Q_TRACE") && n_tiles + 16 <= g_trace_tiles) ? g_trace : nullptr;
         P.seg_cap = c->policy == POLICY_FAST1 ? c->seg_cap : 0;
         cudaEvent_t t0 = timing_begin(c);
         rc = launch_tile_dyn(c, P, O, n_tiles);
         timing_end(c, t0, 0);
         if (rc) return rc;
+    }
+    if (getenv("F2Q_TRACE") && g_trace && n) {
+        cudaStreamSynchronize(c->stream);
+        std::vector<unsigned long long> h(g_trace_tiles * 6);
+        cudaMemcpy(h.data(), g_trace, g_trace_tiles * 48, cudaMemcpyDeviceToHost);
+        FILE* f = fopen(getenv("F2Q_TRACE"), "wb");
+        if (f) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
     }
     // 3. deferred work
     if (c->policy == POLICY_FAST1) {
@@ -673,7 +694,7 @@ F2Q_EXPORT int f2q_begin_sample(f2q_ctx* c) {
     int rc = check_ctx(c); if (rc) return rc;
     if (!c->lib_set) return fail(c, F2Q_ESTATE, "f2q_set_library must be called first in Counter mode");
     if ((rc = dev_alloc(c, c->carry, c->carry_cap + 256))) return rc;
-    if ((rc = dev_alloc(c, c->status_stitch, (c->carry_cap / (64 * 16 * 3) + 2) * 4))) return rc;
+    if ((rc = dev_alloc(c, c->status_stitch, c->carry_cap / (64 * 16 * 3) + 2 + 64))) return rc;
     c->ch_decided = false;
     CU(c, cudaMemsetAsync(c->result.p, 0, ((size_t)c->n_keys + 5) * 8, c->stream));
     CU(c, cudaMemsetAsync(c->d_error, 0, 4, c->stream));
@@ -750,6 +771,9 @@ F2Q_EXPORT int f2q_end_sample(f2q_ctx* c, uint64_t* counts, uint64_t* stats) {
     DevState hs;
     CU(c, cudaMemcpy(&hs, c->dS, sizeof(hs), cudaMemcpyDeviceToHost));
     err |= hs.error;
+    if (getenv("F2Q_DEBUG"))
+        fprintf(stderr, "f2q debug: wait Mcycles  empty(loader) %llu  full(lookback) %llu agg(lookback) %llu  in-lookback %llu | full(consumers) %llu  p0(consumers) %llu | respins %llu | consumer warp Mcycles %llu\n",
+                hs.dbg[0] >> 20, hs.dbg[7] >> 20, hs.dbg[1] >> 20, hs.dbg[4] >> 20, hs.dbg[2] >> 20, hs.dbg[3] >> 20, hs.dbg[5], hs.dbg[6] >> 20);
     if (err & ERR_RECORD_TOO_LONG) return fail(c, F2Q_ETOOLONG, "a FASTQ record is longer than carry_bytes; raise it with f2q_set_option");
     if (err) return fail(c, F2Q_EINTERNAL, "device-side failure, flags=" + std::to_string(err));
     if (counts && c->n_keys) CU(c, cudaMemcpy(counts, c->result.p, (size_t)c->n_keys * 8, cudaMemcpyDeviceToHost));

@@ -109,6 +109,7 @@ struct DevState {
     uint32_t q_count, q_cap;       // (unused; the non-exact key queue is segmented per CTA, see TileParams)
     uint32_t g_count, g_cap;       // generic read queue
     uint32_t pad;
+    unsigned long long dbg[8];     // diagnostics (F2Q_DEBUG=1): failed mbarrier tries per wait site, look-back rounds / spins
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -11,21 +11,29 @@
 // bank-conflict free without a swizzle; the host picks CH so that S is just below the record length).  The first
 // NT-H rows are OWNED by the tile, the last H rows are read-ahead (they are the first rows of the next tile): a read
 // belongs to the tile that owns the newline ending its header line, and finds its other three newlines in the rows
-// behind it.  Persistent CTAs take tiles by atomic ticket and run a 3-stage software pipeline per CTA:
-//     iteration k:   issue the TMA bulk copy (cp.async.bulk + mbarrier) of tile k+2
-//                    issue the look-back loads for tile k            (warp 0; consumed after the scan below)
-//                    scan tile k+1: row masks, counts, position list; publish its newline count (aggregate)
-//                    finish the look-back of tile k -> line phase p0; publish the inclusive prefix
-//                    parse the reads of tile k: thread q takes the q-th read of the tile (dense lanes, no row walk)
-// so HBM latency is hidden by the TMA prefetch, the look-back latency by the scan, and a tile's aggregate is public one
-// whole parse phase before its successors need it.  Tickets are taken in increasing order by every CTA, so the smallest
-// unfinished tile can always make progress: the look-back cannot deadlock even if not all CTAs are resident.
-// The first / last tile of a range (bytes outside [beg, end) must read as 0) is loaded by the threads instead of TMA.
+// behind it.  Persistent CTAs of NT consumer threads + TWO control warps, three tile stages in shared memory, mbarriers:
+//
+//   loader warp, tile i     wait until stage i%3 is free (consumers arrived on `empty`) -> ticket (atomic, taken one tile
+//                           ahead) -> TMA bulk copy (cp.async.bulk, completes on `full`)
+//   look-back warp, tile j  wait for its newline count (`agg`) -> decoupled look-back over the status bytes of the tiles
+//                           before it -> publish the inclusive prefix -> hand the line phase p0 to the consumers (`p0r`)
+//                           All DRAM / L2 / atomic latency of the pipeline lives in these two warps.
+//   consumers, iteration k  wait `full` of tile k+1 -> row masks, counts, ONE named barrier, position list, publish the
+//                           aggregate (global status byte + `agg`)
+//                           wait `p0r` of tile k (long done) -> parse its reads: thread q takes the q-th read of the tile
+//                           (dense lanes, no row walk) -> arrive on `empty`
+//
+// A tile's aggregate never depends on a look-back (it is published right after the scan, one parse phase before the
+// successors need it), tickets are taken in increasing order, and only look-back warps ever spin on other CTAs: the
+// smallest unfinished tile can always make progress, so the look-back cannot deadlock.  Every wait is bounded: a
+// protocol failure sets an error flag instead of hanging the device.
+// The first / last tile of a range (bytes outside [beg, end) must read as 0) is loaded by the consumers instead of TMA.
 #pragma once
 
 #include "f2q_dev.cuh"
 #include "generic.cuh"
 #include "resolve.cuh"
+
 
 namespace f2q {
 
@@ -34,7 +42,7 @@ enum { POLICY_GENERIC = 0, POLICY_FAST1 = 1 };
 struct TileParams {
     const uint8_t* buf;        // 128-byte aligned base of the chunk buffer
     DevState* S;
-    uint32_t* status;          // look-back status words, zeroed before the launch
+    uint8_t* status;           // look-back status bytes, zeroed before the launch
     uint32_t* ticket;          // tile ticket counter, zeroed before the launch
     int stitch;                // 1: parse [0, S->stitch_len) of the carry buffer; 0: parse [S->beg, S->end)
     QEntry* queue;             // grid segments of seg_cap entries each
@@ -43,19 +51,24 @@ struct TileParams {
     GEntry* gqueue;
     uint32_t hist_smem;        // 1: per-CTA shared-memory histogram of n_keys u32
     uint32_t halo_rows;        // H: read-ahead rows at the end of every tile (1 .. NT/2)
+    uint32_t debug;            // 1: count waits into DevState::dbg
+    unsigned long long* trace; // debug: 6 u64 per tile (ticket time, agg time, go time, lb done time, parse start, cta)
 };
 
-constexpr uint32_t LB_SPIN_LIMIT = 1u << 24;
+// status byte of the decoupled look-back: bits [1:0] newline count mod 4, bits [3:2] 0 not ready / 1 aggregate / 2 prefix
+constexpr uint32_t SB_AGG = 0x04u, SB_PREFIX = 0x08u;
+constexpr uint32_t WAIT_SPIN_LIMIT = 1u << 22;
 constexpr int TILE_STAGES = 3;
+constexpr int TILE_CTRL_THREADS = 64;                // loader warp + look-back warp
 
 template <int CH, int NT_>
 struct TileGeom {
     static constexpr int S = CH * 16;                                   // bytes per row
-    static constexpr int NT = NT_;                                      // rows per tile = threads per CTA
+    static constexpr int NT = NT_;                                      // rows per tile = consumer threads per CTA
     static constexpr int NS = TILE_STAGES;
     static constexpr int LOAD_BYTES = NT * S;
     static constexpr int STAGE_BYTES = ((LOAD_BYTES + 16 + 127) / 128) * 128;   // +16: word reads may run past the end
-    static constexpr int CAP = 8 * NT;                                  // newline positions kept per tile
+    static constexpr int CAP = 6 * NT;                                  // newline positions kept per tile
     static constexpr int NL_OFF = NS * STAGE_BYTES;                     // two u16[CAP + 8] position lists
     static constexpr int NL_STRIDE = (CAP + 8) * 2;
     static constexpr int EXCL_OFF = NL_OFF + 2 * NL_STRIDE;             // two u16[NT]: newlines of the tile before each row
@@ -76,16 +89,30 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug must not hang the GPU — after ~2^22 failed tries the kernel traps (the launch fails loudly)
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile uint32_t* abort, unsigned long long* dbg = nullptr) {
+    if (*abort) return false;
+    const long long t0 = dbg ? clock64() : 0;
+    for (uint32_t spins = 0; spins < WAIT_SPIN_LIMIT; spins++) {
+        if (mbar_try_wait(bar, parity)) { if (dbg && (threadIdx.x & 31) == 0) atomicAdd(dbg, (unsigned long long)(clock64() - t0)); return true; }
+        if ((spins & 1023u) == 1023u && *abort) return false;
+    }
+    *abort = 1u;
+    __trap();
+    return false;
 }
 // global -> shared bulk copy by the TMA unit; completion is signalled on the mbarrier (bytes % 16 == 0, 16-byte aligned)
 __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
@@ -93,77 +120,29 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+template <int THREADS>
+__device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
+
+__device__ __forceinline__ uint32_t ld_volatile_u8(const uint8_t* p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u8(uint8_t* p, uint32_t v) {
+    asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
 
 // a constant the compiler must keep in a register (so that LOP3 can combine it with two other register operands)
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ uint32_t reg_const(uint32_t v) {
     uint32_t r;
     asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
     return r;
 }
-
-// ---- byte access to the tile ---------------------------------------------------------------------------
-// @region WordReader
-struct WordReader {                 // 4 bytes at an arbitrary tile offset, little endian
-    const uint8_t* tile; uint32_t a, sh, prev;
-    __device__ __forceinline__ WordReader(const uint8_t* t, uint32_t o) : tile(t), a(o & ~3u), sh((o & 3u) * 8u) {
-        prev = *reinterpret_cast<const uint32_t*>(tile + a);
-    }
-    __device__ __forceinline__ uint32_t next() {
-        a += 4;
-        uint32_t nx = *reinterpret_cast<const uint32_t*>(tile + a);
-        uint32_t w = __funnelshift_r(prev, nx, sh);
-        prev = nx;
-        return w;
-    }
-};
-
-// @region qual_fails
-// any byte b of tile[o, o+n) with 33 <= b <= fmax ?   (fast2q.py:357 with the fail set of :1127)
-__device__ __forceinline__ bool qual_fails_tile(const uint8_t* tile, uint32_t o, int n, int fmax) {
-    if (fmax == 0 || n <= 0) return false;
-    const uint32_t add_ge = (0x80u - 33u) * 0x01010101u, add_gt = (0x80u - (uint32_t)(fmax + 1)) * 0x01010101u;
-    WordReader rd(tile, o);
-    uint32_t acc = 0;
-    auto test = [&](uint32_t w) {
-        const uint32_t lo7 = w & 0x7F7F7F7Fu;
-        const uint32_t ge33 = lo7 + add_ge;                            // bit 7: low 7 bits >= 33
-        const uint32_t gtmax = lo7 + add_gt;                           // bit 7: low 7 bits >  fmax
-        acc |= ge33 & ~gtmax & ~w;                                     // bytes >= 0x80 never fail
-    };
-    const int full = n >> 2;
-    for (int k = 0; k < full; k++) test(rd.next());
-    if (n & 3) test(rd.next() & ((1u << (8 * (n & 3))) - 1u));         // bytes past the slice become 0 (never fail)
-    return (acc & 0x80808080u) != 0;
-}
-
-// @region pack
-// 2-bit pack of tile[o, o+n), n <= 32.  bad = mask of symbols outside ACGT (after upper()); their key bits are 0
-__device__ __forceinline__ void pack_tile(const uint8_t* tile, uint32_t o, int n, uint64_t& key, uint32_t& bad) {
-    key = 0; bad = 0;
-    if (n <= 0) return;
-    WordReader rd(tile, o);
-    const int words = (n + 3) >> 2;
-    uint32_t klo = 0, khi = 0;
-    for (int kw = 0; kw < words; kw++) {
-        uint32_t w = rd.next();
-        if (kw == words - 1 && (n & 3)) { const uint32_t keep = (1u << (8 * (n & 3))) - 1u; w = (w & keep) | (0x41414141u & ~keep); }   // pad with 'A' (code 0)
-        uint32_t codes = (w >> 1) & 0x03030303u;
-        uint32_t t = (codes | (codes >> 4)) & 0x00330033u;
-        t = (t | (t >> 8)) & 0x3333u;                                  // nibble i = code of byte i
-        const uint32_t expect = __byte_perm(0x47544341u, 0u, t);        // code -> 'A','C','T','G'
-        const uint32_t diff = (w & 0xDFDFDFDFu) ^ expect;               // 0 where the upper-cased byte is that base
-        if (diff) {                                                     // some symbol is not A/C/G/T: flag it, zero its bits
-            const uint32_t nz = ((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff;     // bit 7 of every non-zero byte
-            const uint32_t nb = nz & 0x80808080u;
-            bad |= ((nb * 0x00204081u) >> 28) << (4 * kw);
-            codes &= ~((nb >> 7) * 3u);
-        }
-        const uint32_t p = (codes * 0x01041040u) >> 24;                 // 4 symbols -> 8 bits (one multiply, no carries)
-        if (kw < 4) klo |= p << (8 * kw); else khi |= p << (8 * (kw - 4));
-    }
-    key = ((uint64_t)khi << 32) | klo;
-}
-
 
 // @region window_words
 // W words starting at an arbitrary tile offset: W+1 aligned loads, W funnel shifts, everything unrolled so the
@@ -193,10 +172,18 @@ __device__ __forceinline__ bool qual_fails_w(const uint8_t* tile, uint32_t o, in
     return (acc & 0x80808080u) != 0;
 }
 
-// 2-bit pack of a window of W words; returns non-zero when some symbol is not A/C/G/T (the caller then takes pack_tile)
+// spread the low 16 bits to the even bit positions of a 32-bit word
+__device__ __forceinline__ uint32_t spread16(uint32_t x) {
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    return (x | (x << 1)) & 0x55555555u;
+}
+
+// 2-bit pack of a window of W words (n symbols).  bad = mask of symbols outside ACGT after upper(); their key bits are 0
 template <int W>
-__device__ __forceinline__ uint32_t pack_w(const uint8_t* tile, uint32_t o, int n, uint32_t& klo, uint32_t& khi) {
-    uint32_t w[W];
+__device__ __forceinline__ void pack_w(const uint8_t* tile, uint32_t o, int n, uint32_t& klo, uint32_t& khi, uint32_t& bad) {
+    uint32_t w[W], d[W];
     load_words<W>(tile, o, w);
     if (n & 3) { const uint32_t keep = (1u << (8 * (n & 3))) - 1u; w[W - 1] = (w[W - 1] & keep) | (0x41414141u & ~keep); }   // pad with 'A'
     uint32_t lo = 0, hi = 0, any = 0;
@@ -205,12 +192,22 @@ __device__ __forceinline__ uint32_t pack_w(const uint8_t* tile, uint32_t o, int 
         const uint32_t codes = (w[i] >> 1) & 0x03030303u;
         uint32_t t = (codes | (codes >> 4)) & 0x00330033u;
         t = (t | (t >> 8)) & 0x3333u;                                  // nibble k = code of byte k
-        any |= (w[i] & 0xDFDFDFDFu) ^ __byte_perm(0x47544341u, 0u, t);  // upper-cased byte vs the base its code stands for
+        d[i] = (w[i] & 0xDFDFDFDFu) ^ __byte_perm(0x47544341u, 0u, t);  // upper-cased byte vs the base its code stands for
+        any |= d[i];
         const uint32_t p = (codes * 0x01041040u) >> 24;                 // 4 symbols -> 8 bits (one multiply, no carries)
         if (i < 4) lo |= p << (8 * (i & 3)); else hi |= p << (8 * (i & 3));
     }
+    bad = 0;
+    if (any) {                                                         // rare per read but common per warp: kept short
+        #pragma unroll
+        for (int i = 0; i < W; i++) {
+            const uint32_t nz = (((d[i] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d[i]) & 0x80808080u;     // bit 7 of every non-zero byte
+            bad |= ((nz * 0x00204081u) >> 28) << (4 * i);
+        }
+        lo &= ~(spread16(bad & 0xFFFFu) * 3u);
+        hi &= ~(spread16(bad >> 16) * 3u);
+    }
     klo = lo; khi = hi;
-    return any;
 }
 
 #define F2Q_WORDS_SWITCH(words, CALL)                                                                   \
@@ -253,19 +250,98 @@ __device__ __noinline__ void slow_record(const uint8_t* buf, uint64_t hdr_end, u
     g_process_read(G, T, E, O, Rp, g_rstrip(Rp, (int)(pos[1] - pos[0] - 1)), Qp, g_rstrip(Qp, (int)(pos[3] - pos[2] - 1)), gst);
 }
 
+// @region lookback
+__device__ __forceinline__ uint4 ld_volatile_v4(const void* p) {
+    uint4 r;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+
+// control warp: newlines (mod 4) of the range before tile `rel`, by decoupled look-back over the status bytes.
+// Each lane inspects 16 tiles (one 16-byte load), the warp 512 tiles per step, nearest first; the walk stops at the nearest
+// tile that already published an inclusive prefix and needs every tile between to have published its aggregate.
+__device__ __noinline__ uint32_t tile_lookback(const uint8_t* status, uint64_t rel, uint32_t lane, volatile uint32_t* abort, unsigned long long* dbg) {
+    uint32_t p0 = 0;
+    int64_t hi = (int64_t)rel;                                          // tiles [hi, rel) are accounted for
+    if (rel > 0) {
+        // first wait for the tile right before this one, with ONE lane polling ONE byte: tickets are taken in time order, so
+        // when it has published, (nearly) everything before it has too.  Polling the wide window from the start would have
+        // every look-back warp of the grid hammer the same few L2 lines, which delays the very stores they wait for.
+        uint32_t b = 0, spins = 0;
+        for (;;) {
+            if (lane == 0) b = ld_volatile_u8(status + rel - 1);
+            b = __shfl_sync(0xffffffffu, b, 0);
+            if (b & 0x0Cu) break;
+            if (++spins > WAIT_SPIN_LIMIT || *abort) { *abort = 1u; __trap(); return 0; }
+            __nanosleep(200);
+        }
+        if (b & SB_PREFIX) return b & 3u;
+    }
+    while (hi > 0) {
+        const int64_t q = ((hi - 1) >> 4) - (int64_t)lane;             // this lane's group: tiles 16q .. 16q+15
+        uint32_t sum = 0, spins = 0;
+        bool found = false, ok = false;
+        for (;;) {
+            if (!ok) {                                                  // (a group that was complete stays complete: only late lanes poll)
+                uint4 v = make_uint4(0x08080808u, 0x08080808u, 0x08080808u, 0x08080808u);      // before the range: prefix 0
+                if (q >= 0) v = ld_volatile_v4(status + 16 * q);
+                uint32_t w[4] = {v.w, v.z, v.y, v.x};                   // nearest word first
+                if (lane == 0 && (hi & 15)) {                           // tiles >= hi are not part of this step: neutral (aggregate 0)
+                    const int valid = (int)(hi & 15);
+                    #pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int nb = min(max(valid - 4 * (3 - j), 0), 4);     // valid bytes of word j (word 3-j in memory order)
+                        const uint32_t keep = nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
+                        w[j] = (w[j] & keep) | (0x04040404u & ~keep);
+                    }
+                }
+                found = false; ok = true; sum = 0;
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (found) continue;
+                    const uint32_t pre = (w[j] >> 3) & 0x01010101u, rdy = ((w[j] >> 2) | (w[j] >> 3)) & 0x01010101u;
+                    uint32_t vals = w[j] & 0x03030303u;
+                    if (pre) {
+                        const uint32_t pi = (31u - (uint32_t)__clz((int)pre)) >> 3;          // nearest prefix byte of this word
+                        const uint32_t need = pi >= 3 ? 0u : (0x01010101u << (8 * (pi + 1)));
+                        ok = ok && ((rdy & need) == need);
+                        vals &= 0xFFFFFFFFu << (8 * pi);
+                        found = true;
+                    } else ok = ok && (rdy == 0x01010101u);
+                    sum += (vals * 0x01010101u) >> 24;
+                }
+            }
+            const uint32_t has = __ballot_sync(0xffffffffu, found);
+            const uint32_t first = has ? (uint32_t)__ffs((int)has) - 1u : 32u;
+            const bool wait = !ok && lane <= first;
+            if (!__any_sync(0xffffffffu, wait)) {
+                p0 += __reduce_add_sync(0xffffffffu, lane <= first ? sum : 0u);
+                if (has) return p0 & 3u;
+                break;
+            }
+            if (lane > first) ok = true;                                // beyond the nearest prefix: never needed again in this step
+            if (dbg && lane == 0) atomicAdd(dbg + 5, 1ull);
+            if (++spins > WAIT_SPIN_LIMIT || *abort) { *abort = 1u; __trap(); return 0; }
+            __nanosleep(400);                                           // (a tile that published out of order: rare)
+        }
+        hi = (((hi - 1) >> 4) - 31) << 4;                               // everything from this lane-31 group upwards is summed
+    }
+    return p0 & 3u;
+}
+
 // @region kernel_prologue
 template <int POLICY, int CH, int NT>
-__global__ void __launch_bounds__(NT, POLICY == POLICY_FAST1 ? (512 / NT) : (256 / NT))
+__global__ void __launch_bounds__(NT + TILE_CTRL_THREADS, POLICY == POLICY_FAST1 ? (512 / NT) : (256 / NT))
 k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, Outputs O) {
     using G_ = TileGeom<CH, NT>;
     constexpr int S = G_::S, NS = G_::NS, CAP = G_::CAP;
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem + G_::HIST_OFF);
-    __shared__ uint32_t s_wsum[NT / 32];
-    __shared__ uint32_t s_ticket[NS], s_mode[NS];                      // per stage: tile ticket, 0 none / 1 TMA / 2 loaded by threads
-    __shared__ uint32_t s_total_own[2], s_total_all[2];
-    __shared__ uint32_t s_p0, s_qn;
-    __shared__ __align__(8) uint64_t s_bar[NS];
+    __shared__ uint32_t s_wsum[2][NT / 32];
+    __shared__ uint32_t s_ticket[NS], s_mode[NS];                      // per stage: tile ticket, 0 none / 1 TMA / 2 loaded by the consumers
+    __shared__ uint32_t s_total_own[NS], s_total_all[NS], s_p0[NS];
+    __shared__ uint32_t s_qn, s_abort;
+    __shared__ __align__(8) uint64_t bar_full[NS], bar_empty[NS], bar_agg[NS], bar_p0[NS], bar_go[NS];
     __shared__ GenericCfg s_G;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -276,27 +352,96 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     if (end <= beg) { if (tid == 0 && P.seg_cap) P.seg_count[blockIdx.x] = 0; return; }
 
     if (POLICY == POLICY_GENERIC)                                      // the packed policy keeps its few scalars in registers
-        for (uint32_t i = tid; i < sizeof(GenericCfg) / 4; i += NT)
+        for (uint32_t i = tid; i < sizeof(GenericCfg) / 4; i += blockDim.x)
             reinterpret_cast<uint32_t*>(&s_G)[i] = reinterpret_cast<const uint32_t*>(Gp)[i];
-    if (P.hist_smem) for (uint32_t i = tid; i < T.n_keys; i += NT) hist[i] = 0;
+    if (P.hist_smem) for (uint32_t i = tid; i < T.n_keys; i += blockDim.x) hist[i] = 0;
     if (tid == 0) {
-        for (int s = 0; s < NS; s++) { mbar_init(&s_bar[s], 1); s_mode[s] = 0; }
+        for (int s = 0; s < NS; s++) {
+            mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], NT / 32); mbar_init(&bar_agg[s], 1); mbar_init(&bar_p0[s], 1); mbar_init(&bar_go[s], 1);
+            s_mode[s] = 0;
+        }
         mbar_fence_init();
-        s_qn = 0;
+        s_qn = 0; s_abort = 0;
     }
-    const GenericCfg& G = (POLICY == POLICY_GENERIC) ? s_G : *Gp;
-    const int c_start = Gp->c.starts[0], c_length = Gp->c.length, c_fmax = Gp->c.fmax_ph, c_miss = Gp->c.miss;
+    __syncthreads();
+    volatile uint32_t* abort = &s_abort;
+    unsigned long long* dbg = P.debug ? St->dbg : nullptr;
 
     const uint32_t own_rows = NT - P.halo_rows;
     const uint32_t own_bytes = own_rows * S;
     const uint64_t first_tile = beg / own_bytes;
     const uint64_t n_tiles = (end - 1) / own_bytes + 1;
     const uint8_t* __restrict__ buf = P.buf;
+
+    // =====================================================================================================
+    // @region control_warps
+    if (warp == NT / 32) {
+        // ---- loader warp: stage free -> ticket -> bulk copy.  It never waits for anything but the consumers, so a tile's
+        // bytes (and with them its aggregate) never depend on a look-back.  A CTA must not own CONSECUTIVE tiles: its
+        // second would be scanned only after its first is parsed, and the CTA owning the tile behind would queue up
+        // behind that — a convoy through all CTAs.  So the tickets of the first tiles are spaced by a load latency
+        // (by then every other CTA has taken its own), and later ones are taken only when a stage is free.
+        for (uint32_t i = 0;; i++) {
+            const uint32_t s = i % NS;
+            if (i >= (uint32_t)NS) { if (!mbar_wait(&bar_empty[s], ((i / NS) - 1u) & 1u, abort, dbg ? dbg + 0 : nullptr)) break; }   // tile i-NS is parsed
+            else if (i >= 1) { if (!mbar_wait(&bar_full[i - 1], 0u, abort)) break; }
+            uint32_t tk = 0;
+            if (lane == 0) tk = atomicAdd(P.ticket, 1u);
+            tk = __shfl_sync(0xffffffffu, tk, 0);
+            const uint64_t t = first_tile + tk;
+            uint32_t mode = 0;
+            if (t < n_tiles) {
+                const uint64_t b0 = t * own_bytes;
+                mode = (b0 >= beg && b0 + G_::LOAD_BYTES <= end) ? 1u : 2u;
+            }
+            if (lane == 0) {
+                if (P.trace && mode) { P.trace[6 * (uint64_t)tk + 0] = gtime(); P.trace[6 * (uint64_t)tk + 5] = blockIdx.x; }
+                s_ticket[s] = tk; s_mode[s] = mode;
+                if (mode == 1) {                                        // interior tile: one TMA bulk copy
+                    mbar_expect_tx(&bar_full[s], G_::LOAD_BYTES);
+                    tma_load_1d(smem + s * G_::STAGE_BYTES, buf + t * own_bytes, G_::LOAD_BYTES, &bar_full[s]);
+                } else mbar_arrive(&bar_full[s]);                       // the consumers load it themselves / nothing left
+            }
+            if (mode == 0) break;
+        }
+        return;
+    }
+    if (warp == NT / 32 + 1) {
+        // ---- look-back warp: tile j's newline count (from the consumers' scan) -> walk the status bytes of the tiles
+        // before it -> publish the inclusive prefix -> hand the line phase to the consumers.  The only code that ever
+        // spins on other CTAs.
+        for (uint32_t j = 0;; j++) {
+            const uint32_t s = j % NS, par = (j / NS) & 1u;
+            if (!mbar_wait(&bar_full[s], par, abort, dbg ? dbg + 7 : nullptr)) break;            // (only to learn whether tile j exists)
+            if (s_mode[s] == 0) break;
+            if (!mbar_wait(&bar_agg[s], par, abort, dbg ? dbg + 1 : nullptr)) break;
+            // start the walk when the consumers begin to parse tile j-1: a whole parse phase before p0 is needed, and late
+            // enough that the tiles before this one have (nearly always) published — polling early slows everything down
+            if (!mbar_wait(&bar_go[s], par, abort)) break;
+            const uint32_t A = s_total_own[s], tk = s_ticket[s];
+            if (P.trace && lane == 0) P.trace[6 * (uint64_t)tk + 2] = gtime();
+            const long long tl0 = dbg ? clock64() : 0;
+            const uint32_t p0 = P.debug == 2 ? 0u : tile_lookback(P.status, tk, lane, abort, dbg);
+            if (dbg && lane == 0) atomicAdd(dbg + 4, (unsigned long long)(clock64() - tl0));
+            if (lane == 0) {
+                st_volatile_u8(P.status + tk, SB_PREFIX | ((p0 + A) & 3u));
+                if (first_tile + tk == n_tiles - 1 && !P.stitch) St->nl_total = (p0 + A) & 3u;
+                s_p0[s] = p0;
+                if (P.trace) P.trace[6 * (uint64_t)tk + 3] = gtime();
+                mbar_arrive(&bar_p0[s]);
+            }
+        }
+        return;
+    }
+
+    // =====================================================================================================
+    // consumers
+    const GenericCfg& G = (POLICY == POLICY_GENERIC) ? s_G : *Gp;
+    const int c_start = Gp->c.starts[0], c_length = Gp->c.length, c_fmax = Gp->c.fmax_ph, c_miss = Gp->c.miss;
     QEntry* const myq = P.queue + (size_t)blockIdx.x * P.seg_cap;
     Acc acc{0, 0, 0, 0, 0, 0};
     unsigned long long gst[F2Q_N_STATS] = {0, 0, 0, 0, 0};            // stats of reads handled by the generic code
-    uint32_t bar_phase = 0;                                            // bit s: parity the next wait on stage s uses
-    uint32_t reads = 0, perfect = 0, nonal = 0, qfail = 0;            // per-thread counts of this launch (a chunk is < 2^32 bytes per thread)
+    uint32_t reads = 0, perfect = 0, imperfect = 0, nonal = 0, qfail = 0;   // per-thread counts of this launch
     const int c_end = c_start + c_length;
     const bool simple_slice = c_start >= 0 && c_length >= 0;
     const uint32_t add_ge = (0x80u - 33u) * 0x01010101u, add_gt = (0x80u - (uint32_t)(c_fmax + 1)) * 0x01010101u;
@@ -314,36 +459,15 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         return (lo >> 7) | (hi << 1);
     };
 
-    // @region issue
-    // thread 0: take the ticket of local iteration i and start its load into stage i % NS
-    auto issue = [&](uint32_t i) {
-        const uint32_t s = i % NS;
-        const uint32_t tk = atomicAdd(P.ticket, 1u);
-        s_ticket[s] = tk;
-        const uint64_t t = first_tile + tk;
-        uint32_t mode = 0;
-        if (t < n_tiles) {
-            const uint64_t b0 = t * own_bytes;
-            if (b0 >= beg && b0 + G_::LOAD_BYTES <= end) {               // interior tile: one TMA bulk copy
-                mode = 1;
-                mbar_expect_tx(&s_bar[s], G_::LOAD_BYTES);
-                tma_load_1d(smem + s * G_::STAGE_BYTES, buf + b0, G_::LOAD_BYTES, &s_bar[s]);
-            } else mode = 2;
-        }
-        s_mode[s] = mode;
-    };
-
     // @region scan_wait_load
-    // all threads: newline masks, counts and position list of local iteration i (its stage is loaded or gets loaded here)
+    // all consumers: newline masks, counts and position list of local tile i (its bytes are in stage i % NS or get
+    // loaded here); ONE consumer barrier inside
     auto scan = [&](uint32_t i) {
         const uint32_t s = i % NS, par = i & 1u;
         uint8_t* tile = smem + s * G_::STAGE_BYTES;
         const uint64_t t = first_tile + s_ticket[s];
         const uint64_t base = t * own_bytes;
-        if (s_mode[s] == 1) {
-            mbar_wait(&s_bar[s], (bar_phase >> s) & 1u);
-            bar_phase ^= 1u << s;
-        } else {
+        if (s_mode[s] == 2) {
             // first / last tile of the range: loaded by the threads, bytes outside [beg, end) become 0
             for (uint32_t c = tid; c < G_::LOAD_BYTES / 16; c += NT) {
                 const uint64_t g = base + (uint64_t)c * 16;
@@ -362,7 +486,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 }
                 *reinterpret_cast<uint4*>(tile + c * 16) = v;
             }
-            __syncthreads();
+            consumer_barrier<NT>();
         }
         // @region scan_masks_blockscan
         uint32_t m16[8];
@@ -375,20 +499,22 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         uint32_t incl = cnt;
         #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
-        if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
-        uint32_t wv = lane < NT / 32 ? s_wsum[lane] : 0u, wi = wv;        // warp totals, scanned again inside every warp
+        if (lane == 31) s_wsum[par][warp] = incl;
+        consumer_barrier<NT>();                                        // (also: every consumer is done parsing tile i-2)
+        uint32_t wv = lane < NT / 32 ? s_wsum[par][lane] : 0u, wi = wv;  // warp totals, scanned again inside every warp
         #pragma unroll
         for (int d = 1; d < NT / 32; d <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += y; }
         const uint32_t wbase = __shfl_sync(0xffffffffu, wi - wv, warp);
         const uint32_t excl = wbase + incl - cnt;                      // newlines of the tile before this row
         reinterpret_cast<uint16_t*>(smem + G_::EXCL_OFF)[par * NT + tid] = (uint16_t)min(excl, 0xFFFFu);
         if (tid == own_rows) {                                         // excl of the first read-ahead row = newlines of the owned rows
-            s_total_own[par] = excl;
+            s_total_own[s] = excl;
             const uint64_t rel = t - first_tile;
-            if (rel != 0) st_volatile_u32(P.status + rel, LB_FLAG_AGG | (excl & LB_VALUE_MASK));
+            if (rel != 0) st_volatile_u8(P.status + rel, SB_AGG | (excl & 3u));
+            if (P.trace) P.trace[6 * rel + 1] = gtime();
+            mbar_arrive(&bar_agg[s]);
         }
-        if (tid == NT - 1) s_total_all[par] = excl + cnt;
+        if (tid == NT - 1) s_total_all[s] = excl + cnt;
         // @region scan_nlpos
         uint16_t* nl = reinterpret_cast<uint16_t*>(smem + G_::NL_OFF + par * G_::NL_STRIDE);
         uint32_t o = excl;
@@ -414,91 +540,42 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     };
 
     // @region loop_top
-    // ---- prologue: tickets + loads of the first NS-1 local iterations, scan of the first ----
-    __syncthreads();
-    if (tid == 0) for (uint32_t i = 0; i + 1 < (uint32_t)NS; i++) issue(i);
-    __syncthreads();
-    if (s_mode[0] != 0) scan(0);
-
-    for (uint32_t k = 0;; k++) {
-        __syncthreads();                                               // tile k-1 is parsed: its stage and lists are free
-        const uint32_t s = k % NS, par = k & 1u;
-        if (s_mode[s] == 0) break;                                     // tickets are monotone: nothing further for this CTA
-        const uint64_t t = first_tile + s_ticket[s];
-        const uint64_t rel = t - first_tile;
-        if (tid == 0) issue(k + NS - 1);
-        // ---- look-back, part 1 (warp 0): request the status of the 128 tiles before this one ----
-        uint32_t lbw[4] = {0, 0, 0, 0};
-        if (warp == 0 && rel != 0) {
-            #pragma unroll
-            for (int g = 0; g < 4; g++) {
-                const int64_t idx = (int64_t)rel - 1 - lane - 32 * g;
-                lbw[g] = idx >= 0 ? ld_volatile_u32(P.status + idx) : LB_FLAG_PREFIX;
-            }
-        }
-        if (s_mode[(k + 1) % NS] != 0) scan(k + 1);                    // (its ticket was taken one iteration ago)
-        // @region lookback2
-        // ---- look-back, part 2 (warp 0): line phase of tile k ----
-        if (warp == 0) {
-            const uint32_t A = s_total_own[par];
-            uint32_t p0 = 0;
-            if (rel != 0) {
-                int64_t look = (int64_t)rel - 1;
-                for (int g = 0;; g++) {
-                    const int64_t idx = look - lane;
-                    uint32_t sw = lbw[0];                               // groups 0..3 were requested before the scan
-                    lbw[0] = lbw[1]; lbw[1] = lbw[2]; lbw[2] = lbw[3];
-                    if (g >= 4) sw = idx >= 0 ? ld_volatile_u32(P.status + idx) : LB_FLAG_PREFIX;
-                    uint32_t is_prefix, spins = 0;
-                    for (;;) {
-                        is_prefix = __ballot_sync(0xffffffffu, (sw >> 30) == 2);
-                        const uint32_t first = is_prefix ? (uint32_t)__ffs((int)is_prefix) - 1u : 32u;
-                        const bool wait = (sw >> 30) == 0 && lane <= first;
-                        if (!__any_sync(0xffffffffu, wait)) break;
-                        if (wait) sw = ld_volatile_u32(P.status + idx);     // idx >= 0 here: negative indices read as PREFIX
-                        if (++spins > LB_SPIN_LIMIT) { if (lane == 0) atomicOr(O.error, ERR_LOOKBACK_TIMEOUT); if ((sw >> 30) == 0) sw = LB_FLAG_PREFIX; }
-                    }
-                    const uint32_t first = is_prefix ? (uint32_t)__ffs((int)is_prefix) - 1u : 32u;
-                    const uint32_t contrib = (lane <= first) ? (sw & LB_VALUE_MASK) : 0u;
-                    p0 += __reduce_add_sync(0xffffffffu, contrib);
-                    if (is_prefix) break;
-                    look -= 32;
-                }
-            }
-            if (lane == 0) {
-                st_volatile_u32(P.status + rel, LB_FLAG_PREFIX | ((p0 + A) & LB_VALUE_MASK));
-                s_p0 = p0;
-                if (t == n_tiles - 1 && !P.stitch) St->nl_total = (p0 + A) & LB_VALUE_MASK;
-            }
-        }
-        __syncthreads();
+    const long long t_begin = dbg ? clock64() : 0;
+    bool live = mbar_wait(&bar_full[0], 0u, abort) && s_mode[0] != 0;
+    if (live) { if (tid == 0) mbar_arrive(&bar_go[0]); scan(0); }
+    for (uint32_t k = 0; live; k++) {
+        const uint32_t s = k % NS, par = k & 1u, s1 = (k + 1) % NS;
+        // ---- next tile first: its aggregate is public one parse phase before the successors need it ----
+        if (!mbar_wait(&bar_full[s1], ((k + 1) / NS) & 1u, abort, dbg ? dbg + 2 : nullptr)) break;
+        const bool more = s_mode[s1] != 0;
+        if (more) scan(k + 1);
+        else consumer_barrier<NT>();                                   // (the last scan's lists are visible to everyone)
+        if (!mbar_wait(&bar_p0[s], (k / NS) & 1u, abort, dbg ? dbg + 3 : nullptr)) break;
+        const uint32_t p0 = s_p0[s];
+        if (tid == 0 && more) mbar_arrive(&bar_go[s1]);                // the look-back of tile k+1 may start now
+        if (P.trace && tid == 0) P.trace[6 * (uint64_t)s_ticket[s] + 4] = gtime();
 
         // @region parse_setup
         // ---- reads of tile k: thread q takes the q-th read whose header line ends in the owned rows ----
         const uint8_t* tile = smem + s * G_::STAGE_BYTES;
         const uint16_t* nl = reinterpret_cast<const uint16_t*>(smem + G_::NL_OFF + par * G_::NL_STRIDE);
+        const uint64_t t = first_tile + s_ticket[s];
         const uint64_t base = t * own_bytes;
-        const uint32_t p0 = s_p0;
-        const uint32_t total_own = s_total_own[par], total_all = s_total_all[par];
-        const uint32_t region_end = (uint32_t)min((uint64_t)G_::LOAD_BYTES, end - base);   // valid bytes of the loaded region
-        const bool region_has_eof = (base + G_::LOAD_BYTES >= end);
+        const uint32_t total_own = s_total_own[s], total_all = s_total_all[s];
         const uint32_t jf = (4u - (p0 & 3u)) & 3u;                     // first newline of the tile that ends a header line
 
         if (total_all > (uint32_t)CAP) {
             // more newlines than the position list holds (a tile of very short lines): every owned row walks its own
             // header ends and finishes each read in global memory
             if (tid < own_rows) {
-                const uint32_t excl = reinterpret_cast<const uint16_t*>(smem + G_::EXCL_OFF)[par * NT + tid];
-                uint32_t idx = excl;                                   // (excl is exact: total_all <= NT*S < 65536)
+                uint32_t idx = reinterpret_cast<const uint16_t*>(smem + G_::EXCL_OFF)[par * NT + tid];   // exact: total_all <= NT*S < 65536
                 for (uint32_t b = 0; b < (uint32_t)S; b++) {
                     if (tile[tid * S + b] != '\n') continue;
                     if (((p0 + idx) & 3u) == 0) slow_record(buf, base + tid * S + b, end, eof, G, T, E, O, acc, gst);
                     idx++;
                 }
             }
-            continue;
-        }
-
+        } else
         for (uint32_t j = jf + 4u * tid; j < total_own; j += 4u * NT) {
             const uint32_t h0 = nl[j];
             if (j + 3 >= total_all) {
@@ -541,50 +618,60 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             // @region parse_k4
             // ---- K4: pack, exact lookup, count ----
             const uint32_t klen = (uint32_t)(hi - lo);
-            uint32_t klo = 0, khi = 0, bad = 0, any = 0;
+            uint32_t klo = 0, khi = 0, bad = 0;
             if (klen) {
-                #define F2Q_PCALL(W) any = pack_w<W>(tile, s0 + lo, (int)klen, klo, khi)
+                #define F2Q_PCALL(W) pack_w<W>(tile, s0 + lo, (int)klen, klo, khi, bad)
                 F2Q_WORDS_SWITCH((klen + 3) >> 2, F2Q_PCALL)
                 #undef F2Q_PCALL
             }
-            uint64_t key = ((uint64_t)khi << 32) | klo;
-            if (any) pack_tile(tile, s0 + lo, (int)klen, key, bad);     // a symbol outside ACGT: the exact (slower) packer flags it
             const bool generic_len = (T.generic_len_mask >> min(klen, 63u)) & 1ull;
             uint32_t idx = SLOT_EMPTY;
             if (!generic_len && bad == 0) {
                 if (T.cslots) { if (klen == T.c_len) idx = compact_lookup(T, klo, khi); }
-                else idx = fast_lookup(T, key, klen);
+                else idx = fast_lookup(T, ((uint64_t)khi << 32) | klo, klen);
             }
             if (idx != SLOT_EMPTY) {
                 perfect++;
                 if (P.hist_smem) atomicAdd(hist + idx, 1u);
                 else atomicAdd(O.counts + idx, 1ull);
-            } else if (generic_len) {
+                continue;
+            }
+            if (generic_len) {
                 // library keys of this length exist that the packed tables cannot hold
                 GEntry ge; ge.seq_addr = (uint64_t)(buf + base + s0); ge.seq_len = e0 - s0;
                 ge.qual_addr = (uint64_t)(buf + base + s3); ge.qual_len = e3 - s3;
                 const uint32_t slot = atomicAdd(&St->g_count, 1u);
                 if (slot < St->g_cap) P.gqueue[slot] = ge;
                 else g_process_read(G, T, E, O, (const uint8_t*)ge.seq_addr, (int)ge.seq_len, (const uint8_t*)ge.qual_addr, (int)ge.qual_len, gst);
-            } else if (c_miss <= 0) nonal++;
-            else {
-                const uint32_t sl = atomicAdd(&s_qn, 1u);              // this CTA's private queue segment
-                if (sl < P.seg_cap) { QEntry e; e.key = key; e.bad = bad; e.len = klen; myq[sl] = e; }
-                else {                                                 // segment full: resolve right here
-                    const uint32_t r = resolve_seed_thread(T, c_miss, key, bad, klen);
-                    if (r != RES_NONE) { atomicAdd(O.counts + r, 1ull); acc.imperfect++; } else nonal++;
-                }
+                continue;
+            }
+            if (c_miss <= 0) { nonal++; continue; }
+            // non-exact key: one slot of this CTA's private queue segment, reserved once per warp
+            const uint64_t key = ((uint64_t)khi << 32) | klo;
+            const uint32_t peers = __activemask();
+            const uint32_t leader = (uint32_t)__ffs((int)peers) - 1u;
+            uint32_t sl = 0;
+            if (lane == leader) sl = atomicAdd(&s_qn, (uint32_t)__popc(peers));
+            sl = __shfl_sync(peers, sl, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+            if (sl < P.seg_cap) { QEntry e; e.key = key; e.bad = bad; e.len = klen; myq[sl] = e; }
+            else {                                                     // segment full: resolve right here
+                const uint32_t r = resolve_seed_thread(T, c_miss, key, bad, klen);
+                if (r != RES_NONE) { atomicAdd(O.counts + r, 1ull); imperfect++; } else nonal++;
             }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bar_empty[s]);                     // this warp is done with stage s
+        live = more;
     }
 
+    if (dbg && lane == 0) atomicAdd(dbg + 6, (unsigned long long)(clock64() - t_begin));
     // @region epilogue
-    // ---- CTA epilogue: queue segment length, histogram, statistics ----
-    __syncthreads();
+    // ---- CTA epilogue (consumers): queue segment length, histogram, statistics ----
+    consumer_barrier<NT>();
     if (tid == 0 && P.seg_cap) P.seg_count[blockIdx.x] = min(s_qn, P.seg_cap);
     if (P.hist_smem)
         for (uint32_t i = tid; i < T.n_keys; i += NT) { uint32_t v = hist[i]; if (v) atomicAdd(O.counts + i, (unsigned long long)v); }
-    acc.reads += reads; acc.perfect += perfect; acc.nonal += nonal; acc.qfail += qfail;
+    acc.reads += reads; acc.perfect += perfect; acc.imperfect += imperfect; acc.nonal += nonal; acc.qfail += qfail;
     acc.perfect += gst[F2Q_STAT_PERFECT]; acc.imperfect += gst[F2Q_STAT_IMPERFECT];
     acc.nonal += gst[F2Q_STAT_NON_ALIGNED]; acc.qfail += gst[F2Q_STAT_QUALITY_FAILED];
     unsigned long long v[5] = {acc.reads, acc.perfect, acc.imperfect, acc.nonal, acc.qfail};
