@@ -80,6 +80,7 @@ SYMBOLS = {
     "f2q_memcpy_h2d": (C.c_int, [_VP, _VP, _VP, C.c_uint64]),
     "f2q_launch_count": (C.c_uint64, [_VP]),
     "f2q_kernel_times": (C.c_int, [_VP, C.POINTER(C.c_double), _U64P]),
+    "f2q_spec_counts": (C.c_int, [_VP, _U64P, _U64P]),
 }
 
 _lib = None
@@ -317,11 +318,17 @@ class Engine:
     def launches(self) -> int:
         return int(self.L.f2q_launch_count(self.h))
 
+    def spec_counts(self):
+        """(chunks committed by the speculative kernel, chunks parsed by the exact kernel) of the last finished sample"""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.f2q_spec_counts(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def kernel_times(self):
-        """{'tile': (ms, launches), 'resolve': ..., 'generic': ...} of the last finished sample (option time_kernels)"""
-        ms, n = (C.c_double * 3)(), (C.c_uint64 * 3)()
+        """{'tile': (ms, launches), 'resolve': ..., 'generic': ..., 'aux': ...} of the last finished sample (option time_kernels)"""
+        ms, n = (C.c_double * 4)(), (C.c_uint64 * 4)()
         self._ck(self.L.f2q_kernel_times(self.h, ms, n))
-        return {k: (ms[i], int(n[i])) for i, k in enumerate(("tile", "resolve", "generic"))}
+        return {k: (ms[i], int(n[i])) for i, k in enumerate(("tile", "resolve", "generic", "aux"))}
 
 
 def border_finder_device(seq: bytes, read: bytes, mismatch: int, start_place: int = 0, device: int = 0):

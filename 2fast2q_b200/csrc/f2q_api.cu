@@ -17,6 +17,7 @@
 #include "resolve.cuh"
 #include "stream.cuh"
 #include "tile.cuh"
+#include "spec.cuh"
 
 using namespace f2q;
 
@@ -81,14 +82,21 @@ struct f2q_ctx {
     std::string err;
     uint64_t launches = 0;
     int tile_blocks[2][8][2] = {{{0}}};
+    // speculative streaming kernel (spec.cuh)
+    int spec = 1;                      // 0: always the exact look-back kernel
+    int spec_warps = 16;               // warps per CTA (one CTA per SM): 12 or 16
+    int spec_range_tiles = 0;          // 0 auto | tiles per range
+    int spec_ready[2][8][2] = {{{0}}}; // function attributes set for (policy, ch, warps == 16)
+    DevBuf spec_rec, spec_scratch;
+    uint64_t spec_counts[2] = {0, 0};  // last finished sample: chunks committed by the speculation / parsed by the exact kernel
     int nt = 128;                      // threads (= owned rows) per tile-kernel CTA: 128 or 256
     // optional per-kernel timing (option "time_kernels"): event pairs around the tile / resolver / generic launches
     bool time_kernels = false;
     struct Timed { cudaEvent_t a, b; int kind; };
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> event_pool;
-    double kernel_ms[3] = {0, 0, 0};
-    uint64_t kernel_launches[3] = {0, 0, 0};
+    double kernel_ms[4] = {0, 0, 0, 0};
+    uint64_t kernel_launches[4] = {0, 0, 0, 0};
 };
 
 namespace {
@@ -237,6 +245,49 @@ int launch_tile(f2q_ctx* c, const TileParams& P, Outputs O, uint64_t n_tiles_upp
 int tile_grid_dyn(f2q_ctx* c, unsigned* grid) { F2Q_DISPATCH(tile_grid, c, grid); }
 int launch_tile_dyn(f2q_ctx* c, const TileParams& P, Outputs O, uint64_t n_tiles_upper) { F2Q_DISPATCH(launch_tile, c, P, O, n_tiles_upper); }
 
+// ---- speculative streaming kernel: one CTA of W warps per SM ----
+constexpr size_t SM_SMEM_BYTES = 233472, SPEC_SMEM_MARGIN = 4096;     // 228 KB per SM; static shared + the per-CTA reservation
+
+template <int POLICY, int CH, int W>
+int launch_spec(f2q_ctx* c, const SpecParams& P, Outputs O) {
+    SpecParams p = P;
+    const uint32_t H = p.halo_rows;
+    const size_t base_smem = spec_smem_bytes<CH, W>(H, 0);
+    const bool hist = (POLICY == POLICY_FAST1) && c->n_keys > 0 && base_smem + (size_t)c->n_keys * 4 + sizeof(GenericCfg) + SPEC_SMEM_MARGIN <= SM_SMEM_BYTES;
+    p.hist_smem = hist;
+    const size_t smem = spec_smem_bytes<CH, W>(H, hist ? c->n_keys : 0);
+    if (smem + sizeof(GenericCfg) + SPEC_SMEM_MARGIN > SM_SMEM_BYTES) return 1;        // does not fit with W warps: the caller retries with fewer
+    int& ready = c->spec_ready[POLICY][CH][W == 16];
+    if (!ready) {
+        CU(c, cudaFuncSetAttribute(k_spec<POLICY, CH, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMEM_BYTES - sizeof(GenericCfg) - SPEC_SMEM_MARGIN)));
+        ready = 1;
+    }
+    k_spec<POLICY, CH, W><<<(unsigned)c->sm_count, W * 32, smem, c->stream>>>(p, c->dG, c->T, c->E, O);
+    c->launches++;
+    CU(c, cudaGetLastError());
+    return F2Q_OK;
+}
+
+int launch_spec_dyn(f2q_ctx* c, const SpecParams& P, Outputs O) {
+    const bool f = c->policy == POLICY_FAST1;
+    int rc12;
+#define F2Q_SPEC_CASE(CHV)                                                                                         \
+    case CHV:                                                                                                      \
+        if (c->spec_warps == 16) {                                                                                 \
+            const int rc16 = f ? launch_spec<POLICY_FAST1, CHV, 16>(c, P, O) : launch_spec<POLICY_GENERIC, CHV, 16>(c, P, O); \
+            if (rc16 != 1) return rc16;                                                                            \
+        }                                                                                                          \
+        rc12 = f ? launch_spec<POLICY_FAST1, CHV, 12>(c, P, O) : launch_spec<POLICY_GENERIC, CHV, 12>(c, P, O);      \
+        return rc12 == 1 ? fail(c, F2Q_EINTERNAL, "speculative kernel does not fit on an SM") : rc12;
+    switch (c->ch) {
+        F2Q_SPEC_CASE(3)
+        F2Q_SPEC_CASE(5)
+        default:
+        F2Q_SPEC_CASE(7)
+    }
+#undef F2Q_SPEC_CASE
+}
+
 // record length of ordinary FASTQ from the first bytes of a sample -> row size of the tile kernel (16*ch just below it)
 void decide_ch(f2q_ctx* c, const uint8_t* head, size_t n) {
     size_t nl = 0, pos = 0;
@@ -269,7 +320,7 @@ void timing_end(f2q_ctx* c, cudaEvent_t a, int kind) {
     c->timed.push_back({a, e, kind});
 }
 void timing_collect(f2q_ctx* c) {
-    for (int k = 0; k < 3; k++) { c->kernel_ms[k] = 0; c->kernel_launches[k] = 0; }
+    for (int k = 0; k < 4; k++) { c->kernel_ms[k] = 0; c->kernel_launches[k] = 0; }
     for (auto& t : c->timed) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) { c->kernel_ms[t.kind] += ms; c->kernel_launches[t.kind]++; }
@@ -366,6 +417,18 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     if ((rc = dev_alloc(c, c->status, n_tiles + 64))) return rc;
     unsigned grid = 0;
     if ((rc = tile_grid_dyn(c, &grid))) return rc;
+    // the speculative streaming kernel runs first in Counter mode (its results can be dropped; Extract+Count inserts cannot)
+    const bool use_spec = c->spec && n && c->cfg.mode == F2Q_MODE_COUNT;
+    const uint64_t spec_own = 512ull * c->ch;
+    uint64_t spec_range_tiles = 0;
+    if (use_spec) {
+        grid = std::max<unsigned>(grid, (unsigned)c->sm_count);        // one queue segment per CTA of either kernel
+        const uint64_t tiles = (delta + n) / spec_own + 1, streams = (uint64_t)c->sm_count * c->spec_warps;
+        spec_range_tiles = c->spec_range_tiles > 0 ? (uint64_t)c->spec_range_tiles : std::min<uint64_t>(64, std::max<uint64_t>(8, tiles / (streams * 4)));
+        const uint64_t n_rec = (delta + n) / (spec_range_tiles * spec_own) + 2;
+        if ((rc = dev_alloc(c, c->spec_rec, n_rec))) return rc;
+        CU(c, cudaMemsetAsync(c->spec_rec.p, 0, n_rec, c->stream));
+    }
     // queues sized for the chunk: one entry per 64 bytes covers every non-exact read of ordinary FASTQ; anything
     // beyond that is resolved in place by the tile kernel, so capacity never changes results
     uint64_t want_q = c->opt_queue_entries > 0 ? (uint64_t)c->opt_queue_entries : std::max<uint64_t>(1 << 16, n / 64 + 1024);
@@ -389,6 +452,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     CU(c, cudaMemsetAsync(c->seg_count.p, 0, (size_t)c->n_segs * 4, c->stream));
     k_prepare<<<1, PREP_THREADS, 0, c->stream>>>(c->dS, base, delta, n, is_last ? 1u : 0u, reinterpret_cast<uint8_t*>(c->carry.p),
                                                  c->carry_cap, c->d_tickets, c->q_cap, c->g_cap);
+    CU(c, cudaMemsetAsync(c->d_tickets + 2, 0, 4, c->stream));
     c->launches++;
     Outputs O = outputs_of(c);
     TileParams P{};
@@ -400,20 +464,43 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         if (!g_trace) { g_trace_tiles = n_tiles + 16; cudaMalloc(&g_trace, g_trace_tiles * 48); }
         cudaMemsetAsync(g_trace, 0, g_trace_tiles * 48, c->stream);
     }
-    // 1. the record stitched from the carried tail and the head of this chunk (lives in the carry buffer)
-    P.buf = reinterpret_cast<const uint8_t*>(c->carry.p); P.status = reinterpret_cast<uint8_t*>(c->status_stitch.p);
-    P.ticket = c->d_tickets; P.stitch = 1; P.seg_count = reinterpret_cast<uint32_t*>(c->seg_count.p); P.seg_cap = 0;
-    if ((rc = launch_tile_dyn(c, P, O, 4))) return rc;
-    // 2. the chunk itself
+    P.seg_count = reinterpret_cast<uint32_t*>(c->seg_count.p);
+    // 1. the chunk itself: speculative streaming kernel -> verify -> commit or drop; then the exact kernel, which returns at
+    //    once when the speculation held
+    if (use_spec) {
+        SpecParams Q{};
+        Q.buf = base; Q.S = c->dS; Q.ticket = c->d_tickets + 2; Q.rec = reinterpret_cast<uint8_t*>(c->spec_rec.p);
+        Q.range_bytes = spec_range_tiles * spec_own;
+        Q.queue = P.queue; Q.seg_count = P.seg_count; Q.seg_cap = c->policy == POLICY_FAST1 ? c->seg_cap : 0; Q.gqueue = P.gqueue;
+        Q.halo_rows = (uint32_t)std::min<int>(c->halo_rows, (int)SPEC_MAX_HALO);
+        Outputs O2 = O;
+        O2.counts = reinterpret_cast<unsigned long long*>(c->spec_scratch.p); O2.stats = O2.counts + c->n_keys;
+        cudaEvent_t t0 = timing_begin(c);
+        rc = launch_spec_dyn(c, Q, O2);
+        timing_end(c, t0, 0);
+        if (rc) return rc;
+        cudaEvent_t t3 = timing_begin(c);
+        k_spec_verify<<<1, SPEC_VERIFY_THREADS, 0, c->stream>>>(c->dS, Q.rec, Q.range_bytes, (uint32_t)spec_own, P.seg_count, c->n_segs);
+        const uint64_t nres = (uint64_t)c->n_keys + 5;
+        k_spec_merge<<<(unsigned)std::min<uint64_t>((nres + 255) / 256, (uint64_t)c->sm_count * 8), 256, 0, c->stream>>>(c->dS, O2.counts, O.counts, nres);
+        c->launches += 2;
+        timing_end(c, t3, 3);
+    }
     if (n) {
         P.buf = base; P.status = reinterpret_cast<uint8_t*>(c->status.p); P.ticket = c->d_tickets + 1; P.stitch = 0;
         P.trace = (getenv("F2Q_TRACE") && n_tiles + 16 <= g_trace_tiles) ? g_trace : nullptr;
         P.seg_cap = c->policy == POLICY_FAST1 ? c->seg_cap : 0;
+        P.skip_if_spec_ok = use_spec ? 1u : 0u;
         cudaEvent_t t0 = timing_begin(c);
         rc = launch_tile_dyn(c, P, O, n_tiles);
-        timing_end(c, t0, 0);
+        timing_end(c, t0, use_spec ? 3 : 0);
         if (rc) return rc;
+        P.skip_if_spec_ok = 0; P.trace = nullptr;
     }
+    // 2. the record stitched from the carried tail and the head of this chunk (lives in the carry buffer)
+    P.buf = reinterpret_cast<const uint8_t*>(c->carry.p); P.status = reinterpret_cast<uint8_t*>(c->status_stitch.p);
+    P.ticket = c->d_tickets; P.stitch = 1; P.seg_cap = 0;
+    if ((rc = launch_tile_dyn(c, P, O, 4))) return rc;
     if (getenv("F2Q_TRACE") && g_trace && n) {
         cudaStreamSynchronize(c->stream);
         std::vector<unsigned long long> h(g_trace_tiles * 6);
@@ -517,10 +604,10 @@ F2Q_EXPORT int f2q_create(const f2q_config* cfg, int device, void* stream, f2q_c
     if (stream) c->stream = reinterpret_cast<cudaStream_t>(stream);
     else { if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(F2Q_ECUDA, "cudaStreamCreate failed"); c->own_stream = true; }
     if (cudaMalloc(&c->dG, sizeof(GenericCfg)) != cudaSuccess || cudaMalloc(&c->d_error, 4) != cudaSuccess ||
-        cudaMalloc(&c->dS, sizeof(DevState)) != cudaSuccess || cudaMalloc(&c->d_tickets, 8) != cudaSuccess)
+        cudaMalloc(&c->dS, sizeof(DevState)) != cudaSuccess || cudaMalloc(&c->d_tickets, 16) != cudaSuccess)
         return bail(F2Q_ENOMEM, "cudaMalloc failed");
     cudaMemcpy(c->dG, &G, sizeof(G), cudaMemcpyHostToDevice);
-    cudaMemset(c->d_error, 0, 4); cudaMemset(c->dS, 0, sizeof(DevState)); cudaMemset(c->d_tickets, 0, 8);
+    cudaMemset(c->d_error, 0, 4); cudaMemset(c->dS, 0, sizeof(DevState)); cudaMemset(c->d_tickets, 0, 16);
     decide_policy(c);
     if (cfg->mode == F2Q_MODE_EXTRACT_COUNT) {
         // no library in this mode: results are [stats 5]
@@ -539,7 +626,7 @@ F2Q_EXPORT void f2q_destroy(f2q_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& b : c->lib_bufs) b.release();
     c->result.release(); c->carry.release(); c->status.release(); c->status_stitch.release(); c->queue.release(); c->gqueue.release();
-    c->seg_count.release();
+    c->seg_count.release(); c->spec_rec.release(); c->spec_scratch.release();
     c->ec_slots.release(); c->ec_counts.release(); c->ec_arena.release(); c->ec_meta.release();
     for (auto p : c->d_stage) cudaFree(p);
     for (auto e : c->ev_copied) cudaEventDestroy(e);
@@ -570,6 +657,9 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "halo_rows") { if (value < 0 || value > 128) return fail(c, F2Q_EINVAL, "halo_rows must be 0 (auto) .. 128"); c->force_halo = (int)value; }
     else if (n == "row_chunks") { if (value != 0 && value != 3 && value != 5 && value != 7) return fail(c, F2Q_EINVAL, "row_chunks must be 0 (auto), 3, 5 or 7"); c->force_ch = (int)value; }
     else if (n == "time_kernels") c->time_kernels = value != 0;
+    else if (n == "spec") c->spec = value != 0;
+    else if (n == "spec_warps") { if (value != 12 && value != 16) return fail(c, F2Q_EINVAL, "spec_warps must be 12 or 16"); c->spec_warps = (int)value; }
+    else if (n == "spec_range_tiles") { if (value < 0 || value > (1 << 20)) return fail(c, F2Q_EINVAL, "spec_range_tiles out of range"); c->spec_range_tiles = (int)value; }
     else if (n == "force_generic") { if (value) c->policy = POLICY_GENERIC; else decide_policy(c); }
     else return fail(c, F2Q_EINVAL, "unknown option " + n);
     return F2Q_OK;
@@ -686,6 +776,8 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
     c->n_keys = n_keys;
     c->result.release();
     if ((rc = dev_alloc(c, c->result, ((size_t)n_keys + 5) * 8))) return rc;
+    c->spec_scratch.release();
+    if ((rc = dev_alloc(c, c->spec_scratch, ((size_t)n_keys + 5) * 8))) return rc;
     c->lib_set = true;
     return F2Q_OK;
 }
@@ -697,6 +789,7 @@ F2Q_EXPORT int f2q_begin_sample(f2q_ctx* c) {
     if ((rc = dev_alloc(c, c->status_stitch, c->carry_cap / (64 * 16 * 3) + 2 + 64))) return rc;
     c->ch_decided = false;
     CU(c, cudaMemsetAsync(c->result.p, 0, ((size_t)c->n_keys + 5) * 8, c->stream));
+    if (c->spec_scratch.p) CU(c, cudaMemsetAsync(c->spec_scratch.p, 0, ((size_t)c->n_keys + 5) * 8, c->stream));
     CU(c, cudaMemsetAsync(c->d_error, 0, 4, c->stream));
     CU(c, cudaMemsetAsync(c->dS, 0, sizeof(DevState), c->stream));
     if (c->cfg.mode == F2Q_MODE_EXTRACT_COUNT) {
@@ -771,6 +864,7 @@ F2Q_EXPORT int f2q_end_sample(f2q_ctx* c, uint64_t* counts, uint64_t* stats) {
     DevState hs;
     CU(c, cudaMemcpy(&hs, c->dS, sizeof(hs), cudaMemcpyDeviceToHost));
     err |= hs.error;
+    c->spec_counts[0] = hs.spec_commits; c->spec_counts[1] = hs.spec_fallbacks;
     if (getenv("F2Q_DEBUG"))
         fprintf(stderr, "f2q debug: wait Mcycles  empty(loader) %llu  full(lookback) %llu agg(lookback) %llu  in-lookback %llu | full(consumers) %llu  p0(consumers) %llu | respins %llu | consumer warp Mcycles %llu\n",
                 hs.dbg[0] >> 20, hs.dbg[7] >> 20, hs.dbg[1] >> 20, hs.dbg[4] >> 20, hs.dbg[2] >> 20, hs.dbg[3] >> 20, hs.dbg[5], hs.dbg[6] >> 20);
@@ -863,9 +957,15 @@ F2Q_EXPORT int f2q_memcpy_h2d(f2q_ctx* c, void* dptr, const void* host, uint64_t
 
 F2Q_EXPORT uint64_t f2q_launch_count(const f2q_ctx* c) { return c ? c->launches : 0; }
 
+F2Q_EXPORT int f2q_spec_counts(const f2q_ctx* c, uint64_t* committed, uint64_t* fell_back) {
+    if (!c || !committed || !fell_back) return F2Q_EINVAL;
+    *committed = c->spec_counts[0]; *fell_back = c->spec_counts[1];
+    return F2Q_OK;
+}
+
 F2Q_EXPORT int f2q_kernel_times(f2q_ctx* c, double* ms, uint64_t* launches) {
     if (!c || !ms || !launches) return F2Q_EINVAL;
-    for (int k = 0; k < 3; k++) { ms[k] = c->kernel_ms[k]; launches[k] = c->kernel_launches[k]; }
+    for (int k = 0; k < 4; k++) { ms[k] = c->kernel_ms[k]; launches[k] = c->kernel_launches[k]; }
     return F2Q_OK;
 }
 

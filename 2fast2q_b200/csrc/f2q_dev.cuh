@@ -108,7 +108,10 @@ struct DevState {
     uint32_t error;
     uint32_t q_count, q_cap;       // (unused; the non-exact key queue is segmented per CTA, see TileParams)
     uint32_t g_count, g_cap;       // generic read queue
-    uint32_t pad;
+    uint32_t spec_fail;            // speculative kernel (spec.cuh): some range could not guess its line phase / met an odd tile
+    uint32_t spec_ok;              // k_spec_verify: every speculated phase was right, the scratch results are committed
+    uint32_t spec_off;             // sticky per sample: a speculation failed, later chunks go straight to the exact kernel
+    uint32_t spec_commits, spec_fallbacks;   // chunks of this sample whose speculation held / that the exact kernel parsed
     unsigned long long dbg[8];     // diagnostics (F2Q_DEBUG=1): failed mbarrier tries per wait site, look-back rounds / spins
 };
 

@@ -1,0 +1,390 @@
+// spec.cuh — the streaming form of the fused hot kernel: warp-autonomous, speculative line phase, verified afterwards.
+//
+// Records are "every 4 lines from byte 0" (fast2q.py:324-328), so a byte range can only be parsed when the number of
+// newlines before it (mod 4, the LINE PHASE) is known.  k_tile (tile.cuh) gets it exactly with a decoupled look-back
+// across tiles; that chain couples every CTA to its predecessors and costs more than the parsing itself.  Here the chain
+// is cut:
+//
+//   * the chunk is cut into RANGES of range_bytes; a warp takes a range by ticket and streams its tiles (32 rows of
+//     S = 16*CH bytes + read-ahead rows) through its own 3-stage TMA ring in shared memory (cp.async.bulk + mbarrier,
+//     SASS UBLKCP).  Inside a range the phase is carried in a register: no CTA barrier, no other warp is ever waited for.
+//   * the phase at the START of a range (other than the first, which is a record start) is SPECULATED from the local
+//     record structure: exactly one of the four alignments must show '+' on line 2, '@' on the next header and
+//     len(line 1) == len(line 3) for the first two records.  Anything ambiguous fails the speculation.
+//   * every range publishes (newline count mod 4, speculated phase).  k_spec_verify adds them up: if every speculated
+//     phase equals the true prefix, the results (which were accumulated into a SCRATCH count vector and the CTA-private
+//     queue segments) are committed by k_spec_merge; otherwise they are dropped and the exact kernel k_tile parses the
+//     chunk (it is launched unconditionally and returns at once when the speculation held).  The outcome is therefore
+//     always exactly the reference's, whatever the bytes are; only the speed depends on the FASTQ being ordinary.
+//
+// Per tile a warp does: wait for tile i+1 -> newline masks / positions of its 32 rows (lane = row) -> parse tile i
+// (lane q = q-th read; reads running into tile i+1 use its first rows' positions and the read-ahead bytes) -> refill the
+// stage of tile i.  The range ends with one scan-only tile (the first tile of the next range).
+#pragma once
+
+#include "tile.cuh"
+
+namespace f2q {
+
+constexpr int SPEC_STAGES = 3;
+constexpr int SPEC_CAP = 6 * 32;                     // newline positions kept per tile (its 32 own rows)
+constexpr uint32_t SPEC_MAX_HALO = 16;
+
+struct SpecParams {
+    const uint8_t* buf;        // 128-byte aligned base of the chunk buffer
+    DevState* S;
+    uint32_t* ticket;          // range ticket counter, zeroed before the launch
+    uint8_t* rec;              // one byte per range, zeroed before the launch: 0x80 | speculated phase << 2 | newline count & 3
+    uint64_t range_bytes;      // multiple of the tile's own bytes (32 * 16 * CH)
+    QEntry* queue;             // grid segments of seg_cap entries each
+    uint32_t* seg_count;
+    uint32_t seg_cap;
+    GEntry* gqueue;
+    uint32_t hist_smem;        // 1: per-CTA shared-memory histogram of n_keys u32
+    uint32_t halo_rows;        // H: read-ahead rows loaded behind the 32 own rows (1 .. SPEC_MAX_HALO)
+};
+
+template <int CH>
+struct SpecGeom {
+    static constexpr int S = CH * 16;
+    static constexpr int OWN = 32 * S;
+    static constexpr int MW = (CH + 1) / 2;                            // 32-bit newline mask words per row
+    static constexpr int NL_LIST = SPEC_CAP + 8;                       // u16 entries of one position list
+    __host__ __device__ static constexpr uint32_t stage_bytes(uint32_t H) { return (((32u + H) * S + 16u + 127u) / 128u) * 128u; }
+    __host__ __device__ static constexpr uint32_t warp_bytes(uint32_t H) { return ((SPEC_STAGES * stage_bytes(H) + 2u * NL_LIST * 2u + 127u) / 128u) * 128u; }
+};
+
+template <int CH, int W>
+__host__ __device__ inline size_t spec_smem_bytes(uint32_t H, uint32_t hist_entries) {
+    return (size_t)W * SpecGeom<CH>::warp_bytes(H) + (size_t)hist_entries * 4;
+}
+
+__device__ __forceinline__ uint64_t spec_n_ranges(uint64_t beg, uint64_t end, uint64_t own, uint64_t range_bytes, uint64_t& origin0) {
+    origin0 = (beg / own) * own;
+    const uint64_t n = (end - origin0) / range_bytes;                 // the last range takes the remainder
+    return n ? n : 1;
+}
+
+// @region spec_kernel
+template <int POLICY, int CH, int W>
+__global__ void __launch_bounds__(W * 32, 1)
+k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, Outputs O) {
+    using G_ = SpecGeom<CH>;
+    constexpr int S = G_::S, OWN = G_::OWN, NS = SPEC_STAGES, CAP = SPEC_CAP, MW = G_::MW;
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar_full[W][NS];
+    __shared__ uint4 s_desc[W][NS];                                    // per stage: {tile base lo, hi, range, flags}
+    __shared__ uint32_t s_qn, s_abort;
+    __shared__ GenericCfg s_G;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    DevState* St = P.S;
+    const uint64_t beg = St->beg, end = St->end;
+    const bool eof = St->is_last != 0;
+    const uint32_t H = P.halo_rows;
+    const uint32_t stage_bytes = G_::stage_bytes(H), warp_bytes = G_::warp_bytes(H), load_bytes = (32u + H) * S;
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem + (size_t)W * warp_bytes);
+    if (St->spec_off || end <= beg) return;                            // (a sample whose speculation failed once stays on the exact kernel)
+
+    if (POLICY == POLICY_GENERIC)
+        for (uint32_t i = tid; i < sizeof(GenericCfg) / 4; i += blockDim.x)
+            reinterpret_cast<uint32_t*>(&s_G)[i] = reinterpret_cast<const uint32_t*>(Gp)[i];
+    if (P.hist_smem) for (uint32_t i = tid; i < T.n_keys; i += blockDim.x) hist[i] = 0;
+    if (lane == 0) {
+        for (int s = 0; s < NS; s++) mbar_init(&bar_full[warp][s], 1);
+        mbar_fence_init();
+    }
+    if (tid == 0) { s_qn = 0; s_abort = 0; }
+    __syncthreads();
+    volatile uint32_t* abort = &s_abort;
+
+    const GenericCfg& G = (POLICY == POLICY_GENERIC) ? s_G : *Gp;
+    Fast1Ctx F;
+    F.init(Gp);
+    F.hist = P.hist_smem ? hist : nullptr; F.myq = P.queue + (size_t)blockIdx.x * P.seg_cap; F.seg_cap = P.seg_cap; F.s_qn = &s_qn;
+    F.gqueue = P.gqueue; F.St = St;
+    Acc acc{0, 0, 0, 0, 0, 0};
+    unsigned long long gst[F2Q_N_STATS] = {0, 0, 0, 0, 0};
+    Fast1Counts cn{0, 0, 0, 0, 0};
+
+    uint64_t origin0;
+    const uint64_t RB = P.range_bytes;
+    const uint64_t n_ranges = spec_n_ranges(beg, end, OWN, RB, origin0);
+    const uint8_t* __restrict__ buf = P.buf;
+    uint8_t* const wsm = smem + (size_t)warp * warp_bytes;
+    uint16_t* const nlist = reinterpret_cast<uint16_t*>(wsm + NS * stage_bytes);
+    uint64_t* const bars = bar_full[warp];
+    uint4* const desc = s_desc[warp];
+
+    // @region spec_loader
+    // the warp's tile stream: tiles 0 .. nown-1 of a range are parsed, tile nown (the first tile of the next range, when
+    // there is one) is only scanned for the newlines of its first rows; then the next range is taken by ticket.
+    // flags: [1:0] 0 end of stream / 1 TMA / 2 loaded by the lanes (touches bytes outside [beg, end)), 4 first tile of
+    // a range, 8 last parsed tile of a range, 16 scan-only tile
+    uint32_t ld_range = 0, ld_ti = 1, ld_last = 0, ld_nown = 0, issued = 0;
+    bool ld_end = false;
+    auto issue_next = [&]() {
+        const uint32_t s = issued % NS;
+        uint64_t base = 0;
+        uint32_t flags = 0, rng = 0;
+        if (!ld_end) {
+            if (ld_ti > ld_last) {
+                uint32_t tk = 0xFFFFFFFFu;
+                if (lane == 0) { tk = atomicAdd(P.ticket, 1u); if (ld_volatile_u32(&St->spec_fail)) tk = 0xFFFFFFFFu; }
+                tk = __shfl_sync(0xffffffffu, tk, 0);
+                if ((uint64_t)tk >= n_ranges) ld_end = true;
+                else {
+                    const uint64_t rb = origin0 + (uint64_t)tk * RB, re = ((uint64_t)tk == n_ranges - 1) ? end : rb + RB;
+                    ld_range = tk; ld_ti = 0;
+                    ld_nown = (uint32_t)((re - rb + OWN - 1) / OWN);
+                    ld_last = (rb + (uint64_t)ld_nown * OWN < end) ? ld_nown : ld_nown - 1;
+                }
+            }
+            if (!ld_end) {
+                base = origin0 + (uint64_t)ld_range * RB + (uint64_t)ld_ti * OWN;
+                const bool tma = base >= beg && base + load_bytes <= end;
+                flags = (tma ? 1u : 2u) | (ld_ti == 0 ? 4u : 0u) | (ld_ti + 1 == ld_nown ? 8u : 0u) | (ld_ti == ld_nown ? 16u : 0u);
+                rng = ld_range; ld_ti++;
+            }
+        }
+        if (lane == 0) {
+            desc[s] = make_uint4((uint32_t)base, (uint32_t)(base >> 32), rng, flags);
+            if ((flags & 3u) == 1u) {
+                mbar_expect_tx(&bars[s], load_bytes);
+                tma_load_1d(wsm + s * stage_bytes, buf + base, load_bytes, &bars[s]);
+            }
+        }
+        issued++;
+        __syncwarp();
+    };
+
+    const uint32_t c0A = reg_const(0x0A0A0A0Au), c7F = reg_const(0x7F7F7F7Fu), c80 = reg_const(0x80808080u);
+    auto chunk_mask = [&](const uint8_t* p16) -> uint32_t {            // newline flags of one 16-byte chunk (see tile.cuh)
+        const uint4 v = *reinterpret_cast<const uint4*>(p16);
+        const uint32_t z0 = ~(((v.x ^ c0A) & c7F) + c7F | v.x) & c80, z1 = ~(((v.y ^ c0A) & c7F) + c7F | v.y) & c80;
+        const uint32_t z2 = ~(((v.z ^ c0A) & c7F) + c7F | v.z) & c80, z3 = ~(((v.w ^ c0A) & c7F) + c7F | v.w) & c80;
+        const uint32_t lo = __dp4a(z0, 0x08040201u, __dp4a(z1, 0x80402010u, 0u));
+        const uint32_t hi = __dp4a(z2, 0x08040201u, __dp4a(z3, 0x80402010u, 0u));
+        return (lo >> 7) | (hi << 1);
+    };
+
+    // @region spec_scan
+    // newline positions of the tile's 32 own rows (lane = row) -> nl[0 .. total); hcnt = newlines of its first H rows
+    auto scan = [&](const uint8_t* tile, uint16_t* nl, uint32_t& total, uint32_t& hcnt) {
+        uint32_t mw[MW];
+        #pragma unroll
+        for (int w = 0; w < MW; w++) mw[w] = 0;
+        #pragma unroll
+        for (int j = 0; j < CH; j++) mw[j >> 1] |= chunk_mask(tile + lane * S + j * 16) << (16 * (j & 1));
+        uint32_t cnt = 0;
+        #pragma unroll
+        for (int w = 0; w < MW; w++) cnt += __popc(mw[w]);
+        uint32_t incl = cnt;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += y; }
+        const uint32_t excl = incl - cnt;
+        total = __shfl_sync(0xffffffffu, incl, 31);
+        hcnt = __shfl_sync(0xffffffffu, excl, H);                      // (H <= 16 < 32)
+        uint32_t o = excl;
+        const uint32_t rowbase = lane * S;
+        #pragma unroll
+        for (int w = 0; w < MW; w++) {
+            uint32_t m = mw[w];
+            #pragma unroll
+            for (int step = 0; step < 2; step++) {                     // two predicated steps: no divergence for ordinary FASTQ
+                const bool has = m != 0;
+                const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+                if (has && o < (uint32_t)CAP) nl[o] = (uint16_t)(rowbase + 32u * w + b);
+                o += has ? 1u : 0u;
+                m &= m - 1u;
+            }
+            while (m) {
+                const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+                m &= m - 1u;
+                if (o < (uint32_t)CAP) nl[o] = (uint16_t)(rowbase + 32u * w + b);
+                o++;
+            }
+        }
+    };
+
+    // @region spec_loop
+    for (int k = 0; k < NS; k++) issue_next();
+    bool have_prev = false;
+    uint32_t prev_s = 0, prev_total = 0, prev_range = 0, prev_flags = 0;
+    uint64_t prev_base = 0;
+    uint32_t phase = 0, range_cnt = 0, spec_p0 = 0, par_bits = 0;
+    for (uint32_t i = 0;; i++) {
+        const uint32_t s = i % NS, par = i & 1u;
+        const uint4 d = desc[s];
+        const uint32_t flags = d.w;
+        const bool live = (flags & 3u) != 0;
+        const uint64_t base = ((uint64_t)d.y << 32) | d.x;
+        uint8_t* const tile = wsm + s * stage_bytes;
+        uint16_t* const nl = nlist + par * G_::NL_LIST;
+        uint32_t total = 0, hcnt = 0;
+        if (live) {
+            if ((flags & 3u) == 1u) {
+                if (!mbar_wait(&bars[s], (par_bits >> s) & 1u, abort)) break;
+                par_bits ^= 1u << s;
+            } else {
+                // first / last tiles of the chunk: loaded by the lanes, bytes outside [beg, end) become 0
+                for (uint32_t c = lane; c < load_bytes / 16; c += 32) {
+                    const uint64_t g = base + (uint64_t)c * 16;
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (g + 16 > beg && g < end) {
+                        v = ldg_stream(reinterpret_cast<const uint4*>(buf + g));
+                        if (g < beg || g + 16 > end) {
+                            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                            #pragma unroll
+                            for (int b = 0; b < 16; b++) {
+                                const uint64_t pos = g + b;
+                                if (pos < beg || pos >= end) w[b >> 2] &= ~(0xFFu << (8 * (b & 3)));
+                            }
+                            v = make_uint4(w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(tile + c * 16) = v;
+                }
+                __syncwarp();
+            }
+            scan(tile, nl, total, hcnt);
+            __syncwarp();
+        }
+        if (have_prev) {
+            // @region spec_parse
+            // ---- reads of the previous tile: lane q takes the q-th read whose header line ends in its own rows ----
+            const bool cont = live && d.z == prev_range && !(flags & 4u);      // this tile directly follows it
+            const uint32_t total_own = prev_total, hc = cont ? hcnt : 0u, total_all = total_own + hc;
+            const uint8_t* ptile = wsm + prev_s * stage_bytes;
+            const uint16_t* nlA = nlist + (par ^ 1u) * G_::NL_LIST;
+            const uint16_t* nlB = nl;
+            if (total_own > (uint32_t)CAP || hc > (uint32_t)CAP) {
+                if (lane == 0) St->spec_fail = 1u;                     // a tile of very short lines: left to the exact kernel
+            } else {
+                const uint32_t jf = (4u - (phase & 3u)) & 3u;          // first newline of the tile that ends a header line
+                auto pos = [&](uint32_t j) -> uint32_t { return j < total_own ? (uint32_t)nlA[j] : (uint32_t)nlB[j - total_own] + (uint32_t)OWN; };
+                for (uint32_t j = jf + 4u * lane; j < total_own; j += 128u) {
+                    const uint32_t h0 = nlA[j];
+                    if (j + 3 >= total_all) {
+                        // the read's last newline is not in the loaded rows (a long record, or the end of the chunk)
+                        slow_record(buf, prev_base + h0, end, eof, G, T, E, O, acc, gst);
+                        continue;
+                    }
+                    const uint32_t s0 = h0 + 1u, e0 = pos(j + 1), s3 = pos(j + 2) + 1u, e3 = pos(j + 3);
+                    cn.reads++;
+                    acc.last_end = (unsigned long long)(prev_base + e3 + 1);
+                    if (POLICY == POLICY_GENERIC) {
+                        const uint8_t* Rp = ptile + s0; const uint8_t* Qp = ptile + s3;
+                        g_process_read(G, T, E, O, Rp, g_rstrip(Rp, (int)(e0 - s0)), Qp, g_rstrip(Qp, (int)(e3 - s3)), gst);
+                        continue;
+                    }
+                    fast1_read(F, ptile, s0, e0, s3, e3, buf + prev_base + s0, buf + prev_base + s3, G, T, E, O, cn, gst, lane);
+                }
+            }
+            __syncwarp();
+            phase += prev_total; range_cnt += prev_total;
+            if ((prev_flags & 8u) && lane == 0) P.rec[prev_range] = (uint8_t)(0x80u | (spec_p0 << 2) | (range_cnt & 3u));
+            issue_next();                                              // refill the stage of the parsed tile
+            have_prev = false;
+        }
+        if (!live) break;
+        if (flags & 4u) {
+            // @region spec_speculate
+            range_cnt = 0; spec_p0 = 0; phase = 0;                     // (range 0 starts at a record start)
+            if (d.z != 0) {
+                const uint32_t n = min(total, (uint32_t)CAP);
+                bool cand = false;
+                if (lane < 4) {
+                    bool ok = true; int K = 0;
+                    #pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        const uint32_t j = lane + 4u * k;
+                        if (j + 3 >= n) break;
+                        const uint32_t a = nl[j], b = nl[j + 1], c = nl[j + 2], e = nl[j + 3];
+                        ok = ok && tile[b + 1] == '+' && tile[e + 1] == '@' && (b - a) == (e - c);
+                        K++;
+                    }
+                    cand = ok && K > 0;
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, cand) & 0xFu;
+                if (__popc(m) == 1) { spec_p0 = (4u - ((uint32_t)__ffs((int)m) - 1u)) & 3u; phase = spec_p0; }
+                else if (lane == 0) St->spec_fail = 1u;
+            }
+        }
+        if (flags & 16u) issue_next();                                 // scan-only tile: its stage is free again
+        else { have_prev = true; prev_s = s; prev_total = total; prev_range = d.z; prev_flags = flags; prev_base = base; }
+    }
+
+    // @region spec_epilogue
+    __syncthreads();
+    if (tid == 0 && P.seg_cap) P.seg_count[blockIdx.x] = min(s_qn, P.seg_cap);
+    if (P.hist_smem)
+        for (uint32_t i = tid; i < T.n_keys; i += blockDim.x) { const uint32_t v = hist[i]; if (v) atomicAdd(O.counts + i, (unsigned long long)v); }
+    acc.reads += cn.reads; acc.perfect += cn.perfect; acc.imperfect += cn.imperfect; acc.nonal += cn.nonal; acc.qfail += cn.qfail;
+    acc.perfect += gst[F2Q_STAT_PERFECT]; acc.imperfect += gst[F2Q_STAT_IMPERFECT];
+    acc.nonal += gst[F2Q_STAT_NON_ALIGNED]; acc.qfail += gst[F2Q_STAT_QUALITY_FAILED];
+    unsigned long long v[5] = {acc.reads, acc.perfect, acc.imperfect, acc.nonal, acc.qfail};
+    #pragma unroll
+    for (int k = 0; k < 5; k++) {
+        unsigned long long x = v[k];
+        #pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) x += __shfl_down_sync(0xffffffffu, x, dd);
+        if (lane == 0 && x) atomicAdd(O.stats + k, x);
+    }
+    unsigned long long le = acc.last_end;
+    #pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) le = max(le, __shfl_down_sync(0xffffffffu, le, dd));
+    if (lane == 0 && le) atomicMax(&St->last_rec_end, le);
+}
+
+// @region spec_verify
+// one CTA: true phase of every range = prefix sum of the published newline counts; the speculation holds iff every range
+// finished and guessed exactly that.  On failure everything the speculative kernel left behind is reset.
+constexpr int SPEC_VERIFY_THREADS = 1024;
+__global__ void __launch_bounds__(SPEC_VERIFY_THREADS) k_spec_verify(DevState* St, const uint8_t* __restrict__ rec, uint64_t range_bytes,
+                                                                    uint32_t own_bytes, uint32_t* seg_count, uint32_t n_segs) {
+    __shared__ uint32_t s_sum[SPEC_VERIFY_THREADS];
+    __shared__ uint32_t s_bad, s_total;
+    const uint32_t tid = threadIdx.x;
+    const uint64_t beg = St->beg, end = St->end;
+    if (tid == 0) { s_bad = (St->spec_off || St->spec_fail) ? 1u : 0u; s_total = 0; }
+    __syncthreads();
+    uint32_t total = 0;
+    if (end > beg && !s_bad) {
+        uint64_t origin0;
+        const uint64_t n_ranges = spec_n_ranges(beg, end, own_bytes, range_bytes, origin0);
+        const uint64_t per = (n_ranges + SPEC_VERIFY_THREADS - 1) / SPEC_VERIFY_THREADS;
+        const uint64_t r0 = min(n_ranges, (uint64_t)tid * per), r1 = min(n_ranges, r0 + per);
+        uint32_t sum = 0, bad = 0;
+        for (uint64_t r = r0; r < r1; r++) { const uint32_t v = rec[r]; bad |= (v & 0x80u) ? 0u : 1u; sum += v & 3u; }
+        s_sum[tid] = sum;
+        __syncthreads();
+        if (tid == 0) { uint32_t run = 0; for (int k = 0; k < SPEC_VERIFY_THREADS; k++) { const uint32_t x = s_sum[k]; s_sum[k] = run; run += x; } }
+        __syncthreads();
+        uint32_t ph = s_sum[tid];
+        for (uint64_t r = r0; r < r1; r++) { const uint32_t v = rec[r]; if (r > 0 && ((v >> 2) & 3u) != (ph & 3u)) bad = 1u; ph += v & 3u; }
+        if (bad) atomicOr(&s_bad, 1u);
+        if (r1 == n_ranges && r0 < r1) s_total = ph;                   // the thread that owns the last range
+    }
+    __syncthreads();
+    total = s_total;
+    const bool ok = s_bad == 0;
+    if (tid == 0) {
+        St->spec_ok = ok ? 1u : 0u;
+        if (ok) { if (end > beg) { St->nl_total = total & 3u; St->spec_commits++; } }
+        else { St->last_rec_end = 0; St->g_count = 0; St->spec_off = 1u; St->spec_fallbacks++; }
+    }
+    if (!ok) for (uint32_t i = tid; i < n_segs; i += SPEC_VERIFY_THREADS) seg_count[i] = 0;
+}
+
+// commit (or drop) the scratch count vector of the speculative kernel; scratch is left zeroed for the next chunk
+__global__ void __launch_bounds__(256) k_spec_merge(const DevState* St, unsigned long long* __restrict__ scratch,
+                                                    unsigned long long* __restrict__ result, uint64_t n) {
+    const bool ok = St->spec_ok != 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long v = scratch[i];
+        if (v) { if (ok) result[i] += v; scratch[i] = 0; }
+    }
+}
+
+}  // namespace f2q

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_prepare(DevState* S, const uin
     if (tid == 0) {
         S->q_count = 0; S->g_count = 0; S->q_cap = q_cap; S->g_cap = g_cap;
         S->last_rec_end = 0; S->nl_total = 0; S->stitch_len = 0; S->stitch_eof = 0; S->appended = 0;
-        S->is_last = is_last; S->end = delta + n; S->beg = delta;
+        S->is_last = is_last; S->end = delta + n; S->beg = delta; S->spec_fail = 0; S->spec_ok = 0;
         tickets[0] = 0; tickets[1] = 0;
         s_found = 0; s_cnt = 0; s_h = 0;
     }

@@ -51,6 +51,7 @@ struct TileParams {
     GEntry* gqueue;
     uint32_t hist_smem;        // 1: per-CTA shared-memory histogram of n_keys u32
     uint32_t halo_rows;        // H: read-ahead rows at the end of every tile (1 .. NT/2)
+    uint32_t skip_if_spec_ok;  // 1: return at once when the speculative kernel's results were committed (spec.cuh)
     uint32_t debug;            // 1: count waits into DevState::dbg
     unsigned long long* trace; // debug: 6 u64 per tile (ticket time, agg time, go time, lb done time, parse start, cta)
 };
@@ -250,6 +251,94 @@ __device__ __noinline__ void slow_record(const uint8_t* buf, uint64_t hdr_end, u
     g_process_read(G, T, E, O, Rp, g_rstrip(Rp, (int)(pos[1] - pos[0] - 1)), Qp, g_rstrip(Qp, (int)(pos[3] - pos[2] - 1)), gst);
 }
 
+// @region fast1_read
+// per-thread constants of the packed single-window policy (fixed position, one feature, <= 32 symbols)
+struct Fast1Ctx {
+    int c_start, c_end, c_fmax, c_miss;
+    bool simple_slice;
+    uint32_t add_ge, add_gt;           // SWAR constants of the Phred fail-set test: fail iff 33 <= byte <= c_fmax
+    uint32_t* hist;                    // this CTA's shared-memory histogram, or nullptr (global atomics)
+    QEntry* myq;                       // this CTA's segment of the non-exact key queue
+    uint32_t seg_cap;
+    uint32_t* s_qn;                    // shared-memory fill count of the segment
+    GEntry* gqueue;
+    DevState* St;
+    __device__ __forceinline__ void init(const GenericCfg* Gp) {
+        c_start = Gp->c.starts[0]; c_end = c_start + Gp->c.length; c_fmax = Gp->c.fmax_ph; c_miss = Gp->c.miss;
+        simple_slice = c_start >= 0 && Gp->c.length >= 0;
+        add_ge = (0x80u - 33u) * 0x01010101u; add_gt = (0x80u - (uint32_t)(c_fmax + 1)) * 0x01010101u;
+    }
+};
+struct Fast1Counts { uint32_t reads, perfect, imperfect, nonal, qfail; };
+
+// one read of the packed policy: sequence line at tile[s0, e0), quality line at tile[s3, e3) (both before rstrip);
+// gseq / gqual = global addresses of the same two lines (for reads deferred to the generic queue)
+__device__ __forceinline__ void fast1_read(const Fast1Ctx& F, const uint8_t* tile, uint32_t s0, uint32_t e0, uint32_t s3, uint32_t e3,
+                                           const uint8_t* gseq, const uint8_t* gqual, const GenericCfg& G, const LibTables& T,
+                                           const EcTable& E, const Outputs& O, Fast1Counts& n, unsigned long long* gst, uint32_t lane) {
+    // ---- K2: rstrip, window, Phred test ----
+    if (is_py_space(tile[e0 - 1])) while (e0 > s0 && is_py_space(tile[e0 - 1])) e0--;     // (tile[s0 - 1] is the '\n' before the line)
+    if (is_py_space(tile[e3 - 1])) while (e3 > s3 && is_py_space(tile[e3 - 1])) e3--;
+    int lo, hi, qlo, qhi;
+    if (F.simple_slice) {
+        const int ls = (int)(e0 - s0), lq = (int)(e3 - s3);
+        lo = min(F.c_start, ls); hi = min(F.c_end, ls); qlo = min(F.c_start, lq); qhi = min(F.c_end, lq);
+    } else {
+        py_slice((int)(e0 - s0), F.c_start, F.c_end, lo, hi);
+        py_slice((int)(e3 - s3), F.c_start, F.c_end, qlo, qhi);
+    }
+    const int qn = qhi - qlo;
+    if (F.c_fmax != 0 && qn > 0) {
+        bool fails;
+        #define F2Q_QCALL(W) fails = qual_fails_w<W>(tile, s3 + qlo, qn, F.add_ge, F.add_gt)
+        F2Q_WORDS_SWITCH((qn + 3) >> 2, F2Q_QCALL)
+        #undef F2Q_QCALL
+        if (fails) { n.qfail++; return; }
+    }
+    // ---- K4: pack, exact lookup, count ----
+    const uint32_t klen = (uint32_t)(hi - lo);
+    uint32_t klo = 0, khi = 0, bad = 0;
+    if (klen) {
+        #define F2Q_PCALL(W) pack_w<W>(tile, s0 + lo, (int)klen, klo, khi, bad)
+        F2Q_WORDS_SWITCH((klen + 3) >> 2, F2Q_PCALL)
+        #undef F2Q_PCALL
+    }
+    const bool generic_len = (T.generic_len_mask >> min(klen, 63u)) & 1ull;
+    uint32_t idx = SLOT_EMPTY;
+    if (!generic_len && bad == 0) {
+        if (T.cslots) { if (klen == T.c_len) idx = compact_lookup(T, klo, khi); }
+        else idx = fast_lookup(T, ((uint64_t)khi << 32) | klo, klen);
+    }
+    if (idx != SLOT_EMPTY) {
+        n.perfect++;
+        if (F.hist) atomicAdd(F.hist + idx, 1u);
+        else atomicAdd(O.counts + idx, 1ull);
+        return;
+    }
+    if (generic_len) {
+        // library keys of this length exist that the packed tables cannot hold
+        GEntry ge; ge.seq_addr = (uint64_t)gseq; ge.seq_len = e0 - s0;
+        ge.qual_addr = (uint64_t)gqual; ge.qual_len = e3 - s3;
+        const uint32_t slot = atomicAdd(&F.St->g_count, 1u);
+        if (slot < F.St->g_cap) F.gqueue[slot] = ge;
+        else g_process_read(G, T, E, O, (const uint8_t*)ge.seq_addr, (int)ge.seq_len, (const uint8_t*)ge.qual_addr, (int)ge.qual_len, gst);
+        return;
+    }
+    if (F.c_miss <= 0) { n.nonal++; return; }
+    // non-exact key: one slot of this CTA's private queue segment, reserved once per warp
+    const uint64_t key = ((uint64_t)khi << 32) | klo;
+    const uint32_t peers = __activemask();
+    const uint32_t leader = (uint32_t)__ffs((int)peers) - 1u;
+    uint32_t sl = 0;
+    if (lane == leader) sl = atomicAdd(F.s_qn, (uint32_t)__popc(peers));
+    sl = __shfl_sync(peers, sl, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+    if (sl < F.seg_cap) { QEntry e; e.key = key; e.bad = bad; e.len = klen; F.myq[sl] = e; }
+    else {                                                     // segment full: resolve right here
+        const uint32_t r = resolve_seed_thread(T, F.c_miss, key, bad, klen);
+        if (r != RES_NONE) { atomicAdd(O.counts + r, 1ull); n.imperfect++; } else n.nonal++;
+    }
+}
+
 // @region lookback
 __device__ __forceinline__ uint4 ld_volatile_v4(const void* p) {
     uint4 r;
@@ -349,6 +438,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     const uint64_t beg = P.stitch ? 0ull : St->beg;
     const uint64_t end = P.stitch ? (uint64_t)St->stitch_len : St->end;
     const bool eof = P.stitch ? (St->stitch_eof != 0) : (St->is_last != 0);
+    if (P.skip_if_spec_ok && St->spec_ok) return;
     if (end <= beg) { if (tid == 0 && P.seg_cap) P.seg_count[blockIdx.x] = 0; return; }
 
     if (POLICY == POLICY_GENERIC)                                      // the packed policy keeps its few scalars in registers
@@ -437,14 +527,13 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     // =====================================================================================================
     // consumers
     const GenericCfg& G = (POLICY == POLICY_GENERIC) ? s_G : *Gp;
-    const int c_start = Gp->c.starts[0], c_length = Gp->c.length, c_fmax = Gp->c.fmax_ph, c_miss = Gp->c.miss;
-    QEntry* const myq = P.queue + (size_t)blockIdx.x * P.seg_cap;
+    Fast1Ctx F;
+    F.init(Gp);
+    F.hist = P.hist_smem ? hist : nullptr; F.myq = P.queue + (size_t)blockIdx.x * P.seg_cap; F.seg_cap = P.seg_cap; F.s_qn = &s_qn;
+    F.gqueue = P.gqueue; F.St = St;
     Acc acc{0, 0, 0, 0, 0, 0};
     unsigned long long gst[F2Q_N_STATS] = {0, 0, 0, 0, 0};            // stats of reads handled by the generic code
-    uint32_t reads = 0, perfect = 0, imperfect = 0, nonal = 0, qfail = 0;   // per-thread counts of this launch
-    const int c_end = c_start + c_length;
-    const bool simple_slice = c_start >= 0 && c_length >= 0;
-    const uint32_t add_ge = (0x80u - 33u) * 0x01010101u, add_gt = (0x80u - (uint32_t)(c_fmax + 1)) * 0x01010101u;
+    Fast1Counts cn{0, 0, 0, 0, 0};                                     // per-thread counts of this launch
 
     const uint32_t c0A = reg_const(0x0A0A0A0Au), c7F = reg_const(0x7F7F7F7Fu), c80 = reg_const(0x80808080u);
     // @region scan_chunk_mask
@@ -588,7 +677,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             uint32_t e0 = nl[j + 1];
             const uint32_t s3 = (uint32_t)nl[j + 2] + 1u;
             uint32_t e3 = nl[j + 3];
-            reads++;
+            cn.reads++;
             acc.last_end = (unsigned long long)(base + e3 + 1);         // (a thread meets its reads in stream order)
             if (POLICY == POLICY_GENERIC) {
                 const uint8_t* Rp = tile + s0; const uint8_t* Qp = tile + s3;
@@ -596,68 +685,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 continue;
             }
             // @region parse_k2
-            // ---- K2: rstrip, window, Phred test ----
-            if (is_py_space(tile[e0 - 1])) while (e0 > s0 && is_py_space(tile[e0 - 1])) e0--;     // (tile[s0 - 1] is the '\n' before the line)
-            if (is_py_space(tile[e3 - 1])) while (e3 > s3 && is_py_space(tile[e3 - 1])) e3--;
-            int lo, hi, qlo, qhi;
-            if (simple_slice) {
-                const int ls = (int)(e0 - s0), lq = (int)(e3 - s3);
-                lo = min(c_start, ls); hi = min(c_end, ls); qlo = min(c_start, lq); qhi = min(c_end, lq);
-            } else {
-                py_slice((int)(e0 - s0), c_start, c_end, lo, hi);
-                py_slice((int)(e3 - s3), c_start, c_end, qlo, qhi);
-            }
-            const int qn = qhi - qlo;
-            if (c_fmax != 0 && qn > 0) {
-                bool fails;
-                #define F2Q_QCALL(W) fails = qual_fails_w<W>(tile, s3 + qlo, qn, add_ge, add_gt)
-                F2Q_WORDS_SWITCH((qn + 3) >> 2, F2Q_QCALL)
-                #undef F2Q_QCALL
-                if (fails) { qfail++; continue; }
-            }
-            // @region parse_k4
-            // ---- K4: pack, exact lookup, count ----
-            const uint32_t klen = (uint32_t)(hi - lo);
-            uint32_t klo = 0, khi = 0, bad = 0;
-            if (klen) {
-                #define F2Q_PCALL(W) pack_w<W>(tile, s0 + lo, (int)klen, klo, khi, bad)
-                F2Q_WORDS_SWITCH((klen + 3) >> 2, F2Q_PCALL)
-                #undef F2Q_PCALL
-            }
-            const bool generic_len = (T.generic_len_mask >> min(klen, 63u)) & 1ull;
-            uint32_t idx = SLOT_EMPTY;
-            if (!generic_len && bad == 0) {
-                if (T.cslots) { if (klen == T.c_len) idx = compact_lookup(T, klo, khi); }
-                else idx = fast_lookup(T, ((uint64_t)khi << 32) | klo, klen);
-            }
-            if (idx != SLOT_EMPTY) {
-                perfect++;
-                if (P.hist_smem) atomicAdd(hist + idx, 1u);
-                else atomicAdd(O.counts + idx, 1ull);
-                continue;
-            }
-            if (generic_len) {
-                // library keys of this length exist that the packed tables cannot hold
-                GEntry ge; ge.seq_addr = (uint64_t)(buf + base + s0); ge.seq_len = e0 - s0;
-                ge.qual_addr = (uint64_t)(buf + base + s3); ge.qual_len = e3 - s3;
-                const uint32_t slot = atomicAdd(&St->g_count, 1u);
-                if (slot < St->g_cap) P.gqueue[slot] = ge;
-                else g_process_read(G, T, E, O, (const uint8_t*)ge.seq_addr, (int)ge.seq_len, (const uint8_t*)ge.qual_addr, (int)ge.qual_len, gst);
-                continue;
-            }
-            if (c_miss <= 0) { nonal++; continue; }
-            // non-exact key: one slot of this CTA's private queue segment, reserved once per warp
-            const uint64_t key = ((uint64_t)khi << 32) | klo;
-            const uint32_t peers = __activemask();
-            const uint32_t leader = (uint32_t)__ffs((int)peers) - 1u;
-            uint32_t sl = 0;
-            if (lane == leader) sl = atomicAdd(&s_qn, (uint32_t)__popc(peers));
-            sl = __shfl_sync(peers, sl, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-            if (sl < P.seg_cap) { QEntry e; e.key = key; e.bad = bad; e.len = klen; myq[sl] = e; }
-            else {                                                     // segment full: resolve right here
-                const uint32_t r = resolve_seed_thread(T, c_miss, key, bad, klen);
-                if (r != RES_NONE) { atomicAdd(O.counts + r, 1ull); imperfect++; } else nonal++;
-            }
+            fast1_read(F, tile, s0, e0, s3, e3, buf + base + s0, buf + base + s3, G, T, E, O, cn, gst, lane);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&bar_empty[s]);                     // this warp is done with stage s
@@ -671,7 +699,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     if (tid == 0 && P.seg_cap) P.seg_count[blockIdx.x] = min(s_qn, P.seg_cap);
     if (P.hist_smem)
         for (uint32_t i = tid; i < T.n_keys; i += NT) { uint32_t v = hist[i]; if (v) atomicAdd(O.counts + i, (unsigned long long)v); }
-    acc.reads += reads; acc.perfect += perfect; acc.imperfect += imperfect; acc.nonal += nonal; acc.qfail += qfail;
+    acc.reads += cn.reads; acc.perfect += cn.perfect; acc.imperfect += cn.imperfect; acc.nonal += cn.nonal; acc.qfail += cn.qfail;
     acc.perfect += gst[F2Q_STAT_PERFECT]; acc.imperfect += gst[F2Q_STAT_IMPERFECT];
     acc.nonal += gst[F2Q_STAT_NON_ALIGNED]; acc.qfail += gst[F2Q_STAT_QUALITY_FAILED];
     unsigned long long v[5] = {acc.reads, acc.perfect, acc.imperfect, acc.nonal, acc.qfail};

@@ -111,6 +111,10 @@ const char* f2q_last_error(const f2q_ctx* ctx);   /* ctx may be NULL: last creat
  *   "halo_rows"       0 auto | read-ahead rows at the end of every tile (reads reaching further finish in global memory)
  *   "tile_threads"    128 | 256: threads (= rows) per CTA of the fused tile kernel
  *   "time_kernels"    1: bracket the tile / resolver / generic launches with CUDA events (see f2q_kernel_times)
+ *   "spec"            1 (default): Counter mode parses each chunk with the speculative streaming kernel first and
+ *                     falls back to the exact look-back kernel when its line-phase guesses do not verify | 0: exact only
+ *   "spec_warps"      12 | 16: warps per CTA of the streaming kernel (one CTA per SM)
+ *   "spec_range_tiles" 0 auto | tiles (32 rows each) per speculated range
  */
 int f2q_set_option(f2q_ctx* ctx, const char* name, int64_t value);
 
@@ -208,10 +212,15 @@ int f2q_memcpy_h2d(f2q_ctx* ctx, void* dptr, const void* host, uint64_t nbytes);
 /* number of kernel launches issued by this context so far (bench.py reports it as gpu_launches) */
 uint64_t f2q_launch_count(const f2q_ctx* ctx);
 
+/* last finished sample: number of chunks whose speculative parse verified and was committed, and number of chunks the
+ * exact look-back kernel had to parse instead (always 0 / every chunk with option "spec" = 0) */
+int f2q_spec_counts(const f2q_ctx* ctx, uint64_t* committed, uint64_t* fell_back);
+
 /* device time of the last finished sample per kernel class, measured with CUDA events on the context's stream
- * (needs option "time_kernels" = 1): [0] fused tile kernel over the chunk, [1] mismatch resolver, [2] generic queue.
- * launches[k] = number of launches ms[k] sums over. */
-int f2q_kernel_times(f2q_ctx* ctx, double ms[3], uint64_t launches[3]);
+ * (needs option "time_kernels" = 1): [0] fused tile kernel over the chunk (the streaming kernel when "spec" is on),
+ * [1] mismatch resolver, [2] generic queue, [3] speculation verify + commit + the exact kernel behind it (which
+ * returns at once when the speculation held).  launches[k] = number of event brackets ms[k] sums over. */
+int f2q_kernel_times(f2q_ctx* ctx, double ms[4], uint64_t launches[4]);
 
 #ifdef __cplusplus
 }
