@@ -516,7 +516,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
             if (res == 2 && c->cfg.miss > 32) res = 3;
             cudaEvent_t t1 = timing_begin(c);
             if (res == 1) k_resolve_probe<<<c->n_segs, 256, 0, c->stream>>>(c->T, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
-            else if (res == 2) k_resolve_seed<<<c->n_segs, 256, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
+            else if (res == 2) k_resolve_seed<<<dim3(c->n_segs, 8), 256, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
             else k_resolve_scan<<<c->n_segs, SCAN_THREADS, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
             timing_end(c, t1, 1);
             c->launches++;
@@ -723,6 +723,37 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
             cslots[h] = fk[k] | ((uint64_t)fi[k] << (2 * c_len));
         }
     }
+    // two-choice cuckoo form of the compact table: <= 1/4 full, random-walk insertion, new multipliers until it builds
+    std::vector<uint64_t> cuckoo;
+    uint32_t ck_mask = 0, ck_mul[4] = {0, 0, 0, 0};
+    if (compact) {
+        const uint32_t tcap = pow2_at_least(2 * (uint64_t)fk.size());
+        ck_mask = tcap - 1;
+        uint64_t seed = 0x2FA572ull ^ 0x9E3779B97F4A7C15ull;
+        bool built = false;
+        for (int attempt = 0; attempt < 64 && !built; attempt++) {
+            for (int k = 0; k < 4; k++) { seed = sm_fin(seed + 0x9E3779B97F4A7C15ull * (uint64_t)(attempt * 4 + k + 1)); ck_mul[k] = (uint32_t)(seed >> 16) | 1u; }
+            cuckoo.assign(2 * (size_t)tcap, ~0ull);
+            built = true;
+            for (size_t k = 0; k < fk.size() && built; k++) {
+                uint64_t cur = fk[k] | ((uint64_t)fi[k] << (2 * c_len));
+                const uint64_t kmask = (1ull << (2 * c_len)) - 1ull;
+                int kicks = 0;
+                uint32_t from = 0xFFFFFFFFu;                            // slot `cur` was evicted from
+                for (;; kicks++) {
+                    uint32_t h1, h2;
+                    cuckoo_slots(ck_mul, ck_mask, (uint32_t)(cur & kmask), (uint32_t)((cur & kmask) >> 32), h1, h2);
+                    if (cuckoo[h1] == ~0ull) { cuckoo[h1] = cur; break; }
+                    if (cuckoo[h2] == ~0ull) { cuckoo[h2] = cur; break; }
+                    if (kicks >= 500) { built = false; break; }
+                    const uint32_t h = (h1 == from) ? h2 : h1;          // never straight back to where it came from
+                    std::swap(cur, cuckoo[h]);
+                    from = h;
+                }
+            }
+        }
+        if (!built) cuckoo.clear();
+    }
     const uint32_t gcap = pow2_at_least(2 * (uint64_t)n_keys + 2);
     std::vector<uint32_t> gh(gcap, 0);
     for (uint32_t i = 0; i < n_keys; i++) {
@@ -770,6 +801,10 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
     if (compact) {
         if ((rc = upload(c, cslots, &c->T.cslots))) return rc;
         c->T.c_mask = c_mask; c->T.c_len = c_len; c->T.c_keybits = 2 * c_len;
+        if (!cuckoo.empty()) {
+            if ((rc = upload(c, cuckoo, &c->T.cuckoo))) return rc;
+            c->T.ck_mask = ck_mask; for (int k = 0; k < 4; k++) c->T.ck_mul[k] = ck_mul[k];
+        }
     }
     c->T.slot_mask = cap - 1; c->T.n_fast = (uint32_t)fk.size(); c->T.n_keys = n_keys; c->T.ghash_mask = gcap - 1;
     c->T.n_generic = n_generic; c->T.generic_len_mask = gmask;

@@ -57,6 +57,11 @@ struct LibTables {
     uint32_t c_mask;           // capacity - 1
     uint32_t c_len;
     uint32_t c_keybits;        // 2 * c_len
+    // the same slots as a two-choice cuckoo table (built when the compact form exists): table 0 at [0, ck_mask], table 1 behind it;
+    // a lookup is exactly two independent loads, no probe loop, so all lanes of a warp finish together (spec.cuh)
+    const uint64_t* cuckoo;
+    uint32_t ck_mask;          // slots per table - 1
+    uint32_t ck_mul[4];        // odd multipliers of the two multiplicative hashes (chosen by the host until the build succeeds)
     const uint64_t* fast_keys; // n_fast packed keys grouped by length (for the tile-scan resolver)
     const uint32_t* fast_lens;
     const uint32_t* fast_idx;
@@ -209,6 +214,29 @@ __device__ __forceinline__ uint32_t compact_lookup(const LibTables& T, uint32_t 
         if (sl == ~0ull) return SLOT_EMPTY;
         h = (h + 1) & T.c_mask;
     }
+}
+#endif  // __CUDACC__
+
+// the two slots a packed key can live in (host and device must agree)
+__host__ __device__ __forceinline__ void cuckoo_slots(const uint32_t mul[4], uint32_t mask, uint32_t klo, uint32_t khi, uint32_t& h1, uint32_t& h2) {
+    h1 = ((klo * mul[0] + khi * mul[1]) >> 9) & mask;
+    h2 = ((((klo * mul[2]) ^ (khi * mul[3])) >> 9) & mask) + mask + 1u;
+}
+
+#ifdef __CUDACC__
+// two-choice lookup (caller checked len == T.c_len); feature index or SLOT_EMPTY
+__device__ __forceinline__ uint32_t cuckoo_lookup(const LibTables& T, uint32_t klo, uint32_t khi) {
+    uint32_t h1, h2;
+    cuckoo_slots(T.ck_mul, T.ck_mask, klo, khi, h1, h2);
+    const uint2 ra = __ldg(reinterpret_cast<const uint2*>(T.cuckoo) + h1);
+    const uint2 rb = __ldg(reinterpret_cast<const uint2*>(T.cuckoo) + h2);
+    const uint64_t a = ((uint64_t)ra.y << 32) | ra.x, b = ((uint64_t)rb.y << 32) | rb.x;
+    const uint64_t key = ((uint64_t)khi << 32) | klo;
+    const uint64_t keymask = (1ull << T.c_keybits) - 1ull;             // (c_len < 32)
+    uint32_t idx = SLOT_EMPTY;
+    if ((a & keymask) == key && a != ~0ull) idx = (uint32_t)(a >> T.c_keybits);
+    if ((b & keymask) == key && b != ~0ull) idx = (uint32_t)(b >> T.c_keybits);
+    return idx;
 }
 #endif  // __CUDACC__
 

@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(256) k_resolve_seed(LibTables T, int m, const 
     for (uint32_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
         const uint32_t n = min(seg_count[seg], seg_cap);
         const QEntry* __restrict__ q = queue + (size_t)seg * seg_cap;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        for (uint32_t i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {     // gridDim.y CTAs share a segment
             const QEntry e = q[i];
             const uint32_t r = resolve_seed_thread(T, m, e.key, e.bad, e.len);
             if (r != RES_NONE) { atomicAdd(counts + r, 1ull); imperfect++; } else nonal++;

@@ -121,10 +121,12 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     // there is one) is only scanned for the newlines of its first rows; then the next range is taken by ticket.
     // flags: [1:0] 0 end of stream / 1 TMA / 2 loaded by the lanes (touches bytes outside [beg, end)), 4 first tile of
     // a range, 8 last parsed tile of a range, 16 scan-only tile
-    uint32_t ld_range = 0, ld_ti = 1, ld_last = 0, ld_nown = 0, issued = 0;
+    uint32_t ld_range = 0, ld_ti = 1, ld_last = 0, ld_nown = 0, iss_s = 0;
+    uint64_t ld_base = 0;                                              // base of the next tile of the current range
     bool ld_end = false;
     auto issue_next = [&]() {
-        const uint32_t s = issued % NS;
+        const uint32_t s = iss_s;
+        iss_s = (iss_s == (uint32_t)NS - 1u) ? 0u : iss_s + 1u;
         uint64_t base = 0;
         uint32_t flags = 0, rng = 0;
         if (!ld_end) {
@@ -135,13 +137,13 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 if ((uint64_t)tk >= n_ranges) ld_end = true;
                 else {
                     const uint64_t rb = origin0 + (uint64_t)tk * RB, re = ((uint64_t)tk == n_ranges - 1) ? end : rb + RB;
-                    ld_range = tk; ld_ti = 0;
+                    ld_range = tk; ld_ti = 0; ld_base = rb;
                     ld_nown = (uint32_t)((re - rb + OWN - 1) / OWN);
                     ld_last = (rb + (uint64_t)ld_nown * OWN < end) ? ld_nown : ld_nown - 1;
                 }
             }
             if (!ld_end) {
-                base = origin0 + (uint64_t)ld_range * RB + (uint64_t)ld_ti * OWN;
+                base = ld_base; ld_base += OWN;
                 const bool tma = base >= beg && base + load_bytes <= end;
                 flags = (tma ? 1u : 2u) | (ld_ti == 0 ? 4u : 0u) | (ld_ti + 1 == ld_nown ? 8u : 0u) | (ld_ti == ld_nown ? 16u : 0u);
                 rng = ld_range; ld_ti++;
@@ -154,7 +156,6 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 tma_load_1d(wsm + s * stage_bytes, buf + base, load_bytes, &bars[s]);
             }
         }
-        issued++;
         __syncwarp();
     };
 
@@ -187,23 +188,18 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         hcnt = __shfl_sync(0xffffffffu, excl, H);                      // (H <= 16 < 32)
         uint32_t o = excl;
         const uint32_t rowbase = lane * S;
+        const bool fits = incl <= (uint32_t)CAP;                       // (a tile with more newlines than CAP is not parsed at all)
         #pragma unroll
         for (int w = 0; w < MW; w++) {
-            uint32_t m = mw[w];
-            #pragma unroll
-            for (int step = 0; step < 2; step++) {                     // two predicated steps: no divergence for ordinary FASTQ
-                const bool has = m != 0;
-                const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
-                if (has && o < (uint32_t)CAP) nl[o] = (uint16_t)(rowbase + 32u * w + b);
-                o += has ? 1u : 0u;
-                m &= m - 1u;
+            const uint32_t m = fits ? mw[w] : 0u;
+            const uint32_t c = __popc(m), m1 = m & (m - 1u);
+            if (c >= 1) nl[o] = (uint16_t)(rowbase + 32u * w + (uint32_t)__ffs((int)m) - 1u);
+            if (c >= 2) nl[o + 1] = (uint16_t)(rowbase + 32u * w + (uint32_t)__ffs((int)m1) - 1u);
+            if (c > 2) {                                               // three or more newlines within 32 bytes: not ordinary FASTQ
+                uint32_t m2 = m1 & (m1 - 1u), k = o + 2;
+                while (m2) { nl[k++] = (uint16_t)(rowbase + 32u * w + (uint32_t)__ffs((int)m2) - 1u); m2 &= m2 - 1u; }
             }
-            while (m) {
-                const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
-                m &= m - 1u;
-                if (o < (uint32_t)CAP) nl[o] = (uint16_t)(rowbase + 32u * w + b);
-                o++;
-            }
+            o += c;
         }
     };
 
@@ -213,8 +209,8 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     uint32_t prev_s = 0, prev_total = 0, prev_range = 0, prev_flags = 0;
     uint64_t prev_base = 0;
     uint32_t phase = 0, range_cnt = 0, spec_p0 = 0, par_bits = 0;
-    for (uint32_t i = 0;; i++) {
-        const uint32_t s = i % NS, par = i & 1u;
+    for (uint32_t i = 0, s = 0;; i++, s = (s == (uint32_t)NS - 1u) ? 0u : s + 1u) {
+        const uint32_t par = i & 1u;
         const uint4 d = desc[s];
         const uint32_t flags = d.w;
         const bool live = (flags & 3u) != 0;
@@ -262,23 +258,33 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 if (lane == 0) St->spec_fail = 1u;                     // a tile of very short lines: left to the exact kernel
             } else {
                 const uint32_t jf = (4u - (phase & 3u)) & 3u;          // first newline of the tile that ends a header line
-                auto pos = [&](uint32_t j) -> uint32_t { return j < total_own ? (uint32_t)nlA[j] : (uint32_t)nlB[j - total_own] + (uint32_t)OWN; };
-                for (uint32_t j = jf + 4u * lane; j < total_own; j += 128u) {
-                    const uint32_t h0 = nlA[j];
-                    if (j + 3 >= total_all) {
+                for (uint32_t j0 = jf; j0 < total_own; j0 += 128u) {   // (uniform: the warp stays converged through a pass)
+                    const uint32_t j = j0 + 4u * lane;
+                    bool valid = j < total_own;
+                    if (valid && j + 3 >= total_all) {
                         // the read's last newline is not in the loaded rows (a long record, or the end of the chunk)
-                        slow_record(buf, prev_base + h0, end, eof, G, T, E, O, acc, gst);
-                        continue;
+                        slow_record(buf, prev_base + nlA[j], end, eof, G, T, E, O, acc, gst);
+                        valid = false;
                     }
-                    const uint32_t s0 = h0 + 1u, e0 = pos(j + 1), s3 = pos(j + 2) + 1u, e3 = pos(j + 3);
-                    cn.reads++;
-                    acc.last_end = (unsigned long long)(prev_base + e3 + 1);
+                    uint32_t s0 = 0, e0 = 0, s3 = 0, e3 = 0;
+                    if (valid) {
+                        const uint32_t j1 = j + 1, j2 = j + 2, j3 = j + 3;
+                        s0 = (uint32_t)nlA[j] + 1u;
+                        e0 = j1 < total_own ? (uint32_t)nlA[j1] : (uint32_t)nlB[j1 - total_own] + (uint32_t)OWN;
+                        s3 = (j2 < total_own ? (uint32_t)nlA[j2] : (uint32_t)nlB[j2 - total_own] + (uint32_t)OWN) + 1u;
+                        e3 = j3 < total_own ? (uint32_t)nlA[j3] : (uint32_t)nlB[j3 - total_own] + (uint32_t)OWN;
+                        cn.reads++;
+                        acc.last_end = (unsigned long long)(prev_base + e3 + 1);
+                    }
                     if (POLICY == POLICY_GENERIC) {
-                        const uint8_t* Rp = ptile + s0; const uint8_t* Qp = ptile + s3;
-                        g_process_read(G, T, E, O, Rp, g_rstrip(Rp, (int)(e0 - s0)), Qp, g_rstrip(Qp, (int)(e3 - s3)), gst);
-                        continue;
+                        if (valid) {
+                            const uint8_t* Rp = ptile + s0; const uint8_t* Qp = ptile + s3;
+                            g_process_read(G, T, E, O, Rp, g_rstrip(Rp, (int)(e0 - s0)), Qp, g_rstrip(Qp, (int)(e3 - s3)), gst);
+                        }
+                    } else {
+                        __syncwarp();
+                        fast1_read_warp(F, valid, ptile, s0, e0, s3, e3, buf + prev_base + s0, buf + prev_base + s3, G, T, E, O, cn, gst, lane);
                     }
-                    fast1_read(F, ptile, s0, e0, s3, e3, buf + prev_base + s0, buf + prev_base + s3, G, T, E, O, cn, gst, lane);
                 }
             }
             __syncwarp();

@@ -339,6 +339,85 @@ __device__ __forceinline__ void fast1_read(const Fast1Ctx& F, const uint8_t* til
     }
 }
 
+// @region fast1_read_warp
+// The same read, written for a CONVERGED warp (spec.cuh): every lane calls it, `valid` lanes hold a read.  Nothing returns
+// early: the quality test, the pack and the two-load cuckoo lookup run for all lanes at once, the outcomes are sorted out at
+// the end, and the queue slots of the warp's non-exact keys are reserved with one ballot.  Results are those of fast1_read.
+__device__ __forceinline__ void fast1_read_warp(const Fast1Ctx& F, bool valid, const uint8_t* tile, uint32_t s0, uint32_t e0, uint32_t s3,
+                                                uint32_t e3, const uint8_t* gseq, const uint8_t* gqual, const GenericCfg& G, const LibTables& T,
+                                                const EcTable& E, const Outputs& O, Fast1Counts& n, unsigned long long* gst, uint32_t lane) {
+    if (!valid) { s0 = e0 = s3 = e3 = 0; }
+    else {
+        if (is_py_space(tile[e0 - 1])) while (e0 > s0 && is_py_space(tile[e0 - 1])) e0--;
+        if (is_py_space(tile[e3 - 1])) while (e3 > s3 && is_py_space(tile[e3 - 1])) e3--;
+    }
+    int lo, hi, qlo, qhi;
+    if (F.simple_slice) {
+        const int ls = (int)(e0 - s0), lq = (int)(e3 - s3);
+        lo = min(F.c_start, ls); hi = min(F.c_end, ls); qlo = min(F.c_start, lq); qhi = min(F.c_end, lq);
+    } else {
+        py_slice((int)(e0 - s0), F.c_start, F.c_end, lo, hi);
+        py_slice((int)(e3 - s3), F.c_start, F.c_end, qlo, qhi);
+    }
+    const int qn = qhi - qlo;
+    bool fails = false;
+    if (F.c_fmax != 0 && qn > 0) {
+        #define F2Q_QCALL(W) fails = qual_fails_w<W>(tile, s3 + qlo, qn, F.add_ge, F.add_gt)
+        F2Q_WORDS_SWITCH((qn + 3) >> 2, F2Q_QCALL)
+        #undef F2Q_QCALL
+    }
+    const uint32_t klen = (uint32_t)(hi - lo);
+    uint32_t klo = 0, khi = 0, bad = 0;
+    if (klen) {
+        #define F2Q_PCALL(W) pack_w<W>(tile, s0 + lo, (int)klen, klo, khi, bad)
+        F2Q_WORDS_SWITCH((klen + 3) >> 2, F2Q_PCALL)
+        #undef F2Q_PCALL
+    }
+    const bool live = valid && !fails;
+    const bool generic_len = live && ((T.generic_len_mask >> min(klen, 63u)) & 1ull);
+    const bool can = live && !generic_len && bad == 0;
+    uint32_t idx = SLOT_EMPTY;
+    if (T.cuckoo) {                                            // (uniform) every lane loads; lanes without a key read some slot and ignore it
+        const uint32_t r = cuckoo_lookup(T, klo, khi);
+        if (can && klen == T.c_len) idx = r;
+    } else if (can) {
+        if (T.cslots) { if (klen == T.c_len) idx = compact_lookup(T, klo, khi); }
+        else idx = fast_lookup(T, ((uint64_t)khi << 32) | klo, klen);
+    }
+    const bool hit = idx != SLOT_EMPTY;
+    n.qfail += (valid && fails) ? 1u : 0u;
+    n.perfect += hit ? 1u : 0u;
+    if (hit) {
+        if (F.hist) atomicAdd(F.hist + idx, 1u);
+        else atomicAdd(O.counts + idx, 1ull);
+    }
+    if (__any_sync(0xffffffffu, generic_len)) {
+        if (generic_len) {
+            GEntry ge; ge.seq_addr = (uint64_t)gseq; ge.seq_len = e0 - s0;
+            ge.qual_addr = (uint64_t)gqual; ge.qual_len = e3 - s3;
+            const uint32_t slot = atomicAdd(&F.St->g_count, 1u);
+            if (slot < F.St->g_cap) F.gqueue[slot] = ge;
+            else g_process_read(G, T, E, O, (const uint8_t*)ge.seq_addr, (int)ge.seq_len, (const uint8_t*)ge.qual_addr, (int)ge.qual_len, gst);
+        }
+    }
+    const bool miss = live && !hit && !generic_len;
+    if (F.c_miss <= 0) { n.nonal += miss ? 1u : 0u; return; }
+    const uint32_t mq = __ballot_sync(0xffffffffu, miss);
+    if (mq) {
+        uint32_t sl = 0;
+        if (lane == 0) sl = atomicAdd(F.s_qn, (uint32_t)__popc(mq));
+        sl = __shfl_sync(0xffffffffu, sl, 0) + (uint32_t)__popc(mq & ((1u << lane) - 1u));
+        if (miss) {
+            const uint64_t key = ((uint64_t)khi << 32) | klo;
+            if (sl < F.seg_cap) { QEntry e; e.key = key; e.bad = bad; e.len = klen; F.myq[sl] = e; }
+            else {                                                 // segment full: resolve right here
+                const uint32_t r = resolve_seed_thread(T, F.c_miss, key, bad, klen);
+                if (r != RES_NONE) { atomicAdd(O.counts + r, 1ull); n.imperfect++; } else n.nonal++;
+            }
+        }
+    }
+}
+
 // @region lookback
 __device__ __forceinline__ uint4 ld_volatile_v4(const void* p) {
     uint4 r;
