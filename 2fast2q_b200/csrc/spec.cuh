@@ -50,8 +50,9 @@ struct SpecGeom {
     static constexpr int OWN = 32 * S;
     static constexpr int MW = (CH + 1) / 2;                            // 32-bit newline mask words per row
     static constexpr int NL_LIST = SPEC_CAP + 8;                       // u16 entries of one position list
+    static constexpr int NL_HALO = 6 * (int)16 + 8;                    // ... of the list of a range's last read-ahead rows (SPEC_MAX_HALO rows)
     __host__ __device__ static constexpr uint32_t stage_bytes(uint32_t H) { return (((32u + H) * S + 16u + 127u) / 128u) * 128u; }
-    __host__ __device__ static constexpr uint32_t warp_bytes(uint32_t H) { return ((SPEC_STAGES * stage_bytes(H) + 2u * NL_LIST * 2u + 127u) / 128u) * 128u; }
+    __host__ __device__ static constexpr uint32_t warp_bytes(uint32_t H) { return ((SPEC_STAGES * stage_bytes(H) + (2u * NL_LIST + NL_HALO) * 2u + 127u) / 128u) * 128u; }
 };
 
 template <int CH, int W>
@@ -117,11 +118,10 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     uint4* const desc = s_desc[warp];
 
     // @region spec_loader
-    // the warp's tile stream: tiles 0 .. nown-1 of a range are parsed, tile nown (the first tile of the next range, when
-    // there is one) is only scanned for the newlines of its first rows; then the next range is taken by ticket.
+    // the warp's tile stream: the tiles of a range in order, then the next range taken by ticket.
     // flags: [1:0] 0 end of stream / 1 TMA / 2 loaded by the lanes (touches bytes outside [beg, end)), 4 first tile of
-    // a range, 8 last parsed tile of a range, 16 scan-only tile
-    uint32_t ld_range = 0, ld_ti = 1, ld_last = 0, ld_nown = 0, iss_s = 0;
+    // a range, 8 last tile of a range
+    uint32_t ld_range = 0, ld_ti = 0, ld_nown = 0, iss_s = 0;
     uint64_t ld_base = 0;                                              // base of the next tile of the current range
     bool ld_end = false;
     auto issue_next = [&]() {
@@ -130,7 +130,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         uint64_t base = 0;
         uint32_t flags = 0, rng = 0;
         if (!ld_end) {
-            if (ld_ti > ld_last) {
+            if (ld_ti >= ld_nown) {
                 uint32_t tk = 0xFFFFFFFFu;
                 if (lane == 0) { tk = atomicAdd(P.ticket, 1u); if (ld_volatile_u32(&St->spec_fail)) tk = 0xFFFFFFFFu; }
                 tk = __shfl_sync(0xffffffffu, tk, 0);
@@ -139,13 +139,12 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                     const uint64_t rb = origin0 + (uint64_t)tk * RB, re = ((uint64_t)tk == n_ranges - 1) ? end : rb + RB;
                     ld_range = tk; ld_ti = 0; ld_base = rb;
                     ld_nown = (uint32_t)((re - rb + OWN - 1) / OWN);
-                    ld_last = (rb + (uint64_t)ld_nown * OWN < end) ? ld_nown : ld_nown - 1;
                 }
             }
             if (!ld_end) {
                 base = ld_base; ld_base += OWN;
                 const bool tma = base >= beg && base + load_bytes <= end;
-                flags = (tma ? 1u : 2u) | (ld_ti == 0 ? 4u : 0u) | (ld_ti + 1 == ld_nown ? 8u : 0u) | (ld_ti == ld_nown ? 16u : 0u);
+                flags = (tma ? 1u : 2u) | (ld_ti == 0 ? 4u : 0u) | (ld_ti + 1 == ld_nown ? 8u : 0u);
                 rng = ld_range; ld_ti++;
             }
         }
@@ -170,13 +169,19 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     };
 
     // @region spec_scan
-    // newline positions of the tile's 32 own rows (lane = row) -> nl[0 .. total); hcnt = newlines of its first H rows
-    auto scan = [&](const uint8_t* tile, uint16_t* nl, uint32_t& total, uint32_t& hcnt) {
+    // newline positions of 32 rows of the tile (lane scans row row0 + lane when act) -> nl[0 .. total), at most cap of them;
+    // hcnt = newlines of the first H of these rows.  row0 = 0: the tile's own rows; row0 = 32: its read-ahead rows
+    auto scan = [&](const uint8_t* tile, uint32_t row0, bool act, uint16_t* nl, uint32_t cap, uint32_t& total, uint32_t& hcnt) {
         uint32_t mw[MW];
         #pragma unroll
         for (int w = 0; w < MW; w++) mw[w] = 0;
+        const uint32_t rowbase = (row0 + (act ? lane : 0u)) * S;
         #pragma unroll
-        for (int j = 0; j < CH; j++) mw[j >> 1] |= chunk_mask(tile + lane * S + j * 16) << (16 * (j & 1));
+        for (int j = 0; j < CH; j++) mw[j >> 1] |= chunk_mask(tile + rowbase + j * 16) << (16 * (j & 1));
+        if (!act) {
+            #pragma unroll
+            for (int w = 0; w < MW; w++) mw[w] = 0;
+        }
         uint32_t cnt = 0;
         #pragma unroll
         for (int w = 0; w < MW; w++) cnt += __popc(mw[w]);
@@ -187,8 +192,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         total = __shfl_sync(0xffffffffu, incl, 31);
         hcnt = __shfl_sync(0xffffffffu, excl, H);                      // (H <= 16 < 32)
         uint32_t o = excl;
-        const uint32_t rowbase = lane * S;
-        const bool fits = incl <= (uint32_t)CAP;                       // (a tile with more newlines than CAP is not parsed at all)
+        const bool fits = incl <= cap;                                 // (a tile with more newlines than that is not parsed at all)
         #pragma unroll
         for (int w = 0; w < MW; w++) {
             const uint32_t m = fits ? mw[w] : 0u;
@@ -205,10 +209,12 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
 
     // @region spec_loop
     for (int k = 0; k < NS; k++) issue_next();
-    bool have_prev = false;
+    bool have_prev = false, have_pend = false;
     uint32_t prev_s = 0, prev_total = 0, prev_range = 0, prev_flags = 0;
     uint64_t prev_base = 0;
     uint32_t phase = 0, range_cnt = 0, spec_p0 = 0, par_bits = 0;
+    Fast1Pending pend;
+    uint16_t* const nl_halo = nlist + 2 * G_::NL_LIST;
     for (uint32_t i = 0, s = 0;; i++, s = (s == (uint32_t)NS - 1u) ? 0u : s + 1u) {
         const uint32_t par = i & 1u;
         const uint4 d = desc[s];
@@ -243,17 +249,27 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 }
                 __syncwarp();
             }
-            scan(tile, nl, total, hcnt);
+            scan(tile, 0u, true, nl, (uint32_t)CAP, total, hcnt);
             __syncwarp();
         }
+        // the lookups issued for the tile before the previous one have long arrived: count them
+        if (have_pend) { fast1_warp_commit(F, pend, T, O, cn, lane); have_pend = false; }
         if (have_prev) {
             // @region spec_parse
             // ---- reads of the previous tile: lane q takes the q-th read whose header line ends in its own rows ----
-            const bool cont = live && d.z == prev_range && !(flags & 4u);      // this tile directly follows it
-            const uint32_t total_own = prev_total, hc = cont ? hcnt : 0u, total_all = total_own + hc;
             const uint8_t* ptile = wsm + prev_s * stage_bytes;
             const uint16_t* nlA = nlist + (par ^ 1u) * G_::NL_LIST;
             const uint16_t* nlB = nl;
+            uint32_t hc = hcnt;
+            if (!(live && d.z == prev_range && !(flags & 4u))) {
+                // the last tile of a range: the newlines of its read-ahead rows are found in its own stage
+                uint32_t dummy;
+                scan(ptile, 32u, lane < H, nl_halo, (uint32_t)G_::NL_HALO - 8u, hc, dummy);
+                __syncwarp();
+                nlB = nl_halo;
+                if (hc > (uint32_t)G_::NL_HALO - 8u) hc = (uint32_t)CAP + 1u;       // too many to list
+            }
+            const uint32_t total_own = prev_total, total_all = total_own + hc;
             if (total_own > (uint32_t)CAP || hc > (uint32_t)CAP) {
                 if (lane == 0) St->spec_fail = 1u;                     // a tile of very short lines: left to the exact kernel
             } else {
@@ -270,9 +286,9 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                     if (valid) {
                         const uint32_t j1 = j + 1, j2 = j + 2, j3 = j + 3;
                         s0 = (uint32_t)nlA[j] + 1u;
-                        e0 = j1 < total_own ? (uint32_t)nlA[j1] : (uint32_t)nlB[j1 - total_own] + (uint32_t)OWN;
-                        s3 = (j2 < total_own ? (uint32_t)nlA[j2] : (uint32_t)nlB[j2 - total_own] + (uint32_t)OWN) + 1u;
-                        e3 = j3 < total_own ? (uint32_t)nlA[j3] : (uint32_t)nlB[j3 - total_own] + (uint32_t)OWN;
+                        e0 = j1 < total_own ? (uint32_t)nlA[j1] : (uint32_t)nlB[j1 - total_own] + (nlB == nl_halo ? 0u : (uint32_t)OWN);
+                        s3 = (j2 < total_own ? (uint32_t)nlA[j2] : (uint32_t)nlB[j2 - total_own] + (nlB == nl_halo ? 0u : (uint32_t)OWN)) + 1u;
+                        e3 = j3 < total_own ? (uint32_t)nlA[j3] : (uint32_t)nlB[j3 - total_own] + (nlB == nl_halo ? 0u : (uint32_t)OWN);
                         cn.reads++;
                         acc.last_end = (unsigned long long)(prev_base + e3 + 1);
                     }
@@ -283,7 +299,9 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                         }
                     } else {
                         __syncwarp();
-                        fast1_read_warp(F, valid, ptile, s0, e0, s3, e3, buf + prev_base + s0, buf + prev_base + s3, G, T, E, O, cn, gst, lane);
+                        if (have_pend) fast1_warp_commit(F, pend, T, O, cn, lane);     // (a second pass over the same tile: rare)
+                        pend = fast1_warp_issue(F, valid, ptile, s0, e0, s3, e3, buf + prev_base + s0, buf + prev_base + s3, G, T, E, O, cn, gst);
+                        have_pend = true;
                     }
                 }
             }
@@ -317,9 +335,9 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 else if (lane == 0) St->spec_fail = 1u;
             }
         }
-        if (flags & 16u) issue_next();                                 // scan-only tile: its stage is free again
-        else { have_prev = true; prev_s = s; prev_total = total; prev_range = d.z; prev_flags = flags; prev_base = base; }
+        have_prev = true; prev_s = s; prev_total = total; prev_range = d.z; prev_flags = flags; prev_base = base;
     }
+    if (have_pend) fast1_warp_commit(F, pend, T, O, cn, lane);
 
     // @region spec_epilogue
     __syncthreads();

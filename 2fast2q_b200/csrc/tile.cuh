@@ -340,12 +340,21 @@ __device__ __forceinline__ void fast1_read(const Fast1Ctx& F, const uint8_t* til
 }
 
 // @region fast1_read_warp
-// The same read, written for a CONVERGED warp (spec.cuh): every lane calls it, `valid` lanes hold a read.  Nothing returns
-// early: the quality test, the pack and the two-load cuckoo lookup run for all lanes at once, the outcomes are sorted out at
-// the end, and the queue slots of the warp's non-exact keys are reserved with one ballot.  Results are those of fast1_read.
-__device__ __forceinline__ void fast1_read_warp(const Fast1Ctx& F, bool valid, const uint8_t* tile, uint32_t s0, uint32_t e0, uint32_t s3,
-                                                uint32_t e3, const uint8_t* gseq, const uint8_t* gqual, const GenericCfg& G, const LibTables& T,
-                                                const EcTable& E, const Outputs& O, Fast1Counts& n, unsigned long long* gst, uint32_t lane) {
+// The same read, written for a CONVERGED warp (spec.cuh) and split in two so that the table lookup's L2 latency hides behind
+// the scan of the next tile.  Every lane calls both halves, `valid` lanes hold a read; nothing returns early.
+//   fast1_warp_issue   rstrip, window, Phred test, pack, reads for the generic queue; issues the two cuckoo loads
+//   fast1_warp_commit  compares the loaded slots, counts, and reserves the queue slots of the warp's non-exact keys with one ballot
+// Together they compute exactly what fast1_read computes.
+struct Fast1Pending {
+    uint2 ra, rb;              // the two candidate slots (cuckoo), or ra.x = feature index found by the probing tables
+    uint32_t klo, khi, bad;
+    uint32_t meta;             // [5:0] key length, bit 8: may be an exact hit, bit 9: counts as non-exact when it is not, bit 10: ra.x is the index
+};
+
+__device__ __forceinline__ Fast1Pending fast1_warp_issue(const Fast1Ctx& F, bool valid, const uint8_t* tile, uint32_t s0, uint32_t e0, uint32_t s3,
+                                                         uint32_t e3, const uint8_t* gseq, const uint8_t* gqual, const GenericCfg& G,
+                                                         const LibTables& T, const EcTable& E, const Outputs& O, Fast1Counts& n,
+                                                         unsigned long long* gst) {
     if (!valid) { s0 = e0 = s3 = e3 = 0; }
     else {
         if (is_py_space(tile[e0 - 1])) while (e0 > s0 && is_py_space(tile[e0 - 1])) e0--;
@@ -366,33 +375,19 @@ __device__ __forceinline__ void fast1_read_warp(const Fast1Ctx& F, bool valid, c
         F2Q_WORDS_SWITCH((qn + 3) >> 2, F2Q_QCALL)
         #undef F2Q_QCALL
     }
+    Fast1Pending p;
     const uint32_t klen = (uint32_t)(hi - lo);
-    uint32_t klo = 0, khi = 0, bad = 0;
+    p.klo = 0; p.khi = 0; p.bad = 0;
     if (klen) {
-        #define F2Q_PCALL(W) pack_w<W>(tile, s0 + lo, (int)klen, klo, khi, bad)
+        #define F2Q_PCALL(W) pack_w<W>(tile, s0 + lo, (int)klen, p.klo, p.khi, p.bad)
         F2Q_WORDS_SWITCH((klen + 3) >> 2, F2Q_PCALL)
         #undef F2Q_PCALL
     }
+    n.qfail += (valid && fails) ? 1u : 0u;
     const bool live = valid && !fails;
     const bool generic_len = live && ((T.generic_len_mask >> min(klen, 63u)) & 1ull);
-    const bool can = live && !generic_len && bad == 0;
-    uint32_t idx = SLOT_EMPTY;
-    if (T.cuckoo) {                                            // (uniform) every lane loads; lanes without a key read some slot and ignore it
-        const uint32_t r = cuckoo_lookup(T, klo, khi);
-        if (can && klen == T.c_len) idx = r;
-    } else if (can) {
-        if (T.cslots) { if (klen == T.c_len) idx = compact_lookup(T, klo, khi); }
-        else idx = fast_lookup(T, ((uint64_t)khi << 32) | klo, klen);
-    }
-    const bool hit = idx != SLOT_EMPTY;
-    n.qfail += (valid && fails) ? 1u : 0u;
-    n.perfect += hit ? 1u : 0u;
-    if (hit) {
-        if (F.hist) atomicAdd(F.hist + idx, 1u);
-        else atomicAdd(O.counts + idx, 1ull);
-    }
     if (__any_sync(0xffffffffu, generic_len)) {
-        if (generic_len) {
+        if (generic_len) {                                     // library keys of this length exist that the packed tables cannot hold
             GEntry ge; ge.seq_addr = (uint64_t)gseq; ge.seq_len = e0 - s0;
             ge.qual_addr = (uint64_t)gqual; ge.qual_len = e3 - s3;
             const uint32_t slot = atomicAdd(&F.St->g_count, 1u);
@@ -400,7 +395,43 @@ __device__ __forceinline__ void fast1_read_warp(const Fast1Ctx& F, bool valid, c
             else g_process_read(G, T, E, O, (const uint8_t*)ge.seq_addr, (int)ge.seq_len, (const uint8_t*)ge.qual_addr, (int)ge.qual_len, gst);
         }
     }
-    const bool miss = live && !hit && !generic_len;
+    bool can = live && !generic_len && p.bad == 0;
+    p.ra = make_uint2(SLOT_EMPTY, 0); p.rb = make_uint2(0, 0);
+    uint32_t direct = 0;
+    if (T.cuckoo) {                                            // (uniform) every lane loads; lanes without a key read some slot and ignore it
+        can = can && klen == T.c_len;
+        uint32_t h1, h2;
+        cuckoo_slots(T.ck_mul, T.ck_mask, p.klo, p.khi, h1, h2);
+        p.ra = __ldg(reinterpret_cast<const uint2*>(T.cuckoo) + h1);
+        p.rb = __ldg(reinterpret_cast<const uint2*>(T.cuckoo) + h2);
+    } else {
+        direct = 1u << 10;
+        if (can) {
+            if (T.cslots) { if (klen == T.c_len) p.ra.x = compact_lookup(T, p.klo, p.khi); }
+            else p.ra.x = fast_lookup(T, ((uint64_t)p.khi << 32) | p.klo, klen);
+        }
+    }
+    p.meta = klen | (can ? 1u << 8 : 0u) | ((live && !generic_len) ? 1u << 9 : 0u) | direct;
+    return p;
+}
+
+__device__ __forceinline__ void fast1_warp_commit(const Fast1Ctx& F, const Fast1Pending& p, const LibTables& T, const Outputs& O, Fast1Counts& n,
+                                                  uint32_t lane) {
+    uint32_t idx = SLOT_EMPTY;
+    if (p.meta & (1u << 10)) idx = p.ra.x;
+    else {
+        const uint64_t a = ((uint64_t)p.ra.y << 32) | p.ra.x, b = ((uint64_t)p.rb.y << 32) | p.rb.x;
+        const uint64_t key = ((uint64_t)p.khi << 32) | p.klo, keymask = (1ull << T.c_keybits) - 1ull;
+        if ((a & keymask) == key && a != ~0ull) idx = (uint32_t)(a >> T.c_keybits);
+        if ((b & keymask) == key && b != ~0ull) idx = (uint32_t)(b >> T.c_keybits);
+    }
+    const bool hit = (p.meta & (1u << 8)) && idx != SLOT_EMPTY;
+    n.perfect += hit ? 1u : 0u;
+    if (hit) {
+        if (F.hist) atomicAdd(F.hist + idx, 1u);
+        else atomicAdd(O.counts + idx, 1ull);
+    }
+    const bool miss = (p.meta & (1u << 9)) && !hit;
     if (F.c_miss <= 0) { n.nonal += miss ? 1u : 0u; return; }
     const uint32_t mq = __ballot_sync(0xffffffffu, miss);
     if (mq) {
@@ -408,10 +439,11 @@ __device__ __forceinline__ void fast1_read_warp(const Fast1Ctx& F, bool valid, c
         if (lane == 0) sl = atomicAdd(F.s_qn, (uint32_t)__popc(mq));
         sl = __shfl_sync(0xffffffffu, sl, 0) + (uint32_t)__popc(mq & ((1u << lane) - 1u));
         if (miss) {
-            const uint64_t key = ((uint64_t)khi << 32) | klo;
-            if (sl < F.seg_cap) { QEntry e; e.key = key; e.bad = bad; e.len = klen; F.myq[sl] = e; }
+            const uint64_t key = ((uint64_t)p.khi << 32) | p.klo;
+            const uint32_t klen = p.meta & 63u;
+            if (sl < F.seg_cap) { QEntry e; e.key = key; e.bad = p.bad; e.len = klen; F.myq[sl] = e; }
             else {                                                 // segment full: resolve right here
-                const uint32_t r = resolve_seed_thread(T, F.c_miss, key, bad, klen);
+                const uint32_t r = resolve_seed_thread(T, F.c_miss, key, p.bad, klen);
                 if (r != RES_NONE) { atomicAdd(O.counts + r, 1ull); n.imperfect++; } else n.nonal++;
             }
         }

@@ -9,7 +9,7 @@ One "step" = one pass of the hot path over the whole synthetic sample (R reads p
   value   M reads/s with the sample resident in HBM (f2q_submit_device); device-timed, max over ranks
   e2e     the same through the C-ABI call a user makes with HOST buffers (f2q_submit from pinned memory):
           H2D of every byte + D2H of the counts inside the timed region
-  roofline achieved HBM GB/s of the fused tile kernel = algorithmic bytes (118 B/read) / its CUDA-event time
+  roofline achieved HBM GB/s of the fused streaming kernel k_spec = algorithmic bytes (118 B/read) / its CUDA-event time
   cpu_baseline  the oracle port (oracle/f2q_oracle.c, the reference's algorithm in C) on a bounded sample, 1 core
 --impl reference times that port on all host threads (file-parallel, like the reference's multiprocessing mode).
 Data are synthetic (K0 generator, bit-identical to oracle/synth.py); weak scaling: every rank owns its own R reads.
@@ -96,7 +96,7 @@ def measured_peak():
 
 
 def committed_traffic():
-    """dram bytes per launch of the tile kernel from the committed ncu --set full capture, if one matches this workload"""
+    """dram bytes per read of the dominant kernel from the committed ncu --set full capture (profiles/), scaled to this launch"""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "tile_kernel_traffic.json")))
         return t
@@ -226,6 +226,7 @@ def run_gpu(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_res = float(t.item())
     ktimes = eng.kernel_times()
+    spec_counts = eng.spec_counts()
 
     # ---- end-to-end leg: host (pinned) buffers through f2q_submit ----
     e2e = None
@@ -280,11 +281,14 @@ def run_gpu(args, rank, local_rank, world):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
-                         "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-                         "kernel": "k_tile<POLICY_FAST1>", "kernel_ms_per_launch": tile_avg, "peak_source": peak_src,
+                         "traffic": traffic["dram_bytes_per_read"] * n_reads if traffic else None,
+                         "kernel": "k_spec<POLICY_FAST1, CH=7, W=16> (speculative streaming kernel, csrc/spec.cuh)",
+                         "kernel_ms_per_launch": tile_avg, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n_reads * REC,
-                         "other_kernels_ms_per_step": {"resolve": ktimes["resolve"][0], "generic": ktimes["generic"][0]},
+                         "other_kernels_ms_per_step": {"resolve": ktimes["resolve"][0], "generic": ktimes["generic"][0],
+                                                       "verify_commit_fallback": ktimes["aux"][0]},
                          "traffic_note": traffic.get("note") if traffic else "no committed ncu --set full capture yet"},
+            "speculation": {"chunks_committed": spec_counts[0], "chunks_parsed_by_exact_kernel": spec_counts[1]},
             "stats": stats,
         }
         if not args.no_cpu:
@@ -315,7 +319,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="f2q")
     ap.add_argument("--reads", type=int, default=100_000_000, help="reads per GPU (configs[1] = 100 M)")
-    ap.add_argument("--cpu-reads", type=int, default=2_000_000)
+    ap.add_argument("--cpu-reads", type=int, default=6_000_000)
     ap.add_argument("--ref-reads-per-thread", type=int, default=400_000)
     ap.add_argument("--tile-threads", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")

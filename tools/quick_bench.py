@@ -22,4 +22,4 @@ with lib.Engine(cfg, 0, None, time_kernels=1, **{k: int(v) for k, v in opts.item
         e.begin(); e.submit_device(d, reads * rec, True); c, s = e.end()
         kt = e.kernel_times()
     print("stats", s)
-    print("tile ms %.3f  resolve ms %.3f  -> %.1f GB/s, %.2f G reads/s (tile only)" % (kt["tile"][0], kt["resolve"][0], reads * rec / kt["tile"][0] / 1e6, reads / kt["tile"][0] / 1e6))
+    print("tile ms %.3f  resolve ms %.3f  aux ms %.3f  spec %s -> %.1f GB/s, %.2f G reads/s (tile only)" % (kt["tile"][0], kt["resolve"][0], kt["aux"][0], e.spec_counts(), reads * rec / kt["tile"][0] / 1e6, reads / kt["tile"][0] / 1e6))
