@@ -22,6 +22,8 @@
 // stage of tile i.  The range ends with one scan-only tile (the first tile of the next range).
 #pragma once
 
+#include <type_traits>
+
 #include "tile.cuh"
 
 namespace f2q {
@@ -107,6 +109,13 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     Acc acc{0, 0, 0, 0, 0, 0};
     unsigned long long gst[F2Q_N_STATS] = {0, 0, 0, 0, 0};
     Fast1Counts cn{0, 0, 0, 0, 0};
+    // ordinary-read code (fast1_ord_issue): fixed window inside the line, one-length library in the cuckoo table
+    uint32_t ord_words = 0;
+    {
+        const int c_len = F.c_end - F.c_start;
+        if (F.simple_slice && c_len >= 1 && c_len <= 31 && T.cuckoo && T.c_len == (uint32_t)c_len && !((T.generic_len_mask >> c_len) & 1ull))
+            ord_words = (uint32_t)(c_len + 3) >> 2;
+    }
 
     uint64_t origin0;
     const uint64_t RB = P.range_bytes;
@@ -274,6 +283,9 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 if (lane == 0) St->spec_fail = 1u;                     // a tile of very short lines: left to the exact kernel
             } else {
                 const uint32_t jf = (4u - (phase & 3u)) & 3u;          // first newline of the tile that ends a header line
+                const uint32_t halo_off = (nlB == nl_halo) ? 0u : (uint32_t)OWN;
+                auto passes = [&](auto Wc) {
+                constexpr int WW = decltype(Wc)::value;                // words of the window (ordinary-read code), 0 = general code
                 for (uint32_t j0 = jf; j0 < total_own; j0 += 128u) {   // (uniform: the warp stays converged through a pass)
                     const uint32_t j = j0 + 4u * lane;
                     bool valid = j < total_own;
@@ -286,9 +298,9 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                     if (valid) {
                         const uint32_t j1 = j + 1, j2 = j + 2, j3 = j + 3;
                         s0 = (uint32_t)nlA[j] + 1u;
-                        e0 = j1 < total_own ? (uint32_t)nlA[j1] : (uint32_t)nlB[j1 - total_own] + (nlB == nl_halo ? 0u : (uint32_t)OWN);
-                        s3 = (j2 < total_own ? (uint32_t)nlA[j2] : (uint32_t)nlB[j2 - total_own] + (nlB == nl_halo ? 0u : (uint32_t)OWN)) + 1u;
-                        e3 = j3 < total_own ? (uint32_t)nlA[j3] : (uint32_t)nlB[j3 - total_own] + (nlB == nl_halo ? 0u : (uint32_t)OWN);
+                        e0 = j1 < total_own ? (uint32_t)nlA[j1] : (uint32_t)nlB[j1 - total_own] + halo_off;
+                        s3 = (j2 < total_own ? (uint32_t)nlA[j2] : (uint32_t)nlB[j2 - total_own] + halo_off) + 1u;
+                        e3 = j3 < total_own ? (uint32_t)nlA[j3] : (uint32_t)nlB[j3 - total_own] + halo_off;
                         cn.reads++;
                         acc.last_end = (unsigned long long)(prev_base + e3 + 1);
                     }
@@ -300,9 +312,18 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                     } else {
                         __syncwarp();
                         if (have_pend) fast1_warp_commit(F, pend, T, O, cn, lane);     // (a second pass over the same tile: rare)
-                        pend = fast1_warp_issue(F, valid, ptile, s0, e0, s3, e3, buf + prev_base + s0, buf + prev_base + s3, G, T, E, O, cn, gst);
+                        if constexpr (WW == 0) pend = fast1_warp_issue(F, valid, ptile, s0, e0, s3, e3, buf + prev_base + s0, buf + prev_base + s3, G, T, E, O, cn, gst);
+                        else pend = fast1_ord_issue<WW>(F, valid, ptile, s0, e0, s3, e3, buf + prev_base + s0, buf + prev_base + s3, G, T, E, O, cn, gst, lane);
                         have_pend = true;
                     }
+                }
+                };
+                if (POLICY == POLICY_GENERIC) passes(std::integral_constant<int, 0>{});
+                else switch (ord_words) {
+                    case 4: passes(std::integral_constant<int, 4>{}); break;
+                    case 5: passes(std::integral_constant<int, 5>{}); break;
+                    case 6: passes(std::integral_constant<int, 6>{}); break;
+                    default: passes(std::integral_constant<int, 0>{}); break;
                 }
             }
             __syncwarp();

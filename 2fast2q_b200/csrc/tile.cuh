@@ -415,6 +415,34 @@ __device__ __forceinline__ Fast1Pending fast1_warp_issue(const Fast1Ctx& F, bool
     return p;
 }
 
+// the ordinary read, W = words of the window known at compile time: both lines reach the end of the window (so the window
+// is [c_start, c_end) exactly), the library is one-length with a cuckoo table and no key of that length outside it (the
+// caller checked).  rstrip cannot change such a read unless a non-ACGT byte sits in the window AND the line ends in
+// whitespace (a window of pure ACGT lies before any whitespace tail; whitespace is never in the Phred fail set): that
+// case, short lines and everything else unusual take fast1_read.  Same results, a third of the instructions.
+template <int W>
+__device__ __forceinline__ Fast1Pending fast1_ord_issue(const Fast1Ctx& F, bool valid, const uint8_t* tile, uint32_t s0, uint32_t e0, uint32_t s3,
+                                                        uint32_t e3, const uint8_t* gseq, const uint8_t* gqual, const GenericCfg& G,
+                                                        const LibTables& T, const EcTable& E, const Outputs& O, Fast1Counts& n,
+                                                        unsigned long long* gst, uint32_t lane) {
+    const int c_len = F.c_end - F.c_start;
+    bool ord = valid && (int)(e0 - s0) >= F.c_end && (int)(e3 - s3) >= F.c_end;
+    const uint32_t so = ord ? s0 + (uint32_t)F.c_start : 0u, qo = ord ? s3 + (uint32_t)F.c_start : 0u;
+    const bool fails = F.c_fmax != 0 && qual_fails_w<W>(tile, qo, c_len, F.add_ge, F.add_gt);
+    Fast1Pending p;
+    pack_w<W>(tile, so, c_len, p.klo, p.khi, p.bad);
+    if (ord && p.bad != 0 && is_py_space(tile[e0 - 1])) ord = false;
+    if (valid && !ord) fast1_read(F, tile, s0, e0, s3, e3, gseq, gqual, G, T, E, O, n, gst, lane);
+    n.qfail += (ord && fails) ? 1u : 0u;
+    const bool live = ord && !fails;
+    uint32_t h1, h2;
+    cuckoo_slots(T.ck_mul, T.ck_mask, p.klo, p.khi, h1, h2);
+    p.ra = __ldg(reinterpret_cast<const uint2*>(T.cuckoo) + h1);
+    p.rb = __ldg(reinterpret_cast<const uint2*>(T.cuckoo) + h2);
+    p.meta = (uint32_t)c_len | ((live && p.bad == 0) ? 1u << 8 : 0u) | (live ? 1u << 9 : 0u);
+    return p;
+}
+
 __device__ __forceinline__ void fast1_warp_commit(const Fast1Ctx& F, const Fast1Pending& p, const LibTables& T, const Outputs& O, Fast1Counts& n,
                                                   uint32_t lane) {
     uint32_t idx = SLOT_EMPTY;

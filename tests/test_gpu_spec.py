@@ -131,3 +131,38 @@ def test_extract_count_never_speculates(gu):
     with gu.lib.Engine(cfg, 0, None, spec_range_tiles=1) as e:
         e.run(c["fastq"])
         assert e.spec_counts() == (0, 0)
+
+
+@pytest.mark.parametrize("length,start", [(20, 0), (13, 5), (24, 2), (17, 30)])
+def test_ordinary_read_code_with_whitespace_tails_and_short_lines(gu, oracle, length, start):
+    """the compile-time-window code of the streaming kernel must hand the reads it cannot decide to the general code:
+    CRLF / blank tails (rstrip), N inside the window, lines that end inside the window, empty lines"""
+    from oracle import synth
+    r = synth.SM64(99 + length)
+    guides = [r.dna(length) for _ in range(300)]
+    out = []
+    for i in range(20_000):
+        g = r.choice(guides)
+        k = r.below(10)
+        if k == 0:
+            g = synth.mutate(r, g, 1)
+        s = r.dna(start) + g + r.dna(r.below(12))
+        if k == 1:
+            s = s[:start + r.below(length + 1)]                  # the line ends inside (or right at the start of) the window
+        if k == 2:
+            p = start + r.below(length)
+            s = s[:p] + b"N" + s[p + 1:]
+        q = synth.qual_line(r, len(s), 0.05)
+        tail = [b"", b"\r", b"  ", b"\t \r", b""][r.below(5)]
+        if k == 3:
+            q = q[:start + r.below(length + 1)]
+        if k == 4 and len(s) > start + 2:
+            s = s[:start + 2] + b" " * (len(s) - start - 2)        # whitespace reaching back into the window
+        out.append(b"@r%d%s\n" % (i, tail) + s + tail + b"\n+" + tail + b"\n" + q + tail + b"\n")
+    data = b"".join(out)
+    keys = list(dict.fromkeys(guides))
+    params = dict(miss=1, length=length, start=str(start))
+    want_c, want_s = oracle.count(oracle.make_config(**params), keys, data)
+    for opts in (dict(), dict(spec_range_tiles=2), dict(spec=0)):
+        c, s, _ = _run(gu, params, keys, data, **opts)
+        assert s == want_s and np.array_equal(c, want_c), (length, start, opts)
