@@ -765,7 +765,7 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
     }
     // pigeonhole seed index for <= miss mismatches (resolve.cuh)
     std::vector<uint4> seed_slots(16, make_uint4(0, 0, 0, 0));
-    std::vector<uint32_t> seed_items;
+    std::vector<uint4> seed_recs;
     const uint32_t parts = (uint32_t)std::max(1, std::min(c->cfg.miss, 32) + 1);
     if (c->cfg.miss > 0 && !fk.empty()) {
         std::vector<std::pair<uint64_t, uint32_t>> ent;
@@ -782,17 +782,17 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
         for (size_t i = 0; i < ent.size(); i++) if (i == 0 || ent[i].first != ent[i - 1].first) uniq++;
         const uint32_t scap = pow2_at_least(2 * (uint64_t)uniq + 2);
         seed_slots.assign(scap, make_uint4(0, 0, 0, 0));
-        seed_items.resize(ent.size());
+        seed_recs.resize(ent.size());
         for (size_t i = 0; i < ent.size();) {
             size_t e = i;
-            while (e < ent.size() && ent[e].first == ent[i].first) { seed_items[e] = ent[e].second; e++; }
+            while (e < ent.size() && ent[e].first == ent[i].first) { const uint32_t j = ent[e].second; seed_recs[e] = make_uint4((uint32_t)fk[j], (uint32_t)(fk[j] >> 32), fi[j], 0u); e++; }
             uint32_t h = seed_hash(ent[i].first) & (scap - 1);
             while (seed_slots[h].x | seed_slots[h].y) h = (h + 1) & (scap - 1);
             seed_slots[h] = make_uint4((uint32_t)ent[i].first, (uint32_t)(ent[i].first >> 32), (uint32_t)i, (uint32_t)(e - i));
             i = e;
         }
     }
-    if ((rc = upload(c, seed_slots, &c->T.seed_slots)) || (rc = upload(c, seed_items, &c->T.seed_items))) return rc;
+    if ((rc = upload(c, seed_slots, &c->T.seed_slots)) || (rc = upload(c, seed_recs, &c->T.seed_recs))) return rc;
     c->T.seed_mask = (uint32_t)seed_slots.size() - 1; c->T.seed_parts = parts;
     if ((rc = upload(c, slots, &c->T.slots)) || (rc = upload(c, fk, &c->T.fast_keys)) || (rc = upload(c, fl, &c->T.fast_lens)) ||
         (rc = upload(c, fi, &c->T.fast_idx)) || (rc = upload(c, bytes, &c->T.key_bytes)) || (rc = upload(c, off, &c->T.key_off)) ||

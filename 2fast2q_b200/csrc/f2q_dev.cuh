@@ -74,9 +74,9 @@ struct LibTables {
     uint32_t n_generic;        // keys that are NOT in the packed table
     uint64_t generic_len_mask; // bit L set: some non-packed key has length L (L < 64); bit 63: some length >= 63
     // pigeonhole seed index over the packed keys (resolver 2)
-    const uint4* seed_slots;   // {tag lo, tag hi, start, count}: hash of (len, segment, value) -> range in seed_items; tag 0 = empty
+    const uint4* seed_slots;   // {tag lo, tag hi, start, count}: hash of (len, segment, value) -> range in seed_recs; tag 0 = empty
     uint32_t seed_mask;
-    const uint32_t* seed_items;   // indices into fast_keys
+    const uint4* seed_recs;    // {packed key lo, hi, feature index, 0} of every (key, segment), grouped by seed slot
     uint32_t seed_parts;       // miss + 1
 };
 

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_resolve_scan(LibTables T, int 
     }
 }
 // ---- pigeonhole seed index: a key within m mismatches of a library entry agrees exactly with it on at least one
-// of m+1 segments.  seed_slots hashes (length, segment, segment value) -> range of seed_items (indices into fast_keys).
+// of m+1 segments.  seed_slots hashes (length, segment, segment value) -> range of seed_recs (candidate keys stored inline, bucket-contiguous).
 __host__ __device__ __forceinline__ uint64_t seed_tag(uint32_t len, uint32_t seg, uint64_t v) {
     return (1ull << 63) | ((uint64_t)len << 40) | ((uint64_t)seg << 32) | v;
 }
@@ -213,14 +213,14 @@ __device__ inline uint32_t resolve_seed_thread(const LibTables& T, int m, uint64
             h = (h + 1) & T.seed_mask;
         }
         for (uint32_t c = 0; c < count; c++) {
-            const uint32_t j = __ldg(T.seed_items + start + c);
-            const uint64_t x = key ^ __ldg(T.fast_keys + j);
+            const uint4 it = __ldg(T.seed_recs + start + c);           // {key lo, key hi, feature index, -}: one load per candidate
+            const uint64_t x = key ^ (((uint64_t)it.y << 32) | it.x);
             const uint64_t diff = (((x | (x >> 1)) & lenmask) | badeven);     // even bit 2p: symbol p differs (or is bad)
             bool dup = false;                                          // already seen through an earlier agreeing segment?
             for (uint32_t s2 = 0; s2 < s; s2++)
                 if ((diff & even_range(s2 * len / parts, (s2 + 1) * len / parts)) == 0) { dup = true; break; }
             if (dup) continue;
-            b.add(__popcll(diff), __ldg(T.fast_idx + j), m);
+            b.add(__popcll(diff), it.z, m);
         }
     }
     return (b.d <= m && b.n == 1) ? b.idx : RES_NONE;

@@ -183,7 +183,7 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {
 
 // 2-bit pack of a window of W words (n symbols).  bad = mask of symbols outside ACGT after upper(); their key bits are 0
 template <int W>
-__device__ __forceinline__ void pack_w(const uint8_t* tile, uint32_t o, int n, uint32_t& klo, uint32_t& khi, uint32_t& bad) {
+__device__ __forceinline__ void pack_w(const uint8_t* tile, uint32_t o, int n, uint32_t& klo, uint32_t& khi, uint32_t& bad, bool act = true) {
     uint32_t w[W], d[W];
     load_words<W>(tile, o, w);
     if (n & 3) { const uint32_t keep = (1u << (8 * (n & 3))) - 1u; w[W - 1] = (w[W - 1] & keep) | (0x41414141u & ~keep); }   // pad with 'A'
@@ -199,7 +199,7 @@ __device__ __forceinline__ void pack_w(const uint8_t* tile, uint32_t o, int n, u
         if (i < 4) lo |= p << (8 * (i & 3)); else hi |= p << (8 * (i & 3));
     }
     bad = 0;
-    if (any) {                                                         // rare per read but common per warp: kept short
+    if (any && act) {                                                  // rare per read but common per warp: kept short (lanes without a read: skipped)
         #pragma unroll
         for (int i = 0; i < W; i++) {
             const uint32_t nz = (((d[i] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d[i]) & 0x80808080u;     // bit 7 of every non-zero byte
@@ -430,7 +430,7 @@ __device__ __forceinline__ Fast1Pending fast1_ord_issue(const Fast1Ctx& F, bool 
     const uint32_t so = ord ? s0 + (uint32_t)F.c_start : 0u, qo = ord ? s3 + (uint32_t)F.c_start : 0u;
     const bool fails = F.c_fmax != 0 && qual_fails_w<W>(tile, qo, c_len, F.add_ge, F.add_gt);
     Fast1Pending p;
-    pack_w<W>(tile, so, c_len, p.klo, p.khi, p.bad);
+    pack_w<W>(tile, so, c_len, p.klo, p.khi, p.bad, ord);
     if (ord && p.bad != 0 && is_py_space(tile[e0 - 1])) ord = false;
     if (valid && !ord) fast1_read(F, tile, s0, e0, s3, e3, gseq, gqual, G, T, E, O, n, gst, lane);
     n.qfail += (ord && fails) ? 1u : 0u;

@@ -165,6 +165,7 @@ def run_gpu(args, rank, local_rank, world):
     import torch.distributed as dist
     f2q = importlib.import_module("2fast2q_b200")
     lib = f2q._lib
+    multi = importlib.import_module("2fast2q_b200.multi")
     lib.load()                                                     # raises if the CUDA library is missing
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -193,7 +194,7 @@ def run_gpu(args, rank, local_rank, world):
     def merge():
         if world > 1:
             with torch.cuda.stream(stream):
-                dist.all_reduce(result_t)            # ncclAllReduce(sum) of [counts | stats] over NVLink (merge_feature_dicts)
+                multi.merge_results(result_t)        # ncclAllReduce(sum) of [counts | stats] over NVLink (merge_feature_dicts)
 
     def step_resident():
         eng.begin()
