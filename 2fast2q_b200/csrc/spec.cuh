@@ -202,17 +202,26 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         hcnt = __shfl_sync(0xffffffffu, excl, H);                      // (H <= 16 < 32)
         uint32_t o = excl;
         const bool fits = incl <= cap;                                 // (a tile with more newlines than that is not parsed at all)
+        uint32_t crowded = 0;                                          // some 32-byte word of this row holds three or more newlines
         #pragma unroll
         for (int w = 0; w < MW; w++) {
             const uint32_t m = fits ? mw[w] : 0u;
             const uint32_t c = __popc(m), m1 = m & (m - 1u);
             if (c >= 1) nl[o] = (uint16_t)(rowbase + 32u * w + (uint32_t)__ffs((int)m) - 1u);
             if (c >= 2) nl[o + 1] = (uint16_t)(rowbase + 32u * w + (uint32_t)__ffs((int)m1) - 1u);
-            if (c > 2) {                                               // three or more newlines within 32 bytes: not ordinary FASTQ
-                uint32_t m2 = m1 & (m1 - 1u), k = o + 2;
-                while (m2) { nl[k++] = (uint16_t)(rowbase + 32u * w + (uint32_t)__ffs((int)m2) - 1u); m2 &= m2 - 1u; }
-            }
+            crowded |= m1 & (m1 - 1u);
             o += c;
+        }
+        if (__any_sync(0xffffffffu, crowded != 0)) {                   // not ordinary FASTQ: the rest of those words, one branch per tile
+            o = excl;
+            #pragma unroll
+            for (int w = 0; w < MW; w++) {
+                const uint32_t m = fits ? mw[w] : 0u;
+                uint32_t m2 = m & (m - 1u), k = o + 2;
+                m2 &= m2 - 1u;
+                while (m2) { nl[k++] = (uint16_t)(rowbase + 32u * w + (uint32_t)__ffs((int)m2) - 1u); m2 &= m2 - 1u; }
+                o += __popc(m);
+            }
         }
     };
 
