@@ -207,8 +207,9 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         for (int w = 0; w < MW; w++) {
             const uint32_t m = fits ? mw[w] : 0u;
             const uint32_t c = __popc(m), m1 = m & (m - 1u);
-            if (c >= 1) nl[o] = (uint16_t)(rowbase + 32u * w + (uint32_t)__ffs((int)m) - 1u);
-            if (c >= 2) nl[o + 1] = (uint16_t)(rowbase + 32u * w + (uint32_t)__ffs((int)m1) - 1u);
+            // branch-free: a word without a first / second newline stores into the spare slot behind the list
+            nl[c >= 1 ? o : cap + 7u] = (uint16_t)(rowbase + 32u * w + (uint32_t)__ffs((int)m) - 1u);
+            nl[c >= 2 ? o + 1u : cap + 7u] = (uint16_t)(rowbase + 32u * w + (uint32_t)__ffs((int)m1) - 1u);
             crowded |= m1 & (m1 - 1u);
             o += c;
         }
@@ -244,7 +245,8 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         uint32_t total = 0, hcnt = 0;
         if (live) {
             if ((flags & 3u) == 1u) {
-                if (!mbar_wait(&bars[s], (par_bits >> s) & 1u, abort)) break;
+                uint32_t spins = 0;                                    // (bounded: a lost copy traps instead of hanging the device)
+                while (!mbar_try_wait(&bars[s], (par_bits >> s) & 1u)) if (++spins > WAIT_SPIN_LIMIT) __trap();
                 par_bits ^= 1u << s;
             } else {
                 // first / last tiles of the chunk: loaded by the lanes, bytes outside [beg, end) become 0

@@ -443,10 +443,11 @@ __device__ __forceinline__ Fast1Pending fast1_ord_issue(const Fast1Ctx& F, bool 
     return p;
 }
 
+template <bool ORD = false>                                    // ORD: the slots always come from the cuckoo table (fast1_ord_issue)
 __device__ __forceinline__ void fast1_warp_commit(const Fast1Ctx& F, const Fast1Pending& p, const LibTables& T, const Outputs& O, Fast1Counts& n,
                                                   uint32_t lane) {
     uint32_t idx = SLOT_EMPTY;
-    if (p.meta & (1u << 10)) idx = p.ra.x;
+    if (!ORD && (p.meta & (1u << 10))) idx = p.ra.x;
     else {
         const uint64_t a = ((uint64_t)p.ra.y << 32) | p.ra.x, b = ((uint64_t)p.rb.y << 32) | p.rb.x;
         const uint64_t key = ((uint64_t)p.khi << 32) | p.klo, keymask = (1ull << T.c_keybits) - 1ull;
