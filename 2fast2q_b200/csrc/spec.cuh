@@ -228,11 +228,12 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
 
     // @region spec_loop
     for (int k = 0; k < NS; k++) issue_next();
-    bool have_prev = false, have_pend = false;
+    bool have_prev = false;
     uint32_t prev_s = 0, prev_total = 0, prev_range = 0, prev_flags = 0;
     uint64_t prev_base = 0;
     uint32_t phase = 0, range_cnt = 0, spec_p0 = 0, par_bits = 0;
-    Fast1Pending pend;
+    Fast1Pending pend;                                                 // meta == 0: nothing pending (committing it is a no-op)
+    pend.ra = make_uint2(0, 0); pend.rb = make_uint2(0, 0); pend.klo = pend.khi = pend.bad = pend.meta = 0;
     uint16_t* const nl_halo = nlist + 2 * G_::NL_LIST;
     for (uint32_t i = 0, s = 0;; i++, s = (s == (uint32_t)NS - 1u) ? 0u : s + 1u) {
         const uint32_t par = i & 1u;
@@ -273,7 +274,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             __syncwarp();
         }
         // the lookups issued for the tile before the previous one have long arrived: count them
-        if (have_pend) { fast1_warp_commit(F, pend, T, O, cn, lane); have_pend = false; }
+        if (POLICY == POLICY_FAST1) { fast1_warp_commit(F, pend, T, O, cn, lane); pend.meta = 0; }
         if (have_prev) {
             // @region spec_parse
             // ---- reads of the previous tile: lane q takes the q-th read whose header line ends in its own rows ----
@@ -293,8 +294,11 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             if (total_own > (uint32_t)CAP || hc > (uint32_t)CAP) {
                 if (lane == 0) St->spec_fail = 1u;                     // a tile of very short lines: left to the exact kernel
             } else {
+                // a read needs at most three newlines behind the tile's own: append them, the list is then contiguous
+                uint16_t* const nlW = nlist + (par ^ 1u) * G_::NL_LIST;
+                if (lane < 3u && lane < hc) nlW[total_own + lane] = (uint16_t)((uint32_t)nlB[lane] + ((nlB == nl_halo) ? 0u : (uint32_t)OWN));
+                __syncwarp();
                 const uint32_t jf = (4u - (phase & 3u)) & 3u;          // first newline of the tile that ends a header line
-                const uint32_t halo_off = (nlB == nl_halo) ? 0u : (uint32_t)OWN;
                 auto passes = [&](auto Wc) {
                 constexpr int WW = decltype(Wc)::value;                // words of the window (ordinary-read code), 0 = general code
                 for (uint32_t j0 = jf; j0 < total_own; j0 += 128u) {   // (uniform: the warp stays converged through a pass)
@@ -307,11 +311,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                     }
                     uint32_t s0 = 0, e0 = 0, s3 = 0, e3 = 0;
                     if (valid) {
-                        const uint32_t j1 = j + 1, j2 = j + 2, j3 = j + 3;
-                        s0 = (uint32_t)nlA[j] + 1u;
-                        e0 = j1 < total_own ? (uint32_t)nlA[j1] : (uint32_t)nlB[j1 - total_own] + halo_off;
-                        s3 = (j2 < total_own ? (uint32_t)nlA[j2] : (uint32_t)nlB[j2 - total_own] + halo_off) + 1u;
-                        e3 = j3 < total_own ? (uint32_t)nlA[j3] : (uint32_t)nlB[j3 - total_own] + halo_off;
+                        s0 = (uint32_t)nlA[j] + 1u; e0 = nlA[j + 1]; s3 = (uint32_t)nlA[j + 2] + 1u; e3 = nlA[j + 3];
                         cn.reads++;
                         acc.last_end = (unsigned long long)(prev_base + e3 + 1);
                     }
@@ -322,10 +322,9 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                         }
                     } else {
                         __syncwarp();
-                        if (have_pend) fast1_warp_commit(F, pend, T, O, cn, lane);     // (a second pass over the same tile: rare)
+                        if (j0 != jf) fast1_warp_commit(F, pend, T, O, cn, lane);      // (a second pass over the same tile: rare)
                         if constexpr (WW == 0) pend = fast1_warp_issue(F, valid, ptile, s0, e0, s3, e3, buf + prev_base + s0, buf + prev_base + s3, G, T, E, O, cn, gst);
                         else pend = fast1_ord_issue<WW>(F, valid, ptile, s0, e0, s3, e3, buf + prev_base + s0, buf + prev_base + s3, G, T, E, O, cn, gst, lane);
-                        have_pend = true;
                     }
                 }
                 };
@@ -369,7 +368,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         }
         have_prev = true; prev_s = s; prev_total = total; prev_range = d.z; prev_flags = flags; prev_base = base;
     }
-    if (have_pend) fast1_warp_commit(F, pend, T, O, cn, lane);
+    if (POLICY == POLICY_FAST1) fast1_warp_commit(F, pend, T, O, cn, lane);
 
     // @region spec_epilogue
     __syncthreads();
