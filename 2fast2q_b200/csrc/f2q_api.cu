@@ -88,6 +88,10 @@ struct f2q_ctx {
     int spec_range_tiles = 0;          // 0 auto | tiles per range
     int spec_ready[2][8][2] = {{{0}}}; // function attributes set for (policy, ch, warps == 16)
     DevBuf spec_rec, spec_scratch;
+    // [0] tables + result outputs, [1] tables + scratch outputs, in device memory (SlowArgs, generic.cuh); re-uploaded when they change
+    DevBuf slow_args;
+    SlowArgs slow_host[2];
+    bool slow_valid = false;
     uint64_t spec_counts[2] = {0, 0};  // last finished sample: chunks committed by the speculation / parsed by the exact kernel
     int nt = 128;                      // threads (= owned rows) per tile-kernel CTA: 128 or 256
     // optional per-kernel timing (option "time_kernels"): event pairs around the tile / resolver / generic launches
@@ -219,7 +223,7 @@ int launch_tile(f2q_ctx* c, const TileParams& P, Outputs O, uint64_t n_tiles_upp
     unsigned grid = 0;
     int rc = tile_grid<POLICY, CH, NT>(c, &grid); if (rc) return rc;
     if (p.seg_cap == 0) grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(grid, n_tiles_upper));   // main launches keep one segment per CTA
-    k_tile<POLICY, CH, NT><<<grid, NT + TILE_CTRL_THREADS, smem, c->stream>>>(p, c->dG, c->T, c->E, O);
+    k_tile<POLICY, CH, NT><<<grid, NT + TILE_CTRL_THREADS, smem, c->stream>>>(p, c->dG, c->T, c->E, O, reinterpret_cast<const SlowArgs*>(c->slow_args.p));
     c->launches++;
     CU(c, cudaGetLastError());
     return F2Q_OK;
@@ -262,7 +266,7 @@ int launch_spec(f2q_ctx* c, const SpecParams& P, Outputs O) {
         CU(c, cudaFuncSetAttribute(k_spec<POLICY, CH, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMEM_BYTES - sizeof(GenericCfg) - SPEC_SMEM_MARGIN)));
         ready = 1;
     }
-    k_spec<POLICY, CH, W><<<(unsigned)c->sm_count, W * 32, smem, c->stream>>>(p, c->dG, c->T, c->E, O);
+    k_spec<POLICY, CH, W><<<(unsigned)c->sm_count, W * 32, smem, c->stream>>>(p, c->dG, c->T, c->E, O, reinterpret_cast<const SlowArgs*>(c->slow_args.p) + 1);
     c->launches++;
     CU(c, cudaGetLastError());
     return F2Q_OK;
@@ -455,6 +459,20 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     CU(c, cudaMemsetAsync(c->d_tickets + 2, 0, 4, c->stream));
     c->launches++;
     Outputs O = outputs_of(c);
+    {
+        // the global-memory copy of the tables and outputs that the non-inlined device functions read
+        SlowArgs now[2];
+        memset(now, 0, sizeof(now));
+        now[0].T = c->T; now[0].E = c->E; now[0].O = O;
+        now[1] = now[0];
+        if (c->spec_scratch.p) { now[1].O.counts = reinterpret_cast<unsigned long long*>(c->spec_scratch.p); now[1].O.stats = now[1].O.counts + c->n_keys; }
+        if ((rc = dev_alloc(c, c->slow_args, sizeof(now)))) return rc;
+        if (!c->slow_valid || memcmp(now, c->slow_host, sizeof(now)) != 0) {
+            memcpy(c->slow_host, now, sizeof(now));
+            CU(c, cudaMemcpyAsync(c->slow_args.p, c->slow_host, sizeof(now), cudaMemcpyHostToDevice, c->stream));
+            c->slow_valid = true;
+        }
+    }
     TileParams P{};
     P.S = c->dS; P.queue = reinterpret_cast<QEntry*>(c->queue.p); P.gqueue = reinterpret_cast<GEntry*>(c->gqueue.p);
     P.halo_rows = (uint32_t)c->halo_rows;
@@ -522,7 +540,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
             c->launches++;
         }
         cudaEvent_t t2 = timing_begin(c);
-        k_generic_queue<<<(unsigned)c->sm_count, 128, 0, c->stream>>>(c->dG, c->T, c->E, O, P.gqueue, c->dS);
+        k_generic_queue<<<(unsigned)c->sm_count, 128, 0, c->stream>>>(c->dG, reinterpret_cast<const SlowArgs*>(c->slow_args.p), P.gqueue, c->dS);
         timing_end(c, t2, 2);
         c->launches++;
     }
@@ -626,7 +644,7 @@ F2Q_EXPORT void f2q_destroy(f2q_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& b : c->lib_bufs) b.release();
     c->result.release(); c->carry.release(); c->status.release(); c->status_stitch.release(); c->queue.release(); c->gqueue.release();
-    c->seg_count.release(); c->spec_rec.release(); c->spec_scratch.release();
+    c->seg_count.release(); c->spec_rec.release(); c->spec_scratch.release(); c->slow_args.release();
     c->ec_slots.release(); c->ec_counts.release(); c->ec_arena.release(); c->ec_meta.release();
     for (auto p : c->d_stage) cudaFree(p);
     for (auto e : c->ev_copied) cudaEventDestroy(e);
@@ -742,7 +760,7 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
                 uint32_t from = 0xFFFFFFFFu;                            // slot `cur` was evicted from
                 for (;; kicks++) {
                     uint32_t h1, h2;
-                    cuckoo_slots(ck_mul, ck_mask, (uint32_t)(cur & kmask), (uint32_t)((cur & kmask) >> 32), h1, h2);
+                    cuckoo_slots(ck_mul[0], ck_mul[1], ck_mul[2], ck_mul[3], ck_mask, (uint32_t)(cur & kmask), (uint32_t)((cur & kmask) >> 32), h1, h2);
                     if (cuckoo[h1] == ~0ull) { cuckoo[h1] = cur; break; }
                     if (cuckoo[h2] == ~0ull) { cuckoo[h2] = cur; break; }
                     if (kicks >= 500) { built = false; break; }

@@ -171,6 +171,13 @@ __device__ __forceinline__ uint32_t eq_bytes(uint32_t w, uint32_t c4) {
     return ~(t | x) & 0x80808080u;
 }
 
+// 8-byte read-only load that stays where it is written (the compiler may not sink it towards its use): issued early on purpose
+__device__ __forceinline__ uint2 ldg_u2_here(const uint2* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
 // streaming 16-byte global load (read once, do not keep in L1)
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     uint4 r;
@@ -217,17 +224,19 @@ __device__ __forceinline__ uint32_t compact_lookup(const LibTables& T, uint32_t 
 }
 #endif  // __CUDACC__
 
-// the two slots a packed key can live in (host and device must agree)
-__host__ __device__ __forceinline__ void cuckoo_slots(const uint32_t mul[4], uint32_t mask, uint32_t klo, uint32_t khi, uint32_t& h1, uint32_t& h2) {
-    h1 = ((klo * mul[0] + khi * mul[1]) >> 9) & mask;
-    h2 = ((((klo * mul[2]) ^ (khi * mul[3])) >> 9) & mask) + mask + 1u;
+// the two slots a packed key can live in (host and device must agree).  Multipliers by value: as kernel parameters they
+// stay constant-bank operands of the multiplies (an array argument would turn them into constant LOADS on the hot path)
+__host__ __device__ __forceinline__ void cuckoo_slots(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t mask, uint32_t klo, uint32_t khi,
+                                                      uint32_t& h1, uint32_t& h2) {
+    h1 = ((klo * m0 + khi * m1) >> 9) & mask;
+    h2 = ((((klo * m2) ^ (khi * m3)) >> 9) & mask) + mask + 1u;
 }
 
 #ifdef __CUDACC__
 // two-choice lookup (caller checked len == T.c_len); feature index or SLOT_EMPTY
 __device__ __forceinline__ uint32_t cuckoo_lookup(const LibTables& T, uint32_t klo, uint32_t khi) {
     uint32_t h1, h2;
-    cuckoo_slots(T.ck_mul, T.ck_mask, klo, khi, h1, h2);
+    cuckoo_slots(T.ck_mul[0], T.ck_mul[1], T.ck_mul[2], T.ck_mul[3], T.ck_mask, klo, khi, h1, h2);
     const uint2 ra = __ldg(reinterpret_cast<const uint2*>(T.cuckoo) + h1);
     const uint2 rb = __ldg(reinterpret_cast<const uint2*>(T.cuckoo) + h2);
     const uint64_t a = ((uint64_t)ra.y << 32) | ra.x, b = ((uint64_t)rb.y << 32) | rb.x;

@@ -34,6 +34,15 @@ struct Outputs {
     uint32_t* error;
 };
 
+// The same three blocks in GLOBAL memory, for everything that is not inlined into a kernel's hot loop (g_process_read,
+// slow_record, the in-place resolver).  Those take references; a reference to a by-value kernel parameter would make the
+// compiler keep a copy of the whole parameter block in local memory and read even hot-path fields from there.
+struct SlowArgs {
+    LibTables T;
+    EcTable E;
+    Outputs O;
+};
+
 struct Piece { uint32_t off, len; };
 
 // ---- binary_subtract / border_finder (fast2q.py:601-658), byte-wise ---------------------------
@@ -225,7 +234,7 @@ __device__ __forceinline__ int g_rstrip(const uint8_t* p, int n) {
 }
 
 // drains the generic read queue: one thread per entry
-__global__ void __launch_bounds__(128) k_generic_queue(const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, Outputs O,
+__global__ void __launch_bounds__(128) k_generic_queue(const GenericCfg* __restrict__ Gp, const SlowArgs* __restrict__ X,
                                                        const GEntry* q, const DevState* S) {
     __shared__ GenericCfg G;
     for (uint32_t i = threadIdx.x; i < sizeof(GenericCfg) / 4; i += blockDim.x)
@@ -237,9 +246,9 @@ __global__ void __launch_bounds__(128) k_generic_queue(const GenericCfg* __restr
         GEntry e = q[i];
         const uint8_t* R = reinterpret_cast<const uint8_t*>(e.seq_addr);
         const uint8_t* Q = reinterpret_cast<const uint8_t*>(e.qual_addr);
-        g_process_read(G, T, E, O, R, g_rstrip(R, (int)e.seq_len), Q, g_rstrip(Q, (int)e.qual_len), st);
+        g_process_read(G, X->T, X->E, X->O, R, g_rstrip(R, (int)e.seq_len), Q, g_rstrip(Q, (int)e.qual_len), st);
     }
-    for (int k = 1; k < F2Q_N_STATS; k++) if (st[k]) atomicAdd(O.stats + k, st[k]);
+    for (int k = 1; k < F2Q_N_STATS; k++) if (st[k]) atomicAdd(X->O.stats + k, st[k]);
 }
 
 // ---- single-read helpers behind f2q_border_finder / f2q_sequence_tinder ------------------------

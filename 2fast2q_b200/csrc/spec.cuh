@@ -71,7 +71,7 @@ __device__ __forceinline__ uint64_t spec_n_ranges(uint64_t beg, uint64_t end, ui
 // @region spec_kernel
 template <int POLICY, int CH, int W>
 __global__ void __launch_bounds__(W * 32, 1)
-k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, Outputs O) {
+k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, Outputs O, const SlowArgs* __restrict__ X) {
     using G_ = SpecGeom<CH>;
     constexpr int S = G_::S, OWN = G_::OWN, NS = SPEC_STAGES, CAP = SPEC_CAP, MW = G_::MW;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -105,7 +105,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     Fast1Ctx F;
     F.init(Gp);
     F.hist = P.hist_smem ? hist : nullptr; F.myq = P.queue + (size_t)blockIdx.x * P.seg_cap; F.seg_cap = P.seg_cap; F.s_qn = &s_qn;
-    F.gqueue = P.gqueue; F.St = St;
+    F.gqueue = P.gqueue; F.St = St; F.X = X;
     Acc acc{0, 0, 0, 0, 0, 0};
     unsigned long long gst[F2Q_N_STATS] = {0, 0, 0, 0, 0};
     Fast1Counts cn{0, 0, 0, 0, 0};
@@ -306,7 +306,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                     bool valid = j < total_own;
                     if (valid && j + 3 >= total_all) {
                         // the read's last newline is not in the loaded rows (a long record, or the end of the chunk)
-                        slow_record(buf, prev_base + nlA[j], end, eof, G, T, E, O, acc, gst);
+                        slow_record(buf, prev_base + nlA[j], end, eof, G, X, acc, gst);
                         valid = false;
                     }
                     uint32_t s0 = 0, e0 = 0, s3 = 0, e3 = 0;
@@ -318,7 +318,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                     if (POLICY == POLICY_GENERIC) {
                         if (valid) {
                             const uint8_t* Rp = ptile + s0; const uint8_t* Qp = ptile + s3;
-                            g_process_read(G, T, E, O, Rp, g_rstrip(Rp, (int)(e0 - s0)), Qp, g_rstrip(Qp, (int)(e3 - s3)), gst);
+                            g_process_read(G, X->T, X->E, X->O, Rp, g_rstrip(Rp, (int)(e0 - s0)), Qp, g_rstrip(Qp, (int)(e3 - s3)), gst);
                         }
                     } else {
                         __syncwarp();

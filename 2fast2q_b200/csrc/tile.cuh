@@ -232,7 +232,7 @@ struct Acc {
 // holds): finish the geometry in global memory and run the byte-wise generic code on it.  hdr_end = absolute buffer
 // offset of the newline that ends the header line.  Rare by construction; exactness matters here, speed does not.
 __device__ __noinline__ void slow_record(const uint8_t* buf, uint64_t hdr_end, uint64_t end, bool eof, const GenericCfg& G,
-                                         const LibTables& T, const EcTable& E, const Outputs& O, Acc& acc, unsigned long long* gst) {
+                                         const SlowArgs* X, Acc& acc, unsigned long long* gst) {
     uint64_t pos[4];
     pos[0] = hdr_end;
     uint64_t from = hdr_end + 1;
@@ -248,7 +248,7 @@ __device__ __noinline__ void slow_record(const uint8_t* buf, uint64_t hdr_end, u
     const unsigned long long le = (unsigned long long)(pos[3] + 1 < end ? pos[3] + 1 : end);
     acc.last_end = acc.last_end > le ? acc.last_end : le;
     const uint8_t* Rp = buf + pos[0] + 1; const uint8_t* Qp = buf + pos[2] + 1;
-    g_process_read(G, T, E, O, Rp, g_rstrip(Rp, (int)(pos[1] - pos[0] - 1)), Qp, g_rstrip(Qp, (int)(pos[3] - pos[2] - 1)), gst);
+    g_process_read(G, X->T, X->E, X->O, Rp, g_rstrip(Rp, (int)(pos[1] - pos[0] - 1)), Qp, g_rstrip(Qp, (int)(pos[3] - pos[2] - 1)), gst);
 }
 
 // @region fast1_read
@@ -263,6 +263,7 @@ struct Fast1Ctx {
     uint32_t* s_qn;                    // shared-memory fill count of the segment
     GEntry* gqueue;
     DevState* St;
+    const SlowArgs* X;                 // tables / outputs in global memory for the calls that are not inlined
     __device__ __forceinline__ void init(const GenericCfg* Gp) {
         c_start = Gp->c.starts[0]; c_end = c_start + Gp->c.length; c_fmax = Gp->c.fmax_ph; c_miss = Gp->c.miss;
         simple_slice = c_start >= 0 && Gp->c.length >= 0;
@@ -321,7 +322,7 @@ __device__ __forceinline__ void fast1_read(const Fast1Ctx& F, const uint8_t* til
         ge.qual_addr = (uint64_t)gqual; ge.qual_len = e3 - s3;
         const uint32_t slot = atomicAdd(&F.St->g_count, 1u);
         if (slot < F.St->g_cap) F.gqueue[slot] = ge;
-        else g_process_read(G, T, E, O, (const uint8_t*)ge.seq_addr, (int)ge.seq_len, (const uint8_t*)ge.qual_addr, (int)ge.qual_len, gst);
+        else g_process_read(G, F.X->T, F.X->E, F.X->O, (const uint8_t*)ge.seq_addr, (int)ge.seq_len, (const uint8_t*)ge.qual_addr, (int)ge.qual_len, gst);
         return;
     }
     if (F.c_miss <= 0) { n.nonal++; return; }
@@ -334,7 +335,7 @@ __device__ __forceinline__ void fast1_read(const Fast1Ctx& F, const uint8_t* til
     sl = __shfl_sync(peers, sl, leader) + (uint32_t)__popc(peers & ((1u << lane) - 1u));
     if (sl < F.seg_cap) { QEntry e; e.key = key; e.bad = bad; e.len = klen; F.myq[sl] = e; }
     else {                                                     // segment full: resolve right here
-        const uint32_t r = resolve_seed_thread(T, F.c_miss, key, bad, klen);
+        const uint32_t r = resolve_seed_thread(F.X->T, F.c_miss, key, bad, klen);
         if (r != RES_NONE) { atomicAdd(O.counts + r, 1ull); n.imperfect++; } else n.nonal++;
     }
 }
@@ -392,7 +393,7 @@ __device__ __forceinline__ Fast1Pending fast1_warp_issue(const Fast1Ctx& F, bool
             ge.qual_addr = (uint64_t)gqual; ge.qual_len = e3 - s3;
             const uint32_t slot = atomicAdd(&F.St->g_count, 1u);
             if (slot < F.St->g_cap) F.gqueue[slot] = ge;
-            else g_process_read(G, T, E, O, (const uint8_t*)ge.seq_addr, (int)ge.seq_len, (const uint8_t*)ge.qual_addr, (int)ge.qual_len, gst);
+            else g_process_read(G, F.X->T, F.X->E, F.X->O, (const uint8_t*)ge.seq_addr, (int)ge.seq_len, (const uint8_t*)ge.qual_addr, (int)ge.qual_len, gst);
         }
     }
     bool can = live && !generic_len && p.bad == 0;
@@ -401,9 +402,9 @@ __device__ __forceinline__ Fast1Pending fast1_warp_issue(const Fast1Ctx& F, bool
     if (T.cuckoo) {                                            // (uniform) every lane loads; lanes without a key read some slot and ignore it
         can = can && klen == T.c_len;
         uint32_t h1, h2;
-        cuckoo_slots(T.ck_mul, T.ck_mask, p.klo, p.khi, h1, h2);
-        p.ra = __ldg(reinterpret_cast<const uint2*>(T.cuckoo) + h1);
-        p.rb = __ldg(reinterpret_cast<const uint2*>(T.cuckoo) + h2);
+        cuckoo_slots(T.ck_mul[0], T.ck_mul[1], T.ck_mul[2], T.ck_mul[3], T.ck_mask, p.klo, p.khi, h1, h2);
+        p.ra = ldg_u2_here(reinterpret_cast<const uint2*>(T.cuckoo) + h1);
+        p.rb = ldg_u2_here(reinterpret_cast<const uint2*>(T.cuckoo) + h2);
     } else {
         direct = 1u << 10;
         if (can) {
@@ -436,9 +437,9 @@ __device__ __forceinline__ Fast1Pending fast1_ord_issue(const Fast1Ctx& F, bool 
     n.qfail += (ord && fails) ? 1u : 0u;
     const bool live = ord && !fails;
     uint32_t h1, h2;
-    cuckoo_slots(T.ck_mul, T.ck_mask, p.klo, p.khi, h1, h2);
-    p.ra = __ldg(reinterpret_cast<const uint2*>(T.cuckoo) + h1);
-    p.rb = __ldg(reinterpret_cast<const uint2*>(T.cuckoo) + h2);
+    cuckoo_slots(T.ck_mul[0], T.ck_mul[1], T.ck_mul[2], T.ck_mul[3], T.ck_mask, p.klo, p.khi, h1, h2);
+    p.ra = ldg_u2_here(reinterpret_cast<const uint2*>(T.cuckoo) + h1);
+    p.rb = ldg_u2_here(reinterpret_cast<const uint2*>(T.cuckoo) + h2);
     p.meta = (uint32_t)c_len | ((live && p.bad == 0) ? 1u << 8 : 0u) | (live ? 1u << 9 : 0u);
     return p;
 }
@@ -472,7 +473,7 @@ __device__ __forceinline__ void fast1_warp_commit(const Fast1Ctx& F, const Fast1
             const uint32_t klen = p.meta & 63u;
             if (sl < F.seg_cap) { QEntry e; e.key = key; e.bad = p.bad; e.len = klen; F.myq[sl] = e; }
             else {                                                 // segment full: resolve right here
-                const uint32_t r = resolve_seed_thread(T, F.c_miss, key, p.bad, klen);
+                const uint32_t r = resolve_seed_thread(F.X->T, F.c_miss, key, p.bad, klen);
                 if (r != RES_NONE) { atomicAdd(O.counts + r, 1ull); n.imperfect++; } else n.nonal++;
             }
         }
@@ -561,7 +562,7 @@ __device__ __noinline__ uint32_t tile_lookback(const uint8_t* status, uint64_t r
 // @region kernel_prologue
 template <int POLICY, int CH, int NT>
 __global__ void __launch_bounds__(NT + TILE_CTRL_THREADS, POLICY == POLICY_FAST1 ? (512 / NT) : (256 / NT))
-k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, Outputs O) {
+k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, Outputs O, const SlowArgs* __restrict__ X) {
     using G_ = TileGeom<CH, NT>;
     constexpr int S = G_::S, NS = G_::NS, CAP = G_::CAP;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -670,7 +671,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     Fast1Ctx F;
     F.init(Gp);
     F.hist = P.hist_smem ? hist : nullptr; F.myq = P.queue + (size_t)blockIdx.x * P.seg_cap; F.seg_cap = P.seg_cap; F.s_qn = &s_qn;
-    F.gqueue = P.gqueue; F.St = St;
+    F.gqueue = P.gqueue; F.St = St; F.X = X;
     Acc acc{0, 0, 0, 0, 0, 0};
     unsigned long long gst[F2Q_N_STATS] = {0, 0, 0, 0, 0};            // stats of reads handled by the generic code
     Fast1Counts cn{0, 0, 0, 0, 0};                                     // per-thread counts of this launch
@@ -800,7 +801,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 uint32_t idx = reinterpret_cast<const uint16_t*>(smem + G_::EXCL_OFF)[par * NT + tid];   // exact: total_all <= NT*S < 65536
                 for (uint32_t b = 0; b < (uint32_t)S; b++) {
                     if (tile[tid * S + b] != '\n') continue;
-                    if (((p0 + idx) & 3u) == 0) slow_record(buf, base + tid * S + b, end, eof, G, T, E, O, acc, gst);
+                    if (((p0 + idx) & 3u) == 0) slow_record(buf, base + tid * S + b, end, eof, G, X, acc, gst);
                     idx++;
                 }
             }
@@ -810,7 +811,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             if (j + 3 >= total_all) {
                 // the read's last newline is not in the loaded rows (a long record, or the end of the range where only
                 // an unterminated final quality line can still complete it): finish it in global memory
-                slow_record(buf, base + h0, end, eof, G, T, E, O, acc, gst);
+                slow_record(buf, base + h0, end, eof, G, X, acc, gst);
                 continue;
             }
             const uint32_t s0 = h0 + 1u;
@@ -821,7 +822,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             acc.last_end = (unsigned long long)(base + e3 + 1);         // (a thread meets its reads in stream order)
             if (POLICY == POLICY_GENERIC) {
                 const uint8_t* Rp = tile + s0; const uint8_t* Qp = tile + s3;
-                g_process_read(G, T, E, O, Rp, g_rstrip(Rp, (int)(e0 - s0)), Qp, g_rstrip(Qp, (int)(e3 - s3)), gst);
+                g_process_read(G, X->T, X->E, X->O, Rp, g_rstrip(Rp, (int)(e0 - s0)), Qp, g_rstrip(Qp, (int)(e3 - s3)), gst);
                 continue;
             }
             // @region parse_k2
