@@ -43,14 +43,55 @@ def env_int(k, d):
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+    """samples SM clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe).  NVML from a thread
+    every 5 ms (the resident leg lasts tens of milliseconds, too short for `nvidia-smi -lms`); nvidia-smi if NVML is missing."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, gpu_index):
-        self.gpu, self.rows, self.p = gpu_index, [], None
+    def __init__(self, gpu_index, uuid=None):
+        self.gpu, self.uuid, self.rows, self.p, self.nv, self.stop_flag = gpu_index, uuid, [], None, None, False
+        self.sm, self.mx, self.reasons = [], [], set()
+
+    def _nvml_loop(self):
+        nv, h = self.nv
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                for u in (f"GPU-{self.uuid}", str(self.uuid)):
+                    try:
+                        h = nv.nvmlDeviceGetHandleByUUID(u if isinstance(u, bytes) else u.encode()); break
+                    except Exception:
+                        try:
+                            h = nv.nvmlDeviceGetHandleByUUID(u); break
+                        except Exception:
+                            h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.mx = [float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))]
+            self.nv = (nv, h)
+            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                        "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -64,6 +105,11 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
+        if self.nv:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx[0] if self.mx else None,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, 5 ms period, resident + end-to-end timed regions"}
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -84,7 +130,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100, resident + end-to-end timed regions"}
 
 
 def measured_peak():
@@ -206,7 +252,11 @@ def run_gpu(args, rank, local_rank, world):
     for _ in range(args.warmup):
         counts, stats = step_resident()
     assert stats["reads"] == n_reads * world, stats
-    clocks = ClockSampler(local_rank)
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        gpu_uuid = None
+    clocks = ClockSampler(local_rank, gpu_uuid)
     tile_ms = []
     barrier()
     if rank == 0:
@@ -220,7 +270,6 @@ def run_gpu(args, rank, local_rank, world):
     e1.record(stream)
     barrier()
     launches = eng.launches - l0
-    clk = clocks.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1) / args.steps
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -262,6 +311,7 @@ def run_gpu(args, rank, local_rank, world):
                "d2h_bytes_per_step": (len(keys) + 5) * 8, "ms_per_step": ms2, "wall_ms_per_step": wall,
                "h2d_gbs_per_gpu": nbytes / (ms2 / 1e3) / 1e9}
         pin.free()
+    clk = clocks.stop() if rank == 0 else None
 
     if rank == 0:
         peak, peak_src = measured_peak()
