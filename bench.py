@@ -28,6 +28,15 @@ import time
 
 import numpy as np
 
+_JSON_OUT = None
+
+
+def emit(obj):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -189,7 +198,7 @@ def run_reference(args, rank, world):
     dt = (time.perf_counter() - t0) / args.steps
     v = threads * per / dt / 1e6
     sample = f"{threads} threads x {per} reads of the config-2 stream per step (one shard per thread, counts merged by addition)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "M reads/s", "value": v, "unit": "M reads/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
@@ -197,7 +206,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": v, "unit": "M reads/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "M reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -214,6 +223,11 @@ def run_gpu(args, rank, local_rank, world):
     multi = importlib.import_module("2fast2q_b200.multi")
     lib.load()                                                     # raises if the CUDA library is missing
     torch.cuda.set_device(local_rank)
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        gpu_uuid = None
+    placement = numa_bind(gpu_uuid, local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
@@ -252,10 +266,6 @@ def run_gpu(args, rank, local_rank, world):
     for _ in range(args.warmup):
         counts, stats = step_resident()
     assert stats["reads"] == n_reads * world, stats
-    try:
-        gpu_uuid = str(torch.cuda.get_device_properties(dev).uuid)
-    except Exception:
-        gpu_uuid = None
     clocks = ClockSampler(local_rank, gpu_uuid)
     tile_ms = []
     barrier()
@@ -326,7 +336,8 @@ def run_gpu(args, rank, local_rank, world):
             "config": {"workload": "config2: synthetic 50bp reads vs 2000-guide library, --st 0 --l 20 --m 1 --ph 30",
                        "reads_per_gpu": n_reads, "bytes_per_read": REC, "input_bytes_per_gpu": nbytes,
                        "l2": "inputs (%.1f GB/GPU) are far larger than the 126 MB L2; no flush needed" % (nbytes / 1e9),
-                       "parallelism": f"reads sharded by contiguous range over {world} GPU(s); counts merged by NCCL all-reduce"},
+                       "parallelism": f"reads sharded by contiguous range over {world} GPU(s); counts merged by NCCL all-reduce",
+                       "host_placement": placement},
             "clocks": clk,
             "e2e": e2e,
             "gpu_launches": launches,
@@ -344,7 +355,7 @@ def run_gpu(args, rank, local_rank, world):
         }
         if not args.no_cpu:
             out["cpu_baseline"] = cpu_baseline(eng, data.data_ptr(), args.cpu_reads, keys)
-        print(json.dumps(out))
+        emit(out)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -363,7 +374,34 @@ def cpu_baseline(eng, dptr, n, keys):
             "sample": f"first {n} reads of the same synthetic stream, oracle/f2q_oracle.c single thread, {dt:.1f} s"}
 
 
+def numa_bind(gpu_uuid, gpu_index):
+    """run this rank (and first-touch its pinned buffers) on the CPUs nearest to its GPU, when the container allows it"""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        try:
+            h = nv.nvmlDeviceGetHandleByUUID(f"GPU-{gpu_uuid}".encode()) if gpu_uuid else nv.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:
+            h = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+        allowed = os.sched_getaffinity(0)
+        words = nv.nvmlDeviceGetCpuAffinity(h, (max(allowed) // 64) + 1)
+        ideal = {64 * w + b for w, x in enumerate(words) for b in range(64) if (int(x) >> b) & 1}
+        both = allowed & ideal
+        if both and both != allowed:
+            os.sched_setaffinity(0, both)
+            return f"bound to {len(both)} of {len(allowed)} allowed CPUs near the GPU"
+        return "not bound (all allowed CPUs are equally near, or none is)"
+    except Exception as e:                                        # noqa: BLE001 — placement is an optimisation only
+        return f"not bound ({type(e).__name__})"
+
+
 def main():
+    # anything a library prints on stdout (NCCL's version banner) must not precede the ONE JSON line: fd 1 -> stderr,
+    # the line itself goes to the saved descriptor
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
