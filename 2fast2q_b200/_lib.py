@@ -65,6 +65,7 @@ SYMBOLS = {
     "f2q_sync": (C.c_int, [_VP]),
     "f2q_sync_copies": (C.c_int, [_VP]),
     "f2q_end_sample": (C.c_int, [_VP, _VP, _VP]),
+    "f2q_end_sample_async": (C.c_int, [_VP, _VP]),
     "f2q_result_device": (C.c_int, [_VP, C.POINTER(_VP), _U64P]),
     "f2q_ec_size": (C.c_int, [_VP, _U64P, _U64P]),
     "f2q_ec_drain": (C.c_int, [_VP, _VP, _VP, _VP]),
@@ -259,6 +260,18 @@ class Engine:
         stats = np.zeros(N_STATS, dtype=np.uint64)
         self._ck(self.L.f2q_end_sample(self.h, counts.ctypes.data, stats.ctypes.data))
         return counts[:self.n_keys], dict(zip(STAT_NAMES, (int(x) for x in stats)))
+
+    def end_async(self, pinned: "PinnedBuffer"):
+        """finish the sample without waiting; `pinned` (>= 8 * (n_keys + 6) bytes) holds the result after sync()"""
+        assert pinned.nbytes >= 8 * (self.n_keys + 6)
+        self._ck(self.L.f2q_end_sample_async(self.h, pinned.ptr))
+
+    def read_async_result(self, pinned: "PinnedBuffer"):
+        """(counts, stats) from a buffer filled by end_async — call sync() first"""
+        v = np.frombuffer(pinned.array, dtype=np.uint64, count=self.n_keys + 6)
+        if int(v[self.n_keys + 5]):
+            raise F2QError(-8, f"device-side failure, flags={int(v[self.n_keys + 5]):#x}")
+        return v[:self.n_keys].copy(), dict(zip(STAT_NAMES, (int(x) for x in v[self.n_keys:self.n_keys + 5])))
 
     def result_device(self):
         p, n = C.c_void_p(), C.c_uint64()

@@ -92,6 +92,7 @@ struct f2q_ctx {
     DevBuf slow_args;
     SlowArgs slow_host[2];
     bool slow_valid = false;
+    bool async_pending = false;        // f2q_end_sample_async results not yet waited for (kernel timings are collected by f2q_sync)
     uint64_t spec_counts[2] = {0, 0};  // last finished sample: chunks committed by the speculation / parsed by the exact kernel
     int nt = 128;                      // threads (= owned rows) per tile-kernel CTA: 128 or 256
     // optional per-kernel timing (option "time_kernels"): event pairs around the tile / resolver / generic launches
@@ -888,6 +889,7 @@ F2Q_EXPORT int f2q_sync(f2q_ctx* c) {
     int rc = check_ctx(c); if (rc) return rc;
     if (c->copy_stream) CU(c, cudaStreamSynchronize(c->copy_stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    if (c->async_pending && !c->in_sample) { timing_collect(c); c->async_pending = false; }
     return F2Q_OK;
 }
 
@@ -925,6 +927,21 @@ F2Q_EXPORT int f2q_end_sample(f2q_ctx* c, uint64_t* counts, uint64_t* stats) {
     if (err) return fail(c, F2Q_EINTERNAL, "device-side failure, flags=" + std::to_string(err));
     if (counts && c->n_keys) CU(c, cudaMemcpy(counts, c->result.p, (size_t)c->n_keys * 8, cudaMemcpyDeviceToHost));
     CU(c, cudaMemcpy(stats, reinterpret_cast<uint8_t*>(c->result.p) + (size_t)c->n_keys * 8, 5 * 8, cudaMemcpyDeviceToHost));
+    return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_end_sample_async(f2q_ctx* c, uint64_t* pinned_out) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (!c->in_sample) return fail(c, F2Q_ESTATE, "f2q_end_sample_async outside a sample");
+    if (!pinned_out) return fail(c, F2Q_EINVAL, "null output");
+    if (c->cfg.mode != F2Q_MODE_COUNT) return fail(c, F2Q_EUNSUPPORTED, "f2q_end_sample_async is for Counter mode (Extract+Count results are drained by f2q_ec_drain)");
+    if (!c->closed && (rc = process_device_chunk(c, nullptr, 0, 1))) return rc;     // flush a carried final record
+    const size_t n = (size_t)c->n_keys + 5;
+    pinned_out[n] = 0;
+    CU(c, cudaMemcpyAsync(pinned_out, c->result.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(pinned_out + n, c->d_error, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(pinned_out + n) + 4, &c->dS->error, 4, cudaMemcpyDeviceToHost, c->stream));
+    c->in_sample = false; c->async_pending = true;
     return F2Q_OK;
 }
 

@@ -158,6 +158,15 @@ int f2q_sync_copies(f2q_ctx* ctx);
  */
 int f2q_end_sample(f2q_ctx* ctx, uint64_t* counts, uint64_t stats[F2Q_N_STATS]);
 
+/*
+ * Counter mode, many samples back to back: finish the sample WITHOUT waiting.  The stream is closed (a carried final
+ * record is flushed) and [counts[n_keys] | stats[5] | error word] (n_keys + 6 uint64) is copied, stream-ordered, into
+ * pinned_out, which must come from f2q_host_alloc.  f2q_begin_sample may follow at once; the numbers are valid after the
+ * next f2q_sync (or any later blocking call).  A non-zero error word reports a device-side failure of that sample
+ * (low half: kernel error flags, high half: stream state flags; F2Q_ETOOLONG's bit is 2 of the high half).
+ */
+int f2q_end_sample_async(f2q_ctx* ctx, uint64_t* pinned_out);
+
 /* device address of the uint64 vector [counts[n_keys] | stats[5]] of the current sample, valid after
  * the work was enqueued; for an in-place NCCL all-reduce over ranks (merge_feature_dicts,
  * fast2q.py:439-445, 487-495).  After a reduce call f2q_end_sample as usual. */

@@ -203,3 +203,28 @@ def test_resident_device_submit_large(gu, oracle):
     assert int(c1.sum()) == s1["perfect_counter"] + s1["imperfect_counter"]
     want_c, want_s = oracle.count(oracle.make_config(miss=1), keys, host)
     assert want_s == s1 and np.array_equal(want_c, c1)
+
+
+def test_end_sample_async_back_to_back(gu, oracle):
+    """three samples without a host round trip in between: every pinned result equals the blocking path's"""
+    from oracle import synth
+    spec = synth.default_spec(2)
+    names, keys = synth.make_library(2, 700, 20)
+    datas = [synth.fixed_reads(keys, 1000 * k, 40_000 + 777 * k, **spec).tobytes() for k in range(3)]
+    cfg = gu.lib.make_config(miss=1)
+    with gu.lib.Engine(cfg) as e:
+        e.set_library(keys)
+        want = [e.run(d) for d in datas]
+        bufs = [gu.lib.PinnedBuffer(8 * (len(keys) + 6)) for _ in datas]
+        for d, b in zip(datas, bufs):
+            e.begin()
+            e.submit(d[:len(d) // 2], False)
+            e.submit(d[len(d) // 2:], False)          # not closed: end_sample_async flushes the carried record itself
+            e.end_async(b)
+        e.sync()
+        for (wc, ws), b, d in zip(want, bufs, datas):
+            c, s = e.read_async_result(b)
+            assert s == ws and np.array_equal(c, wc)
+            oc, os_ = oracle.count(oracle.make_config(miss=1), keys, d)
+            assert s == os_ and np.array_equal(c, oc)
+            b.free()
