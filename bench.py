@@ -52,94 +52,57 @@ def env_int(k, d):
 
 
 class ClockSampler:
-    """samples SM clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe).  NVML from a thread
-    every 5 ms (the resident leg lasts tens of milliseconds, too short for `nvidia-smi -lms`); nvidia-smi if NVML is missing."""
+    """samples SM clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe) with an `nvidia-smi`
+    subprocess polling every 20 ms.  Deliberately NOT in-process NVML: measured on this pool, one NVML query from a thread
+    of the benchmark process blocks its CUDA launches for ~15 ms, three times the length of a whole resident pass."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index, uuid=None):
-        self.gpu, self.uuid, self.rows, self.p, self.nv, self.stop_flag = gpu_index, uuid, [], None, None, False
-        self.sm, self.mx, self.reasons = [], [], set()
-
-    def _nvml_loop(self):
-        nv, h = self.nv
-        while not self.stop_flag:
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                except Exception:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in self.BITS.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.005)
+        self.gpu, self.uuid, self.rows, self.p = gpu_index, uuid, [], None
 
     def start(self):
+        sel = f"GPU-{self.uuid}" if self.uuid and not str(self.uuid).startswith("GPU-") else (self.uuid or str(self.gpu))
         try:
-            import pynvml as nv
-            nv.nvmlInit()
-            h = None
-            if self.uuid:
-                for u in (f"GPU-{self.uuid}", str(self.uuid)):
-                    try:
-                        h = nv.nvmlDeviceGetHandleByUUID(u if isinstance(u, bytes) else u.encode()); break
-                    except Exception:
-                        try:
-                            h = nv.nvmlDeviceGetHandleByUUID(u); break
-                        except Exception:
-                            h = None
-            if h is None:
-                h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
-            self.mx = [float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))]
-            self.nv = (nv, h)
-            self.t = threading.Thread(target=self._nvml_loop, daemon=True)
-            self.t.start()
-            return
-        except Exception:
-            self.nv = None
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                       "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
+                                       "-i", str(sel)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            time.sleep(0.5)                                        # let it come up before the timed region starts
         except OSError:
             self.p = None
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([time.perf_counter()] + [x.strip() for x in line.split(",")])
 
-    def stop(self):
-        if self.nv:
-            self.stop_flag = True
-            self.t.join(timeout=1)
-            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.mx[0] if self.mx else None,
-                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml, 5 ms period, resident + end-to-end timed regions"}
+    def stop(self, windows=()):
+        """windows: (t0, t1) perf_counter intervals of the timed regions; samples inside them are counted separately"""
         if not self.p:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.p.terminate()
         try:
             self.p.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.p.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, inside = [], [], set(), [0] * len(windows)
         for r in self.rows:
-            if len(r) < 8:
+            if len(r) < 9:
                 continue
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                sm.append(float(r[2])); mx.append(float(r[3]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+            for k, (a, b) in enumerate(windows):
+                if a <= r[0] <= b + 0.02:
+                    inside[k] += 1
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100, resident + end-to-end timed regions"}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_regions": inside,
+                "source": "nvidia-smi -lms 20 from just before the resident timed region to the end of the end-to-end timed region"}
 
 
 def measured_peak():
@@ -268,15 +231,16 @@ def run_gpu(args, rank, local_rank, world):
     assert stats["reads"] == n_reads * world, stats
     clocks = ClockSampler(local_rank, gpu_uuid)
     tile_ms = []
-    barrier()
-    if rank == 0:
+    if rank == 0 and not os.environ.get("F2Q_BENCH_NO_CLOCKS"):
         clocks.start()
+    barrier()
     l0 = eng.launches
     # the K timed passes run back to back: each one ends with f2q_end_sample_async, i.e. its [counts | stats] vector is
     # copied into its own pinned host buffer, stream-ordered, and checked after the timed region (no host round trip
     # between passes; the end-to-end leg below does the blocking read every step)
     res_bufs = [lib.PinnedBuffer(8 * (len(keys) + 6)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w_res0 = time.perf_counter()
     e0.record(stream)
     for k in range(args.steps):
         eng.begin()
@@ -286,6 +250,7 @@ def run_gpu(args, rank, local_rank, world):
     e1.record(stream)
     barrier()
     eng.sync()
+    windows = [(w_res0, time.perf_counter())]
     tile_ms.append(eng.kernel_times()["tile"])
     for b in res_bufs:
         c_k, s_k = eng.read_async_result(b)
@@ -323,6 +288,7 @@ def run_gpu(args, rank, local_rank, world):
             step_e2e()
         f1.record(stream)
         barrier()
+        windows.append((t0, time.perf_counter()))
         wall = (time.perf_counter() - t0) / args.steps * 1e3
         ms2 = max(f0.elapsed_time(f1) / args.steps, 0.0)
         t = torch.tensor([ms2, wall], dtype=torch.float64, device=dev)
@@ -333,7 +299,7 @@ def run_gpu(args, rank, local_rank, world):
                "d2h_bytes_per_step": (len(keys) + 5) * 8, "ms_per_step": ms2, "wall_ms_per_step": wall,
                "h2d_gbs_per_gpu": nbytes / (ms2 / 1e3) / 1e9}
         pin.free()
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(windows) if rank == 0 else None
 
     if rank == 0:
         peak, peak_src = measured_peak()
