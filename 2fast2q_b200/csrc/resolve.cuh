@@ -192,14 +192,18 @@ __host__ __device__ __forceinline__ uint64_t even_range(uint32_t b0, uint32_t b1
     return (hi & ~lo) & 0x5555555555555555ull;
 }
 
-__device__ inline uint32_t resolve_seed_thread(const LibTables& T, int m, uint64_t key, uint32_t bad, uint32_t len) {
+// bounds (optional): segment boundaries s * len / parts for every (len <= 32, s <= parts) as bytes at [len * SEED_BOUND_STRIDE + s]
+// (the resolver kernel keeps them in shared memory: the integer divisions were most of its instructions)
+constexpr uint32_t SEED_BOUND_STRIDE = 34;
+__device__ inline uint32_t resolve_seed_thread(const LibTables& T, int m, uint64_t key, uint32_t bad, uint32_t len, const uint8_t* bounds = nullptr) {
     const int nbad = __popc(bad);
     if (m <= 0 || nbad > m) return RES_NONE;
     const uint32_t parts = T.seed_parts;
     const uint64_t lenmask = even_range(0, len), badeven = spread_even(bad) & lenmask;
+    const uint8_t* bl = bounds ? bounds + len * SEED_BOUND_STRIDE : nullptr;
     Best b{m + 1, 0, 0};
     for (uint32_t s = 0; s < parts; s++) {
-        const uint32_t b0 = s * len / parts, b1 = (s + 1) * len / parts;
+        const uint32_t b0 = bl ? bl[s] : s * len / parts, b1 = bl ? bl[s + 1] : (s + 1) * len / parts;
         const uint64_t seg = even_range(b0, b1);
         if (badeven & seg) continue;                                   // a non-ACGT symbol can never agree exactly
         const uint64_t v = (key >> (2 * b0)) & ((seg | (seg << 1)) >> (2 * b0));
@@ -218,7 +222,7 @@ __device__ inline uint32_t resolve_seed_thread(const LibTables& T, int m, uint64
             const uint64_t diff = (((x | (x >> 1)) & lenmask) | badeven);     // even bit 2p: symbol p differs (or is bad)
             bool dup = false;                                          // already seen through an earlier agreeing segment?
             for (uint32_t s2 = 0; s2 < s; s2++)
-                if ((diff & even_range(s2 * len / parts, (s2 + 1) * len / parts)) == 0) { dup = true; break; }
+                if ((diff & even_range(bl ? bl[s2] : s2 * len / parts, bl ? bl[s2 + 1] : (s2 + 1) * len / parts)) == 0) { dup = true; break; }
             if (dup) continue;
             b.add(__popcll(diff), it.z, m);
         }
@@ -228,13 +232,19 @@ __device__ inline uint32_t resolve_seed_thread(const LibTables& T, int m, uint64
 
 __global__ void __launch_bounds__(256) k_resolve_seed(LibTables T, int m, const QEntry* __restrict__ queue, const uint32_t* __restrict__ seg_count,
                                                       uint32_t seg_cap, uint32_t n_segs, unsigned long long* counts, unsigned long long* stats) {
+    __shared__ uint8_t s_bounds[33 * SEED_BOUND_STRIDE];
+    for (uint32_t i = threadIdx.x; i < 33u * SEED_BOUND_STRIDE; i += blockDim.x) {
+        const uint32_t len = i / SEED_BOUND_STRIDE, sg = i % SEED_BOUND_STRIDE;
+        s_bounds[i] = (uint8_t)(min(sg, T.seed_parts) * len / T.seed_parts);
+    }
+    __syncthreads();
     uint32_t imperfect = 0, nonal = 0;
     for (uint32_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
         const uint32_t n = min(seg_count[seg], seg_cap);
         const QEntry* __restrict__ q = queue + (size_t)seg * seg_cap;
         for (uint32_t i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {     // gridDim.y CTAs share a segment
             const QEntry e = q[i];
-            const uint32_t r = resolve_seed_thread(T, m, e.key, e.bad, e.len);
+            const uint32_t r = resolve_seed_thread(T, m, e.key, e.bad, e.len, e.len <= 32 ? s_bounds : nullptr);
             if (r != RES_NONE) { atomicAdd(counts + r, 1ull); imperfect++; } else nonal++;
         }
     }
