@@ -811,6 +811,43 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
             i = e;
         }
     }
+    // byte-level seed index over every key (generic path)
+    {
+        std::vector<uint4> gslots(16, make_uint4(0, 0, 0, 0));
+        std::vector<uint32_t> gitems;
+        uint32_t gparts = 0;
+        if (c->cfg.miss >= 1 && c->cfg.miss + 1 <= (int)GSEED_MAX_PARTS && n_keys) {
+            gparts = (uint32_t)c->cfg.miss + 1;
+            std::vector<std::pair<uint64_t, uint32_t>> ent;
+            ent.reserve((size_t)n_keys * gparts);
+            for (uint32_t i = 0; i < n_keys; i++) {
+                const uint32_t len = (uint32_t)(off[i + 1] - off[i]);
+                if (len < gparts) continue;                            // (such keys are found by the linear scan: the device takes it for klen < parts)
+                for (uint32_t sg = 0; sg < gparts; sg++) {
+                    uint32_t a, b;
+                    gseed_init(len, sg, a, b);
+                    for (uint32_t k = sg * len / gparts; k < (sg + 1) * len / gparts; k++) gseed_step(bytes[off[i] + k], a, b);
+                    ent.emplace_back(gseed_tag(a, b), i);
+                }
+            }
+            std::sort(ent.begin(), ent.end());
+            size_t uniq = 0;
+            for (size_t i = 0; i < ent.size(); i++) if (i == 0 || ent[i].first != ent[i - 1].first) uniq++;
+            const uint32_t scap = pow2_at_least(2 * (uint64_t)uniq + 2);
+            gslots.assign(scap, make_uint4(0, 0, 0, 0));
+            gitems.resize(ent.size());
+            for (size_t i = 0; i < ent.size();) {
+                size_t e = i;
+                while (e < ent.size() && ent[e].first == ent[i].first) { gitems[e] = ent[e].second; e++; }
+                uint32_t h = gseed_hash(ent[i].first) & (scap - 1);
+                while (gslots[h].x | gslots[h].y) h = (h + 1) & (scap - 1);
+                gslots[h] = make_uint4((uint32_t)ent[i].first, (uint32_t)(ent[i].first >> 32), (uint32_t)i, (uint32_t)(e - i));
+                i = e;
+            }
+        }
+        if ((rc = upload(c, gslots, &c->T.gseed_slots)) || (rc = upload(c, gitems, &c->T.gseed_items))) return rc;
+        c->T.gseed_mask = (uint32_t)gslots.size() - 1; c->T.gseed_parts = gparts;
+    }
     if ((rc = upload(c, seed_slots, &c->T.seed_slots)) || (rc = upload(c, seed_recs, &c->T.seed_recs))) return rc;
     c->T.seed_mask = (uint32_t)seed_slots.size() - 1; c->T.seed_parts = parts;
     if ((rc = upload(c, slots, &c->T.slots)) || (rc = upload(c, fk, &c->T.fast_keys)) || (rc = upload(c, fl, &c->T.fast_lens)) ||

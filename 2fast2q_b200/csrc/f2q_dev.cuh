@@ -78,6 +78,11 @@ struct LibTables {
     uint32_t seed_mask;
     const uint4* seed_recs;    // {packed key lo, hi, feature index, 0} of every (key, segment), grouped by seed slot
     uint32_t seed_parts;       // miss + 1
+    // the same idea over the raw key BYTES of every library entry (generic path: multi-feature 'X:Y' keys, odd alphabets, > 32 symbols)
+    const uint4* gseed_slots;  // {tag lo, tag hi, start, count}; tag = 64-bit hash of (key length, segment, segment bytes), 0 = empty
+    uint32_t gseed_mask;
+    const uint32_t* gseed_items;   // key indices
+    uint32_t gseed_parts;      // miss + 1 when the index exists (1 <= miss <= 7), else 0
 };
 
 // entry of the deferred non-exact key queue (filled by the tile kernel, drained by the resolver kernel)

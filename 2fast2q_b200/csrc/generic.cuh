@@ -56,6 +56,20 @@ __device__ __forceinline__ bool g_within(const uint8_t* a, const uint8_t* b, int
 }
 
 __device__ inline int g_border_finder(const uint8_t* seq, int s, const uint8_t* read, int r, int mismatch, int start_place) {
+    if (start_place >= 0 && s >= 1) {
+        // the ordinary call: only positions with the whole search sequence inside the read can be returned (a shorter tail
+        // slice is compared but then cut off by fall_over).  Written for a warp: every position costs the same s byte
+        // compares (no data-dependent inner exit), so the lanes of a warp walk their reads in lockstep and only leave at
+        // their own first match — the byte-wise early-exit form ran at 2.4 active lanes per instruction.
+        const int last = r - s;
+        for (int p = start_place; p <= last; p++) {
+            int miss = 0;
+            #pragma unroll 4
+            for (int i = 0; i < s; i++) miss += (seq[i] != read[p + i]) ? 1 : 0;
+            if (miss <= mismatch) return p;
+        }
+        return -1;
+    }
     int fall_over = r - s;
     int lo, hi;
     py_slice(r, start_place, r, lo, hi);
@@ -74,8 +88,9 @@ __device__ inline int g_border_finder(const uint8_t* seq, int s, const uint8_t* 
 __device__ __forceinline__ bool g_slice_fails(const uint8_t* q, int n, int a, int b, const ByteSet& s) {
     int lo, hi;
     py_slice(n, a, b, lo, hi);
-    for (int i = lo; i < hi; i++) if (in_set(s, q[i])) return true;
-    return false;
+    bool fails = false;                                               // (no early exit: the slice length is the same for every lane)
+    for (int i = lo; i < hi; i++) fails |= in_set(s, q[i]);
+    return fails;
 }
 
 // sequence_tinder (fast2q.py:215-285)
@@ -144,6 +159,24 @@ __host__ __device__ __forceinline__ uint32_t fnv_step(uint32_t h, uint32_t b) { 
 constexpr uint32_t FNV_INIT = 2166136261u;
 __host__ __device__ __forceinline__ uint32_t fnv_final(uint32_t h) { h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 12; return h; }
 
+// byte-level pigeonhole seeds (see LibTables::gseed_*): two 32-bit FNV streams make the 64-bit tag of one key segment
+constexpr uint32_t GSEED_MAX_PARTS = 8;
+__host__ __device__ __forceinline__ void gseed_init(uint32_t len, uint32_t seg, uint32_t& a, uint32_t& b) {
+    a = fnv_step(fnv_step(FNV_INIT, len & 0xFFu), seg + 1u);
+    b = (0x9E3779B9u ^ (len * 0x85EBCA6Bu)) + seg * 0xC2B2AE35u;
+}
+__host__ __device__ __forceinline__ void gseed_step(uint32_t sym, uint32_t& a, uint32_t& b) {
+    a = fnv_step(a, sym);
+    b = (b ^ (sym + 0x7Fu)) * 0x01000193u + 0x9E3779B9u;
+}
+__host__ __device__ __forceinline__ uint64_t gseed_tag(uint32_t a, uint32_t b) {
+    return (1ull << 63) | ((uint64_t)fnv_final(b) << 32) | fnv_final(a);
+}
+__host__ __device__ __forceinline__ uint32_t gseed_hash(uint64_t tag) {
+    uint64_t h = tag * 0x9E3779B97F4A7C15ull;
+    return (uint32_t)(h >> 32) ^ (uint32_t)h;
+}
+
 __device__ __forceinline__ bool g_key_equals(const uint8_t* R, const Piece* pc, int np, const uint8_t* lib, uint32_t len) {
     uint32_t i = 0; bool eq = true;
     g_for_each_symbol(R, pc, np, [&](uint32_t s) { eq = (lib[i++] == s); return eq; });
@@ -170,6 +203,45 @@ __device__ inline void g_count_key(const GenericCfg& G, const LibTables& T, cons
     const int m = G.c.miss;
     if (m <= 0) { st[F2Q_STAT_NON_ALIGNED]++; return; }
     int best_d = m + 1; uint32_t best_n = 0, best_g = 0;
+    const uint32_t parts = T.gseed_parts;
+    if (parts && klen >= parts) {
+        // pigeonhole: an entry within m mismatches agrees exactly with the key on one of m+1 segments.  Tags of the key's
+        // segments in one pass, then per segment: bucket -> candidates -> full distance.  An entry reached through several
+        // segments is counted at the first segment it agrees on.  Same answer as the scan below.
+        uint32_t ha[GSEED_MAX_PARTS], hb[GSEED_MAX_PARTS], bnd[GSEED_MAX_PARTS + 1];
+        for (uint32_t sg = 0; sg <= parts; sg++) bnd[sg] = sg * klen / parts;
+        for (uint32_t sg = 0; sg < parts; sg++) gseed_init(klen, sg, ha[sg], hb[sg]);
+        { uint32_t i = 0, cs = 0;
+          g_for_each_symbol(R, pc, np, [&](uint32_t sym) { while (i >= bnd[cs + 1]) cs++; gseed_step(sym, ha[cs], hb[cs]); i++; return true; }); }
+        for (uint32_t sg = 0; sg < parts; sg++) {
+            const uint64_t tag = gseed_tag(ha[sg], hb[sg]);
+            uint32_t start = 0, count = 0;
+            for (uint32_t hh = gseed_hash(tag) & T.gseed_mask;; hh = (hh + 1) & T.gseed_mask) {
+                const uint4 raw = __ldg(T.gseed_slots + hh);
+                const uint64_t t = ((uint64_t)raw.y << 32) | raw.x;
+                if (t == 0) break;
+                if (t == tag) { start = raw.z; count = raw.w; break; }
+            }
+            for (uint32_t c = 0; c < count; c++) {
+                const uint32_t g = __ldg(T.gseed_items + start + c);
+                const uint64_t o0 = __ldg(T.key_off + g), o1 = __ldg(T.key_off + g + 1);
+                if ((uint32_t)(o1 - o0) != klen) continue;
+                const uint8_t* lib = T.key_bytes + o0;
+                int d = 0; uint32_t i = 0, cs = 0, segbad = 0;
+                g_for_each_symbol(R, pc, np, [&](uint32_t sym) {
+                    while (i >= bnd[cs + 1]) cs++;
+                    const uint32_t ne = lib[i++] != sym;
+                    d += (int)ne; segbad |= ne << cs;
+                    return d <= m;
+                });
+                if (d > m) continue;
+                const uint32_t agree = ~segbad & ((1u << parts) - 1u);
+                if (agree == 0 || (uint32_t)__ffs((int)agree) - 1u != sg) continue;      // a hash collision, or counted at an earlier segment
+                if (d < best_d) { best_d = d; best_n = 1; best_g = g; }
+                else if (d == best_d) best_n++;
+            }
+        }
+    } else
     for (uint32_t g = 0; g < T.n_keys; g++) {                              // features_all_vs_all, fast2q.py:660-690
         uint64_t o0 = __ldg(T.key_off + g), o1 = __ldg(T.key_off + g + 1);
         if ((uint32_t)(o1 - o0) != klen) continue;
