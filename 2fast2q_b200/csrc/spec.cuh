@@ -167,11 +167,11 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         __syncwarp();
     };
 
-    const uint32_t c0A = reg_const(0x0A0A0A0Au), c7F = reg_const(0x7F7F7F7Fu), c80 = reg_const(0x80808080u);
+    const uint32_t c0A = reg_const(0x0A0A0A0Au), c7F = reg_const(0x7F7F7F7Fu), c80 = reg_const(0x80808080u), one = reg_const(1u);
     auto chunk_mask = [&](const uint8_t* p16) -> uint32_t {            // newline flags of one 16-byte chunk (see tile.cuh)
         const uint4 v = *reinterpret_cast<const uint4*>(p16);
-        const uint32_t z0 = ~(((v.x ^ c0A) & c7F) + c7F | v.x) & c80, z1 = ~(((v.y ^ c0A) & c7F) + c7F | v.y) & c80;
-        const uint32_t z2 = ~(((v.z ^ c0A) & c7F) + c7F | v.z) & c80, z3 = ~(((v.w ^ c0A) & c7F) + c7F | v.w) & c80;
+        const uint32_t z0 = ~(add_on_fma((v.x ^ c0A) & c7F, one, c7F) | v.x) & c80, z1 = ~(add_on_fma((v.y ^ c0A) & c7F, one, c7F) | v.y) & c80;
+        const uint32_t z2 = ~(add_on_fma((v.z ^ c0A) & c7F, one, c7F) | v.z) & c80, z3 = ~(add_on_fma((v.w ^ c0A) & c7F, one, c7F) | v.w) & c80;
         const uint32_t lo = __dp4a(z0, 0x08040201u, __dp4a(z1, 0x80402010u, 0u));
         const uint32_t hi = __dp4a(z2, 0x08040201u, __dp4a(z3, 0x80402010u, 0u));
         return (lo >> 7) | (hi << 1);

@@ -139,6 +139,13 @@ __device__ __forceinline__ unsigned long long gtime() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+// a + b issued as a multiply-add (a * one + b, `one` from reg_const(1)): integer adds and logic ops share the ALU pipe (one
+// warp instruction per 2 cycles), multiply-adds run on the FMA pipe next to it; the byte-parallel loops are ALU-pipe bound
+__device__ __forceinline__ uint32_t add_on_fma(uint32_t a, uint32_t one, uint32_t b) {
+    uint32_t r;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
+    return r;
+}
 __device__ __forceinline__ uint32_t reg_const(uint32_t v) {
     uint32_t r;
     asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));

@@ -280,6 +280,13 @@ def run_gpu(args, rank, local_rank, world):
         for _ in range(max(1, min(args.warmup, 3))):
             c2, s2 = step_e2e()
         assert s2 == stats and np.array_equal(c2, counts)
+        # the ingest roofline: a plain pinned -> device copy of the same bytes on the same link (best of 2)
+        pcie = 0.0
+        for _ in range(2):
+            torch.cuda.synchronize(dev)
+            tp = time.perf_counter()
+            eng.h2d(data.data_ptr(), pin.array)
+            pcie = max(pcie, nbytes / (time.perf_counter() - tp) / 1e9)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -297,7 +304,8 @@ def run_gpu(args, rank, local_rank, world):
         ms2, wall = float(t[0].item()), float(t[1].item())
         e2e = {"value": world * n_reads / (ms2 / 1e3) / 1e6, "unit": "M reads/s", "h2d_bytes_per_step": nbytes,
                "d2h_bytes_per_step": (len(keys) + 5) * 8, "ms_per_step": ms2, "wall_ms_per_step": wall,
-               "h2d_gbs_per_gpu": nbytes / (ms2 / 1e3) / 1e9}
+               "h2d_gbs_per_gpu": nbytes / (ms2 / 1e3) / 1e9, "pcie_copy_gbs_measured": pcie,
+               "pcie_frac": (nbytes / (ms2 / 1e3) / 1e9) / pcie if pcie else None}
         pin.free()
     clk = clocks.stop(windows) if rank == 0 else None
 
