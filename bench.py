@@ -333,8 +333,8 @@ def run_gpu(args, rank, local_rank, world):
                          "kernel": "k_spec<POLICY_FAST1, CH=7, W=16> (speculative streaming kernel, csrc/spec.cuh)",
                          "kernel_ms_per_launch": tile_avg, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n_reads * REC,
-                         "other_kernels_ms_per_step": {"resolve": ktimes["resolve"][0], "generic": ktimes["generic"][0],
-                                                       "verify_commit_fallback": ktimes["aux"][0]},
+                         "other_kernels_ms_per_step": {"resolve": ktimes["resolve"][0] / args.steps, "generic": ktimes["generic"][0] / args.steps,
+                                                       "verify_commit_fallback": ktimes["aux"][0] / args.steps},
                          "traffic_note": traffic.get("note") if traffic else "no committed ncu --set full capture yet"},
             "speculation": {"chunks_committed": spec_counts[0], "chunks_parsed_by_exact_kernel": spec_counts[1]},
             "stats": stats,
