@@ -742,26 +742,65 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
             cslots[h] = fk[k] | ((uint64_t)fi[k] << (2 * c_len));
         }
     }
-    // two-choice cuckoo form of the compact table: <= 1/4 full, random-walk insertion, new multipliers until it builds
+    // two-choice cuckoo form of the compact table: <= 1/4 full, random-walk insertion, new multipliers until it builds.
+    // Slot = packed key | value << 2*c_len, value = feature index << 1 | imperfect.  With m >= 1 the table also holds every
+    // Hamming-1 NEIGHBOUR of every key (3*c_len per key): value = the one key at distance 1 (imperfect = 1), or CK_AMBIG
+    // when two or more keys are at distance 1 (the reference's unique-hit rule then gives "not aligned" for every m).  A
+    // neighbour that is itself a library key keeps its exact entry.  A non-exact read whose window is pure ACGT is thus
+    // decided by the same two loads as an exact one; only keys with other symbols, and keys further away when m >= 2, go
+    // to the queue and the resolver kernel.
     std::vector<uint64_t> cuckoo;
     uint32_t ck_mask = 0, ck_mul[4] = {0, 0, 0, 0};
+    bool ck_neighbours = false;
+    uint32_t ck_shift_out = 28, ck_hshift_out = 0;
     if (compact) {
-        const uint32_t tcap = pow2_at_least(2 * (uint64_t)fk.size());
+        const uint32_t keybits = 2 * c_len, hshift = (keybits > 32 ? keybits : 32) - 32;   // the value sits in the high word above bit hshift
+        const uint64_t kmask = (1ull << keybits) - 1ull;
+        const uint64_t valmax = cuckoo_valmax(hshift);                                      // all ones = empty slot
+        ck_hshift_out = hshift;
+        std::vector<std::pair<uint64_t, uint64_t>> ent;                                    // (packed key, value)
+        bool fits = (((uint64_t)n_keys << 1) | 1ull) < valmax - 1ull;
+        if (fits) {
+            for (size_t k = 0; k < fk.size(); k++) ent.emplace_back(fk[k], (uint64_t)fi[k] << 1);
+            // (only while the table stays a few MB: it must live in L2 next to the stream; a 100 000-guide library would need 270 MB,
+            // measured slower than the queue + resolver kernel)
+            const uint64_t n_nb = (uint64_t)fk.size() * 3ull * c_len;
+            if (c->cfg.miss >= 1 && n_nb + fk.size() <= (1ull << 20)) {
+                std::vector<std::pair<uint64_t, uint32_t>> nb;
+                nb.reserve((size_t)n_nb);
+                for (size_t k = 0; k < fk.size(); k++)
+                    for (uint32_t pos = 0; pos < c_len; pos++)
+                        for (uint64_t d = 1; d < 4; d++) nb.emplace_back(fk[k] ^ (d << (2 * pos)), fi[k]);
+                std::sort(nb.begin(), nb.end());
+                std::vector<uint64_t> exact(fk);
+                std::sort(exact.begin(), exact.end());
+                for (size_t i = 0; i < nb.size();) {
+                    size_t e = i;
+                    while (e < nb.size() && nb[e].first == nb[i].first) e++;
+                    if (!std::binary_search(exact.begin(), exact.end(), nb[i].first))
+                        ent.emplace_back(nb[i].first, e - i == 1 ? (((uint64_t)nb[i].second << 1) | 1ull) : valmax - 1ull);
+                    i = e;
+                }
+                ck_neighbours = true;
+            }
+        }
+        const uint32_t tcap = pow2_at_least(2 * (uint64_t)ent.size());
         ck_mask = tcap - 1;
+        uint32_t ck_shift = 32; while ((1ull << (32 - ck_shift)) < tcap) ck_shift--;
+        ck_shift_out = ck_shift;
         uint64_t seed = 0x2FA572ull ^ 0x9E3779B97F4A7C15ull;
         bool built = false;
-        for (int attempt = 0; attempt < 64 && !built; attempt++) {
+        for (int attempt = 0; attempt < 64 && !built && fits; attempt++) {
             for (int k = 0; k < 4; k++) { seed = sm_fin(seed + 0x9E3779B97F4A7C15ull * (uint64_t)(attempt * 4 + k + 1)); ck_mul[k] = (uint32_t)(seed >> 16) | 1u; }
             cuckoo.assign(2 * (size_t)tcap, ~0ull);
             built = true;
-            for (size_t k = 0; k < fk.size() && built; k++) {
-                uint64_t cur = fk[k] | ((uint64_t)fi[k] << (2 * c_len));
-                const uint64_t kmask = (1ull << (2 * c_len)) - 1ull;
+            for (size_t k = 0; k < ent.size() && built; k++) {
+                uint64_t cur = ent[k].first | (ent[k].second << (32 + hshift));
                 int kicks = 0;
                 uint32_t from = 0xFFFFFFFFu;                            // slot `cur` was evicted from
                 for (;; kicks++) {
                     uint32_t h1, h2;
-                    cuckoo_slots(ck_mul[0], ck_mul[1], ck_mul[2], ck_mul[3], ck_mask, (uint32_t)(cur & kmask), (uint32_t)((cur & kmask) >> 32), h1, h2);
+                    cuckoo_slots(ck_mul[0], ck_mul[1], ck_mul[2], ck_mul[3], ck_shift, (uint32_t)(cur & kmask), (uint32_t)((cur & kmask) >> 32), h1, h2);
                     if (cuckoo[h1] == ~0ull) { cuckoo[h1] = cur; break; }
                     if (cuckoo[h2] == ~0ull) { cuckoo[h2] = cur; break; }
                     if (kicks >= 500) { built = false; break; }
@@ -771,7 +810,10 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
                 }
             }
         }
-        if (!built) cuckoo.clear();
+        if (!built) {
+            if (fits) fprintf(stderr, "libf2q: the two-choice lookup table did not build (%zu entries); using the probing table and the resolver kernel\n", ent.size());
+            cuckoo.clear(); ck_neighbours = false;
+        }
     }
     const uint32_t gcap = pow2_at_least(2 * (uint64_t)n_keys + 2);
     std::vector<uint32_t> gh(gcap, 0);
@@ -860,6 +902,7 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
         if (!cuckoo.empty()) {
             if ((rc = upload(c, cuckoo, &c->T.cuckoo))) return rc;
             c->T.ck_mask = ck_mask; for (int k = 0; k < 4; k++) c->T.ck_mul[k] = ck_mul[k];
+            c->T.ck_neighbours = ck_neighbours ? 1u : 0u; c->T.ck_shift = ck_shift_out; c->T.ck_hshift = ck_hshift_out;
         }
     }
     c->T.slot_mask = cap - 1; c->T.n_fast = (uint32_t)fk.size(); c->T.n_keys = n_keys; c->T.ghash_mask = gcap - 1;

@@ -61,7 +61,10 @@ struct LibTables {
     // a lookup is exactly two independent loads, no probe loop, so all lanes of a warp finish together (spec.cuh)
     const uint64_t* cuckoo;
     uint32_t ck_mask;          // slots per table - 1
+    uint32_t ck_shift;         // 32 - log2(slots per table)
+    uint32_t ck_hshift;        // bit of the slot's high word where the value starts = max(2 * c_len, 32) - 32
     uint32_t ck_mul[4];        // odd multipliers of the two multiplicative hashes (chosen by the host until the build succeeds)
+    uint32_t ck_neighbours;    // 1: the table also holds every Hamming-1 neighbour of every key (value bit 0 = imperfect, CK_AMBIG = tie)
     const uint64_t* fast_keys; // n_fast packed keys grouped by length (for the tile-scan resolver)
     const uint32_t* fast_lens;
     const uint32_t* fast_idx;
@@ -229,28 +232,29 @@ __device__ __forceinline__ uint32_t compact_lookup(const LibTables& T, uint32_t 
 }
 #endif  // __CUDACC__
 
-// the two slots a packed key can live in (host and device must agree).  Multipliers by value: as kernel parameters they
-// stay constant-bank operands of the multiplies (an array argument would turn them into constant LOADS on the hot path)
-__host__ __device__ __forceinline__ void cuckoo_slots(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t mask, uint32_t klo, uint32_t khi,
+// the two slots a packed key can live in (host and device must agree).  Multiplicative hashing keeps the TOP bits of
+// the products: every key bit reaches them (the table also holds keys that differ from each other in one 2-bit symbol
+// only).  Multipliers by value: as kernel parameters they stay constant-bank operands of the multiplies.
+__host__ __device__ __forceinline__ void cuckoo_slots(uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3, uint32_t shift, uint32_t klo, uint32_t khi,
                                                       uint32_t& h1, uint32_t& h2) {
-    h1 = ((klo * m0 + khi * m1) >> 9) & mask;
-    h2 = ((((klo * m2) ^ (khi * m3)) >> 9) & mask) + mask + 1u;
+    h1 = (klo * m0 + khi * m1) >> shift;
+    h2 = (((klo * m2) ^ (khi * m3)) >> shift) + (1u << (32u - shift));
 }
 
 #ifdef __CUDACC__
-// two-choice lookup (caller checked len == T.c_len); feature index or SLOT_EMPTY
-__device__ __forceinline__ uint32_t cuckoo_lookup(const LibTables& T, uint32_t klo, uint32_t khi) {
-    uint32_t h1, h2;
-    cuckoo_slots(T.ck_mul[0], T.ck_mul[1], T.ck_mul[2], T.ck_mul[3], T.ck_mask, klo, khi, h1, h2);
-    const uint2 ra = __ldg(reinterpret_cast<const uint2*>(T.cuckoo) + h1);
-    const uint2 rb = __ldg(reinterpret_cast<const uint2*>(T.cuckoo) + h2);
-    const uint64_t a = ((uint64_t)ra.y << 32) | ra.x, b = ((uint64_t)rb.y << 32) | rb.x;
-    const uint64_t key = ((uint64_t)khi << 32) | klo;
-    const uint64_t keymask = (1ull << T.c_keybits) - 1ull;             // (c_len < 32)
-    uint32_t idx = SLOT_EMPTY;
-    if ((a & keymask) == key && a != ~0ull) idx = (uint32_t)(a >> T.c_keybits);
-    if ((b & keymask) == key && b != ~0ull) idx = (uint32_t)(b >> T.c_keybits);
-    return idx;
+// two-choice lookup (caller checked len == T.c_len).  Slot layout: low word = key bits 0..31, high word = key bits 32..
+// below bit ck_hshift and the VALUE above it (feature index << 1 | imperfect; all ones = empty slot, all ones - 1 = the
+// tie marker), so that matching and decoding are 32-bit operations.  Returns the value or CK_NONE.
+constexpr uint32_t CK_NONE = 0xFFFFFFFFu;
+__host__ __device__ __forceinline__ uint32_t cuckoo_valmax(uint32_t hshift) { return 0xFFFFFFFFu >> hshift; }
+__device__ __forceinline__ uint32_t cuckoo_ambig(const LibTables& T) { return cuckoo_valmax(T.ck_hshift) - 1u; }
+__device__ __forceinline__ uint32_t cuckoo_match(const LibTables& T, uint2 ra, uint2 rb, uint32_t klo, uint32_t khi) {
+    const uint32_t hs = T.ck_hshift, himask = hs ? (0xFFFFFFFFu >> (32u - hs)) : 0u, empty = cuckoo_valmax(hs);
+    const uint32_t va = ra.y >> hs, vb = rb.y >> hs;
+    uint32_t v = CK_NONE;
+    if (ra.x == klo && (ra.y & himask) == khi && va != empty) v = va;
+    if (rb.x == klo && (rb.y & himask) == khi && vb != empty) v = vb;
+    return v;
 }
 #endif  // __CUDACC__
 

@@ -409,7 +409,7 @@ __device__ __forceinline__ Fast1Pending fast1_warp_issue(const Fast1Ctx& F, bool
     if (T.cuckoo) {                                            // (uniform) every lane loads; lanes without a key read some slot and ignore it
         can = can && klen == T.c_len;
         uint32_t h1, h2;
-        cuckoo_slots(T.ck_mul[0], T.ck_mul[1], T.ck_mul[2], T.ck_mul[3], T.ck_mask, p.klo, p.khi, h1, h2);
+        cuckoo_slots(T.ck_mul[0], T.ck_mul[1], T.ck_mul[2], T.ck_mul[3], T.ck_shift, p.klo, p.khi, h1, h2);
         p.ra = ldg_u2_here(reinterpret_cast<const uint2*>(T.cuckoo) + h1);
         p.rb = ldg_u2_here(reinterpret_cast<const uint2*>(T.cuckoo) + h2);
     } else {
@@ -444,38 +444,44 @@ __device__ __forceinline__ Fast1Pending fast1_ord_issue(const Fast1Ctx& F, bool 
     n.qfail += (ord && fails) ? 1u : 0u;
     const bool live = ord && !fails;
     uint32_t h1, h2;
-    cuckoo_slots(T.ck_mul[0], T.ck_mul[1], T.ck_mul[2], T.ck_mul[3], T.ck_mask, p.klo, p.khi, h1, h2);
+    cuckoo_slots(T.ck_mul[0], T.ck_mul[1], T.ck_mul[2], T.ck_mul[3], T.ck_shift, p.klo, p.khi, h1, h2);
     p.ra = ldg_u2_here(reinterpret_cast<const uint2*>(T.cuckoo) + h1);
     p.rb = ldg_u2_here(reinterpret_cast<const uint2*>(T.cuckoo) + h2);
     p.meta = (uint32_t)c_len | ((live && p.bad == 0) ? 1u << 8 : 0u) | (live ? 1u << 9 : 0u);
     return p;
 }
 
-template <bool ORD = false>                                    // ORD: the slots always come from the cuckoo table (fast1_ord_issue)
 __device__ __forceinline__ void fast1_warp_commit(const Fast1Ctx& F, const Fast1Pending& p, const LibTables& T, const Outputs& O, Fast1Counts& n,
                                                   uint32_t lane) {
-    uint32_t idx = SLOT_EMPTY;
-    if (!ORD && (p.meta & (1u << 10))) idx = p.ra.x;
-    else {
-        const uint64_t a = ((uint64_t)p.ra.y << 32) | p.ra.x, b = ((uint64_t)p.rb.y << 32) | p.rb.x;
-        const uint64_t key = ((uint64_t)p.khi << 32) | p.klo, keymask = (1ull << T.c_keybits) - 1ull;
-        if ((a & keymask) == key && a != ~0ull) idx = (uint32_t)(a >> T.c_keybits);
-        if ((b & keymask) == key && b != ~0ull) idx = (uint32_t)(b >> T.c_keybits);
-    }
-    const bool hit = (p.meta & (1u << 8)) && idx != SLOT_EMPTY;
-    n.perfect += hit ? 1u : 0u;
+    // value of the key: feature index << 1 | imperfect, the tie marker, or CK_NONE (see the cuckoo build in f2q_set_library)
+    uint32_t v = CK_NONE;
+    const bool direct = (p.meta & (1u << 10)) != 0;
+    if (direct) { if (p.ra.x != SLOT_EMPTY) v = p.ra.x << 1; }
+    else v = cuckoo_match(T, p.ra, p.rb, p.klo, p.khi);
+    const bool can = (p.meta & (1u << 8)) != 0;
+    const bool found = can && v != CK_NONE;
+    const bool ambig = found && !direct && v == cuckoo_ambig(T);
+    const bool hit = found && !ambig;
+    const uint32_t idx = v >> 1, imperfect = v & 1u;
+    n.perfect += (hit && !imperfect) ? 1u : 0u;
+    n.imperfect += (hit && imperfect) ? 1u : 0u;
     if (hit) {
         if (F.hist) atomicAdd(F.hist + idx, 1u);
         else atomicAdd(O.counts + idx, 1ull);
     }
     const bool miss = (p.meta & (1u << 9)) && !hit;
     if (F.c_miss <= 0) { n.nonal += miss ? 1u : 0u; return; }
-    const uint32_t mq = __ballot_sync(0xffffffffu, miss);
+    // decided without the resolver: two or more keys at distance 1 (a tie for every m), or m = 1 and the complete
+    // neighbour table does not know this pure-ACGT key of the library's length
+    const bool final_nonal = miss && (ambig || (can && !direct && T.ck_neighbours != 0 && F.c_miss == 1));
+    n.nonal += final_nonal ? 1u : 0u;
+    const bool to_queue = miss && !final_nonal;
+    const uint32_t mq = __ballot_sync(0xffffffffu, to_queue);
     if (mq) {
         uint32_t sl = 0;
         if (lane == 0) sl = atomicAdd(F.s_qn, (uint32_t)__popc(mq));
         sl = __shfl_sync(0xffffffffu, sl, 0) + (uint32_t)__popc(mq & ((1u << lane) - 1u));
-        if (miss) {
+        if (to_queue) {
             const uint64_t key = ((uint64_t)p.khi << 32) | p.klo;
             const uint32_t klen = p.meta & 63u;
             if (sl < F.seg_cap) { QEntry e; e.key = key; e.bad = p.bad; e.len = klen; F.myq[sl] = e; }
