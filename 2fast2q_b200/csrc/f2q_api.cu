@@ -83,6 +83,7 @@ struct f2q_ctx {
     uint64_t launches = 0;
     int tile_blocks[2][8][2] = {{{0}}};
     // speculative streaming kernel (spec.cuh)
+    bool debug_waits = false;          // option "debug_waits": the exact kernel counts the cycles spent in each of its waits
     int spec = 1;                      // 0: always the exact look-back kernel
     int spec_warps = 16;               // warps per CTA (one CTA per SM): 12 or 16
     int spec_range_tiles = 0;          // 0 auto | tiles per range
@@ -477,12 +478,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     TileParams P{};
     P.S = c->dS; P.queue = reinterpret_cast<QEntry*>(c->queue.p); P.gqueue = reinterpret_cast<GEntry*>(c->gqueue.p);
     P.halo_rows = (uint32_t)c->halo_rows;
-    P.debug = getenv("F2Q_DEBUG") ? (uint32_t)atoi(getenv("F2Q_DEBUG")) : 0u;
-    static unsigned long long* g_trace = nullptr; static uint64_t g_trace_tiles = 0;
-    if (getenv("F2Q_TRACE")) {
-        if (!g_trace) { g_trace_tiles = n_tiles + 16; cudaMalloc(&g_trace, g_trace_tiles * 48); }
-        cudaMemsetAsync(g_trace, 0, g_trace_tiles * 48, c->stream);
-    }
+    P.debug = c->debug_waits ? 1u : 0u;
     P.seg_count = reinterpret_cast<uint32_t*>(c->seg_count.p);
     // 1. the chunk itself: speculative streaming kernel -> verify -> commit or drop; then the exact kernel, which returns at
     //    once when the speculation held
@@ -507,7 +503,6 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     }
     if (n) {
         P.buf = base; P.status = reinterpret_cast<uint8_t*>(c->status.p); P.ticket = c->d_tickets + 1; P.stitch = 0;
-        P.trace = (getenv("F2Q_TRACE") && n_tiles + 16 <= g_trace_tiles) ? g_trace : nullptr;
         P.seg_cap = c->policy == POLICY_FAST1 ? c->seg_cap : 0;
         P.skip_if_spec_ok = use_spec ? 1u : 0u;
         cudaEvent_t t0 = timing_begin(c);
@@ -520,13 +515,6 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     P.buf = reinterpret_cast<const uint8_t*>(c->carry.p); P.status = reinterpret_cast<uint8_t*>(c->status_stitch.p);
     P.ticket = c->d_tickets; P.stitch = 1; P.seg_cap = 0;
     if ((rc = launch_tile_dyn(c, P, O, 4))) return rc;
-    if (getenv("F2Q_TRACE") && g_trace && n) {
-        cudaStreamSynchronize(c->stream);
-        std::vector<unsigned long long> h(g_trace_tiles * 6);
-        cudaMemcpy(h.data(), g_trace, g_trace_tiles * 48, cudaMemcpyDeviceToHost);
-        FILE* f = fopen(getenv("F2Q_TRACE"), "wb");
-        if (f) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
-    }
     // 3. deferred work
     if (c->policy == POLICY_FAST1) {
         if (c->cfg.miss > 0) {
@@ -676,6 +664,7 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "halo_rows") { if (value < 0 || value > 128) return fail(c, F2Q_EINVAL, "halo_rows must be 0 (auto) .. 128"); c->force_halo = (int)value; }
     else if (n == "row_chunks") { if (value != 0 && value != 3 && value != 5 && value != 7) return fail(c, F2Q_EINVAL, "row_chunks must be 0 (auto), 3, 5 or 7"); c->force_ch = (int)value; }
     else if (n == "time_kernels") c->time_kernels = value != 0;
+    else if (n == "debug_waits") c->debug_waits = value != 0;
     else if (n == "spec") c->spec = value != 0;
     else if (n == "spec_warps") { if (value != 12 && value != 16) return fail(c, F2Q_EINVAL, "spec_warps must be 12 or 16"); c->spec_warps = (int)value; }
     else if (n == "spec_range_tiles") { if (value < 0 || value > (1 << 20)) return fail(c, F2Q_EINVAL, "spec_range_tiles out of range"); c->spec_range_tiles = (int)value; }
@@ -1000,7 +989,7 @@ F2Q_EXPORT int f2q_end_sample(f2q_ctx* c, uint64_t* counts, uint64_t* stats) {
     CU(c, cudaMemcpy(&hs, c->dS, sizeof(hs), cudaMemcpyDeviceToHost));
     err |= hs.error;
     c->spec_counts[0] = hs.spec_commits; c->spec_counts[1] = hs.spec_fallbacks;
-    if (getenv("F2Q_DEBUG"))
+    if (c->debug_waits)
         fprintf(stderr, "f2q debug: wait Mcycles  empty(loader) %llu  full(lookback) %llu agg(lookback) %llu  in-lookback %llu | full(consumers) %llu  p0(consumers) %llu | respins %llu | consumer warp Mcycles %llu\n",
                 hs.dbg[0] >> 20, hs.dbg[7] >> 20, hs.dbg[1] >> 20, hs.dbg[4] >> 20, hs.dbg[2] >> 20, hs.dbg[3] >> 20, hs.dbg[5], hs.dbg[6] >> 20);
     if (err & ERR_RECORD_TOO_LONG) return fail(c, F2Q_ETOOLONG, "a FASTQ record is longer than carry_bytes; raise it with f2q_set_option");

@@ -111,6 +111,7 @@ const char* f2q_last_error(const f2q_ctx* ctx);   /* ctx may be NULL: last creat
  *   "halo_rows"       0 auto | read-ahead rows at the end of every tile (reads reaching further finish in global memory)
  *   "tile_threads"    128 | 256: threads (= rows) per CTA of the fused tile kernel
  *   "time_kernels"    1: bracket the tile / resolver / generic launches with CUDA events (see f2q_kernel_times)
+ *   "debug_waits"     1: the exact kernel counts the cycles of each of its waits; f2q_end_sample prints them on stderr
  *   "spec"            1 (default): Counter mode parses each chunk with the speculative streaming kernel first and
  *                     falls back to the exact look-back kernel when its line-phase guesses do not verify | 0: exact only
  *   "spec_warps"      12 | 16: warps per CTA of the streaming kernel (one CTA per SM)
