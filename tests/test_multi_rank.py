@@ -87,3 +87,57 @@ def test_rank_read_range_partitions_exactly():
             assert parts[0][0] == 0 and sum(c for _, c in parts) == n
             assert all(parts[r][0] + parts[r][1] == parts[r + 1][0] for r in range(world - 1))
             assert max(c for _, c in parts) - min(c for _, c in parts) <= 1
+
+
+def _ec_worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O, synth
+        multi = importlib.import_module("2fast2q_b200.multi")
+        host = importlib.import_module("2fast2q_b200.fast2q")
+        cfg = O.make_config(mode="EC", upstream="GTTCAGAGTTCT", downstream="CTGAATAGGCCA", miss_search_up=1, miss_search_down=1)
+        whole = synth.barseq_reads(4, 9000) + b"@a\n\n+\n\n"                 # (an empty read: the empty key must survive the merge)
+        blocks = [whole[o:o + 50_001] for o in range(0, len(whole), 50_001)]
+        mine = {}
+        for shard, final in multi.rank_shards(host.record_aligned_shards(blocks, 120_000), rank, world):
+            d, _ = O.extract_count(cfg, np.frombuffer(shard, dtype=np.uint8))
+            for k, v in d.items():
+                mine[k] = mine.get(k, 0) + v
+        keys = list(mine)
+        kb = np.frombuffer(b"".join(keys), dtype=np.uint8) if keys else np.zeros(0, dtype=np.uint8)
+        ko = np.cumsum([0] + [len(k) for k in keys]).astype(np.uint64)
+        cn = np.array([mine[k] for k in keys], dtype=np.uint64)
+        mk, mc = multi.merge_ec_tables(kb, ko, cn)
+        want, _ = O.extract_count(cfg, np.frombuffer(whole, dtype=np.uint8))
+        ok = dict(zip(mk, mc)) == want and mk == sorted(mk)
+        allok = torch.tensor([1 if ok else 0])
+        dist.all_reduce(allok, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            out.put((bool(allok.item()), len(mk), len(mine)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_extract_count_allgather_sort_merge_world_size_2():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ec_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        assert p.exitcode == 0
+    ok, n_merged, n_mine = out.get(timeout=5)
+    assert ok and n_merged >= n_mine > 0
+
+
+def test_merge_ec_tables_single_process():
+    multi = importlib.import_module("2fast2q_b200.multi")
+    keys = [b"ACGT", b"", b"A", b"A\x00", b"ACGT"]
+    kb = np.frombuffer(b"".join(keys), dtype=np.uint8)
+    ko = np.cumsum([0] + [len(k) for k in keys]).astype(np.uint64)
+    mk, mc = multi.merge_ec_tables(kb, ko, np.array([3, 1, 2, 5, 4], dtype=np.uint64))
+    assert dict(zip(mk, mc)) == {b"ACGT": 7, b"": 1, b"A": 2, b"A\x00": 5} and mk == sorted(mk)
