@@ -509,7 +509,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         rc = launch_tile_dyn(c, P, O, n_tiles);
         timing_end(c, t0, use_spec ? 3 : 0);
         if (rc) return rc;
-        P.skip_if_spec_ok = 0; P.trace = nullptr;
+        P.skip_if_spec_ok = 0;
     }
     // 2. the record stitched from the carried tail and the head of this chunk (lives in the carry buffer)
     P.buf = reinterpret_cast<const uint8_t*>(c->carry.p); P.status = reinterpret_cast<uint8_t*>(c->status_stitch.p);

@@ -14,11 +14,6 @@ namespace f2q {
 // ------------------------------------------------------------------------------------------------
 // geometry of the tile kernel: see TileGeom<CH, NT> in tile.cuh (NT owned rows of 16*CH bytes + read-ahead rows)
 // ------------------------------------------------------------------------------------------------
-// status word of the decoupled look-back over tiles: [31:30] flag, [29:0] newline count (mod 2^30; only mod 4 is used)
-constexpr uint32_t LB_FLAG_AGG = 1u << 30;
-constexpr uint32_t LB_FLAG_PREFIX = 2u << 30;
-constexpr uint32_t LB_VALUE_MASK = (1u << 30) - 1;
-
 // device error bits (sticky, reported by f2q_end_sample as F2Q_EINTERNAL / F2Q_ETOOLONG)
 constexpr uint32_t ERR_LOOKBACK_TIMEOUT = 1u;
 constexpr uint32_t ERR_RECORD_TOO_LONG = 2u;

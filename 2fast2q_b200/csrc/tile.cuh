@@ -53,7 +53,6 @@ struct TileParams {
     uint32_t halo_rows;        // H: read-ahead rows at the end of every tile (1 .. NT/2)
     uint32_t skip_if_spec_ok;  // 1: return at once when the speculative kernel's results were committed (spec.cuh)
     uint32_t debug;            // 1: count waits into DevState::dbg
-    unsigned long long* trace; // debug: 6 u64 per tile (ticket time, agg time, go time, lb done time, parse start, cta)
 };
 
 // status byte of the decoupled look-back: bits [1:0] newline count mod 4, bits [3:2] 0 not ready / 1 aggregate / 2 prefix
@@ -133,12 +132,6 @@ __device__ __forceinline__ void st_volatile_u8(uint8_t* p, uint32_t v) {
     asm volatile("st.relaxed.gpu.global.u8 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-// a constant the compiler must keep in a register (so that LOP3 can combine it with two other register operands)
-__device__ __forceinline__ unsigned long long gtime() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
 // a + b issued as a multiply-add (a * one + b, `one` from reg_const(1)): integer adds and logic ops share the ALU pipe (one
 // warp instruction per 2 cycles), multiply-adds run on the FMA pipe next to it; the byte-parallel loops are ALU-pipe bound
 __device__ __forceinline__ uint32_t add_on_fma(uint32_t a, uint32_t one, uint32_t b) {
@@ -146,6 +139,7 @@ __device__ __forceinline__ uint32_t add_on_fma(uint32_t a, uint32_t one, uint32_
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b));
     return r;
 }
+// a constant the compiler must keep in a register (so that LOP3 can combine it with two other register operands)
 __device__ __forceinline__ uint32_t reg_const(uint32_t v) {
     uint32_t r;
     asm volatile("mov.u32 %0, %1;" : "=r"(r) : "r"(v));
@@ -639,7 +633,6 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 mode = (b0 >= beg && b0 + G_::LOAD_BYTES <= end) ? 1u : 2u;
             }
             if (lane == 0) {
-                if (P.trace && mode) { P.trace[6 * (uint64_t)tk + 0] = gtime(); P.trace[6 * (uint64_t)tk + 5] = blockIdx.x; }
                 s_ticket[s] = tk; s_mode[s] = mode;
                 if (mode == 1) {                                        // interior tile: one TMA bulk copy
                     mbar_expect_tx(&bar_full[s], G_::LOAD_BYTES);
@@ -663,7 +656,6 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             // enough that the tiles before this one have (nearly always) published — polling early slows everything down
             if (!mbar_wait(&bar_go[s], par, abort)) break;
             const uint32_t A = s_total_own[s], tk = s_ticket[s];
-            if (P.trace && lane == 0) P.trace[6 * (uint64_t)tk + 2] = gtime();
             const long long tl0 = dbg ? clock64() : 0;
             const uint32_t p0 = P.debug == 2 ? 0u : tile_lookback(P.status, tk, lane, abort, dbg);
             if (dbg && lane == 0) atomicAdd(dbg + 4, (unsigned long long)(clock64() - tl0));
@@ -671,7 +663,6 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 st_volatile_u8(P.status + tk, SB_PREFIX | ((p0 + A) & 3u));
                 if (first_tile + tk == n_tiles - 1 && !P.stitch) St->nl_total = (p0 + A) & 3u;
                 s_p0[s] = p0;
-                if (P.trace) P.trace[6 * (uint64_t)tk + 3] = gtime();
                 mbar_arrive(&bar_p0[s]);
             }
         }
@@ -754,7 +745,6 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             s_total_own[s] = excl;
             const uint64_t rel = t - first_tile;
             if (rel != 0) st_volatile_u8(P.status + rel, SB_AGG | (excl & 3u));
-            if (P.trace) P.trace[6 * rel + 1] = gtime();
             mbar_arrive(&bar_agg[s]);
         }
         if (tid == NT - 1) s_total_all[s] = excl + cnt;
@@ -796,7 +786,6 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         if (!mbar_wait(&bar_p0[s], (k / NS) & 1u, abort, dbg ? dbg + 3 : nullptr)) break;
         const uint32_t p0 = s_p0[s];
         if (tid == 0 && more) mbar_arrive(&bar_go[s1]);                // the look-back of tile k+1 may start now
-        if (P.trace && tid == 0) P.trace[6 * (uint64_t)s_ticket[s] + 4] = gtime();
 
         // @region parse_setup
         // ---- reads of tile k: thread q takes the q-th read whose header line ends in the owned rows ----
