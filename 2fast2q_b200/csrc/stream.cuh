@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(PREP_THREADS) k_carry(DevState* S, const uint8
 }
 
 // ------------------------------------------------------------------------------------------------
-// K0: synthetic FASTQ generator (bench / tests).  Bit-identical to oracle/synth.py:fixed_reads().
+// K0: synthetic FASTQ generator (bench / tests).  Bit-identical to 2fast2q_b200/synth.py:fixed_reads().
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint64_t sm_fin(uint64_t z) {
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;

@@ -12,7 +12,7 @@ One "step" = one pass of the hot path over the whole synthetic sample (R reads p
   roofline achieved HBM GB/s of the fused streaming kernel k_spec = algorithmic bytes (118 B/read) / its CUDA-event time
   cpu_baseline  the oracle port (oracle/f2q_oracle.c, the reference's algorithm in C) on a bounded sample, 1 core
 --impl reference times that port on all host threads (file-parallel, like the reference's multiprocessing mode).
-Data are synthetic (K0 generator, bit-identical to oracle/synth.py); weak scaling: every rank owns its own R reads.
+Data are synthetic (K0 generator, bit-identical to 2fast2q_b200/synth.py); weak scaling: every rank owns its own R reads.
 """
 from __future__ import annotations
 
@@ -123,7 +123,7 @@ def committed_traffic():
 
 
 def library():
-    from oracle import synth
+    synth = importlib.import_module("2fast2q_b200.synth")        # generator spec + library builder (not the oracle)
     return synth.make_library(CONFIG, N_GUIDES, FEAT_LEN), synth.default_spec(CONFIG)
 
 
@@ -132,7 +132,8 @@ def run_reference(args, rank, world):
     """the reference's CPU algorithm (oracle port; the Python reference cannot travel to the GPU box) on all host threads"""
     if rank != 0:
         return
-    from oracle import oracle as O, synth
+    from oracle import oracle as O                               # the reference arm IS the oracle port (task statement ④)
+    synth = importlib.import_module("2fast2q_b200.synth")
     (names, keys), spec = library()
     cores = os.cpu_count() or 1
     threads = max(1, min(cores, 64))

@@ -4,7 +4,7 @@ import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 f2q = importlib.import_module("2fast2q_b200"); lib = f2q._lib
-from oracle import synth
+synth = importlib.import_module("2fast2q_b200.synth")
 reads = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
 opts = dict(kv.split("=") for kv in sys.argv[2:])
 cfgno = int(opts.pop("config", 2))

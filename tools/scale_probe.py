@@ -4,7 +4,7 @@ import importlib, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
 f2q = importlib.import_module("2fast2q_b200"); lib = f2q._lib
-from oracle import synth
+synth = importlib.import_module("2fast2q_b200.synth")
 rank, lr, world = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 torch.cuda.set_device(lr); dev = torch.device("cuda", lr)
 if world > 1: dist.init_process_group("nccl", device_id=dev)
