@@ -61,13 +61,11 @@ __device__ inline uint32_t resolve_thread(const LibTables& T, int m, uint64_t ke
             }
         } else {
             for (uint32_t p = 0; p < len; p++) {
-                uint64_t cur = (key >> (2 * p)) & 3ull;
                 for (uint64_t c = 1; c < 4; c++) {
-                    uint64_t k2 = key ^ (c << (2 * p));       // cur ^ c runs over the three other bases
+                    uint64_t k2 = key ^ (c << (2 * p));       // (symbol at p) ^ c runs over the three other bases
                     uint32_t r = fast_lookup(T, k2, len);
                     if (r != SLOT_EMPTY) { hits++; idx = r; }
                 }
-                (void)cur;
             }
         }
         return hits == 1 ? idx : RES_NONE;

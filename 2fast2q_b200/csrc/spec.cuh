@@ -77,7 +77,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[W][NS];
     __shared__ uint4 s_desc[W][NS];                                    // per stage: {tile base lo, hi, range, flags}
-    __shared__ uint32_t s_qn, s_abort;
+    __shared__ uint32_t s_qn;
     __shared__ GenericCfg s_G;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -97,9 +97,8 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         for (int s = 0; s < NS; s++) mbar_init(&bar_full[warp][s], 1);
         mbar_fence_init();
     }
-    if (tid == 0) { s_qn = 0; s_abort = 0; }
+    if (tid == 0) s_qn = 0;
     __syncthreads();
-    volatile uint32_t* abort = &s_abort;
 
     const GenericCfg& G = (POLICY == POLICY_GENERIC) ? s_G : *Gp;
     Fast1Ctx F;
