@@ -19,7 +19,8 @@
 //
 // Per tile a warp does: wait for tile i+1 -> newline masks / positions of its 32 rows (lane = row) -> parse tile i
 // (lane q = q-th read; reads running into tile i+1 use its first rows' positions and the read-ahead bytes) -> refill the
-// stage of tile i.  The range ends with one scan-only tile (the first tile of the next range).
+// stage of tile i.  Behind the last tile of a range the read-ahead rows in its own stage are scanned instead; the tiles
+// of consecutive ranges form one sequence through the ring, so the next range's first tiles are already in flight.
 #pragma once
 
 #include <type_traits>
@@ -76,7 +77,6 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     constexpr int S = G_::S, OWN = G_::OWN, NS = SPEC_STAGES, CAP = SPEC_CAP, MW = G_::MW;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[W][NS];
-    __shared__ uint4 s_desc[W][NS];                                    // per stage: {tile base lo, hi, range, flags}
     __shared__ uint32_t s_qn;
     __shared__ GenericCfg s_G;
 
@@ -123,49 +123,8 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     uint8_t* const wsm = smem + (size_t)warp * warp_bytes;
     uint16_t* const nlist = reinterpret_cast<uint16_t*>(wsm + NS * stage_bytes);
     uint64_t* const bars = bar_full[warp];
-    uint4* const desc = s_desc[warp];
 
     // @region spec_loader
-    // the warp's tile stream: the tiles of a range in order, then the next range taken by ticket.
-    // flags: [1:0] 0 end of stream / 1 TMA / 2 loaded by the lanes (touches bytes outside [beg, end)), 4 first tile of
-    // a range, 8 last tile of a range
-    uint32_t ld_range = 0, ld_ti = 0, ld_nown = 0, iss_s = 0;
-    uint64_t ld_base = 0;                                              // base of the next tile of the current range
-    bool ld_end = false;
-    auto issue_next = [&]() {
-        const uint32_t s = iss_s;
-        iss_s = (iss_s == (uint32_t)NS - 1u) ? 0u : iss_s + 1u;
-        uint64_t base = 0;
-        uint32_t flags = 0, rng = 0;
-        if (!ld_end) {
-            if (ld_ti >= ld_nown) {
-                uint32_t tk = 0xFFFFFFFFu;
-                if (lane == 0) { tk = atomicAdd(P.ticket, 1u); if (ld_volatile_u32(&St->spec_fail)) tk = 0xFFFFFFFFu; }
-                tk = __shfl_sync(0xffffffffu, tk, 0);
-                if ((uint64_t)tk >= n_ranges) ld_end = true;
-                else {
-                    const uint64_t rb = origin0 + (uint64_t)tk * RB, re = ((uint64_t)tk == n_ranges - 1) ? end : rb + RB;
-                    ld_range = tk; ld_ti = 0; ld_base = rb;
-                    ld_nown = (uint32_t)((re - rb + OWN - 1) / OWN);
-                }
-            }
-            if (!ld_end) {
-                base = ld_base; ld_base += OWN;
-                const bool tma = base >= beg && base + load_bytes <= end;
-                flags = (tma ? 1u : 2u) | (ld_ti == 0 ? 4u : 0u) | (ld_ti + 1 == ld_nown ? 8u : 0u);
-                rng = ld_range; ld_ti++;
-            }
-        }
-        if (lane == 0) {
-            desc[s] = make_uint4((uint32_t)base, (uint32_t)(base >> 32), rng, flags);
-            if ((flags & 3u) == 1u) {
-                mbar_expect_tx(&bars[s], load_bytes);
-                tma_load_1d(wsm + s * stage_bytes, buf + base, load_bytes, &bars[s]);
-            }
-        }
-        __syncwarp();
-    };
-
     const uint32_t c0A = reg_const(0x0A0A0A0Au), c7F = reg_const(0x7F7F7F7Fu), c80 = reg_const(0x80808080u), one = reg_const(1u);
     auto chunk_mask = [&](const uint8_t* p16) -> uint32_t {            // newline flags of one 16-byte chunk (see tile.cuh)
         const uint4 v = *reinterpret_cast<const uint4*>(p16);
@@ -226,146 +185,182 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     };
 
     // @region spec_loop
-    for (int k = 0; k < NS; k++) issue_next();
-    bool have_prev = false;
-    uint32_t prev_s = 0, prev_total = 0, prev_range = 0, prev_flags = 0;
-    uint64_t prev_base = 0;
     uint32_t phase = 0, range_cnt = 0, spec_p0 = 0, par_bits = 0;
     Fast1Pending pend;                                                 // meta == 0: nothing pending (committing it is a no-op)
     pend.ra = make_uint2(0, 0); pend.rb = make_uint2(0, 0); pend.klo = pend.khi = pend.bad = pend.meta = 0;
     uint16_t* const nl_halo = nlist + 2 * G_::NL_LIST;
-    for (uint32_t i = 0, s = 0;; i++, s = (s == (uint32_t)NS - 1u) ? 0u : s + 1u) {
-        const uint32_t par = i & 1u;
-        const uint4 d = desc[s];
-        const uint32_t flags = d.w;
-        const bool live = (flags & 3u) != 0;
-        const uint64_t base = ((uint64_t)d.y << 32) | d.x;
-        uint8_t* const tile = wsm + s * stage_bytes;
-        uint16_t* const nl = nlist + par * G_::NL_LIST;
-        uint32_t total = 0, hcnt = 0;
-        if (live) {
-            if ((flags & 3u) == 1u) {
-                uint32_t spins = 0;                                    // (bounded: a lost copy traps instead of hanging the device)
-                while (!mbar_try_wait(&bars[s], (par_bits >> s) & 1u)) if (++spins > WAIT_SPIN_LIMIT) __trap();
-                par_bits ^= 1u << s;
-            } else {
-                // first / last tiles of the chunk: loaded by the lanes, bytes outside [beg, end) become 0
-                for (uint32_t c = lane; c < load_bytes / 16; c += 32) {
-                    const uint64_t g = base + (uint64_t)c * 16;
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (g + 16 > beg && g < end) {
-                        v = ldg_stream(reinterpret_cast<const uint4*>(buf + g));
-                        if (g < beg || g + 16 > end) {
-                            uint32_t w[4] = {v.x, v.y, v.z, v.w};
-                            #pragma unroll
-                            for (int b = 0; b < 16; b++) {
-                                const uint64_t pos = g + b;
-                                if (pos < beg || pos >= end) w[b >> 2] &= ~(0xFFu << (8 * (b & 3)));
-                            }
-                            v = make_uint4(w[0], w[1], w[2], w[3]);
-                        }
-                    }
-                    *reinterpret_cast<uint4*>(tile + c * 16) = v;
-                }
-                __syncwarp();
-            }
-            scan(tile, 0u, true, nl, (uint32_t)CAP, total, hcnt);
-            __syncwarp();
+
+    // @region spec_parse
+    // ---- reads of one tile: lane q takes the q-th read whose header line ends in its own rows.  nlW = the tile's position
+    // list (its first three read-ahead newlines get appended), nlB / hc / halo_off = where those come from
+    auto parse_tile = [&](const uint8_t* ptile, uint64_t pbase, uint16_t* nlW, uint32_t total_own, const uint16_t* nlB, uint32_t hc,
+                          uint32_t halo_off) {
+        const uint32_t total_all = total_own + hc;
+        if (total_own > (uint32_t)CAP || hc > (uint32_t)CAP) {
+            if (lane == 0) St->spec_fail = 1u;                         // a tile of very short lines: left to the exact kernel
+            return;
         }
-        // the lookups issued for the tile before the previous one have long arrived: count them
-        if (POLICY == POLICY_FAST1) { fast1_warp_commit(F, pend, T, O, cn, lane); pend.meta = 0; }
-        if (have_prev) {
-            // @region spec_parse
-            // ---- reads of the previous tile: lane q takes the q-th read whose header line ends in its own rows ----
-            const uint8_t* ptile = wsm + prev_s * stage_bytes;
-            const uint16_t* nlA = nlist + (par ^ 1u) * G_::NL_LIST;
-            const uint16_t* nlB = nl;
-            uint32_t hc = hcnt;
-            if (!(live && d.z == prev_range && !(flags & 4u))) {
-                // the last tile of a range: the newlines of its read-ahead rows are found in its own stage
-                uint32_t dummy;
-                scan(ptile, 32u, lane < H, nl_halo, (uint32_t)G_::NL_HALO - 8u, hc, dummy);
-                __syncwarp();
-                nlB = nl_halo;
-                if (hc > (uint32_t)G_::NL_HALO - 8u) hc = (uint32_t)CAP + 1u;       // too many to list
-            }
-            const uint32_t total_own = prev_total, total_all = total_own + hc;
-            if (total_own > (uint32_t)CAP || hc > (uint32_t)CAP) {
-                if (lane == 0) St->spec_fail = 1u;                     // a tile of very short lines: left to the exact kernel
-            } else {
-                // a read needs at most three newlines behind the tile's own: append them, the list is then contiguous
-                uint16_t* const nlW = nlist + (par ^ 1u) * G_::NL_LIST;
-                if (lane < 3u && lane < hc) nlW[total_own + lane] = (uint16_t)((uint32_t)nlB[lane] + ((nlB == nl_halo) ? 0u : (uint32_t)OWN));
-                __syncwarp();
-                const uint32_t jf = (4u - (phase & 3u)) & 3u;          // first newline of the tile that ends a header line
-                auto passes = [&](auto Wc) {
-                constexpr int WW = decltype(Wc)::value;                // words of the window (ordinary-read code), 0 = general code
-                for (uint32_t j0 = jf; j0 < total_own; j0 += 128u) {   // (uniform: the warp stays converged through a pass)
-                    const uint32_t j = j0 + 4u * lane;
-                    bool valid = j < total_own;
-                    if (valid && j + 3 >= total_all) {
-                        // the read's last newline is not in the loaded rows (a long record, or the end of the chunk)
-                        slow_record(buf, prev_base + nlA[j], end, eof, G, X, acc, gst);
-                        valid = false;
-                    }
-                    uint32_t s0 = 0, e0 = 0, s3 = 0, e3 = 0;
+        // a read needs at most three newlines behind the tile's own: append them, the list is then contiguous
+        if (lane < 3u && lane < hc) nlW[total_own + lane] = (uint16_t)((uint32_t)nlB[lane] + halo_off);
+        __syncwarp();
+        const uint16_t* nlA = nlW;
+        const uint32_t jf = (4u - (phase & 3u)) & 3u;                  // first newline of the tile that ends a header line
+        auto passes = [&](auto Wc) {
+            constexpr int WW = decltype(Wc)::value;                    // words of the window (ordinary-read code), 0 = general code
+            for (uint32_t j0 = jf; j0 < total_own; j0 += 128u) {       // (uniform: the warp stays converged through a pass)
+                const uint32_t j = j0 + 4u * lane;
+                bool valid = j < total_own;
+                if (valid && j + 3 >= total_all) {
+                    // the read's last newline is not in the loaded rows (a long record, or the end of the chunk)
+                    slow_record(buf, pbase + nlA[j], end, eof, G, X, acc, gst);
+                    valid = false;
+                }
+                uint32_t s0 = 0, e0 = 0, s3 = 0, e3 = 0;
+                if (valid) {
+                    s0 = (uint32_t)nlA[j] + 1u; e0 = nlA[j + 1]; s3 = (uint32_t)nlA[j + 2] + 1u; e3 = nlA[j + 3];
+                    cn.reads++;
+                    acc.last_end = (unsigned long long)(pbase + e3 + 1);
+                }
+                if (POLICY == POLICY_GENERIC) {
                     if (valid) {
-                        s0 = (uint32_t)nlA[j] + 1u; e0 = nlA[j + 1]; s3 = (uint32_t)nlA[j + 2] + 1u; e3 = nlA[j + 3];
-                        cn.reads++;
-                        acc.last_end = (unsigned long long)(prev_base + e3 + 1);
+                        const uint8_t* Rp = ptile + s0; const uint8_t* Qp = ptile + s3;
+                        g_process_read(G, X->T, X->E, X->O, Rp, g_rstrip(Rp, (int)(e0 - s0)), Qp, g_rstrip(Qp, (int)(e3 - s3)), gst);
                     }
-                    if (POLICY == POLICY_GENERIC) {
-                        if (valid) {
-                            const uint8_t* Rp = ptile + s0; const uint8_t* Qp = ptile + s3;
-                            g_process_read(G, X->T, X->E, X->O, Rp, g_rstrip(Rp, (int)(e0 - s0)), Qp, g_rstrip(Qp, (int)(e3 - s3)), gst);
+                } else {
+                    __syncwarp();
+                    if (j0 != jf) fast1_warp_commit(F, pend, T, O, cn, lane);          // (a second pass over the same tile: rare)
+                    if constexpr (WW == 0) pend = fast1_warp_issue(F, valid, ptile, s0, e0, s3, e3, buf + pbase + s0, buf + pbase + s3, G, T, E, O, cn, gst);
+                    else pend = fast1_ord_issue<WW>(F, valid, ptile, s0, e0, s3, e3, buf + pbase + s0, buf + pbase + s3, G, T, E, O, cn, gst, lane);
+                }
+            }
+        };
+        if (POLICY == POLICY_GENERIC) passes(std::integral_constant<int, 0>{});
+        else switch (ord_words) {
+            case 4: passes(std::integral_constant<int, 4>{}); break;
+            case 5: passes(std::integral_constant<int, 5>{}); break;
+            case 6: passes(std::integral_constant<int, 6>{}); break;
+            default: passes(std::integral_constant<int, 0>{}); break;
+        }
+    };
+
+    // @region spec_ranges
+    // One range after the other: the tiles of all ranges a warp takes form ONE sequence through the 3-stage ring (sequence
+    // number mod 3 = stage), so the first tiles of the next range (its ticket is taken a range ahead) are already in flight
+    // while the current one ends.  Step ti of a range: wait for tile ti and scan it (ti == nown: scan the read-ahead rows of
+    // the last tile instead) -> count the lookups issued one step ago -> parse tile ti-1 -> refill its stage with the tile
+    // three places further down the sequence.  No per-tile descriptor: everything is a function of (range, ti).
+    struct RangeInfo { uint32_t r, nown, t_lo, t_hi; uint64_t rb; bool ok; };
+    auto take_range = [&]() -> RangeInfo {
+        RangeInfo q{0xFFFFFFFFu, 0, 0, 0, 0, false};
+        uint32_t r = 0xFFFFFFFFu;
+        if (lane == 0) { r = atomicAdd(P.ticket, 1u); if (ld_volatile_u32(&St->spec_fail)) r = 0xFFFFFFFFu; }
+        r = __shfl_sync(0xffffffffu, r, 0);
+        if ((uint64_t)r >= n_ranges) return q;
+        q.r = r; q.ok = true;
+        q.rb = origin0 + (uint64_t)r * RB;
+        const uint64_t re = ((uint64_t)r == n_ranges - 1) ? end : q.rb + RB;
+        q.nown = (uint32_t)((re - q.rb + OWN - 1) / OWN);
+        // tiles [t_lo, t_hi) are plain TMA copies; the others touch bytes outside [beg, end) and are loaded by the lanes
+        q.t_lo = q.rb >= beg ? 0u : 1u;
+        q.t_hi = (end >= q.rb + load_bytes) ? (uint32_t)min((uint64_t)q.nown, (end - q.rb - load_bytes) / OWN + 1u) : 0u;
+        return q;
+    };
+    auto issue_of = [&](const RangeInfo& q, uint32_t ti, uint32_t s) {
+        if (q.ok && ti < q.nown && ti >= q.t_lo && ti < q.t_hi && lane == 0) {
+            mbar_expect_tx(&bars[s], load_bytes);
+            tma_load_1d(wsm + s * stage_bytes, buf + q.rb + (uint64_t)ti * OWN, load_bytes, &bars[s]);
+        }
+    };
+    RangeInfo cur = take_range();
+    uint32_t pre = 0, gs = 0;                                          // tiles of `cur` already issued; stage of its tile 0
+    while (cur.ok) {
+        const RangeInfo nxt = take_range();
+        const uint32_t r = cur.r, nown = cur.nown, t_lo = cur.t_lo, t_hi = cur.t_hi;
+        const uint64_t rb = cur.rb;
+        uint32_t nxt_pre = 0;
+        // place t of the sequence that starts at this range's tile 0 -> stage st
+        auto issue_seq = [&](uint32_t t, uint32_t st) {
+            if (t < nown) issue_of(cur, t, st);
+            else if (t - nown < nxt.nown) { issue_of(nxt, t - nown, st); nxt_pre = t - nown + 1u; }
+        };
+        for (uint32_t t = pre; t < (uint32_t)NS; t++) issue_seq(t, (gs + t) % NS);
+        range_cnt = 0; spec_p0 = 0; phase = 0;                         // (range 0 starts at a record start)
+        uint32_t prev_total = 0, s = gs, sp = gs;                      // s = stage of tile ti, sp = stage of tile ti - 1
+        for (uint32_t ti = 0; ti <= nown; ti++) {
+            const uint32_t par = ti & 1u;
+            uint16_t* const nl = nlist + par * G_::NL_LIST;
+            uint32_t total = 0, hcnt = 0;
+            const bool own = ti < nown;
+            if (own) {
+                uint8_t* const tile = wsm + s * stage_bytes;
+                const uint64_t base = rb + (uint64_t)ti * OWN;
+                if (ti >= t_lo && ti < t_hi) {
+                    uint32_t spins = 0;                                // (bounded: a lost copy traps instead of hanging the device)
+                    while (!mbar_try_wait(&bars[s], (par_bits >> s) & 1u)) if (++spins > WAIT_SPIN_LIMIT) __trap();
+                    par_bits ^= 1u << s;
+                } else {
+                    // first / last tiles of the chunk: loaded by the lanes, bytes outside [beg, end) become 0
+                    for (uint32_t c = lane; c < load_bytes / 16; c += 32) {
+                        const uint64_t g = base + (uint64_t)c * 16;
+                        uint4 v = make_uint4(0, 0, 0, 0);
+                        if (g + 16 > beg && g < end) {
+                            v = ldg_stream(reinterpret_cast<const uint4*>(buf + g));
+                            if (g < beg || g + 16 > end) {
+                                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                                #pragma unroll
+                                for (int b = 0; b < 16; b++) {
+                                    const uint64_t pos = g + b;
+                                    if (pos < beg || pos >= end) w[b >> 2] &= ~(0xFFu << (8 * (b & 3)));
+                                }
+                                v = make_uint4(w[0], w[1], w[2], w[3]);
+                            }
                         }
-                    } else {
-                        __syncwarp();
-                        if (j0 != jf) fast1_warp_commit(F, pend, T, O, cn, lane);      // (a second pass over the same tile: rare)
-                        if constexpr (WW == 0) pend = fast1_warp_issue(F, valid, ptile, s0, e0, s3, e3, buf + prev_base + s0, buf + prev_base + s3, G, T, E, O, cn, gst);
-                        else pend = fast1_ord_issue<WW>(F, valid, ptile, s0, e0, s3, e3, buf + prev_base + s0, buf + prev_base + s3, G, T, E, O, cn, gst, lane);
+                        *reinterpret_cast<uint4*>(tile + c * 16) = v;
                     }
+                    __syncwarp();
                 }
-                };
-                if (POLICY == POLICY_GENERIC) passes(std::integral_constant<int, 0>{});
-                else switch (ord_words) {
-                    case 4: passes(std::integral_constant<int, 4>{}); break;
-                    case 5: passes(std::integral_constant<int, 5>{}); break;
-                    case 6: passes(std::integral_constant<int, 6>{}); break;
-                    default: passes(std::integral_constant<int, 0>{}); break;
-                }
-            }
-            __syncwarp();
-            phase += prev_total; range_cnt += prev_total;
-            if ((prev_flags & 8u) && lane == 0) P.rec[prev_range] = (uint8_t)(0x80u | (spec_p0 << 2) | (range_cnt & 3u));
-            issue_next();                                              // refill the stage of the parsed tile
-            have_prev = false;
-        }
-        if (!live) break;
-        if (flags & 4u) {
-            // @region spec_speculate
-            range_cnt = 0; spec_p0 = 0; phase = 0;                     // (range 0 starts at a record start)
-            if (d.z != 0) {
-                const uint32_t n = min(total, (uint32_t)CAP);
-                bool cand = false;
-                if (lane < 4) {
-                    bool ok = true; int K = 0;
-                    #pragma unroll
-                    for (int k = 0; k < 2; k++) {
-                        const uint32_t j = lane + 4u * k;
-                        if (j + 3 >= n) break;
-                        const uint32_t a = nl[j], b = nl[j + 1], c = nl[j + 2], e = nl[j + 3];
-                        ok = ok && tile[b + 1] == '+' && tile[e + 1] == '@' && (b - a) == (e - c);
-                        K++;
+                scan(tile, 0u, true, nl, (uint32_t)CAP, total, hcnt);
+                __syncwarp();
+                if (ti == 0 && r != 0) {
+                    // @region spec_speculate
+                    const uint32_t n = min(total, (uint32_t)CAP);
+                    bool cand = false;
+                    if (lane < 4) {
+                        bool ok = true; int K = 0;
+                        #pragma unroll
+                        for (int k = 0; k < 2; k++) {
+                            const uint32_t j = lane + 4u * k;
+                            if (j + 3 >= n) break;
+                            const uint32_t a = nl[j], b = nl[j + 1], c = nl[j + 2], e = nl[j + 3];
+                            ok = ok && tile[b + 1] == '+' && tile[e + 1] == '@' && (b - a) == (e - c);
+                            K++;
+                        }
+                        cand = ok && K > 0;
                     }
-                    cand = ok && K > 0;
+                    const uint32_t m = __ballot_sync(0xffffffffu, cand) & 0xFu;
+                    if (__popc(m) == 1) { spec_p0 = (4u - ((uint32_t)__ffs((int)m) - 1u)) & 3u; phase = spec_p0; }
+                    else if (lane == 0) St->spec_fail = 1u;
                 }
-                const uint32_t m = __ballot_sync(0xffffffffu, cand) & 0xFu;
-                if (__popc(m) == 1) { spec_p0 = (4u - ((uint32_t)__ffs((int)m) - 1u)) & 3u; phase = spec_p0; }
-                else if (lane == 0) St->spec_fail = 1u;
+            } else {
+                // behind the last tile of the range: the newlines of its read-ahead rows are found in its own stage
+                uint32_t dummy;
+                scan(wsm + sp * stage_bytes, 32u, lane < H, nl_halo, (uint32_t)G_::NL_HALO - 8u, hcnt, dummy);
+                __syncwarp();
+                if (hcnt > (uint32_t)G_::NL_HALO - 8u) hcnt = (uint32_t)CAP + 1u;      // too many to list
             }
+            // the lookups issued one step ago have long arrived: count them
+            if (POLICY == POLICY_FAST1) { fast1_warp_commit(F, pend, T, O, cn, lane); pend.meta = 0; }
+            if (ti > 0) {
+                parse_tile(wsm + sp * stage_bytes, rb + (uint64_t)(ti - 1) * OWN, nlist + (par ^ 1u) * G_::NL_LIST, prev_total,
+                           own ? nl : nl_halo, hcnt, own ? (uint32_t)OWN : 0u);
+                __syncwarp();
+                phase += prev_total; range_cnt += prev_total;
+                issue_seq(ti - 1 + NS, sp);                            // refill the stage of the parsed tile
+            }
+            if (own) { prev_total = total; sp = s; s = (s == (uint32_t)NS - 1u) ? 0u : s + 1u; }
         }
-        have_prev = true; prev_s = s; prev_total = total; prev_range = d.z; prev_flags = flags; prev_base = base;
+        if (lane == 0) P.rec[r] = (uint8_t)(0x80u | (spec_p0 << 2) | (range_cnt & 3u));
+        gs = s; pre = nxt_pre; cur = nxt;
     }
     if (POLICY == POLICY_FAST1) fast1_warp_commit(F, pend, T, O, cn, lane);
 
