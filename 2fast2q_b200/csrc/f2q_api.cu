@@ -95,7 +95,8 @@ struct f2q_ctx {
     bool slow_valid = false;
     bool async_pending = false;        // f2q_end_sample_async results not yet waited for (kernel timings are collected by f2q_sync)
     uint64_t spec_counts[2] = {0, 0};  // last finished sample: chunks committed by the speculation / parsed by the exact kernel
-    int nt = 128;                      // threads (= owned rows) per tile-kernel CTA: 128 or 256
+    int nt = 256;                      // threads (= owned rows) per tile-kernel CTA: 256 for the packed policy (measured 35 % faster),
+    bool nt_user = false;              // 128 for the generic per-read code, unless option "tile_threads" says otherwise
     // optional per-kernel timing (option "time_kernels"): event pairs around the tile / resolver / generic launches
     bool time_kernels = false;
     struct Timed { cudaEvent_t a, b; int kind; };
@@ -191,6 +192,7 @@ void decide_policy(f2q_ctx* c) {
     const f2q_config& g = c->cfg;
     c->policy = POLICY_GENERIC;
     if (g.mode == F2Q_MODE_COUNT && !g.has_up && !g.has_down && g.n_iter == 1 && g.length >= 0 && g.length <= 32) c->policy = POLICY_FAST1;
+    if (!c->nt_user) c->nt = c->policy == POLICY_FAST1 ? 256 : 128;
 }
 
 constexpr uint32_t HIST_MAX_KEYS = 8192;     // shared-memory histogram up to this many features (32 KB of u32)
@@ -660,7 +662,7 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "stage_slots") { if (value < 1 || value > 16 || !c->d_stage.empty()) return fail(c, F2Q_EINVAL, "stage_slots invalid or staging already allocated"); c->stage_slots = (int)value; }
     else if (n == "resolver") { if (value < 0 || value > 3) return fail(c, F2Q_EINVAL, "resolver must be 0..3"); c->resolver = (int)value; }
     else if (n == "queue_entries") { if (value < 0) return fail(c, F2Q_EINVAL, "queue_entries < 0"); c->opt_queue_entries = value; c->q_cap = 0; c->g_cap = 0; c->n_segs = 0; c->queue.release(); c->gqueue.release(); }
-    else if (n == "tile_threads") { if (value != 128 && value != 256) return fail(c, F2Q_EINVAL, "tile_threads must be 128 or 256"); c->nt = (int)value; c->n_segs = 0; }
+    else if (n == "tile_threads") { if (value != 128 && value != 256) return fail(c, F2Q_EINVAL, "tile_threads must be 128 or 256"); c->nt = (int)value; c->nt_user = true; c->n_segs = 0; }
     else if (n == "halo_rows") { if (value < 0 || value > 128) return fail(c, F2Q_EINVAL, "halo_rows must be 0 (auto) .. 128"); c->force_halo = (int)value; }
     else if (n == "row_chunks") { if (value != 0 && value != 3 && value != 5 && value != 7) return fail(c, F2Q_EINVAL, "row_chunks must be 0 (auto), 3, 5 or 7"); c->force_ch = (int)value; }
     else if (n == "time_kernels") c->time_kernels = value != 0;
@@ -668,7 +670,7 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "spec") c->spec = value != 0;
     else if (n == "spec_warps") { if (value != 12 && value != 16) return fail(c, F2Q_EINVAL, "spec_warps must be 12 or 16"); c->spec_warps = (int)value; }
     else if (n == "spec_range_tiles") { if (value < 0 || value > (1 << 20)) return fail(c, F2Q_EINVAL, "spec_range_tiles out of range"); c->spec_range_tiles = (int)value; }
-    else if (n == "force_generic") { if (value) c->policy = POLICY_GENERIC; else decide_policy(c); }
+    else if (n == "force_generic") { if (value) { c->policy = POLICY_GENERIC; if (!c->nt_user) c->nt = 128; c->n_segs = 0; } else decide_policy(c); }
     else return fail(c, F2Q_EINVAL, "unknown option " + n);
     return F2Q_OK;
 }

@@ -109,7 +109,7 @@ const char* f2q_last_error(const f2q_ctx* ctx);   /* ctx may be NULL: last creat
  *   "force_generic"   1: run every read through the byte-wise generic kernels (cross-check of the packed path)
  *   "row_chunks"      0 auto | 3 | 5 | 7: bytes per tile row / 16 (auto: just below the record length of the sample)
  *   "halo_rows"       0 auto | read-ahead rows at the end of every tile (reads reaching further finish in global memory)
- *   "tile_threads"    128 | 256: threads (= rows) per CTA of the fused tile kernel
+ *   "tile_threads"    128 | 256 (default): threads (= rows) per CTA of the exact look-back kernel
  *   "time_kernels"    1: bracket the tile / resolver / generic launches with CUDA events (see f2q_kernel_times)
  *   "debug_waits"     1: the exact kernel counts the cycles of each of its waits; f2q_end_sample prints them on stderr
  *   "spec"            1 (default): Counter mode parses each chunk with the speculative streaming kernel first and

@@ -23,7 +23,7 @@ def counter_cases():
     return [c for c in G.kat() + G.fuzz() if c["params"]["mode"] == "C"]
 
 
-@pytest.mark.parametrize("opts", [dict(spec=0), dict(spec_range_tiles=1), dict(spec_range_tiles=2, spec_warps=12),
+@pytest.mark.parametrize("opts", [dict(spec=0), dict(spec=0, tile_threads=128), dict(spec_range_tiles=1), dict(spec_range_tiles=2, spec_warps=12),
                                   dict(spec_range_tiles=1, force_generic=1)], ids=str)
 def test_golden_cases_every_path(gu, opts):
     """exact kernel only / one-tile ranges (every tile speculates) / 12-warp CTAs / generic per-read code"""
@@ -34,7 +34,7 @@ def test_golden_cases_every_path(gu, opts):
 
 
 @pytest.mark.parametrize("name", cases.SHAPED)
-@pytest.mark.parametrize("opts", [dict(spec=0), dict(spec_range_tiles=1), dict(spec_range_tiles=3, row_chunks=5)], ids=str)
+@pytest.mark.parametrize("opts", [dict(spec=0), dict(spec=0, tile_threads=128), dict(spec_range_tiles=1), dict(spec_range_tiles=3, row_chunks=5)], ids=str)
 def test_shaped_cases_every_path(gu, name, opts):
     c = [x for x in G.shaped() if x["name"] == name][0]
     params, lib, data = cases.shaped_inputs(name)
