@@ -103,13 +103,15 @@ const char* f2q_last_error(const f2q_ctx* ctx);   /* ctx may be NULL: last creat
  *   "carry_bytes"     max bytes of one partial FASTQ record carried between submits (default 4 MiB)
  *   "stage_bytes"     size of each internal pinned/device staging slot used by f2q_submit (default 64 MiB)
  *   "stage_slots"     number of staging slots (default 3)
- *   "resolver"        0 auto | 1 Hamming-1 neighbour probing | 2 pigeonhole seed index | 3 library tile scan
+ *   "resolver"        kernel for queued non-exact keys: 0 auto | 1 Hamming-1 neighbour probing | 2 pigeonhole seed
+ *                     index | 3 library tile scan (small libraries decide distance-1 keys in the lookup table itself)
  *   "queue_entries"   capacity of the deferred non-exact key queue (default: derived from the chunk size;
  *                     capacity never changes results — overflow is resolved in place)
  *   "force_generic"   1: run every read through the byte-wise generic kernels (cross-check of the packed path)
  *   "row_chunks"      0 auto | 3 | 5 | 7: bytes per tile row / 16 (auto: just below the record length of the sample)
  *   "halo_rows"       0 auto | read-ahead rows at the end of every tile (reads reaching further finish in global memory)
- *   "tile_threads"    128 | 256 (default): threads (= rows) per CTA of the exact look-back kernel
+ *   "tile_threads"    128 | 256: threads (= rows) per CTA of the exact look-back kernel (default: 256 for the packed
+ *                     single-window policy, 128 for the generic per-read code)
  *   "time_kernels"    1: bracket the tile / resolver / generic launches with CUDA events (see f2q_kernel_times)
  *   "debug_waits"     1: the exact kernel counts the cycles of each of its waits; f2q_end_sample prints them on stderr
  *   "spec"            1 (default): Counter mode parses each chunk with the speculative streaming kernel first and
