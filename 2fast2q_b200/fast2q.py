@@ -180,34 +180,111 @@ class TruncatedGzip(Exception):
     """the gzip stream ended before its end-of-stream marker (the reference's EOFError, fast2q.py:405-407)"""
 
 
-def _inflate_blocks(path, want=None):
-    """yields the uncompressed bytes of a (multi-member) gzip file in pieces of <= want bytes; zlib releases the
-    GIL, so several feeder threads inflate in parallel.  Raises TruncatedGzip after the last decodable piece."""
-    want = want or CHUNK_BYTES
-    with open(path, "rb") as f:
-        d = zlib.decompressobj(31)
-        pending = b""
-        fresh = True                                        # at a member boundary, nothing consumed yet
-        while True:
+def _bgzf_block_size(hdr):
+    """total size of the BGZF block that starts with these (>= 18) bytes, or None when this is not a BGZF member
+    (gzip member with FEXTRA whose first subfield is 'B','C' of length 2 holding BSIZE-1: SAM spec §4.1)"""
+    if len(hdr) < 18 or hdr[:4] != b"\x1f\x8b\x08\x04" or hdr[12:16] != b"BC\x02\x00" or (hdr[10] | hdr[11] << 8) < 6:
+        return None
+    return (hdr[16] | hdr[17] << 8) + 1
+
+
+_inflate_pool = None
+_inflate_pool_lock = threading.Lock()
+
+
+def _shared_inflate_pool():
+    """one pool of inflate workers for the whole process (zlib releases the GIL): feeder threads of several files share it"""
+    global _inflate_pool
+    with _inflate_pool_lock:
+        if _inflate_pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            _inflate_pool = ThreadPoolExecutor(max(2, min(32, os.cpu_count() or 2)), thread_name_prefix="f2q-inflate")
+        return _inflate_pool
+
+
+def _inflate_serial(f, want, pending=b""):
+    """the generic path: one zlib stream at a time, multi-member files and zero padding between members included"""
+    d = zlib.decompressobj(31)
+    fresh = True                                            # at a member boundary, nothing consumed yet
+    while True:
+        if not pending:
+            pending = f.read(4 << 20)
             if not pending:
-                pending = f.read(4 << 20)
-                if not pending:
-                    if fresh:
-                        return
-                    raise TruncatedGzip(path)
-            if fresh:
-                pending = pending.lstrip(b"\x00")            # padding between members is skipped (gzip module behaviour)
-                if not pending:
-                    continue
-                fresh = False
-            out = d.decompress(pending, want)
-            pending = d.unconsumed_tail
-            if out:
-                yield out
-            if d.eof:
-                pending = d.unused_data
-                d = zlib.decompressobj(31)
-                fresh = True
+                if fresh:
+                    return
+                raise TruncatedGzip(getattr(f, "name", "gzip stream"))
+        if fresh:
+            pending = pending.lstrip(b"\x00")               # padding between members is skipped (gzip module behaviour)
+            if not pending:
+                continue
+            fresh = False
+        out = d.decompress(pending, want)
+        pending = d.unconsumed_tail
+        if out:
+            yield out
+        if d.eof:
+            pending = d.unused_data
+            d = zlib.decompressobj(31)
+            fresh = True
+
+
+def _inflate_group(blob, sizes):
+    """a run of whole BGZF blocks (their sizes in order) -> their uncompressed bytes"""
+    mv, out, pos = memoryview(blob), [], 0
+    for n in sizes:
+        out.append(zlib.decompress(mv[pos:pos + n], 31))
+        pos += n
+    return b"".join(out)
+
+
+def _inflate_blocks(path, want=None, parallel=True):
+    """yields the uncompressed bytes of a (multi-member) gzip file in pieces of <= want bytes.  zlib releases the GIL, so
+    several feeder threads inflate in parallel; a BGZF file (bgzip: independent blocks of <= 64 KiB that carry their own
+    size) is additionally inflated block-parallel on the shared pool, in order, with a bounded number of groups in
+    flight (host zlib on ONE stream is the end-to-end bound of a single-file run).
+    Raises TruncatedGzip after the last decodable piece."""
+    want = want or CHUNK_BYTES
+    group_bytes = 4 << 20                                   # compressed bytes per task (<= ~16 MiB uncompressed <= want)
+    with open(path, "rb") as f:
+        head = f.read(18)
+        if not (parallel and _bgzf_block_size(head)):
+            yield from _inflate_serial(f, want, head)
+            return
+        pool = _shared_inflate_pool()
+        depth = 2 * pool._max_workers
+        inflight = []                                       # futures, in file order
+        buf = head
+        eof = False
+        while True:
+            # cut whole blocks off the front of buf into one group
+            group_end, pos, fallback, sizes = 0, 0, False, []
+            while pos + 18 <= len(buf) and group_end < group_bytes:
+                n = _bgzf_block_size(buf[pos:pos + 18])
+                if n is None:
+                    fallback = True                         # not BGZF from here on (a foreign member was appended): serial
+                    break
+                if pos + n > len(buf):
+                    break
+                pos += n
+                group_end = pos
+                sizes.append(n)
+            if group_end:
+                inflight.append(pool.submit(_inflate_group, buf[:group_end], sizes))
+                buf = buf[group_end:]
+            while inflight and (len(inflight) >= depth or eof or fallback or inflight[0].done()):
+                out = inflight.pop(0).result()
+                for o in range(0, len(out), want):
+                    yield out[o:o + want]
+            if fallback or (eof and not group_end):
+                break
+            if not group_end or len(buf) < 18:
+                more = f.read(group_bytes)
+                if not more:
+                    eof = True
+                buf += more
+        if buf:
+            # what is left is a partial block (truncated file) or a non-BGZF continuation: the serial reader finishes it
+            yield from _inflate_serial(f, want, buf)
 
 
 def _raw_blocks(path, want=None):

@@ -220,3 +220,48 @@ def test_merge_sample_adds_counts_and_stats():
 def test_seq2bin_known_answer():
     assert fq.seq2bin("GATTACA").tolist() == [71, 65, 84, 84, 65, 67, 65]      # tests/test_mainfunctions.py:4-8
     assert fq.seq2bin("GATTACA").dtype.name == "int8"
+
+
+def _bgzf(data, bs=65280, level=4):
+    """a BGZF (bgzip) file of `data`: independent gzip members with a 'BC' extra field holding their size + the EOF block"""
+    import struct
+    import zlib
+    out = []
+    for o in list(range(0, len(data), bs)) + [None]:
+        chunk = b"" if o is None else data[o:o + bs]
+        c = zlib.compressobj(level, zlib.DEFLATED, -15)
+        cd = c.compress(chunk) + c.flush()
+        out.append(b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", 18 + len(cd) + 8 - 1) + cd
+                   + struct.pack("<II", zlib.crc32(chunk) & 0xFFFFFFFF, len(chunk)))
+    return b"".join(out)
+
+
+def test_bgzf_block_parallel_inflate(tmp_path):
+    """bgzip input is inflated block-parallel, in order; truncation and a foreign trailing member behave like the serial reader"""
+    import gzip
+    import random
+    host = importlib.import_module("2fast2q_b200.fast2q")
+    rnd = random.Random(7)
+    data = b"".join(b"@r%d\n%s\n+\n%s\n" % (i, bytes(rnd.choice(b"ACGT") for _ in range(40)), b"I" * 40) for i in range(30000))
+    blob = _bgzf(data)
+    p = tmp_path / "x.fastq.gz"
+    p.write_bytes(blob)
+    assert gzip.open(p).read() == data                                  # (it IS a valid gzip file)
+    pieces = list(host._inflate_blocks(str(p), want=1 << 20))
+    assert b"".join(pieces) == data and max(map(len, pieces)) <= 1 << 20
+    assert b"".join(host._inflate_blocks(str(p), parallel=False)) == data
+    # cut inside a block: both readers give the same decodable prefix, then TruncatedGzip
+    p.write_bytes(blob[:len(blob) // 2 + 777])
+    got = []
+    for par in (True, False):
+        acc = []
+        with pytest.raises(host.TruncatedGzip):
+            for b in host._inflate_blocks(str(p), parallel=par):
+                acc.append(b)
+        got.append(b"".join(acc))
+    assert got[0] == got[1] and data.startswith(got[0]) and len(got[0]) > len(data) // 3
+    # bgzip blocks followed by an ordinary gzip member, and an ordinary file
+    p.write_bytes(blob + gzip.compress(b"@t\nACGT\n+\nIIII\n"))
+    assert b"".join(host._inflate_blocks(str(p))) == data + b"@t\nACGT\n+\nIIII\n"
+    p.write_bytes(gzip.compress(data))
+    assert b"".join(host._inflate_blocks(str(p))) == data
