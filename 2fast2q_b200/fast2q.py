@@ -190,6 +190,7 @@ def _bgzf_block_size(hdr):
 
 _inflate_pool = None
 _inflate_pool_lock = threading.Lock()
+_INFLATE_WORKERS = max(2, min(32, os.cpu_count() or 2))
 
 
 def _shared_inflate_pool():
@@ -198,7 +199,7 @@ def _shared_inflate_pool():
     with _inflate_pool_lock:
         if _inflate_pool is None:
             from concurrent.futures import ThreadPoolExecutor
-            _inflate_pool = ThreadPoolExecutor(max(2, min(32, os.cpu_count() or 2)), thread_name_prefix="f2q-inflate")
+            _inflate_pool = ThreadPoolExecutor(_INFLATE_WORKERS, thread_name_prefix="f2q-inflate")
         return _inflate_pool
 
 
@@ -251,7 +252,7 @@ def _inflate_blocks(path, want=None, parallel=True):
             yield from _inflate_serial(f, want, head)
             return
         pool = _shared_inflate_pool()
-        depth = 2 * pool._max_workers
+        depth = 2 * _INFLATE_WORKERS
         inflight = []                                       # futures, in file order
         buf = head
         eof = False
