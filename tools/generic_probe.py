@@ -8,12 +8,13 @@ import cases
 f2q = importlib.import_module("2fast2q_b200"); lib = f2q._lib
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 only = sys.argv[2].split(",") if len(sys.argv) > 2 else ("config4_barseq", "config5a_dual_fixed", "config5b_dual_delim", "config3_slice")
+opts = {k: int(v) for k, v in (kv.split("=") for kv in sys.argv[3:])}
 for name in only:
     params, library, data = cases.shaped_inputs(name)
     n_reads = data.count(b"\n") // 4
     blob = np.frombuffer(data * reps, dtype=np.uint8)
     cfg = lib.make_config(**params)
-    with lib.Engine(cfg, 0, None, time_kernels=1) as e:
+    with lib.Engine(cfg, 0, None, time_kernels=1, **opts) as e:
         if library is not None:
             e.set_library([s for _, s in library])
         d = e.device_alloc(blob.size)
