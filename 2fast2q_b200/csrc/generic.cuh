@@ -55,7 +55,7 @@ __device__ __forceinline__ bool g_within(const uint8_t* a, const uint8_t* b, int
     return true;
 }
 
-__device__ inline int g_border_finder(const uint8_t* seq, int s, const uint8_t* read, int r, int mismatch, int start_place) {
+__device__ __noinline__ int g_border_finder(const uint8_t* seq, int s, const uint8_t* read, int r, int mismatch, int start_place) {
     if (start_place >= 0 && s >= 1) {
         // the ordinary call: only positions with the whole search sequence inside the read can be returned (a shorter tail
         // slice is compared but then cut off by fall_over).  Written for a warp: every position costs the same s byte
