@@ -25,8 +25,9 @@ using namespace f2q;
 
 namespace {
 
-std::mutex g_err_mu;
-std::string g_create_err;
+// message of the last failing call that had no context (f2q_create, the helpers): per THREAD, so that feeder threads creating
+// engines concurrently never read a string another thread is replacing
+thread_local std::string g_create_err;
 
 struct DevBuf {
     void* p = nullptr; size_t n = 0;
@@ -63,7 +64,8 @@ struct f2q_ctx {
     int force_ch = 0, force_halo = 0;
     int halo_rows = 6;
     int ch = 7;                        // row chunks of the tile kernel (row = 16*ch bytes), picked per sample from the record length
-    bool ch_decided = false;
+    bool ch_decided = false;           // per sample for host submits (sniffed from the host bytes: free); a context fed with
+    bool ch_from_device = false;       // DEVICE chunks sniffs once (one 4 KiB D2H + sync) and keeps the geometry for later samples
     int64_t opt_queue_entries = 0;
     // staging for host submits
     uint64_t stage_bytes = 64ull << 20;
@@ -78,6 +80,7 @@ struct f2q_ctx {
     std::vector<uint64_t> ec_drain_off, ec_drain_cnt; std::vector<uint8_t> ec_drain_keys; bool ec_drained = false;
     // state
     bool in_sample = false, closed = false;
+    int sample_failed = F2Q_OK;        // a submit of this sample failed: every later submit / end of the sample reports it again
     int sticky = F2Q_OK;
     std::string err;
     uint64_t launches = 0;
@@ -110,7 +113,7 @@ namespace {
 
 int fail(f2q_ctx* c, int code, const std::string& msg) {
     if (c) { c->err = msg; if (code == F2Q_ECUDA) c->sticky = code; }
-    else { std::lock_guard<std::mutex> l(g_err_mu); g_create_err = msg; }
+    else g_create_err = msg;
     return code;
 }
 
@@ -413,11 +416,13 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     const uint8_t* base = n ? reinterpret_cast<const uint8_t*>(addr - delta) : reinterpret_cast<const uint8_t*>(c->carry.p);
     int rc;
     if (!c->ch_decided) {
-        // sniff the record length once per sample (4 KiB of the first chunk) to size the tile rows
+        // device chunks: sniff the record length (4 KiB of the first chunk) to size the tile rows — ONCE per context, so that
+        // back-to-back samples have no host round trip (the geometry only affects speed, never results)
         uint8_t head[4096];
         const size_t hn = (size_t)std::min<uint64_t>(n, sizeof(head));
         if (hn) { CU(c, cudaMemcpyAsync(head, dptr, hn, cudaMemcpyDeviceToHost, c->stream)); CU(c, cudaStreamSynchronize(c->stream)); }
         decide_ch(c, head, hn);
+        c->ch_from_device = hn != 0;
     }
     const uint64_t own_bytes = (uint64_t)(c->nt - c->halo_rows) * 16 * c->ch;
     const uint64_t n_tiles = (delta + n) / own_bytes + 2;
@@ -585,7 +590,6 @@ F2Q_EXPORT int f2q_device_count(void) {
 
 F2Q_EXPORT const char* f2q_last_error(const f2q_ctx* ctx) {
     if (ctx) return ctx->err.c_str();
-    std::lock_guard<std::mutex> l(g_err_mu);
     return g_create_err.c_str();
 }
 
@@ -912,7 +916,7 @@ F2Q_EXPORT int f2q_begin_sample(f2q_ctx* c) {
     if (!c->lib_set) return fail(c, F2Q_ESTATE, "f2q_set_library must be called first in Counter mode");
     if ((rc = dev_alloc(c, c->carry, c->carry_cap + 256))) return rc;
     if ((rc = dev_alloc(c, c->status_stitch, c->carry_cap / (64 * 16 * 3) + 2 + 64))) return rc;
-    c->ch_decided = false;
+    if (!c->ch_from_device) c->ch_decided = false;
     CU(c, cudaMemsetAsync(c->result.p, 0, ((size_t)c->n_keys + 5) * 8, c->stream));
     if (c->spec_scratch.p) CU(c, cudaMemsetAsync(c->spec_scratch.p, 0, ((size_t)c->n_keys + 5) * 8, c->stream));
     CU(c, cudaMemsetAsync(c->d_error, 0, 4, c->stream));
@@ -922,7 +926,7 @@ F2Q_EXPORT int f2q_begin_sample(f2q_ctx* c) {
         if (c->ec_slots.p) { CU(c, cudaMemsetAsync(c->ec_slots.p, 0, c->ec_cap * 8, c->stream)); CU(c, cudaMemsetAsync(c->ec_counts.p, 0, c->ec_cap * 8, c->stream)); }
         c->ec_drained = false;
     }
-    c->in_sample = true; c->closed = false;
+    c->in_sample = true; c->closed = false; c->sample_failed = F2Q_OK;
     return F2Q_OK;
 }
 
@@ -937,9 +941,11 @@ F2Q_EXPORT int f2q_submit_device(f2q_ctx* c, const void* dptr, uint64_t nbytes, 
 F2Q_EXPORT int f2q_submit(f2q_ctx* c, const uint8_t* host_chunk, uint64_t nbytes, int is_last) {
     int rc = check_ctx(c); if (rc) return rc;
     if (!c->in_sample) return fail(c, F2Q_ESTATE, "f2q_submit outside a sample");
+    if (c->sample_failed) return c->sample_failed;
     if (c->closed) return fail(c, F2Q_ESTATE, "stream already closed with is_last");
     if (nbytes && !host_chunk) return fail(c, F2Q_EINVAL, "null chunk");
     if ((rc = ensure_staging(c))) return rc;
+    if (!c->ch_decided && nbytes) { decide_ch(c, host_chunk, (size_t)std::min<uint64_t>(nbytes, 4096)); c->ch_from_device = false; }
     uint64_t done = 0;
     do {
         const uint64_t len = std::min<uint64_t>(c->stage_bytes, nbytes - done);
@@ -950,8 +956,9 @@ F2Q_EXPORT int f2q_submit(f2q_ctx* c, const uint8_t* host_chunk, uint64_t nbytes
         CU(c, cudaEventRecord(c->ev_copied[s], c->copy_stream));
         CU(c, cudaStreamWaitEvent(c->stream, c->ev_copied[s], 0));
         done += len;
-        if ((rc = process_device_chunk(c, c->d_stage[s], len, is_last && done == nbytes))) return rc;
-        CU(c, cudaEventRecord(c->ev_free[s], c->stream));
+        rc = process_device_chunk(c, c->d_stage[s], len, is_last && done == nbytes);
+        CU(c, cudaEventRecord(c->ev_free[s], c->stream));               // (also on failure: kernels already queued may still read the slot)
+        if (rc) { if (!c->sticky) c->sample_failed = rc; return rc; }
     } while (done < nbytes);
     return F2Q_OK;
 }
@@ -995,6 +1002,7 @@ F2Q_EXPORT int f2q_end_sample(f2q_ctx* c, uint64_t* counts, uint64_t* stats) {
         fprintf(stderr, "f2q debug: wait Mcycles  empty(loader) %llu  full(lookback) %llu agg(lookback) %llu  in-lookback %llu | full(consumers) %llu  p0(consumers) %llu | respins %llu | consumer warp Mcycles %llu\n",
                 hs.dbg[0] >> 20, hs.dbg[7] >> 20, hs.dbg[1] >> 20, hs.dbg[4] >> 20, hs.dbg[2] >> 20, hs.dbg[3] >> 20, hs.dbg[5], hs.dbg[6] >> 20);
     if (err & ERR_RECORD_TOO_LONG) return fail(c, F2Q_ETOOLONG, "a FASTQ record is longer than carry_bytes; raise it with f2q_set_option");
+    if (err & ERR_LOOKBACK_TIMEOUT) return fail(c, F2Q_EINTERNAL, "a device-side wait timed out; this sample's counts are invalid (the context stays usable)");
     if (err) return fail(c, F2Q_EINTERNAL, "device-side failure, flags=" + std::to_string(err));
     if (counts && c->n_keys) CU(c, cudaMemcpy(counts, c->result.p, (size_t)c->n_keys * 8, cudaMemcpyDeviceToHost));
     CU(c, cudaMemcpy(stats, reinterpret_cast<uint8_t*>(c->result.p) + (size_t)c->n_keys * 8, 5 * 8, cudaMemcpyDeviceToHost));

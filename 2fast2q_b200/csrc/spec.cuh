@@ -272,6 +272,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         }
     };
     RangeInfo cur = take_range();
+    bool dead = false;                                                 // a bulk copy of this warp timed out
     uint32_t pre = 0, gs = 0;                                          // tiles of `cur` already issued; stage of its tile 0
     while (cur.ok) {
         const RangeInfo nxt = take_range();
@@ -295,8 +296,15 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 uint8_t* const tile = wsm + s * stage_bytes;
                 const uint64_t base = rb + (uint64_t)ti * OWN;
                 if (ti >= t_lo && ti < t_hi) {
-                    uint32_t spins = 0;                                // (bounded: a lost copy traps instead of hanging the device)
-                    while (!mbar_try_wait(&bars[s], (par_bits >> s) & 1u)) if (++spins > WAIT_SPIN_LIMIT) __trap();
+                    // (bounded in time: a copy that never lands fails the speculation — the exact kernel then redoes the
+                    // chunk — and this warp stops taking work; nothing traps, see WAIT_CYCLE_LIMIT in tile.cuh)
+                    if (!mbar_try_wait(&bars[s], (par_bits >> s) & 1u)) {
+                        const long long tw = clock64();
+                        uint32_t spins = 0;
+                        while (!mbar_try_wait(&bars[s], (par_bits >> s) & 1u))
+                            if ((++spins & 1023u) == 0u && clock64() - tw > WAIT_CYCLE_LIMIT) { dead = true; break; }
+                        if (dead) { if (lane == 0) St->spec_fail = 1u; F2Q_TIMEOUT_TRAP(); break; }
+                    }
                     par_bits ^= 1u << s;
                 } else {
                     // first / last tiles of the chunk: loaded by the lanes, bytes outside [beg, end) become 0
@@ -359,6 +367,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             }
             if (own) { prev_total = total; sp = s; s = (s == (uint32_t)NS - 1u) ? 0u : s + 1u; }
         }
+        if (dead) break;                                               // (its range stays unpublished: the verification fails)
         if (lane == 0) P.rec[r] = (uint8_t)(0x80u | (spec_p0 << 2) | (range_cnt & 3u));
         gs = s; pre = nxt_pre; cur = nxt;
     }

@@ -57,7 +57,16 @@ struct TileParams {
 
 // status byte of the decoupled look-back: bits [1:0] newline count mod 4, bits [3:2] 0 not ready / 1 aggregate / 2 prefix
 constexpr uint32_t SB_AGG = 0x04u, SB_PREFIX = 0x08u;
-constexpr uint32_t WAIT_SPIN_LIMIT = 1u << 22;
+// every device-side wait is bounded in TIME (clock64, about 4 s at 2 GHz).  A wait that runs out never traps (a trap would
+// poison the process's whole CUDA context, and with it every other f2q_ctx on the GPU): it raises the CTA's abort flag,
+// sets an error bit in DevState::error (f2q_end_sample then fails this ONE sample with F2Q_EINTERNAL) or, in the
+// speculative kernel, fails the speculation so that the exact kernel redoes the chunk.  -DF2Q_TRAP_ON_TIMEOUT restores the trap.
+constexpr long long WAIT_CYCLE_LIMIT = 1ll << 33;
+#ifdef F2Q_TRAP_ON_TIMEOUT
+#define F2Q_TIMEOUT_TRAP() __trap()
+#else
+#define F2Q_TIMEOUT_TRAP() ((void)0)
+#endif
 constexpr int TILE_STAGES = 3;
 constexpr int TILE_CTRL_THREADS = 64;                // loader warp + look-back warp
 
@@ -102,16 +111,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
-// bounded wait: a protocol bug must not hang the GPU — after ~2^22 failed tries the kernel traps (the launch fails loudly)
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile uint32_t* abort, unsigned long long* dbg = nullptr) {
+// bounded wait: a protocol bug must not hang the GPU.  gerr = the sample's error word (DevState::error)
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile uint32_t* abort, uint32_t* gerr, unsigned long long* dbg = nullptr) {
     if (*abort) return false;
-    const long long t0 = dbg ? clock64() : 0;
-    for (uint32_t spins = 0; spins < WAIT_SPIN_LIMIT; spins++) {
+    const long long t0 = clock64();
+    for (uint32_t spins = 0;; spins++) {
         if (mbar_try_wait(bar, parity)) { if (dbg && (threadIdx.x & 31) == 0) atomicAdd(dbg, (unsigned long long)(clock64() - t0)); return true; }
-        if ((spins & 1023u) == 1023u && *abort) return false;
+        if ((spins & 1023u) == 1023u) {
+            if (*abort) return false;
+            if (clock64() - t0 > WAIT_CYCLE_LIMIT) break;
+        }
     }
     *abort = 1u;
-    __trap();
+    atomicOr(gerr, ERR_LOOKBACK_TIMEOUT);
+    F2Q_TIMEOUT_TRAP();
     return false;
 }
 // global -> shared bulk copy by the TMA unit; completion is signalled on the mbarrier (bytes % 16 == 0, 16-byte aligned)
@@ -497,7 +510,16 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const void* p) {
 // control warp: newlines (mod 4) of the range before tile `rel`, by decoupled look-back over the status bytes.
 // Each lane inspects 16 tiles (one 16-byte load), the warp 512 tiles per step, nearest first; the walk stops at the nearest
 // tile that already published an inclusive prefix and needs every tile between to have published its aggregate.
-__device__ __noinline__ uint32_t tile_lookback(const uint8_t* status, uint64_t rel, uint32_t lane, volatile uint32_t* abort, unsigned long long* dbg) {
+__device__ __noinline__ uint32_t tile_lookback(const uint8_t* status, uint64_t rel, uint32_t lane, volatile uint32_t* abort, uint32_t* gerr, unsigned long long* dbg) {
+    const long long t_start = clock64();
+    // (another CTA that gave up has set the sample's error word: stop waiting for its tiles)
+    auto give_up = [&](uint32_t spins) -> bool {
+        if (*abort) return true;
+        if ((spins & 255u) != 255u) return false;
+        if (clock64() - t_start <= WAIT_CYCLE_LIMIT && ld_volatile_u32(gerr) == 0u) return false;
+        *abort = 1u; atomicOr(gerr, ERR_LOOKBACK_TIMEOUT); F2Q_TIMEOUT_TRAP();
+        return true;
+    };
     uint32_t p0 = 0;
     int64_t hi = (int64_t)rel;                                          // tiles [hi, rel) are accounted for
     if (rel > 0) {
@@ -509,7 +531,7 @@ __device__ __noinline__ uint32_t tile_lookback(const uint8_t* status, uint64_t r
             if (lane == 0) b = ld_volatile_u8(status + rel - 1);
             b = __shfl_sync(0xffffffffu, b, 0);
             if (b & 0x0Cu) break;
-            if (++spins > WAIT_SPIN_LIMIT || *abort) { *abort = 1u; __trap(); return 0; }
+            if (give_up(++spins)) return 0;
             __nanosleep(200);
         }
         if (b & SB_PREFIX) return b & 3u;
@@ -558,7 +580,7 @@ __device__ __noinline__ uint32_t tile_lookback(const uint8_t* status, uint64_t r
             }
             if (lane > first) ok = true;                                // beyond the nearest prefix: never needed again in this step
             if (dbg && lane == 0) atomicAdd(dbg + 5, 1ull);
-            if (++spins > WAIT_SPIN_LIMIT || *abort) { *abort = 1u; __trap(); return 0; }
+            if (give_up(++spins)) return 0;
             __nanosleep(400);                                           // (a tile that published out of order: rare)
         }
         hi = (((hi - 1) >> 4) - 31) << 4;                               // everything from this lane-31 group upwards is summed
@@ -603,6 +625,7 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     }
     __syncthreads();
     volatile uint32_t* abort = &s_abort;
+    uint32_t* const gerr = &St->error;
     unsigned long long* dbg = P.debug ? St->dbg : nullptr;
 
     const uint32_t own_rows = NT - P.halo_rows;
@@ -621,8 +644,8 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         // (by then every other CTA has taken its own), and later ones are taken only when a stage is free.
         for (uint32_t i = 0;; i++) {
             const uint32_t s = i % NS;
-            if (i >= (uint32_t)NS) { if (!mbar_wait(&bar_empty[s], ((i / NS) - 1u) & 1u, abort, dbg ? dbg + 0 : nullptr)) break; }   // tile i-NS is parsed
-            else if (i >= 1) { if (!mbar_wait(&bar_full[i - 1], 0u, abort)) break; }
+            if (i >= (uint32_t)NS) { if (!mbar_wait(&bar_empty[s], ((i / NS) - 1u) & 1u, abort, gerr, dbg ? dbg + 0 : nullptr)) break; }   // tile i-NS is parsed
+            else if (i >= 1) { if (!mbar_wait(&bar_full[i - 1], 0u, abort, gerr)) break; }
             uint32_t tk = 0;
             if (lane == 0) tk = atomicAdd(P.ticket, 1u);
             tk = __shfl_sync(0xffffffffu, tk, 0);
@@ -649,15 +672,15 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         // spins on other CTAs.
         for (uint32_t j = 0;; j++) {
             const uint32_t s = j % NS, par = (j / NS) & 1u;
-            if (!mbar_wait(&bar_full[s], par, abort, dbg ? dbg + 7 : nullptr)) break;            // (only to learn whether tile j exists)
+            if (!mbar_wait(&bar_full[s], par, abort, gerr, dbg ? dbg + 7 : nullptr)) break;            // (only to learn whether tile j exists)
             if (s_mode[s] == 0) break;
-            if (!mbar_wait(&bar_agg[s], par, abort, dbg ? dbg + 1 : nullptr)) break;
+            if (!mbar_wait(&bar_agg[s], par, abort, gerr, dbg ? dbg + 1 : nullptr)) break;
             // start the walk when the consumers begin to parse tile j-1: a whole parse phase before p0 is needed, and late
             // enough that the tiles before this one have (nearly always) published — polling early slows everything down
-            if (!mbar_wait(&bar_go[s], par, abort)) break;
+            if (!mbar_wait(&bar_go[s], par, abort, gerr)) break;
             const uint32_t A = s_total_own[s], tk = s_ticket[s];
             const long long tl0 = dbg ? clock64() : 0;
-            const uint32_t p0 = P.debug == 2 ? 0u : tile_lookback(P.status, tk, lane, abort, dbg);
+            const uint32_t p0 = P.debug == 2 ? 0u : tile_lookback(P.status, tk, lane, abort, gerr, dbg);
             if (dbg && lane == 0) atomicAdd(dbg + 4, (unsigned long long)(clock64() - tl0));
             if (lane == 0) {
                 st_volatile_u8(P.status + tk, SB_PREFIX | ((p0 + A) & 3u));
@@ -774,16 +797,16 @@ k_tile(TileParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
 
     // @region loop_top
     const long long t_begin = dbg ? clock64() : 0;
-    bool live = mbar_wait(&bar_full[0], 0u, abort) && s_mode[0] != 0;
+    bool live = mbar_wait(&bar_full[0], 0u, abort, gerr) && s_mode[0] != 0;
     if (live) { if (tid == 0) mbar_arrive(&bar_go[0]); scan(0); }
     for (uint32_t k = 0; live; k++) {
         const uint32_t s = k % NS, par = k & 1u, s1 = (k + 1) % NS;
         // ---- next tile first: its aggregate is public one parse phase before the successors need it ----
-        if (!mbar_wait(&bar_full[s1], ((k + 1) / NS) & 1u, abort, dbg ? dbg + 2 : nullptr)) break;
+        if (!mbar_wait(&bar_full[s1], ((k + 1) / NS) & 1u, abort, gerr, dbg ? dbg + 2 : nullptr)) break;
         const bool more = s_mode[s1] != 0;
         if (more) scan(k + 1);
         else consumer_barrier<NT>();                                   // (the last scan's lists are visible to everyone)
-        if (!mbar_wait(&bar_p0[s], (k / NS) & 1u, abort, dbg ? dbg + 3 : nullptr)) break;
+        if (!mbar_wait(&bar_p0[s], (k / NS) & 1u, abort, gerr, dbg ? dbg + 3 : nullptr)) break;
         const uint32_t p0 = s_p0[s];
         if (tid == 0 && more) mbar_arrive(&bar_go[s1]);                // the look-back of tile k+1 may start now
 

@@ -34,6 +34,7 @@ import argparse
 import csv
 import datetime
 import glob
+import gzip
 import os
 import queue
 import sys
@@ -461,14 +462,18 @@ def reads_counter(i, raw, features, param, reads_stats, preprocess=False):
     engine.begin()
     try:
         complete = _stream_file(engine, ring, raw, limit_lines=40000 if preprocess else None)
-    except (zlib.error, OSError) as e:
+    except (zlib.error, gzip.BadGzipFile, EOFError) as e:     # (other I/O errors surface, as in the reference: fast2q.py:580)
         try:
             engine.end()
         except _lib.F2QError:
             pass
-        if os.path.splitext(raw)[1] == ".gz":
-            colourful_errors("WARNING", f"{raw} is an incomplete or corrupted gzip file. ({e})")
-            return None
+        colourful_errors("WARNING", f"{raw} is an incomplete or corrupted gzip file. ({e})")
+        return None
+    except BaseException:
+        try:
+            engine.end()                                     # leave the cached engine reusable
+        except _lib.F2QError:
+            pass
         raise
     counts, stats = engine.end()
     if not complete:
@@ -637,9 +642,8 @@ def input_parser(argv=None):
         paths = [[args.s, 'seq_files'], [args.g, 'feature'], [args.o, 'out']]
     else:
         p["test_mode"] = True
-        data = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
-        paths = [[os.path.join(data, "example.fastq.gz"), 'seq_files'], [os.path.join(data, "D39V_guides.csv"), 'feature'],
-                 [os.getcwd(), 'out']]
+        from . import testdata                               # surrogate of the reference's bundled example (see testdata.py)
+        paths = [[testdata.ensure_example(), 'seq_files'], [testdata.GUIDES, 'feature'], [os.getcwd(), 'out']]
     p['out_file_name'] = args.fn if args.fn is not None else "compiled"
     p['length'] = int(args.l) if args.l is not None else 20
     p['Progress bar'] = args.pb is None
@@ -832,7 +836,7 @@ def aligner_mp_dispenser(features, param, start=0):
             tempo = time.perf_counter()
             try:
                 merged, stats, complete = split_file_counter(raw, features, param, n_gpus)
-            except (zlib.error, OSError) as e:
+            except (zlib.error, gzip.BadGzipFile, EOFError) as e:
                 colourful_errors("WARNING", f"{raw} is an incomplete or corrupted gzip file. ({e})")
                 continue
             if not complete:

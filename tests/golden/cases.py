@@ -5,12 +5,14 @@ these inputs and stores its answers; the tests re-create the same inputs and com
 """
 from __future__ import annotations
 
+import importlib
 import hashlib
 import os
 import sys
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
-from oracle import synth  # noqa: E402
+synth = importlib.import_module("2fast2q_b200.synth")
+testdata = importlib.import_module("2fast2q_b200.testdata")
 
 PARAM_KEYS = ("mode", "miss", "phred", "length", "start", "upstream", "downstream", "miss_search_up",
               "miss_search_down", "qual_up", "qual_down")
@@ -346,61 +348,9 @@ def sha(data: bytes) -> str:
 # reference answer is exactly tests/compiled.csv
 # ---------------------------------------------------------------------------------------------------
 def load_guides_csv(path):
-    """features_loader semantics for a clean comma file (fast2q.py:148-166): first sequence wins"""
-    lib, seen = [], set()
-    with open(path) as f:
-        for line in f:
-            parts = line.rstrip().split(",")
-            seq = parts[1].upper().replace(" ", "")
-            if seq not in seen:
-                seen.add(seq)
-                lib.append((parts[0], seq))
-    return lib
+    return testdata.load_guides_csv(path)
 
 
 def config1_surrogate(guides_csv, compiled_csv):
-    import numpy as np
-    lib = load_guides_csv(guides_csv)
-    want = {}
-    with open(compiled_csv) as f:
-        for line in f:
-            if line.startswith("#"):
-                continue
-            n, c = line.rstrip().split(",")
-            want[n] = int(c)
-    seqs = [s.encode() for _, s in lib]
-    arr = np.frombuffer(b"".join(seqs), dtype=np.uint8).reshape(len(seqs), 20)
-    r = synth.SM64(0xC0FF1)
-    recs = []
-    for gi, (name, seq) in enumerate(lib):
-        s = seq.encode()
-        for _ in range(want.get(name, 0)):
-            v = s
-            if r.below(100) < 15:
-                for _try in range(20):
-                    cand = synth.mutate(r, s, 1)
-                    d = (arr != np.frombuffer(cand, dtype=np.uint8)).sum(axis=1)
-                    if (d <= 1).sum() == 1:        # unique within distance 1 -> the reference assigns it to gi
-                        v = cand
-                        break
-            recs.append((v + r.dna(30), synth.qual_line(r, 50, 0.0)))
-    n_al = len(recs)
-    for _ in range(n_al // 12):                     # low quality inside the window -> quality_failed
-        g = r.choice(seqs)
-        q = bytearray(synth.qual_line(r, 50, 0.0))
-        q[r.below(20)] = 33 + r.below(29)
-        recs.append((g + r.dna(30), bytes(q)))
-    for _ in range(n_al // 20):                     # unalignable
-        for _try in range(50):
-            cand = r.dna(20)
-            d = (arr != np.frombuffer(cand, dtype=np.uint8)).sum(axis=1)
-            if d.min() > 1:
-                break
-        recs.append((cand + r.dna(30), synth.qual_line(r, 50, 0.0)))
-    # deterministic shuffle
-    order = list(range(len(recs)))
-    for i in range(len(order) - 1, 0, -1):
-        j = r.below(i + 1)
-        order[i], order[j] = order[j], order[i]
-    data = b"".join(b"@E%07d\n" % k + recs[o][0] + b"\n+\n" + recs[o][1] + b"\n" for k, o in enumerate(order))
-    return lib, want, data
+    """the generator lives in the package (2fast2q_b200/testdata.py) because `-c -t` needs it too"""
+    return testdata.config1_surrogate(guides_csv, compiled_csv)

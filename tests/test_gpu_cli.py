@@ -103,3 +103,19 @@ def test_public_helpers_known_answers():
     assert fq.sequence_tinder(read, qual, info) == (None, None)
     info["miss_search_down"] = 2
     assert fq.sequence_tinder(read, qual, info) == (4, 6)
+
+
+def test_test_mode_equals_reference_compiled_csv(tmp_path, monkeypatch):
+    """`2fast2q -c -t` (BASELINE.json configs[0]; fast2q.py:1237-1240, reference tests/test_cli.py:5-28): the bundled
+    example (a labelled surrogate of the missing example.fastq.gz, see 2fast2q_b200/testdata.py) and D39V_guides.csv give
+    a compiled.csv whose counts equal the reference's own tests/compiled.csv."""
+    monkeypatch.chdir(tmp_path)
+    fq.main(["-c", "-t"])
+    dirs = glob.glob(os.path.join(str(tmp_path), "2FAST2Q_output_*"))
+    assert len(dirs) == 1
+    files = sorted(os.listdir(dirs[0]))
+    assert "compiled.csv" in files and "compiled_stats.csv" in files
+    got = open(os.path.join(dirs[0], "compiled.csv"), newline="").read().split("\r\n")
+    want = open(os.path.join(G.HERE, "ref_compiled.csv"), newline="").read().splitlines()
+    assert got[0] == "#Feature,example"
+    assert [r for r in got[1:] if r] == [w.strip() for w in want[1:] if w.strip()]

@@ -2,6 +2,7 @@
 -m gpu: the CUDA path (through the C-ABI) against the golden vectors of the unmodified reference and against the
 oracle.  Bit-exact: integer counts and the five statistics.
 """
+import importlib
 import os
 
 import numpy as np
@@ -125,7 +126,7 @@ def test_primitives(gu):
 
 def test_long_records_spill_path(gu, oracle):
     """records longer than the tile halo (1 KiB) and than a whole tile take the global-memory path"""
-    from oracle import synth
+    synth = importlib.import_module("2fast2q_b200.synth")
     r = synth.SM64(77)
     guides = [r.dna(20) for _ in range(50)]
     recs = []
@@ -147,7 +148,7 @@ def test_long_records_spill_path(gu, oracle):
 
 def test_short_lines_many_newlines(gu, oracle):
     """more newlines per tile than one rank window holds (lines of 0-3 bytes)"""
-    from oracle import synth
+    synth = importlib.import_module("2fast2q_b200.synth")
     r = synth.SM64(5)
     data = b"".join(r.dna(r.below(4)) + b"\n" for _ in range(60000))
     params = cases.P(mode="EC", length=3)
@@ -162,7 +163,7 @@ def test_short_lines_many_newlines(gu, oracle):
 
 
 def test_synth_generator_matches_numpy(gu):
-    from oracle import synth
+    synth = importlib.import_module("2fast2q_b200.synth")
     for config in (2, 3):
         spec = synth.default_spec(config)
         names, keys = synth.make_library(config, 500, 20)
@@ -178,7 +179,7 @@ def test_synth_generator_matches_numpy(gu):
 
 def test_resident_device_submit_large(gu, oracle):
     """config-2 shape, 2M reads generated on the device: one submit vs many odd-sized submits vs the oracle"""
-    from oracle import synth
+    synth = importlib.import_module("2fast2q_b200.synth")
     spec = synth.default_spec(2)
     names, keys = synth.make_library(2, 2000, 20)
     n = 2_000_000
@@ -207,7 +208,7 @@ def test_resident_device_submit_large(gu, oracle):
 
 def test_end_sample_async_back_to_back(gu, oracle):
     """three samples without a host round trip in between: every pinned result equals the blocking path's"""
-    from oracle import synth
+    synth = importlib.import_module("2fast2q_b200.synth")
     spec = synth.default_spec(2)
     names, keys = synth.make_library(2, 700, 20)
     datas = [synth.fixed_reads(keys, 1000 * k, 40_000 + 777 * k, **spec).tobytes() for k in range(3)]

@@ -4,6 +4,7 @@ the reference's: ordinary FASTQ must be committed by the speculation (so that th
 measure), hostile FASTQ must fall back to the exact look-back kernel and still be bit-exact.
 """
 import numpy as np
+import importlib
 import pytest
 
 import cases
@@ -53,7 +54,7 @@ def _run(gu, params, keys, data, chunk=None, **options):
 
 def test_ordinary_fastq_is_committed_by_the_speculation(gu, oracle):
     """config-2 shape: many ranges, every one must guess its phase right; nothing may reach the exact kernel"""
-    from oracle import synth
+    synth = importlib.import_module("2fast2q_b200.synth")
     spec = synth.default_spec(2)
     names, keys = synth.make_library(2, 2000, 20)
     data = synth.fixed_reads(keys, 0, 300_000, **spec).tobytes()
@@ -71,7 +72,7 @@ def test_ordinary_fastq_is_committed_by_the_speculation(gu, oracle):
 
 def _hostile(kind, n=40_000):
     """FASTQ-shaped bytes that defeat the local phase heuristic"""
-    from oracle import synth
+    synth = importlib.import_module("2fast2q_b200.synth")
     r = synth.SM64(1234)
     guides = [r.dna(20) for _ in range(64)]
     out = []
@@ -114,7 +115,7 @@ def test_hostile_fastq_falls_back_and_stays_exact(gu, oracle, kind):
 def test_wrong_guess_is_caught_by_the_verification(gu, oracle):
     """a clean-looking stretch whose true phase differs from its looks: a 5-line oddity in front shifts every record by
     one line, but each range after it still looks like perfectly aligned FASTQ.  The verification must reject it."""
-    from oracle import synth
+    synth = importlib.import_module("2fast2q_b200.synth")
     spec = synth.default_spec(2)
     names, keys = synth.make_library(2, 500, 20)
     body = synth.fixed_reads(keys, 0, 60_000, **spec).tobytes()
@@ -137,7 +138,7 @@ def test_extract_count_never_speculates(gu):
 def test_ordinary_read_code_with_whitespace_tails_and_short_lines(gu, oracle, length, start):
     """the compile-time-window code of the streaming kernel must hand the reads it cannot decide to the general code:
     CRLF / blank tails (rstrip), N inside the window, lines that end inside the window, empty lines"""
-    from oracle import synth
+    synth = importlib.import_module("2fast2q_b200.synth")
     r = synth.SM64(99 + length)
     guides = [r.dna(length) for _ in range(300)]
     out = []

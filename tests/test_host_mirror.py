@@ -265,3 +265,22 @@ def test_bgzf_block_parallel_inflate(tmp_path):
     assert b"".join(host._inflate_blocks(str(p))) == data + b"@t\nACGT\n+\nIIII\n"
     p.write_bytes(gzip.compress(data))
     assert b"".join(host._inflate_blocks(str(p))) == data
+
+
+def test_test_mode_data_is_bundled(tmp_path, monkeypatch):
+    """`-c -t` must find its data (the data directory was not shipped): the surrogate example.fastq.gz is
+    generated on first use and is the stream whose sha256 the golden fixture pins"""
+    import gzip
+    import hashlib
+    import golden_io as G
+    td = importlib.import_module("2fast2q_b200.testdata")
+    monkeypatch.setattr(td, "EXAMPLE", str(tmp_path / "example.fastq.gz"))
+    path = td.ensure_example()
+    assert os.path.exists(td.GUIDES) and os.path.exists(td.EXPECTED)
+    data = gzip.open(path, "rb").read()
+    assert hashlib.sha256(data).hexdigest() == G.config1()["sha256"]
+    assert open(td.EXPECTED).read() == open(os.path.join(G.HERE, "ref_compiled.csv")).read()
+    fq = importlib.import_module("2fast2q_b200.fast2q")
+    monkeypatch.chdir(tmp_path)
+    p = fq.input_parser(["-c", "-t"])
+    assert p["test_mode"] and p["seq_files"] == path and p["feature"] == td.GUIDES and p["out"] == str(tmp_path)

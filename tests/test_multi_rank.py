@@ -32,7 +32,8 @@ def _worker(rank, world, port, mode, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from oracle import oracle as O, synth
+        from oracle import oracle as O
+        synth = importlib.import_module("2fast2q_b200.synth")
         multi = importlib.import_module("2fast2q_b200.multi")
         host = importlib.import_module("2fast2q_b200.fast2q")
         spec = synth.default_spec(2)
@@ -94,7 +95,8 @@ def _ec_worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from oracle import oracle as O, synth
+        from oracle import oracle as O
+        synth = importlib.import_module("2fast2q_b200.synth")
         multi = importlib.import_module("2fast2q_b200.multi")
         host = importlib.import_module("2fast2q_b200.fast2q")
         cfg = O.make_config(mode="EC", upstream="GTTCAGAGTTCT", downstream="CTGAATAGGCCA", miss_search_up=1, miss_search_down=1)
