@@ -14,6 +14,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libf2q.so")
 
+ABI_VERSION = 2
 MAX_ITER = 8
 MAX_DELIM = 64
 N_STATS = 5
@@ -46,6 +47,7 @@ class SynthSpec(C.Structure):
         ("seed", C.c_uint64), ("first_read", C.c_uint64), ("n_reads", C.c_uint64), ("read_len", C.c_uint32),
         ("feat_len", C.c_uint32), ("n_guides", C.c_uint32), ("cum_exact", C.c_uint32), ("cum_sub1", C.c_uint32),
         ("cum_sub2", C.c_uint32), ("cum_sub3", C.c_uint32), ("cum_n", C.c_uint32), ("lowq_per_65536", C.c_uint32),
+        ("shape", C.c_uint32), ("delim_len", C.c_uint32 * 4), ("delim", (C.c_uint8 * 16) * 4),
     ]
 
 
@@ -98,7 +100,7 @@ def load():
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(L, name)           # AttributeError if the ABI is incomplete
             fn.restype, fn.argtypes = res, args
-        if L.f2q_abi_version() != 1:
+        if L.f2q_abi_version() != ABI_VERSION:
             raise ImportError("libf2q.so ABI version mismatch")
         _lib = L
     return _lib
@@ -142,6 +144,22 @@ def make_config(mode="C", miss=1, phred=30, length=20, start="0", upstream=None,
             for j, b in enumerate(u):
                 dst[i][j] = b
     return c
+
+
+def make_synth_spec(n_seqs: int, first_read: int, n_reads: int, *, seed, read_len, feat_len, lowq_per_65536, shape=0, delims=(),
+                    cum_exact=0, cum_sub1=0, cum_sub2=0, cum_sub3=0, cum_n=0) -> SynthSpec:
+    """struct f2q_synth_spec from the dicts of synth.default_spec / synth.shape_spec; n_seqs = len(guides)"""
+    s = SynthSpec()
+    s.seed, s.first_read, s.n_reads = seed, first_read, n_reads
+    s.read_len, s.feat_len, s.shape = read_len, feat_len, shape
+    s.n_guides = n_seqs // 2 if shape >= 2 else n_seqs
+    s.cum_exact, s.cum_sub1, s.cum_sub2, s.cum_sub3, s.cum_n = cum_exact, cum_sub1, cum_sub2, cum_sub3, cum_n
+    s.lowq_per_65536 = lowq_per_65536
+    for k, d in enumerate(delims):
+        s.delim_len[k] = len(d)
+        for j, ch in enumerate(d):
+            s.delim[k][j] = ch
+    return s
 
 
 def pack_keys(keys):
@@ -318,12 +336,14 @@ class Engine:
         a = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
         self._ck(self.L.f2q_memcpy_h2d(self.h, C.c_void_p(dptr), a.ctypes.data, a.size))
 
-    def synth(self, dptr: int, guides, first_read: int, n_reads: int, **spec):
-        s = SynthSpec()
-        s.seed, s.first_read, s.n_reads = spec["seed"], first_read, n_reads
-        s.read_len, s.feat_len, s.n_guides = spec["read_len"], spec["feat_len"], len(guides)
-        for k in ("cum_exact", "cum_sub1", "cum_sub2", "cum_sub3", "cum_n", "lowq_per_65536"):
-            setattr(s, k, spec[k])
+    def synth(self, dptr: int, guides, first_read: int, n_reads: int, reuse_guides: bool = False, **spec):
+        """K0: write reads [first_read, first_read + n_reads) of the workload `spec` at dptr.  guides: list of equal-length
+        byte strings (shapes 2/3: the X's then the Y's).  reuse_guides=True skips the upload (the table of the previous
+        call is used) and makes the call asynchronous on the engine's stream."""
+        s = make_synth_spec(len(guides), first_read, n_reads, **spec)
+        if reuse_guides:
+            self._ck(self.L.f2q_synth_fastq(self.h, C.byref(s), None, C.c_void_p(dptr)))
+            return
         g = np.frombuffer(b"".join(guides), dtype=np.uint8)
         self._ck(self.L.f2q_synth_fastq(self.h, C.byref(s), g.ctypes.data, C.c_void_p(dptr)))
 

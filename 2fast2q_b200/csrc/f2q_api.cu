@@ -92,6 +92,7 @@ struct f2q_ctx {
     int spec_range_tiles = 0;          // 0 auto | tiles per range
     int spec_ready[2][8][2] = {{{0}}}; // function attributes set for (policy, ch, warps == 16)
     DevBuf spec_rec, spec_scratch;
+    DevBuf synth_guides; size_t synth_guide_bytes = 0;   // guide table of the last f2q_synth_fastq call (K0, bench / tests)
     // [0] tables + result outputs, [1] tables + scratch outputs, in device memory (SlowArgs, generic.cuh); re-uploaded when they change
     DevBuf slow_args;
     SlowArgs slow_host[2];
@@ -639,7 +640,7 @@ F2Q_EXPORT void f2q_destroy(f2q_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto& b : c->lib_bufs) b.release();
     c->result.release(); c->carry.release(); c->status.release(); c->status_stitch.release(); c->queue.release(); c->gqueue.release();
-    c->seg_count.release(); c->spec_rec.release(); c->spec_scratch.release(); c->slow_args.release();
+    c->seg_count.release(); c->spec_rec.release(); c->spec_scratch.release(); c->slow_args.release(); c->synth_guides.release();
     c->ec_slots.release(); c->ec_counts.release(); c->ec_arena.release(); c->ec_meta.release();
     for (auto p : c->d_stage) cudaFree(p);
     for (auto e : c->ev_copied) cudaEventDestroy(e);
@@ -1121,20 +1122,26 @@ F2Q_EXPORT int f2q_kernel_times(f2q_ctx* c, double* ms, uint64_t* launches) {
 // ---- K0 synthetic generator ------------------------------------------------------------------------------
 F2Q_EXPORT int f2q_synth_fastq(f2q_ctx* c, const f2q_synth_spec* spec, const uint8_t* guides, void* dptr) {
     int rc = check_ctx(c); if (rc) return rc;
-    if (!spec || !guides || !dptr) return fail(c, F2Q_EINVAL, "null argument");
-    if (spec->feat_len < 4 || spec->feat_len > 32 || spec->read_len < spec->feat_len || spec->read_len > 150 || spec->n_guides == 0)
+    if (!spec || !dptr) return fail(c, F2Q_EINVAL, "null argument");
+    if (spec->feat_len < 4 || spec->feat_len > 32 || spec->read_len < spec->feat_len || spec->read_len > 150 || spec->n_guides == 0 || spec->shape > 3)
         return fail(c, F2Q_EINVAL, "synthetic spec out of range");
-    DevBuf g;
-    if ((rc = dev_alloc(c, g, (size_t)spec->n_guides * spec->feat_len))) return rc;
-    CU(c, cudaMemcpyAsync(g.p, guides, (size_t)spec->n_guides * spec->feat_len, cudaMemcpyHostToDevice, c->stream));
+    for (int k = 0; k < 4; k++) if (spec->delim_len[k] > 16) return fail(c, F2Q_EINVAL, "synthetic spec: search sequence longer than 16");
+    const size_t gbytes = (size_t)spec->n_guides * spec->feat_len * (spec->shape >= 2 ? 2 : 1);
+    if (guides) {
+        // (synchronous: the caller's host array may go away after the call)
+        CU(c, cudaStreamSynchronize(c->stream));
+        if ((rc = dev_alloc(c, c->synth_guides, gbytes))) return rc;
+        CU(c, cudaMemcpy(c->synth_guides.p, guides, gbytes, cudaMemcpyHostToDevice));
+        c->synth_guide_bytes = gbytes;
+    } else if (!c->synth_guides.p || c->synth_guide_bytes != gbytes)
+        return fail(c, F2Q_ESTATE, "f2q_synth_fastq without guides needs an earlier call that uploaded the same table");
     if (spec->n_reads) {
         const unsigned grid = (unsigned)std::min<uint64_t>((spec->n_reads + 255) / 256, (uint64_t)c->sm_count * 16);
-        k_synth<<<grid, 256, 0, c->stream>>>(*spec, reinterpret_cast<const uint8_t*>(g.p), reinterpret_cast<uint8_t*>(dptr));
+        k_synth<<<grid, 256, 0, c->stream>>>(*spec, reinterpret_cast<const uint8_t*>(c->synth_guides.p), reinterpret_cast<uint8_t*>(dptr));
         c->launches++;
     }
     CU(c, cudaGetLastError());
-    CU(c, cudaStreamSynchronize(c->stream));
-    g.release();
+    if (guides) CU(c, cudaStreamSynchronize(c->stream));
     return F2Q_OK;
 }
 

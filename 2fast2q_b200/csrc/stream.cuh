@@ -7,6 +7,7 @@
 #pragma once
 
 #include "f2q_dev.cuh"
+#include "synth_gen.h"
 
 namespace f2q {
 
@@ -98,59 +99,13 @@ __global__ void __launch_bounds__(PREP_THREADS) k_carry(DevState* S, const uint8
 }
 
 // ------------------------------------------------------------------------------------------------
-// K0: synthetic FASTQ generator (bench / tests).  Bit-identical to 2fast2q_b200/synth.py:fixed_reads().
+// K0: synthetic FASTQ generator (bench / tests).  One thread per read; the record itself is written by synth_record
+// (synth_gen.h), bit-identical to 2fast2q_b200/synth.py.
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ uint64_t sm_fin(uint64_t z) {
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-
 __global__ void __launch_bounds__(256) k_synth(f2q_synth_spec sp, const uint8_t* __restrict__ guides, uint8_t* __restrict__ out) {
-    const uint64_t GOLD = 0x9E3779B97F4A7C15ull, K2 = 0xD1342543DE82EF95ull;
-    const uint32_t L = sp.read_len, F = sp.feat_len;
-    const uint64_t rec = 2ull * L + 18;
-    for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < sp.n_reads; k += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t i = sp.first_read + k;
-        uint8_t* o = out + k * rec;
-        const uint64_t b = sm_fin((sp.seed + 1) * GOLD + i * K2);
-        const uint64_t r0 = sm_fin(b + 1 * GOLD), r1 = sm_fin(b + 2 * GOLD);
-        const uint32_t cls = (uint32_t)(r0 & 0xFFFF), lowsel = (uint32_t)((r0 >> 16) & 0xFFFF);
-        const uint32_t lowpos = (uint32_t)((((r0 >> 32) & 0xFFFF) * L) >> 16);
-        const uint32_t lowq = 2 + (uint32_t)((((r0 >> 48) & 0xFFFF) * 27) >> 16);
-        const uint32_t gi = (uint32_t)(((r1 & 0xFFFFFFFFull) * sp.n_guides) >> 32);
-        o[0] = '@'; o[1] = 'S';
-        uint64_t v = i;
-        for (int d = 0; d < 11; d++) { o[12 - d] = (uint8_t)('0' + v % 10); v /= 10; }
-        o[13] = '\n';
-        uint8_t* s = o + 14;
-        const char ACGT[4] = {'A', 'C', 'G', 'T'};
-        for (uint32_t j = 0; j < F; j++) s[j] = guides[(uint64_t)gi * F + j];
-        const uint32_t a = (uint32_t)((r1 >> 32) & 0xFF), bb = (uint32_t)((r1 >> 40) & 0xFF), cc = (uint32_t)((r1 >> 48) & 0xFF);
-        const uint32_t sb = (uint32_t)((r1 >> 56) & 0xFF);
-        const uint32_t p0 = a % F, d1 = 1 + bb % (F - 1), p1 = (p0 + d1) % F;
-        uint32_t d2 = 1 + cc % (F - 2); d2 += (d2 >= d1);
-        const uint32_t p2 = (p0 + d2) % F;
-        auto code_of = [](uint8_t c) -> uint32_t { return c == 'A' ? 0u : c == 'C' ? 1u : c == 'G' ? 2u : c == 'T' ? 3u : 0u; };
-        auto subst = [&](uint32_t pos, uint32_t delta) { s[pos] = ACGT[(code_of(s[pos]) + 1 + delta % 3) % 4]; };
-        const bool is1 = cls >= sp.cum_exact && cls < sp.cum_sub1, is2 = cls >= sp.cum_sub1 && cls < sp.cum_sub2;
-        const bool is3 = cls >= sp.cum_sub2 && cls < sp.cum_sub3, isn = cls >= sp.cum_sub3 && cls < sp.cum_n, isr = cls >= sp.cum_n;
-        if (is1 || is2 || is3) subst(p0, sb & 3);
-        if (is2 || is3) subst(p1, (sb >> 2) & 3);
-        if (is3) subst(p2, (sb >> 4) & 3);
-        if (isn) s[(sb * F) >> 8] = 'N';
-        if (isr) { const uint64_t rr = sm_fin(b + 5 * GOLD); for (uint32_t j = 0; j < F; j++) s[j] = ACGT[(rr >> (2 * j)) & 3]; }
-        const uint64_t t0 = sm_fin(b + 3 * GOLD), t1 = sm_fin(b + 4 * GOLD);
-        for (uint32_t j = 0; j < L - F; j++) { const uint64_t src = j < 32 ? t0 : t1; s[F + j] = ACGT[(src >> (2 * (j % 32))) & 3]; }
-        s[L] = '\n'; s[L + 1] = '+'; s[L + 2] = '\n';
-        uint8_t* q = s + L + 3;
-        for (uint32_t w = 0; w < (L + 7) / 8; w++) {
-            const uint64_t rq = sm_fin(b + (9 + w) * GOLD);
-            for (uint32_t j = 0; j < 8 && w * 8 + j < L; j++) q[w * 8 + j] = (uint8_t)(63 + ((((rq >> (8 * j)) & 0xFF) * 11) >> 8));
-        }
-        if (lowsel < sp.lowq_per_65536) q[lowpos] = (uint8_t)(33 + lowq);
-        q[L] = '\n';
-    }
+    const uint64_t rec = 2ull * sp.read_len + 18;
+    for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < sp.n_reads; k += (uint64_t)gridDim.x * blockDim.x)
+        synth_record(sp, guides, sp.first_read + k, out + k * rec);
 }
 
 }  // namespace f2q

@@ -73,6 +73,19 @@ def make_library(seed: int, n: int, length: int = 20):
     return names, out
 
 
+def random_kmers(seed: int, n: int, length: int = 20):
+    """n uniform-random `length`-mers (bytes), NOT de-duplicated — the barcode pool of the Bar-seq workload"""
+    idx = np.arange(n, dtype=np.uint64)
+    b = base(seed ^ 0xBA5C, idx)
+    codes = np.zeros((n, ((length + 31) // 32) * 32), dtype=np.uint8)
+    for w in range((length + 31) // 32):
+        r = rnd(b, 200 + w)
+        for j in range(32):
+            codes[:, w * 32 + j] = ((r >> U64(2 * j)) & U64(3)).astype(np.uint8)
+    seqs = ACGT[codes[:, :length]]
+    return [row.tobytes() for row in seqs]
+
+
 def default_spec(config: int):
     """class mixes of BASELINE.json configs 2 and 3, cumulative thresholds out of 65536"""
     if config == 2:
@@ -176,6 +189,156 @@ def fixed_reads(guides, first_read: int, n_reads: int, *, seed, read_len, feat_l
             qual[:, k] = (U64(63) + ((byte * U64(11)) >> U64(8))).astype(np.uint8)     # Q30..Q40
     low = lowsel < lowq_per_65536
     qual[rows[low], lowpos[low]] = U64(33).astype(np.uint8) + lowq[low]                 # Q2..Q28
+    out[:, 17 + 2 * L] = 10
+    return out.reshape(-1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# shapes 1-3 of K0 (csrc/synth_gen.h): Bar-seq, dual fixed, dual delimiters — the workloads of BASELINE configs 4 and 5
+# ---------------------------------------------------------------------------------------------------
+SY1_SUB, SY1_LACK, SY1_LEN = 3277, 5243, 6554
+SY2_XMUT, SY2_YMUT, SY2_XRAND, SY2_MISPAIR = 6554, 9830, 11796, 6554
+F_EXTRA, F_BG0 = 5, 39
+
+BARSEQ_US, BARSEQ_DS = b"GTTCAGAGTTCT", b"CTGAATAGGCCA"
+DUAL_DELIMS = (b"ACCGGT", b"TTGACA", b"GGATCC", b"CAATTG")          # U1, D1, U2, D2
+
+
+def shape_spec(config: str):
+    """generator spec of the non-guide workloads: '4' Bar-seq (config 4), '5a' dual fixed, '5b' dual delimiters"""
+    base_ = dict(read_len=75, feat_len=20, cum_exact=0, cum_sub1=0, cum_sub2=0, cum_sub3=0, cum_n=0)
+    if config == "4":
+        return dict(base_, seed=4, shape=1, delims=(BARSEQ_US, BARSEQ_DS), lowq_per_65536=int(round(0.08 * 65536)))
+    if config == "5a":
+        return dict(base_, seed=5, shape=2, delims=(), lowq_per_65536=int(round(0.08 * 65536)))
+    if config == "5b":
+        return dict(base_, seed=6, shape=3, delims=DUAL_DELIMS, lowq_per_65536=int(round(0.08 * 65536)))
+    raise ValueError(config)
+
+
+def dual_keys(n_pairs: int, seed: int = 5, length: int = 20):
+    """config-5 library: n_pairs 'X:Y' keys plus their single X and Y entries (names d/x/y%06d); returns
+    (names, keys, xs, ys); the generator takes xs + ys as its guide table"""
+    _, seqs = make_library(seed ^ 0xD0A1, 2 * n_pairs, length)
+    xs, ys = seqs[:n_pairs], seqs[n_pairs:]
+    names, keys = [], []
+    for k in range(n_pairs):
+        names += ["d%06d" % k, "x%06d" % k, "y%06d" % k]
+        keys += [xs[k] + b":" + ys[k], xs[k], ys[k]]
+    return names, keys, xs, ys
+
+
+def shaped_reads(guides, first_read: int, n_reads: int, *, seed, read_len, feat_len, shape, delims=(), lowq_per_65536, **_):
+    """reads [first_read, first_read + n_reads) of shapes 1-3 -> uint8[n_reads * (2L+18)]; numpy restatement of
+    synth_record (csrc/synth_gen.h), bit-identical (tests/test_synth_shapes.py, tests/test_gpu_parity.py)"""
+    L, F = int(read_len), int(feat_len)
+    assert shape in (1, 2, 3) and 4 <= F <= 32 and F <= L <= 150
+    G = np.frombuffer(b"".join(guides), dtype=np.uint8).reshape(len(guides), F)
+    n_g = len(guides) if shape == 1 else len(guides) // 2
+    code_of = np.zeros(256, dtype=np.int64)
+    for c, ch in enumerate(b"ACGT"):
+        code_of[ch] = c
+    n = int(n_reads)
+    idx = np.arange(first_read, first_read + n, dtype=np.uint64)
+    b = base(seed, idx)
+    r0, r1, r2 = rnd(b, F_MISC), rnd(b, F_GUIDE), rnd(b, F_EXTRA)
+    cls = (r0 & U64(0xFFFF)).astype(np.int64)
+    lowsel = ((r0 >> U64(16)) & U64(0xFFFF)).astype(np.int64)
+    lowpos = ((((r0 >> U64(32)) & U64(0xFFFF)) * U64(L)) >> U64(16)).astype(np.int64)
+    lowq = (U64(2) + ((((r0 >> U64(48)) & U64(0xFFFF)) * U64(27)) >> U64(16))).astype(np.uint8)
+    rec = 2 * L + 18
+    out = np.empty((n, rec), dtype=np.uint8)
+    out[:, 0] = ord("@")
+    out[:, 1] = ord("S")
+    v = idx.copy()
+    for d in range(11):
+        out[:, 12 - d] = (v % U64(10)).astype(np.uint8) + ord("0")
+        v //= U64(10)
+    out[:, 13] = 10
+    seq = out[:, 14:14 + L]
+    for w in range((L + 31) // 32):
+        bg = rnd(b, F_BG0 + w)
+        for j in range(32):
+            if w * 32 + j >= L:
+                break
+            seq[:, w * 32 + j] = ACGT[((bg >> U64(2 * j)) & U64(3)).astype(np.int64)]
+    rows = np.arange(n)
+    p = np.zeros(n, dtype=np.int64)
+    NONE = np.full(n, -1, dtype=np.int64)
+
+    def put(src, length, mpos, mdelta, active=None):
+        """src: (n, >= length) per-read bytes or one bytes object; advances p by length for the active reads"""
+        nonlocal p
+        if isinstance(src, (bytes, bytearray)):
+            src = np.broadcast_to(np.frombuffer(bytes(src), dtype=np.uint8), (n, len(src)))
+        act = np.ones(n, dtype=bool) if active is None else active
+        for k in range(length):
+            m = act & (p + k < L)
+            c = src[:, k].copy()
+            mut = m & (mpos == k)
+            c[mut] = ACGT[(code_of[c[mut]] + 1 + mdelta[mut] % 3) % 4]
+            seq[rows[m], (p + k)[m]] = c[m]
+        p = p + np.where(act, length, 0)
+
+    if shape == 1:
+        u32 = r1 & U64(0xFFFFFFFF)
+        sq = (u32 * u32) >> U64(32)
+        bi = ((sq * U64(n_g)) >> U64(32)).astype(np.int64)
+        which = ((r2 >> U64(3)) & U64(1)).astype(np.int64)
+        mdelta = ((r2 >> U64(16)) & U64(3)).astype(np.int64)
+        sub, lack, odd = cls < SY1_SUB, (cls >= SY1_SUB) & (cls < SY1_LACK), (cls >= SY1_LACK) & (cls < SY1_LEN)
+        us, ds = delims
+        sel8 = ((r2 >> U64(8)) & U64(0xFF)).astype(np.int64)
+        p = (r2 & U64(7)).astype(np.int64)
+        skip = lack & (which == 0)
+        put(us, len(us), np.where(sub & (which == 0), (sel8 * len(us)) >> 8, NONE), mdelta, ~skip)
+        p = p + np.where(skip, len(us), 0)
+        short = odd & (((r2 >> U64(4)) & U64(1)) == U64(1))
+        longer = odd & ~short
+        bc = G[bi]
+        put(bc, F - 1, NONE, mdelta)
+        put(bc[:, F - 1:], 1, NONE, mdelta, ~short)
+        p = p + np.where(longer, 1, 0)
+        skip = lack & (which == 1)
+        put(ds, len(ds), np.where(sub & (which == 1), (sel8 * len(ds)) >> 8, NONE), mdelta, ~skip)
+        p = p + np.where(skip, len(ds), 0)
+    else:
+        k = (((r1 & U64(0xFFFFFFFF)) * U64(n_g)) >> U64(32)).astype(np.int64)
+        other = (((r2 >> U64(32)) * U64(n_g)) >> U64(32)).astype(np.int64)
+        ky = np.where((r2 & U64(0xFFFF)).astype(np.int64) < SY2_MISPAIR, other, k)
+        X, Y = G[k], G[n_g + ky]
+        mpos = ((((r2 >> U64(16)) & U64(0xFF)) * U64(F)) >> U64(8)).astype(np.int64)
+        mdelta = ((r2 >> U64(24)) & U64(3)).astype(np.int64)
+        xmut, ymut, xrand = cls < SY2_XMUT, (cls >= SY2_XMUT) & (cls < SY2_YMUT), (cls >= SY2_YMUT) & (cls < SY2_XRAND)
+        if shape == 2:
+            put(X, F, np.where(xmut, mpos, NONE), mdelta, ~xrand)
+            p = p + np.where(xrand, F, 0) + 10
+            put(Y, F, np.where(ymut, mpos, NONE), mdelta)
+        else:
+            u1, d1, u2, d2 = delims
+            p = ((r2 >> U64(26)) & U64(3)).astype(np.int64)
+            put(u1, len(u1), NONE, mdelta)
+            put(X, F, np.where(xmut, mpos, NONE), mdelta, ~xrand)
+            p = p + np.where(xrand, F, 0)
+            put(d1, len(d1), NONE, mdelta)
+            p = p + (((r2 >> U64(28)) & U64(3)) % U64(3)).astype(np.int64)
+            put(u2, len(u2), NONE, mdelta)
+            put(Y, F, np.where(ymut, mpos, NONE), mdelta)
+            put(d2, len(d2), NONE, mdelta)
+    out[:, 14 + L] = 10
+    out[:, 15 + L] = ord("+")
+    out[:, 16 + L] = 10
+    qual = out[:, 17 + L:17 + 2 * L]
+    for w in range((L + 7) // 8):
+        rq = rnd(b, F_QUAL0 + w)
+        for j in range(8):
+            kk = w * 8 + j
+            if kk >= L:
+                break
+            byte = (rq >> U64(8 * j)) & U64(0xFF)
+            qual[:, kk] = (U64(63) + ((byte * U64(11)) >> U64(8))).astype(np.uint8)
+    low = lowsel < lowq_per_65536
+    qual[rows[low], lowpos[low]] = U64(33).astype(np.uint8) + lowq[low]
     out[:, 17 + 2 * L] = 10
     return out.reshape(-1)
 

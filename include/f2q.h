@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define F2Q_ABI_VERSION 1
+#define F2Q_ABI_VERSION 2
 
 #define F2Q_MAX_ITER   8    /* max comma items in --st / --us / --ds (search_iterations, fast2q.py:541,558) */
 #define F2Q_MAX_DELIM  64   /* max bytes of one --us / --ds search sequence */
@@ -211,8 +211,17 @@ typedef struct f2q_synth_spec {
     /* cumulative class thresholds out of 65536: exact | 1 sub | 2 sub | 3 sub | one N | (rest = random) */
     uint32_t cum_exact, cum_sub1, cum_sub2, cum_sub3, cum_n;
     uint32_t lowq_per_65536; /* fraction of reads that get one low-quality byte */
+    /* workload shape: 0 guide at offset 0 + random tail (configs 2, 3; the class thresholds above apply) |
+     * 1 Bar-seq: stagger + delim[0] + barcode + delim[1] + pad (config 4) | 2 dual fixed: X at 0, Y at feat_len+10
+     * (config 5a) | 3 dual delimiters: delim[0] X delim[1] .. delim[2] Y delim[3] (config 5b).  Shapes 2/3 take
+     * 2*n_guides sequences: the X's, then the Y's.  Class mixes of shapes 1-3 are fixed (csrc/synth_gen.h). */
+    uint32_t shape;
+    uint32_t delim_len[4];
+    uint8_t  delim[4][16];
 } f2q_synth_spec;
-/* writes n_reads*(2L+18) bytes at dptr (device); guides = n_guides*feat_len ASCII bytes on the HOST */
+/* writes n_reads*(2L+18) bytes at dptr (device); guides = n_guides*feat_len (shapes 2/3: 2*n_guides*feat_len) ASCII
+ * bytes on the HOST.  Asynchronous on the context's stream when n_guides == 0 && guides == NULL re-uses the guide
+ * table uploaded by the previous call (per-chunk generation of workloads larger than HBM). */
 int f2q_synth_fastq(f2q_ctx* ctx, const f2q_synth_spec* spec, const uint8_t* guides, void* dptr);
 
 /* device memory helpers so that a non-CUDA host language can hold resident chunks */

@@ -42,7 +42,7 @@ def test_exports_nothing_else_with_the_prefix():
 
 def test_no_cpu_fallback_without_a_device():
     L = lib.load()
-    assert L.f2q_abi_version() == 1
+    assert L.f2q_abi_version() == lib.ABI_VERSION
     if L.f2q_device_count() > 0:
         pytest.skip("a B200 is visible: the refusal path needs a machine without one")
     cfg = lib.make_config()

@@ -163,18 +163,32 @@ def test_short_lines_many_newlines(gu, oracle):
 
 
 def test_synth_generator_matches_numpy(gu):
+    """K0 on the device == its numpy restatement, every shape (configs 2, 3, 4, 5a, 5b); the second call re-uses the
+    uploaded guide table asynchronously, as the per-chunk generation of the bench does"""
     synth = importlib.import_module("2fast2q_b200.synth")
+    work = []
     for config in (2, 3):
         spec = synth.default_spec(config)
         names, keys = synth.make_library(config, 500, 20)
-        want = synth.fixed_reads(keys, 12345, 3000, **spec)
-        cfg = gu.lib.make_config()
+        work.append((keys, spec, lambda f, n, keys=keys, spec=spec: synth.fixed_reads(keys, f, n, **spec)))
+    _, pool = synth.make_library(44, 3000, 20)
+    _, _, xs, ys = synth.dual_keys(300)
+    for config, guides in (("4", pool), ("5a", xs + ys), ("5b", xs + ys)):
+        spec = synth.shape_spec(config)
+        work.append((guides, spec, lambda f, n, guides=guides, spec=spec: synth.shaped_reads(guides, f, n, **spec)))
+    cfg = gu.lib.make_config()
+    for guides, spec, gen in work:
+        want = gen(12345, 3000)
+        want2 = gen(999_000_000_000, 1000)
         with gu.lib.Engine(cfg) as e:
             d = e.device_alloc(want.size)
-            e.synth(d, keys, 12345, 3000, **spec)
+            e.synth(d, guides, 12345, 3000, **spec)
             got = e.d2h(d, want.size)
+            e.synth(d, guides, 999_000_000_000, 1000, reuse_guides=True, **spec)
+            got2 = e.d2h(d, want2.size)
             e.device_free(d)
-        assert np.array_equal(got, want)
+        assert np.array_equal(got, want), spec
+        assert np.array_equal(got2, want2), spec
 
 
 def test_resident_device_submit_large(gu, oracle):
