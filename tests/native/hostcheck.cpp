@@ -15,3 +15,62 @@ void hc_synth(const f2q_synth_spec* sp, const uint8_t* guides, uint64_t first, u
 }
 
 }
+
+// ---- flex_core.h: bit-parallel key extraction of one read, against oracle f2qo_build_key -----------------------------
+#include <vector>
+
+#include "../../2fast2q_b200/csrc/flex_core.h"
+
+namespace {
+template <int PW, int K>
+int flex_key_t(const f2q::FlexCfg& C, const uint8_t* read, int r, const uint8_t* qual, int q, uint8_t* out, int* out_len) {
+    // the lines sit at odd offsets of padded buffers, as they do inside a tile
+    std::vector<uint8_t> sb(32 * PW + 64, '\n'), qb(32 * PW + 64, '\n');
+    const uint32_t so = 5, qo = 11;
+    memcpy(sb.data() + so, read, r); memcpy(qb.data() + qo, qual, q);
+    uint32_t sw[8 * PW], qw[8 * PW];
+    f2q::flex_load<8 * PW>(sb.data(), so, sw);
+    f2q::flex_load<8 * PW>(qb.data(), qo, qw);
+    f2q::FlexPiece pc[f2q::FLEX_ITER];
+    const int np = f2q::flex_pieces<PW, K>(C, sw, (uint32_t)r, qw, (uint32_t)q, pc);
+    if (np < 0) return np;
+    int n = 0;
+    for (int p = 0; p < np; p++) {
+        if (p) out[n++] = ':';
+        for (uint32_t i = 0; i < pc[p].len; i++) {
+            uint8_t c = read[pc[p].off + i];
+            if ((pc[p].notok >> i) & 1u) { if (c >= 'a' && c <= 'z') c -= 32; }      // the caller's look at the raw byte
+            else c = (uint8_t)("ACTG"[(pc[p].codes >> (2 * i)) & 3u]);                 // decoded from the packed codes
+            out[n++] = c;
+        }
+    }
+    *out_len = n;
+    return np;
+}
+}  // namespace
+
+extern "C" {
+
+// returns 1 when the configuration is eligible for the bit-parallel path, else 0
+__attribute__((visibility("default")))
+int hc_flex_eligible(const f2q_config* cfg) {
+    f2q::FlexCfg C;
+    return f2q::flex_prepare(*cfg, C) ? 1 : 0;
+}
+
+// key of one read through flex_pieces: returns np >= 0 (key in out), -1 all iterations flagged, -2 generic path needed,
+// -3 not eligible / read too long for pw planes
+__attribute__((visibility("default")))
+int hc_flex_key(const f2q_config* cfg, int pw, const uint8_t* read, int r, const uint8_t* qual, int q, uint8_t* out, int* out_len) {
+    f2q::FlexCfg C;
+    if (!f2q::flex_prepare(*cfg, C)) return -3;
+    if (r > 32 * pw || q > 32 * pw) return -3;
+    const int K = C.max_k;
+#define F2Q_HC_CASE(PWV, KV) if (pw == PWV && K == KV) return flex_key_t<PWV, KV>(C, read, r, qual, q, out, out_len);
+    F2Q_HC_CASE(3, 0) F2Q_HC_CASE(3, 1) F2Q_HC_CASE(3, 2) F2Q_HC_CASE(3, 3)
+    F2Q_HC_CASE(5, 0) F2Q_HC_CASE(5, 1) F2Q_HC_CASE(5, 2) F2Q_HC_CASE(5, 3)
+#undef F2Q_HC_CASE
+    return -3;
+}
+
+}
