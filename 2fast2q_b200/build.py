@@ -8,11 +8,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libf2q.so")
 SOURCES = ["f2q_api.cu"]
-HEADERS = ["f2q_dev.cuh", "generic.cuh", "resolve.cuh", "stream.cuh", "tile.cuh", "spec.cuh", os.path.join("..", "..", "include", "f2q.h")]
+HEADERS = ["f2q_dev.cuh", "generic.cuh", "resolve.cuh", "stream.cuh", "tile.cuh", "spec.cuh", "flex.cuh", "flex_core.h", "synth_gen.h",
+           os.path.join("..", "..", "include", "f2q.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "--expt-relaxed-constexpr", "--extended-lambda",
+    "--expt-relaxed-constexpr", "--extended-lambda", "-split-compile", "0",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "-shared", "-cudart", "static",
 ]
 

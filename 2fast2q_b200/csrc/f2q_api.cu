@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <unordered_set>
@@ -62,6 +63,8 @@ struct f2q_ctx {
     uint32_t q_cap = 0, g_cap = 0;     // q_cap = total queue entries (n_segs * seg_cap)
     uint32_t seg_cap = 0, n_segs = 0;
     int force_ch = 0, force_halo = 0;
+    bool no_flex = false, force_generic = false, flex_big = false;   // options "flex" = 0 / "force_generic"; flex_big: reads longer than 96 (sniffed)
+    size_t rec_bytes = 0;              // record length sniffed from the head of the sample (0 = unknown)
     int halo_rows = 6;
     int ch = 7;                        // row chunks of the tile kernel (row = 16*ch bytes), picked per sample from the record length
     bool ch_decided = false;           // per sample for host submits (sniffed from the host bytes: free); a context fed with
@@ -75,8 +78,19 @@ struct f2q_ctx {
     int next_slot = 0;
     // EC
     EcTable E{};
-    DevBuf ec_slots, ec_counts, ec_arena, ec_meta;   // meta: [arena_used, n_keys]
+    DevBuf ec_slots, ec_counts, ec_arena, ec_meta;   // meta (32 bytes): [arena_used, n_keys of the arena table, n_keys of the packed table, -]
     uint64_t ec_cap = 0;
+    DevBuf ec_pk, ec_compact; uint64_t ec_pk_cap = 0, ec_pk_min = 0;   // packed key table: 16-byte slots; its compacted (tag, count) pairs
+    static constexpr int EC_RING = 16;
+    struct EcPend { cudaEvent_t ev; unsigned long long* host; uint64_t bound_pk, bound_keys, bound_bytes; };
+    std::deque<EcPend> ec_pend;                      // chunks whose fill counters the host has not seen yet, oldest first
+    std::vector<cudaEvent_t> ec_events;
+    unsigned long long* ec_meta_host = nullptr;      // pinned ring of EC_RING x 4 words
+    uint64_t ec_ring_next = 0;
+    unsigned long long ec_known[4] = {0, 0, 0, 0};   // newest counters seen: arena bytes, arena keys, packed keys, spec_off
+    int fx_group = 1, fx_group_opt = 0;              // lanes per key of the flex resolver (auto from the seed index / option)
+    size_t q_entry = 0;                              // bytes per entry the queue buffer was sized for
+    int64_t opt_generic_entries = 0;
     std::vector<uint64_t> ec_drain_off, ec_drain_cnt; std::vector<uint8_t> ec_drain_keys; bool ec_drained = false;
     // state
     bool in_sample = false, closed = false;
@@ -90,7 +104,7 @@ struct f2q_ctx {
     int spec = 1;                      // 0: always the exact look-back kernel
     int spec_warps = 16;               // warps per CTA (one CTA per SM): 12 or 16
     int spec_range_tiles = 0;          // 0 auto | tiles per range
-    int spec_ready[2][8][2] = {{{0}}}; // function attributes set for (policy, ch, warps == 16)
+    int spec_ready[4][8][2] = {{{0}}}; // function attributes set for (policy, ch, warps == 16)
     DevBuf spec_rec, spec_scratch;
     DevBuf synth_guides; size_t synth_guide_bytes = 0;   // guide table of the last f2q_synth_fastq call (K0, bench / tests)
     // [0] tables + result outputs, [1] tables + scratch outputs, in device memory (SlowArgs, generic.cuh); re-uploaded when they change
@@ -165,6 +179,7 @@ int make_generic_cfg(const f2q_config* cfg, GenericCfg& G, std::string& why) {
         memcpy(d.up[i], cfg->up[i], F2Q_MAX_DELIM); memcpy(d.down[i], cfg->down[i], F2Q_MAX_DELIM);
     }
     G.set_ph = fail_set(cfg->phred); G.set_up = fail_set(cfg->qual_up); G.set_down = fail_set(cfg->qual_down);
+    flex_prepare(*cfg, G.flex);                                        // (eligible = 0 when the bit-parallel path cannot run it)
     return F2Q_OK;
 }
 
@@ -192,13 +207,22 @@ int upload(f2q_ctx* c, const std::vector<Tv>& v, const Tv** out) {
 
 uint32_t pow2_at_least(uint64_t n) { uint64_t p = 16; while (p < n) p <<= 1; return (uint32_t)p; }
 
+// per-read code of the streaming kernel: fast1 (one fixed window, Counter) | flex (bit-parallel search sequences / several
+// windows; Counter needs every library key in the flex table, Extract+Count has its packed key table) | byte-wise generic.
+// The exact look-back kernel (stitched records, fallback) runs fast1 or the generic code: results never depend on the path.
 void decide_policy(f2q_ctx* c) {
     const f2q_config& g = c->cfg;
     c->policy = POLICY_GENERIC;
     if (g.mode == F2Q_MODE_COUNT && !g.has_up && !g.has_down && g.n_iter == 1 && g.length >= 0 && g.length <= 32) c->policy = POLICY_FAST1;
+    else if (c->hG.flex.eligible && !c->no_flex && (g.mode == F2Q_MODE_EXTRACT_COUNT || c->T.fx_slots))
+        c->policy = (c->hG.flex.max_k > 1 || c->flex_big) ? POLICY_FLEX_B : POLICY_FLEX_S;
+    if (c->force_generic) c->policy = POLICY_GENERIC;
     if (!c->nt_user) c->nt = c->policy == POLICY_FAST1 ? 256 : 128;
 }
+bool is_flex(const f2q_ctx* c) { return policy_is_flex(c->policy); }
+int tile_policy(const f2q_ctx* c) { return c->policy == POLICY_FAST1 ? POLICY_FAST1 : POLICY_GENERIC; }
 
+constexpr uint64_t EC_SUBCHUNK_BYTES = 1ull << 30;
 constexpr uint32_t HIST_MAX_KEYS = 8192;     // shared-memory histogram up to this many features (32 KB of u32)
 
 // persistent grid of the tile kernel for (policy, ch, nt): SM count x resident CTAs per SM
@@ -239,7 +263,7 @@ int launch_tile(f2q_ctx* c, const TileParams& P, Outputs O, uint64_t n_tiles_upp
 
 #define F2Q_DISPATCH(FN, ...)                                                                                     \
     do {                                                                                                          \
-        const bool f = c->policy == POLICY_FAST1;                                                                 \
+        const bool f = tile_policy(c) == POLICY_FAST1;                                                            \
         if (c->nt == 256) {                                                                                       \
             switch (c->ch) {                                                                                      \
                 case 3: return f ? FN<POLICY_FAST1, 3, 256>(__VA_ARGS__) : FN<POLICY_GENERIC, 3, 256>(__VA_ARGS__); \
@@ -263,11 +287,16 @@ constexpr size_t SM_SMEM_BYTES = 233472, SPEC_SMEM_MARGIN = 4096;     // 228 KB 
 template <int POLICY, int CH, int W>
 int launch_spec(f2q_ctx* c, const SpecParams& P, Outputs O) {
     SpecParams p = P;
-    const uint32_t H = p.halo_rows;
-    const size_t base_smem = spec_smem_bytes<CH, W>(H, 0);
-    const bool hist = (POLICY == POLICY_FAST1) && c->n_keys > 0 && base_smem + (size_t)c->n_keys * 4 + sizeof(GenericCfg) + SPEC_SMEM_MARGIN <= SM_SMEM_BYTES;
+    constexpr bool FLEX = policy_is_flex(POLICY);
+    // (flex: the read-ahead rows shrink until the stages fit; reads reaching further finish through the generic queue)
+    uint32_t H = p.halo_rows;
+    while (FLEX && H > 2 && spec_smem_bytes<POLICY, CH, W>(H, 0) + sizeof(GenericCfg) + SPEC_SMEM_MARGIN > SM_SMEM_BYTES) H--;
+    p.halo_rows = H;
+    const size_t base_smem = spec_smem_bytes<POLICY, CH, W>(H, 0);
+    const bool hist = (POLICY == POLICY_FAST1 || (FLEX && c->cfg.mode == F2Q_MODE_COUNT)) && c->n_keys > 0 &&
+                      base_smem + (size_t)c->n_keys * 4 + sizeof(GenericCfg) + SPEC_SMEM_MARGIN <= SM_SMEM_BYTES;
     p.hist_smem = hist;
-    const size_t smem = spec_smem_bytes<CH, W>(H, hist ? c->n_keys : 0);
+    const size_t smem = spec_smem_bytes<POLICY, CH, W>(H, hist ? c->n_keys : 0);
     if (smem + sizeof(GenericCfg) + SPEC_SMEM_MARGIN > SM_SMEM_BYTES) return 1;        // does not fit with W warps: the caller retries with fewer
     int& ready = c->spec_ready[POLICY][CH][W == 16];
     if (!ready) {
@@ -281,8 +310,15 @@ int launch_spec(f2q_ctx* c, const SpecParams& P, Outputs O) {
 }
 
 int launch_spec_dyn(f2q_ctx* c, const SpecParams& P, Outputs O) {
-    const bool f = c->policy == POLICY_FAST1;
     int rc12;
+    if (is_flex(c)) {
+        // the flex code keeps a read's planes in registers: 12 warps per CTA (170 registers per thread)
+        const int ch = c->ch == 3 ? 5 : c->ch;
+        if (c->policy == POLICY_FLEX_S) rc12 = ch == 5 ? launch_spec<POLICY_FLEX_S, 5, 12>(c, P, O) : launch_spec<POLICY_FLEX_S, 7, 12>(c, P, O);
+        else rc12 = ch == 5 ? launch_spec<POLICY_FLEX_B, 5, 12>(c, P, O) : launch_spec<POLICY_FLEX_B, 7, 12>(c, P, O);
+        return rc12 == 1 ? fail(c, F2Q_EINTERNAL, "speculative kernel does not fit on an SM") : rc12;
+    }
+    const bool f = c->policy == POLICY_FAST1;
 #define F2Q_SPEC_CASE(CHV)                                                                                         \
     case CHV:                                                                                                      \
         if (c->spec_warps == 16) {                                                                                 \
@@ -307,6 +343,9 @@ void decide_ch(f2q_ctx* c, const uint8_t* head, size_t n) {
     c->ch = 7;
     size_t rec = 0;
     if (nl == 8) { rec = pos / 2; c->ch = rec >= 112 ? 7 : rec >= 80 ? 5 : 3; }
+    c->rec_bytes = rec;
+    const bool big = rec > 2 * 96 + 24;                                // reads longer than the 96-position planes
+    if (big != c->flex_big) { c->flex_big = big; decide_policy(c); }
     if (c->force_ch) c->ch = c->force_ch;
     // read-ahead rows at the end of each tile: one and a half records' worth (reads that need more finish in global memory)
     const int S = 16 * c->ch, halo_max = c->nt / 2;
@@ -350,63 +389,138 @@ Outputs outputs_of(f2q_ctx* c) {
     return O;
 }
 
-// grow the Extract+Count table so that `extra` more distinct keys and `extra_bytes` more key bytes fit
-int ec_reserve(f2q_ctx* c, uint64_t extra, uint64_t extra_bytes) {
-    unsigned long long meta[2] = {0, 0};
-    if (c->ec_meta.p) {
-        CU(c, cudaStreamSynchronize(c->stream));
-        CU(c, cudaMemcpy(meta, c->ec_meta.p, sizeof(meta), cudaMemcpyDeviceToHost));
-    } else {
-        int rc = dev_alloc(c, c->ec_meta, sizeof(meta));
-        if (rc) return rc;
-        CU(c, cudaMemset(c->ec_meta.p, 0, sizeof(meta)));
-    }
-    const uint64_t need_slots = 2 * (meta[1] + extra) + 1024, need_arena = meta[0] + extra_bytes + 1024;
-    if (need_arena > c->ec_arena.n) {
-        DevBuf nb; nb.p = nullptr;
-        size_t sz = std::max<size_t>(need_arena, c->ec_arena.n * 2);
-        cudaError_t e = cudaMalloc(&nb.p, sz);
-        if (e != cudaSuccess) return fail(c, F2Q_ENOMEM, "Extract+Count key arena: out of device memory");
-        nb.n = sz;
-        if (c->ec_arena.p && meta[0]) CU(c, cudaMemcpy(nb.p, c->ec_arena.p, meta[0], cudaMemcpyDeviceToDevice));
-        c->ec_arena.release(); c->ec_arena = nb;
-    }
-    if (need_slots > c->ec_cap) {
-        uint64_t cap = 1 << 16; while (cap < need_slots) cap <<= 1;
-        // rehash through the host: the table is small next to the FASTQ stream and growth is geometric
-        std::vector<unsigned long long> hs, hc;
-        std::vector<uint8_t> ar;
-        const uint64_t old = c->ec_cap;
-        if (old && meta[1]) {
-            hs.resize(old); hc.resize(old); ar.resize(meta[0] + 1);
-            CU(c, cudaMemcpy(hs.data(), c->ec_slots.p, old * 8, cudaMemcpyDeviceToHost));
-            CU(c, cudaMemcpy(hc.data(), c->ec_counts.p, old * 8, cudaMemcpyDeviceToHost));
-            if (meta[0]) CU(c, cudaMemcpy(ar.data(), c->ec_arena.p, meta[0], cudaMemcpyDeviceToHost));
-        }
-        c->ec_slots.release(); c->ec_counts.release();
-        int rc = dev_alloc(c, c->ec_slots, cap * 8); if (rc) return rc;
-        rc = dev_alloc(c, c->ec_counts, cap * 8); if (rc) return rc;
-        std::vector<unsigned long long> ns(cap, 0), nc(cap, 0);
-        for (uint64_t i = 0; i < old && meta[1]; i++) {
-            if (!hs[i]) continue;
-            const uint64_t off = (hs[i] - 1) >> 24, len = (hs[i] - 1) & 0xFFFFFF;
-            uint32_t h = FNV_INIT;
-            for (uint64_t k = 0; k < len; k++) h = fnv_step(h, ar[off + k]);
-            uint64_t j = (uint64_t)fnv_final(h) * 0x9E3779B1ull; j = (j ^ (j >> 29)) & (cap - 1);
-            while (ns[j]) j = (j + 1) & (cap - 1);
-            ns[j] = hs[i]; nc[j] = hc[i];
-        }
-        CU(c, cudaMemcpy(c->ec_slots.p, ns.data(), cap * 8, cudaMemcpyHostToDevice));
-        CU(c, cudaMemcpy(c->ec_counts.p, nc.data(), cap * 8, cudaMemcpyHostToDevice));
-        c->ec_cap = cap;
-    }
+// ---- Extract+Count tables: sized WITHOUT a host round trip per chunk ----------------------------------------------
+// Two device tables (generic.cuh: EcTable): the packed table (single ACGT pieces of <= 29 symbols, 16-byte slots) and the
+// byte-arena table (everything else).  The host never waits for the device to learn how full they are: after every chunk
+// the fill counters are copied, stream-ordered, into a pinned slot; before a chunk the host adds to the newest counters it
+// has SEEN an upper bound of what every chunk still in flight (and the new one) can insert.  Only when that bound does not
+// fit does it wait — first for older chunks' counters (the device still has work queued), and, when nothing is in
+// flight and it still does not fit, for a stream sync and a rehash ON THE DEVICE into a table twice the size.
+void ec_bind(f2q_ctx* c) {
+    c->E.pk_slots = reinterpret_cast<unsigned long long*>(c->ec_pk.p);
+    c->E.pk_mask = c->ec_pk_cap ? c->ec_pk_cap - 1 : 0;
     c->E.slots = reinterpret_cast<unsigned long long*>(c->ec_slots.p);
     c->E.counts = reinterpret_cast<unsigned long long*>(c->ec_counts.p);
-    c->E.mask = c->ec_cap - 1;
+    c->E.mask = c->ec_cap ? c->ec_cap - 1 : 0;
     c->E.arena = reinterpret_cast<uint8_t*>(c->ec_arena.p);
     c->E.arena_cap = c->ec_arena.n;
     c->E.arena_used = reinterpret_cast<unsigned long long*>(c->ec_meta.p);
     c->E.n_keys = c->E.arena_used + 1;
+    c->E.pk_n = c->E.arena_used + 2;
+}
+
+void ec_fold_done(f2q_ctx* c, bool wait_oldest) {
+    while (!c->ec_pend.empty()) {
+        f2q_ctx::EcPend& p = c->ec_pend.front();
+        if (wait_oldest) { cudaEventSynchronize(p.ev); wait_oldest = false; }
+        else if (cudaEventQuery(p.ev) != cudaSuccess) { cudaGetLastError(); break; }
+        for (int k = 0; k < 3; k++) c->ec_known[k] = p.host[k];
+        c->ec_known[3] = p.host[3] & 0xFFFFFFFFull;
+        c->ec_events.push_back(p.ev);
+        c->ec_pend.pop_front();
+    }
+}
+
+int ec_reserve(f2q_ctx* c, uint64_t bound_pk, uint64_t bound_keys, uint64_t bound_bytes) {
+    int rc;
+    if (!c->ec_meta.p) {
+        if ((rc = dev_alloc(c, c->ec_meta, 32))) return rc;
+        CU(c, cudaMemsetAsync(c->ec_meta.p, 0, 32, c->stream));
+        CU(c, cudaHostAlloc(reinterpret_cast<void**>(&c->ec_meta_host), 4 * 8 * f2q_ctx::EC_RING, cudaHostAllocDefault));
+        memset(c->ec_meta_host, 0, 4 * 8 * f2q_ctx::EC_RING);
+    }
+    for (;;) {
+        ec_fold_done(c, false);
+        uint64_t pk = c->ec_known[2] + bound_pk, keys = c->ec_known[1] + bound_keys, bytes = c->ec_known[0] + bound_bytes;
+        for (auto& p : c->ec_pend) { pk += p.bound_pk; keys += p.bound_keys; bytes += p.bound_bytes; }
+        const bool fits = 2 * pk + 1024 <= c->ec_pk_cap && 2 * keys + 1024 <= c->ec_cap && bytes + 1024 <= c->ec_arena.n;
+        if (fits && (int)c->ec_pend.size() < f2q_ctx::EC_RING - 1) break;
+        if (!c->ec_pend.empty()) { ec_fold_done(c, true); continue; }        // wait for the OLDEST chunk's counters only
+        // nothing in flight: the counters are exact.  Grow what does not fit (geometric, so this is rare)
+        CU(c, cudaStreamSynchronize(c->stream));
+        if (2 * pk + 1024 > c->ec_pk_cap) {
+            uint64_t cap = std::max<uint64_t>(1 << 16, c->ec_pk_min);
+            while (cap < 4 * pk + 2048) cap <<= 1;
+            DevBuf nb;
+            cudaError_t e = cudaMalloc(&nb.p, cap * 16);
+            if (e != cudaSuccess) { cudaGetLastError(); return fail(c, F2Q_ENOMEM, "Extract+Count packed key table: out of device memory (" + std::to_string(cap * 16) + " bytes)"); }
+            nb.n = cap * 16;
+            CU(c, cudaMemsetAsync(nb.p, 0, cap * 16, c->stream));
+            const uint64_t old_cap = c->ec_pk_cap;
+            DevBuf old = c->ec_pk;
+            c->ec_pk = nb; c->ec_pk_cap = cap;
+            ec_bind(c);
+            if (old_cap && c->ec_known[2]) {
+                k_ec_rehash<<<(unsigned)std::min<uint64_t>((old_cap + 255) / 256, (uint64_t)c->sm_count * 32), 256, 0, c->stream>>>(
+                    reinterpret_cast<const unsigned long long*>(old.p), old_cap, c->E, outputs_of(c));
+                c->launches++;
+                CU(c, cudaStreamSynchronize(c->stream));
+            }
+            old.release();
+        }
+        if (bytes + 1024 > c->ec_arena.n) {
+            DevBuf nb;
+            const size_t sz = std::max<size_t>(bytes + 1024, c->ec_arena.n * 2);
+            cudaError_t e = cudaMalloc(&nb.p, sz);
+            if (e != cudaSuccess) { cudaGetLastError(); return fail(c, F2Q_ENOMEM, "Extract+Count key arena: out of device memory"); }
+            nb.n = sz;
+            if (c->ec_arena.p && c->ec_known[0]) CU(c, cudaMemcpy(nb.p, c->ec_arena.p, c->ec_known[0], cudaMemcpyDeviceToDevice));
+            c->ec_arena.release(); c->ec_arena = nb;
+        }
+        if (2 * keys + 1024 > c->ec_cap) {
+            uint64_t cap = 1 << 14; while (cap < 4 * keys + 2048) cap <<= 1;
+            // the byte-arena table holds the rare keys (other symbols than ACGT, long or multi-piece keys): it is small, and
+            // its growth rehashes through the host
+            std::vector<unsigned long long> hs, hc;
+            std::vector<uint8_t> ar;
+            const uint64_t old = c->ec_cap, used = c->ec_known[0];
+            if (old && c->ec_known[1]) {
+                hs.resize(old); hc.resize(old); ar.resize(used + 1);
+                CU(c, cudaMemcpy(hs.data(), c->ec_slots.p, old * 8, cudaMemcpyDeviceToHost));
+                CU(c, cudaMemcpy(hc.data(), c->ec_counts.p, old * 8, cudaMemcpyDeviceToHost));
+                if (used) CU(c, cudaMemcpy(ar.data(), c->ec_arena.p, used, cudaMemcpyDeviceToHost));
+            }
+            c->ec_slots.release(); c->ec_counts.release();
+            if ((rc = dev_alloc(c, c->ec_slots, cap * 8))) return rc;
+            if ((rc = dev_alloc(c, c->ec_counts, cap * 8))) return rc;
+            if (hs.empty()) {
+                CU(c, cudaMemsetAsync(c->ec_slots.p, 0, cap * 8, c->stream));
+                CU(c, cudaMemsetAsync(c->ec_counts.p, 0, cap * 8, c->stream));
+            } else {
+                std::vector<unsigned long long> ns(cap, 0), nc(cap, 0);
+                for (uint64_t i = 0; i < old; i++) {
+                    if (!hs[i]) continue;
+                    const uint64_t off = (hs[i] - 1) >> 24, len = (hs[i] - 1) & 0xFFFFFF;
+                    uint32_t h = FNV_INIT;
+                    for (uint64_t k = 0; k < len; k++) h = fnv_step(h, ar[off + k]);
+                    uint64_t j = (uint64_t)fnv_final(h) * 0x9E3779B1ull; j = (j ^ (j >> 29)) & (cap - 1);
+                    while (ns[j]) j = (j + 1) & (cap - 1);
+                    ns[j] = hs[i]; nc[j] = hc[i];
+                }
+                CU(c, cudaMemcpy(c->ec_slots.p, ns.data(), cap * 8, cudaMemcpyHostToDevice));
+                CU(c, cudaMemcpy(c->ec_counts.p, nc.data(), cap * 8, cudaMemcpyHostToDevice));
+            }
+            c->ec_cap = cap;
+        }
+        ec_bind(c);
+    }
+    ec_bind(c);
+    // this chunk's bound stays pending until its counters have been seen (ec_after_chunk records the copy)
+    f2q_ctx::EcPend p{};
+    p.bound_pk = bound_pk; p.bound_keys = bound_keys; p.bound_bytes = bound_bytes; p.ev = nullptr; p.host = nullptr;
+    c->ec_pend.push_back(p);
+    return F2Q_OK;
+}
+
+// after the chunk's kernels: copy the fill counters (and the sticky "speculation is off" flag) to the chunk's pinned slot
+int ec_after_chunk(f2q_ctx* c) {
+    f2q_ctx::EcPend& p = c->ec_pend.back();
+    p.host = c->ec_meta_host + 4 * (c->ec_ring_next++ % f2q_ctx::EC_RING);
+    if (!c->ec_events.empty()) { p.ev = c->ec_events.back(); c->ec_events.pop_back(); }
+    else CU(c, cudaEventCreateWithFlags(&p.ev, cudaEventDisableTiming));
+    CU(c, cudaMemcpyAsync(p.host, c->ec_meta.p, 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaMemcpyAsync(p.host + 3, &c->dS->spec_off, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaEventRecord(p.ev, c->stream));
     return F2Q_OK;
 }
 
@@ -425,40 +539,53 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         decide_ch(c, head, hn);
         c->ch_from_device = hn != 0;
     }
+    const bool flex = is_flex(c), ec = c->cfg.mode == F2Q_MODE_EXTRACT_COUNT;
     const uint64_t own_bytes = (uint64_t)(c->nt - c->halo_rows) * 16 * c->ch;
     const uint64_t n_tiles = (delta + n) / own_bytes + 2;
     const uint64_t stitch_tiles = c->carry_cap / (64 * 16 * 3) + 2;
     if ((rc = dev_alloc(c, c->status, n_tiles + 64))) return rc;
     unsigned grid = 0;
     if ((rc = tile_grid_dyn(c, &grid))) return rc;
-    // the speculative streaming kernel runs first in Counter mode (its results can be dropped; Extract+Count inserts cannot)
-    const bool use_spec = c->spec && n && c->cfg.mode == F2Q_MODE_COUNT;
-    const uint64_t spec_own = 512ull * c->ch;
+    // the speculative streaming kernel runs first: Counter mode always (its results can be dropped), Extract+Count on the
+    // flex path (its inserts go through a log that is committed only when the speculation verified)
+    const bool spec_seen_off = ec && c->ec_known[3] != 0;                      // (the device told us: this sample fell back to the exact kernel)
+    const bool use_spec = c->spec && n && (!ec || flex) && !spec_seen_off;
+    const int spec_ch = flex && c->ch == 3 ? 5 : c->ch;
+    const uint64_t spec_own = 512ull * spec_ch;
     uint64_t spec_range_tiles = 0;
     if (use_spec) {
         grid = std::max<unsigned>(grid, (unsigned)c->sm_count);        // one queue segment per CTA of either kernel
-        const uint64_t tiles = (delta + n) / spec_own + 1, streams = (uint64_t)c->sm_count * c->spec_warps;
+        const uint64_t tiles = (delta + n) / spec_own + 1, streams = (uint64_t)c->sm_count * (flex ? 12 : c->spec_warps);
         spec_range_tiles = c->spec_range_tiles > 0 ? (uint64_t)c->spec_range_tiles : std::min<uint64_t>(64, std::max<uint64_t>(8, tiles / (streams * 4)));
         const uint64_t n_rec = (delta + n) / (spec_range_tiles * spec_own) + 2;
         if ((rc = dev_alloc(c, c->spec_rec, n_rec))) return rc;
         CU(c, cudaMemsetAsync(c->spec_rec.p, 0, n_rec, c->stream));
     }
-    // queues sized for the chunk: one entry per 64 bytes covers every non-exact read of ordinary FASTQ; anything
-    // beyond that is resolved in place by the tile kernel, so capacity never changes results
+    // queues sized for the chunk.  fast1: one entry per 64 bytes covers every non-exact read of ordinary FASTQ; flex Counter
+    // the same; flex Extract+Count: the insert log takes EVERY read's key (1.5 x the reads the sniffed record length
+    // predicts).  Anything beyond a queue's capacity is handled in place or by the generic queue, so capacity never changes results
+    const size_t entry = flex ? (ec ? 8 : sizeof(FlexQ)) : sizeof(QEntry);
     uint64_t want_q = c->opt_queue_entries > 0 ? (uint64_t)c->opt_queue_entries : std::max<uint64_t>(1 << 16, n / 64 + 1024);
+    if (flex && ec && c->opt_queue_entries <= 0) want_q = std::max<uint64_t>(1 << 16, (c->rec_bytes ? 3 * n / (2 * c->rec_bytes) : n / 48) + 4096);
     want_q = std::min<uint64_t>(want_q, 0x7FFFFFFFull);
     if (c->policy == POLICY_GENERIC) want_q = grid;
-    if (want_q > c->q_cap || grid != c->n_segs) {
+    if (want_q > c->q_cap || grid != c->n_segs || entry != c->q_entry) {
         want_q = std::max<uint64_t>(want_q, c->q_cap);
-        if ((rc = dev_alloc(c, c->queue, want_q * sizeof(QEntry)))) return rc;
+        if ((rc = dev_alloc(c, c->queue, want_q * entry))) return rc;
         if ((rc = dev_alloc(c, c->seg_count, (size_t)grid * 4))) return rc;
-        c->q_cap = (uint32_t)want_q; c->n_segs = grid; c->seg_cap = (uint32_t)(want_q / grid);
+        c->q_cap = (uint32_t)want_q; c->n_segs = grid; c->seg_cap = (uint32_t)(want_q / grid); c->q_entry = entry;
     }
     uint64_t want_g = c->policy == POLICY_GENERIC ? 16 : std::max<uint64_t>(1 << 14, want_q / 8);
-    if (want_g > c->g_cap) { if ((rc = dev_alloc(c, c->gqueue, want_g * sizeof(GEntry)))) return rc; c->g_cap = (uint32_t)want_g; }
-    if (c->cfg.mode == F2Q_MODE_EXTRACT_COUNT) {
-        // worst case every record is 4 bytes and every key is new; key bytes are bounded by n_iter * stream bytes
-        if ((rc = ec_reserve(c, (n + c->carry_cap) / 4 + 16, (uint64_t)c->cfg.n_iter * (n + c->carry_cap) + 64))) return rc;
+    if (c->opt_generic_entries > 0) want_g = (uint64_t)c->opt_generic_entries;
+    if (want_g > c->g_cap || c->opt_generic_entries > 0) { if ((rc = dev_alloc(c, c->gqueue, want_g * sizeof(GEntry)))) return rc; c->g_cap = (uint32_t)want_g; }
+    if (ec) {
+        const uint64_t worst = (n + c->carry_cap) / 4 + 16, worst_bytes = (uint64_t)c->cfg.n_iter * (n + c->carry_cap) + 64;
+        if (use_spec) {
+            // the streaming kernel can insert at most its log + its generic queue; the stitched record adds one
+            const uint64_t gq = (uint64_t)c->g_cap + 4;
+            rc = ec_reserve(c, (uint64_t)c->seg_cap * c->n_segs + gq, gq, std::min<uint64_t>(worst_bytes, gq * 1024ull * (uint64_t)c->cfg.n_iter));
+        } else rc = ec_reserve(c, worst, worst, worst_bytes);           // exact kernel: every record could be 4 bytes and every key new
+        if (rc) return rc;
     }
 
     CU(c, cudaMemsetAsync(c->status.p, 0, n_tiles + 64, c->stream));
@@ -494,7 +621,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         SpecParams Q{};
         Q.buf = base; Q.S = c->dS; Q.ticket = c->d_tickets + 2; Q.rec = reinterpret_cast<uint8_t*>(c->spec_rec.p);
         Q.range_bytes = spec_range_tiles * spec_own;
-        Q.queue = P.queue; Q.seg_count = P.seg_count; Q.seg_cap = c->policy == POLICY_FAST1 ? c->seg_cap : 0; Q.gqueue = P.gqueue;
+        Q.queue = P.queue; Q.seg_count = P.seg_count; Q.seg_cap = c->policy != POLICY_GENERIC ? c->seg_cap : 0; Q.gqueue = P.gqueue;
         Q.halo_rows = (uint32_t)std::min<int>(c->halo_rows, (int)SPEC_MAX_HALO);
         Outputs O2 = O;
         O2.counts = reinterpret_cast<unsigned long long*>(c->spec_scratch.p); O2.stats = O2.counts + c->n_keys;
@@ -508,6 +635,14 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         k_spec_merge<<<(unsigned)std::min<uint64_t>((nres + 255) / 256, (uint64_t)c->sm_count * 8), 256, 0, c->stream>>>(c->dS, O2.counts, O.counts, nres);
         c->launches += 2;
         timing_end(c, t3, 3);
+        if (flex && ec) {
+            // the verified chunk's insert log -> the packed key table
+            cudaEvent_t t4 = timing_begin(c);
+            k_ec_commit<<<dim3(8, c->n_segs), 256, 0, c->stream>>>(c->dS, c->E, O, reinterpret_cast<const unsigned long long*>(c->queue.p),
+                                                                 P.seg_count, c->seg_cap, c->n_segs);
+            c->launches++;
+            timing_end(c, t4, 1);
+        }
     }
     if (n) {
         P.buf = base; P.status = reinterpret_cast<uint8_t*>(c->status.p); P.ticket = c->d_tickets + 1; P.stitch = 0;
@@ -536,6 +671,19 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
             timing_end(c, t1, 1);
             c->launches++;
         }
+    } else if (flex && !ec && c->cfg.miss > 0 && use_spec) {
+        // (a chunk the exact kernel re-parsed has empty segments: k_spec_verify zeroed them)
+        cudaEvent_t t1 = timing_begin(c);
+        const FlexQ* fq = reinterpret_cast<const FlexQ*>(c->queue.p);
+        const int G = c->fx_group_opt ? c->fx_group_opt : c->fx_group;
+        const dim3 rg(c->n_segs, 8);
+        if (G == 32) k_resolve_flex<32><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, fq, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
+        else if (G == 8) k_resolve_flex<8><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, fq, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
+        else k_resolve_flex<1><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, fq, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
+        timing_end(c, t1, 1);
+        c->launches++;
+    }
+    if (c->policy != POLICY_GENERIC) {
         cudaEvent_t t2 = timing_begin(c);
         k_generic_queue<<<(unsigned)c->sm_count, 128, 0, c->stream>>>(c->dG, reinterpret_cast<const SlowArgs*>(c->slow_args.p), P.gqueue, c->dS);
         timing_end(c, t2, 2);
@@ -545,6 +693,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     k_carry<<<1, PREP_THREADS, 0, c->stream>>>(c->dS, base, reinterpret_cast<uint8_t*>(c->carry.p), c->carry_cap);
     c->launches++;
     CU(c, cudaGetLastError());
+    if (ec && (rc = ec_after_chunk(c))) return rc;
     if (is_last) c->closed = true;
     return F2Q_OK;
 }
@@ -641,7 +790,10 @@ F2Q_EXPORT void f2q_destroy(f2q_ctx* c) {
     for (auto& b : c->lib_bufs) b.release();
     c->result.release(); c->carry.release(); c->status.release(); c->status_stitch.release(); c->queue.release(); c->gqueue.release();
     c->seg_count.release(); c->spec_rec.release(); c->spec_scratch.release(); c->slow_args.release(); c->synth_guides.release();
-    c->ec_slots.release(); c->ec_counts.release(); c->ec_arena.release(); c->ec_meta.release();
+    c->ec_slots.release(); c->ec_counts.release(); c->ec_arena.release(); c->ec_meta.release(); c->ec_pk.release(); c->ec_compact.release();
+    for (auto& p : c->ec_pend) if (p.ev) cudaEventDestroy(p.ev);
+    for (auto e : c->ec_events) cudaEventDestroy(e);
+    if (c->ec_meta_host) cudaFreeHost(c->ec_meta_host);
     for (auto p : c->d_stage) cudaFree(p);
     for (auto e : c->ev_copied) cudaEventDestroy(e);
     for (auto e : c->ev_free) cudaEventDestroy(e);
@@ -667,6 +819,7 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "stage_slots") { if (value < 1 || value > 16 || !c->d_stage.empty()) return fail(c, F2Q_EINVAL, "stage_slots invalid or staging already allocated"); c->stage_slots = (int)value; }
     else if (n == "resolver") { if (value < 0 || value > 3) return fail(c, F2Q_EINVAL, "resolver must be 0..3"); c->resolver = (int)value; }
     else if (n == "queue_entries") { if (value < 0) return fail(c, F2Q_EINVAL, "queue_entries < 0"); c->opt_queue_entries = value; c->q_cap = 0; c->g_cap = 0; c->n_segs = 0; c->queue.release(); c->gqueue.release(); }
+    else if (n == "generic_entries") { if (value < 0 || value > (1 << 28)) return fail(c, F2Q_EINVAL, "generic_entries out of range"); c->opt_generic_entries = value; c->g_cap = 0; }
     else if (n == "tile_threads") { if (value != 128 && value != 256) return fail(c, F2Q_EINVAL, "tile_threads must be 128 or 256"); c->nt = (int)value; c->nt_user = true; c->n_segs = 0; }
     else if (n == "halo_rows") { if (value < 0 || value > 128) return fail(c, F2Q_EINVAL, "halo_rows must be 0 (auto) .. 128"); c->force_halo = (int)value; }
     else if (n == "row_chunks") { if (value != 0 && value != 3 && value != 5 && value != 7) return fail(c, F2Q_EINVAL, "row_chunks must be 0 (auto), 3, 5 or 7"); c->force_ch = (int)value; }
@@ -675,7 +828,10 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "spec") c->spec = value != 0;
     else if (n == "spec_warps") { if (value != 12 && value != 16) return fail(c, F2Q_EINVAL, "spec_warps must be 12 or 16"); c->spec_warps = (int)value; }
     else if (n == "spec_range_tiles") { if (value < 0 || value > (1 << 20)) return fail(c, F2Q_EINVAL, "spec_range_tiles out of range"); c->spec_range_tiles = (int)value; }
-    else if (n == "force_generic") { if (value) { c->policy = POLICY_GENERIC; if (!c->nt_user) c->nt = 128; c->n_segs = 0; } else decide_policy(c); }
+    else if (n == "force_generic") { c->force_generic = value != 0; decide_policy(c); c->n_segs = 0; c->q_cap = 0; }
+    else if (n == "flex") { c->no_flex = value == 0; decide_policy(c); c->n_segs = 0; c->q_cap = 0; }
+    else if (n == "resolve_group") { if (value != 0 && value != 1 && value != 8 && value != 32) return fail(c, F2Q_EINVAL, "resolve_group must be 0 (auto), 1, 8 or 32"); c->fx_group_opt = (int)value; }
+    else if (n == "ec_slots") { if (value < 0 || value > (1ll << 34)) return fail(c, F2Q_EINVAL, "ec_slots out of range"); c->ec_pk_min = (uint64_t)value; }
     else return fail(c, F2Q_EINVAL, "unknown option " + n);
     return F2Q_OK;
 }
@@ -886,6 +1042,84 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
         if ((rc = upload(c, gslots, &c->T.gseed_slots)) || (rc = upload(c, gitems, &c->T.gseed_items))) return rc;
         c->T.gseed_mask = (uint32_t)gslots.size() - 1; c->T.gseed_parts = gparts;
     }
+    // flex tables (flex.cuh): every key as <= 2 ACGT pieces -> 80-bit packed key + signature; exact table, the signature of
+    // every key BYTE length, and the pigeonhole seed index over the packed symbols for the resolver
+    if (c->hG.flex.eligible && !(c->cfg.n_iter == 1 && !c->cfg.has_up && !c->cfg.has_down)) {
+        std::vector<FlexKey> fkeys(n_keys);
+        bool all = n_keys > 0;
+        for (uint32_t i = 0; i < n_keys && all; i++) {
+            const uint8_t* k = bytes.data() + off[i];
+            const size_t len = off[i + 1] - off[i];
+            FlexPiece pc[FLEX_ITER];
+            int np = 1; size_t p0 = 0;
+            for (int q = 0; q < FLEX_ITER; q++) { pc[q].codes = 0; pc[q].notok = 0; pc[q].len = 0; pc[q].off = 0; }
+            for (size_t j = 0; j <= len && all; j++) {
+                if (j == len || k[j] == ':') {
+                    const size_t pl = j - p0;
+                    uint64_t codes = 0;
+                    if (pl > (size_t)FLEX_MAX_PIECE || !packable(k + p0, pl, codes)) { all = false; break; }
+                    pc[np - 1].codes = codes; pc[np - 1].len = (uint32_t)pl;
+                    if (j < len) { if (np == FLEX_ITER) { all = false; break; } np++; p0 = j + 1; }
+                }
+            }
+            if (all) all = fx_assemble(pc, np, fkeys[i]);
+        }
+        if (all) {
+            const uint32_t fcap = pow2_at_least(4 * (uint64_t)n_keys);
+            std::vector<uint4> fslots(fcap, make_uint4(0, 0, 0, FX_EMPTY));
+            std::vector<uint16_t> len_sig(FX_MAX_BYTELEN + 1, 0);
+            for (uint32_t i = 0; i < n_keys; i++) {
+                const FlexKey& k = fkeys[i];
+                const uint32_t z = k.hi | (k.sig << 16);
+                uint32_t h = fx_hash(k.lo, z) & (fcap - 1);
+                while (fslots[h].w != FX_EMPTY) h = (h + 1) & (fcap - 1);
+                fslots[h] = make_uint4((uint32_t)k.lo, (uint32_t)(k.lo >> 32), z, i);
+                uint16_t& ls = len_sig[fx_sig_bytelen(k.sig)];
+                ls = ls == 0 ? (uint16_t)k.sig : (ls == (uint16_t)k.sig ? ls : FX_SIG_MIXED);
+            }
+            // seed index: (signature, segment, segment value) -> keys; shapes with fewer symbols than segments are left to the generic code
+            std::vector<uint4> fs_slots(16, make_uint4(0, 0, 0, 0)), fs_recs;
+            const uint32_t fparts = (uint32_t)c->cfg.miss + 1;
+            if (c->cfg.miss >= 1 && c->cfg.miss <= 15) {
+                std::vector<std::pair<uint64_t, uint32_t>> ent;
+                ent.reserve((size_t)n_keys * fparts);
+                for (uint32_t i = 0; i < n_keys; i++) {
+                    const FlexKey& k = fkeys[i];
+                    const uint32_t ns = fx_sig_symbols(k.sig);
+                    if (ns < fparts || ns > 20 * fparts) { len_sig[fx_sig_bytelen(k.sig)] = FX_SIG_MIXED; continue; }
+                    for (uint32_t sg = 0; sg < fparts; sg++)
+                        ent.emplace_back(fxs_tag(k.sig, sg, fx_segment(k.lo, k.hi, sg * ns / fparts, (sg + 1) * ns / fparts)), i);
+                }
+                std::sort(ent.begin(), ent.end());
+                size_t uniq = 0;
+                for (size_t i = 0; i < ent.size(); i++) if (i == 0 || ent[i].first != ent[i - 1].first) uniq++;
+                const uint32_t scap = pow2_at_least(2 * (uint64_t)uniq + 2);
+                fs_slots.assign(scap, make_uint4(0, 0, 0, 0));
+                fs_recs.resize(ent.size());
+                for (size_t i = 0; i < ent.size();) {
+                    size_t e = i;
+                    while (e < ent.size() && ent[e].first == ent[i].first) {
+                        const FlexKey& k = fkeys[ent[e].second];
+                        fs_recs[e] = make_uint4((uint32_t)k.lo, (uint32_t)(k.lo >> 32), k.hi, ent[e].second);
+                        e++;
+                    }
+                    uint32_t h = fxs_hash(ent[i].first) & (scap - 1);
+                    while (fs_slots[h].x | fs_slots[h].y) h = (h + 1) & (scap - 1);
+                    fs_slots[h] = make_uint4((uint32_t)ent[i].first, (uint32_t)(ent[i].first >> 32), (uint32_t)i, (uint32_t)(e - i));
+                    i = e;
+                }
+                // lanes per key of the resolver: from the mean number of candidates a probe returns (weighted by bucket size)
+                double w = 0, tot = 0;
+                for (size_t i = 0; i < ent.size();) { size_t e = i; while (e < ent.size() && ent[e].first == ent[i].first) e++; w += (double)(e - i) * (double)(e - i); tot += (double)(e - i); i = e; }
+                const double mean = tot > 0 ? w / tot : 0;
+                c->fx_group = mean >= 16 ? 32 : mean >= 3 ? 8 : 1;
+            }
+            if ((rc = upload(c, fslots, &c->T.fx_slots)) || (rc = upload(c, len_sig, &c->T.fx_len_sig)) ||
+                (rc = upload(c, fs_slots, &c->T.fxs_slots)) || (rc = upload(c, fs_recs, &c->T.fxs_recs)))
+                return rc;
+            c->T.fx_mask = fcap - 1; c->T.fxs_mask = (uint32_t)fs_slots.size() - 1; c->T.fxs_parts = fparts;
+        }
+    }
     if ((rc = upload(c, seed_slots, &c->T.seed_slots)) || (rc = upload(c, seed_recs, &c->T.seed_recs))) return rc;
     c->T.seed_mask = (uint32_t)seed_slots.size() - 1; c->T.seed_parts = parts;
     if ((rc = upload(c, slots, &c->T.slots)) || (rc = upload(c, fk, &c->T.fast_keys)) || (rc = upload(c, fl, &c->T.fast_lens)) ||
@@ -909,6 +1143,8 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
     c->spec_scratch.release();
     if ((rc = dev_alloc(c, c->spec_scratch, ((size_t)n_keys + 5) * 8))) return rc;
     c->lib_set = true;
+    decide_policy(c);                                                  // (the flex policy needs the flex table)
+    c->n_segs = 0; c->q_cap = 0;
     return F2Q_OK;
 }
 
@@ -923,8 +1159,11 @@ F2Q_EXPORT int f2q_begin_sample(f2q_ctx* c) {
     CU(c, cudaMemsetAsync(c->d_error, 0, 4, c->stream));
     CU(c, cudaMemsetAsync(c->dS, 0, sizeof(DevState), c->stream));
     if (c->cfg.mode == F2Q_MODE_EXTRACT_COUNT) {
-        if (c->ec_meta.p) CU(c, cudaMemsetAsync(c->ec_meta.p, 0, 16, c->stream));
+        while (!c->ec_pend.empty()) { if (c->ec_pend.front().ev) { cudaEventSynchronize(c->ec_pend.front().ev); c->ec_events.push_back(c->ec_pend.front().ev); } c->ec_pend.pop_front(); }
+        for (int k = 0; k < 4; k++) c->ec_known[k] = 0;
+        if (c->ec_meta.p) CU(c, cudaMemsetAsync(c->ec_meta.p, 0, 32, c->stream));
         if (c->ec_slots.p) { CU(c, cudaMemsetAsync(c->ec_slots.p, 0, c->ec_cap * 8, c->stream)); CU(c, cudaMemsetAsync(c->ec_counts.p, 0, c->ec_cap * 8, c->stream)); }
+        if (c->ec_pk.p) CU(c, cudaMemsetAsync(c->ec_pk.p, 0, c->ec_pk_cap * 16, c->stream));
         c->ec_drained = false;
     }
     c->in_sample = true; c->closed = false; c->sample_failed = F2Q_OK;
@@ -936,7 +1175,17 @@ F2Q_EXPORT int f2q_submit_device(f2q_ctx* c, const void* dptr, uint64_t nbytes, 
     if (!c->in_sample) return fail(c, F2Q_ESTATE, "f2q_submit_device outside a sample");
     if (c->closed) return fail(c, F2Q_ESTATE, "stream already closed with is_last");
     if (nbytes && !dptr) return fail(c, F2Q_EINVAL, "null chunk");
-    return process_device_chunk(c, reinterpret_cast<const uint8_t*>(dptr), nbytes, is_last);
+    if (c->sample_failed) return c->sample_failed;
+    // Extract+Count: bounded sub-chunks, so that the insert log and the table bounds of one launch stay bounded too
+    const uint64_t sub = c->cfg.mode == F2Q_MODE_EXTRACT_COUNT ? EC_SUBCHUNK_BYTES : ~0ull;
+    uint64_t done = 0;
+    do {
+        const uint64_t len = std::min<uint64_t>(sub, nbytes - done);
+        rc = process_device_chunk(c, reinterpret_cast<const uint8_t*>(dptr) + done, len, is_last && done + len == nbytes);
+        if (rc) { if (!c->sticky) c->sample_failed = rc; return rc; }
+        done += len;
+    } while (done < nbytes);
+    return F2Q_OK;
 }
 
 F2Q_EXPORT int f2q_submit(f2q_ctx* c, const uint8_t* host_chunk, uint64_t nbytes, int is_last) {
@@ -1004,6 +1253,7 @@ F2Q_EXPORT int f2q_end_sample(f2q_ctx* c, uint64_t* counts, uint64_t* stats) {
                 hs.dbg[0] >> 20, hs.dbg[7] >> 20, hs.dbg[1] >> 20, hs.dbg[4] >> 20, hs.dbg[2] >> 20, hs.dbg[3] >> 20, hs.dbg[5], hs.dbg[6] >> 20);
     if (err & ERR_RECORD_TOO_LONG) return fail(c, F2Q_ETOOLONG, "a FASTQ record is longer than carry_bytes; raise it with f2q_set_option");
     if (err & ERR_LOOKBACK_TIMEOUT) return fail(c, F2Q_EINTERNAL, "a device-side wait timed out; this sample's counts are invalid (the context stays usable)");
+    if (err & ERR_EC_FULL) return fail(c, F2Q_EINTERNAL, "an Extract+Count table overflowed (a chunk whose line structure defeated the speculation held more keys than were reserved): rerun with option spec = 0");
     if (err) return fail(c, F2Q_EINTERNAL, "device-side failure, flags=" + std::to_string(err));
     if (counts && c->n_keys) CU(c, cudaMemcpy(counts, c->result.p, (size_t)c->n_keys * 8, cudaMemcpyDeviceToHost));
     CU(c, cudaMemcpy(stats, reinterpret_cast<uint8_t*>(c->result.p) + (size_t)c->n_keys * 8, 5 * 8, cudaMemcpyDeviceToHost));
@@ -1026,24 +1276,61 @@ F2Q_EXPORT int f2q_end_sample_async(f2q_ctx* c, uint64_t* pinned_out) {
 }
 
 // ---- Extract+Count results ---------------------------------------------------------------------------
+// number of keys of the packed table and their compacted (tag, count) pairs in c->ec_compact (device)
+static int ec_compact_packed(f2q_ctx* c, uint64_t* n_out) {
+    *n_out = 0;
+    if (!c->ec_pk_cap || !c->ec_meta.p) return F2Q_OK;
+    unsigned long long meta[4];
+    CU(c, cudaMemcpy(meta, c->ec_meta.p, 32, cudaMemcpyDeviceToHost));
+    const uint64_t n = meta[2];
+    if (!n) return F2Q_OK;
+    int rc = dev_alloc(c, c->ec_compact, (n + 1) * 16 + 16); if (rc) return rc;
+    unsigned long long* d_n = reinterpret_cast<unsigned long long*>(c->ec_compact.p);
+    CU(c, cudaMemsetAsync(d_n, 0, 16, c->stream));
+    k_ec_compact<<<(unsigned)std::min<uint64_t>((c->ec_pk_cap + 255) / 256, (uint64_t)c->sm_count * 32), 256, 0, c->stream>>>(
+        reinterpret_cast<const unsigned long long*>(c->ec_pk.p), c->ec_pk_cap, d_n + 2, d_n);
+    c->launches++;
+    CU(c, cudaStreamSynchronize(c->stream));
+    *n_out = n;
+    return F2Q_OK;
+}
+
 static int ec_fetch(f2q_ctx* c) {
     if (c->ec_drained) return F2Q_OK;
     int rc = f2q_sync(c); if (rc) return rc;
     c->ec_drain_off.assign(1, 0); c->ec_drain_cnt.clear(); c->ec_drain_keys.clear();
-    if (c->ec_cap) {
-        unsigned long long meta[2];
-        CU(c, cudaMemcpy(meta, c->ec_meta.p, 16, cudaMemcpyDeviceToHost));
-        std::vector<unsigned long long> hs(c->ec_cap), hc(c->ec_cap);
-        std::vector<uint8_t> ar(meta[0] + 1);
-        CU(c, cudaMemcpy(hs.data(), c->ec_slots.p, c->ec_cap * 8, cudaMemcpyDeviceToHost));
-        CU(c, cudaMemcpy(hc.data(), c->ec_counts.p, c->ec_cap * 8, cudaMemcpyDeviceToHost));
-        if (meta[0]) CU(c, cudaMemcpy(ar.data(), c->ec_arena.p, meta[0], cudaMemcpyDeviceToHost));
-        for (uint64_t i = 0; i < c->ec_cap; i++) {
-            if (!hs[i]) continue;
-            const uint64_t off = (hs[i] - 1) >> 24, len = (hs[i] - 1) & 0xFFFFFF;
-            c->ec_drain_keys.insert(c->ec_drain_keys.end(), ar.begin() + off, ar.begin() + off + len);
+    // packed table: compacted on the device, decoded here (2 bits per symbol -> A C T G)
+    uint64_t npk = 0;
+    if ((rc = ec_compact_packed(c, &npk))) return rc;
+    if (npk) {
+        std::vector<unsigned long long> pairs(2 * npk);
+        CU(c, cudaMemcpy(pairs.data(), reinterpret_cast<const uint8_t*>(c->ec_compact.p) + 16, npk * 16, cudaMemcpyDeviceToHost));
+        c->ec_drain_keys.reserve(npk * 24); c->ec_drain_cnt.reserve(npk); c->ec_drain_off.reserve(npk + 1);
+        for (uint64_t i = 0; i < npk; i++) {
+            const unsigned long long t = pairs[2 * i] - 1;
+            const uint32_t len = (uint32_t)(t & 63u);
+            const uint64_t codes = t >> 6;
+            for (uint32_t k = 0; k < len; k++) c->ec_drain_keys.push_back((uint8_t)("ACTG"[(codes >> (2 * k)) & 3u]));
             c->ec_drain_off.push_back(c->ec_drain_keys.size());
-            c->ec_drain_cnt.push_back(hc[i]);
+            c->ec_drain_cnt.push_back(pairs[2 * i + 1]);
+        }
+    }
+    if (c->ec_cap) {
+        unsigned long long meta[4];
+        CU(c, cudaMemcpy(meta, c->ec_meta.p, 32, cudaMemcpyDeviceToHost));
+        if (meta[1]) {
+            std::vector<unsigned long long> hs(c->ec_cap), hc(c->ec_cap);
+            std::vector<uint8_t> ar(meta[0] + 1);
+            CU(c, cudaMemcpy(hs.data(), c->ec_slots.p, c->ec_cap * 8, cudaMemcpyDeviceToHost));
+            CU(c, cudaMemcpy(hc.data(), c->ec_counts.p, c->ec_cap * 8, cudaMemcpyDeviceToHost));
+            if (meta[0]) CU(c, cudaMemcpy(ar.data(), c->ec_arena.p, meta[0], cudaMemcpyDeviceToHost));
+            for (uint64_t i = 0; i < c->ec_cap; i++) {
+                if (!hs[i]) continue;
+                const uint64_t off = (hs[i] - 1) >> 24, len = (hs[i] - 1) & 0xFFFFFF;
+                c->ec_drain_keys.insert(c->ec_drain_keys.end(), ar.begin() + off, ar.begin() + off + len);
+                c->ec_drain_off.push_back(c->ec_drain_keys.size());
+                c->ec_drain_cnt.push_back(hc[i]);
+            }
         }
     }
     c->ec_drained = true;

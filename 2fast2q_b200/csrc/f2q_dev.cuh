@@ -81,6 +81,14 @@ struct LibTables {
     uint32_t gseed_mask;
     const uint32_t* gseed_items;   // key indices
     uint32_t gseed_parts;      // miss + 1 when the index exists (1 <= miss <= 7), else 0
+    // flex table (flex.cuh): EVERY key as <= 2 pieces of <= 32 ACGT symbols, <= 40 symbols in all; nullptr when some key is not
+    const uint4* fx_slots;     // {lo.x, lo.y, hi | signature << 16, feature index}; index 0xFFFFFFFF = empty
+    uint32_t fx_mask;
+    const uint16_t* fx_len_sig;    // [FX_MAX_BYTELEN + 1] by key BYTE length: 0 no key | the one signature | FX_SIG_MIXED
+    const uint4* fxs_slots;    // seed index over the flex keys: {tag lo, tag hi, start, count}
+    uint32_t fxs_mask;
+    const uint4* fxs_recs;     // {lo.x, lo.y, hi, feature index} grouped by seed slot
+    uint32_t fxs_parts;        // miss + 1
 };
 
 // entry of the deferred non-exact key queue (filled by the tile kernel, drained by the resolver kernel)

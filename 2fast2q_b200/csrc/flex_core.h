@@ -384,7 +384,6 @@ F2Q_HD int flex_pieces(const FlexCfg& C, const uint32_t (&sw)[8 * PW], uint32_t 
     return any ? np : -1;
 }
 
-#if !defined(__CUDA_ARCH__)
 // host side: can this configuration run on the bit-parallel path?  (search sequences pure ACGT, 1..32 symbols, <= FLEX_MAX_K
 // mismatches, at most FLEX_ITER iterations, feature length 0..32)
 inline bool flex_prepare(const f2q_config& g, FlexCfg& C) {
@@ -414,6 +413,5 @@ inline bool flex_prepare(const f2q_config& g, FlexCfg& C) {
     C.eligible = 1;
     return true;
 }
-#endif
 
 }  // namespace f2q

@@ -6,6 +6,7 @@
 #pragma once
 
 #include "f2q_dev.cuh"
+#include "flex_core.h"
 
 namespace f2q {
 
@@ -15,10 +16,16 @@ __host__ __device__ __forceinline__ bool in_set(const ByteSet& s, uint32_t b) { 
 struct GenericCfg {
     DevCfg c;
     ByteSet set_ph, set_up, set_down;   // fail sets (fast2q.py:1127-1129), or explicit sets for the helper API
+    FlexCfg flex;                       // the same configuration prepared for the bit-parallel path (flex_core.h), when eligible
 };
 
 // Extract+Count hash of novel keys (fast2q.py:382-387).  slot word: 0 = empty, else ((arena_off << 24) | len) + 1
 struct EcTable {
+    // packed table (flex.cuh): single-piece keys of <= 29 ACGT symbols, 16-byte slots {tag, count}; everything else lives in
+    // the byte-arena table below.  A key is in exactly one of the two (by its content)
+    unsigned long long* pk_slots;
+    uint64_t pk_mask;              // capacity - 1
+    unsigned long long* pk_n;      // distinct keys in the packed table
     unsigned long long* slots;
     unsigned long long* counts;
     uint64_t mask;                 // capacity - 1
@@ -256,7 +263,16 @@ __device__ inline void g_count_key(const GenericCfg& G, const LibTables& T, cons
 }
 
 // Extract+Count insert-or-increment of one key (fast2q.py:383-387)
+__device__ __forceinline__ void ec_pk_insert(const EcTable& E, const Outputs& O, unsigned long long tag, unsigned long long add);   // flex.cuh
+
 __device__ inline void g_ec_insert(const EcTable& E, const Outputs& O, const uint8_t* R, const Piece* pc, int np) {
+    if (np == 1 && pc[0].len <= 29u && E.pk_slots) {
+        // a single piece of pure ACGT that fits the packed table must go THERE (the streaming kernel puts it there too)
+        uint64_t codes = 0; bool pure = true;
+        const uint8_t* s = R + pc[0].off;
+        for (uint32_t k = 0; k < pc[0].len; k++) { uint32_t code; pure = pure && base_code(s[k], code); codes |= (uint64_t)code << (2u * k); }
+        if (pure) { ec_pk_insert(E, O, ((codes << 6) | pc[0].len) + 1ull, 1ull); return; }
+    }
     uint32_t klen = np ? (uint32_t)(np - 1) : 0, h = FNV_INIT;
     for (int p = 0; p < np; p++) klen += pc[p].len;
     g_for_each_symbol(R, pc, np, [&](uint32_t s) { h = fnv_step(h, s); return true; });

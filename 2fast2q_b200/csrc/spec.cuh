@@ -26,6 +26,7 @@
 #include <type_traits>
 
 #include "tile.cuh"
+#include "flex.cuh"
 
 namespace f2q {
 
@@ -39,13 +40,17 @@ struct SpecParams {
     uint32_t* ticket;          // range ticket counter, zeroed before the launch
     uint8_t* rec;              // one byte per range, zeroed before the launch: 0x80 | speculated phase << 2 | newline count & 3
     uint64_t range_bytes;      // multiple of the tile's own bytes (32 * 16 * CH)
-    QEntry* queue;             // grid segments of seg_cap entries each
+    QEntry* queue;             // grid segments of seg_cap entries each (fast1: QEntry, flex Counter: FlexQ, flex Extract+Count: u64 log)
     uint32_t* seg_count;
     uint32_t seg_cap;
     GEntry* gqueue;
     uint32_t hist_smem;        // 1: per-CTA shared-memory histogram of n_keys u32
     uint32_t halo_rows;        // H: read-ahead rows loaded behind the 32 own rows (1 .. SPEC_MAX_HALO)
 };
+
+// bytes behind the loaded rows of a stage that word reads may touch: the fast1 code reads a few words past a line's end, the
+// flex code loads whole 32 * PW-byte lines (the bytes are masked by the line length afterwards, they only must be readable)
+__host__ __device__ constexpr uint32_t spec_stage_pad(int policy) { return policy_is_flex(policy) ? (uint32_t)(32 * policy_pw(policy) + 16) : 16u; }
 
 template <int CH>
 struct SpecGeom {
@@ -54,13 +59,13 @@ struct SpecGeom {
     static constexpr int MW = (CH + 1) / 2;                            // 32-bit newline mask words per row
     static constexpr int NL_LIST = SPEC_CAP + 8;                       // u16 entries of one position list
     static constexpr int NL_HALO = 6 * (int)16 + 8;                    // ... of the list of a range's last read-ahead rows (SPEC_MAX_HALO rows)
-    __host__ __device__ static constexpr uint32_t stage_bytes(uint32_t H) { return (((32u + H) * S + 16u + 127u) / 128u) * 128u; }
-    __host__ __device__ static constexpr uint32_t warp_bytes(uint32_t H) { return ((SPEC_STAGES * stage_bytes(H) + (2u * NL_LIST + NL_HALO) * 2u + 127u) / 128u) * 128u; }
+    __host__ __device__ static constexpr uint32_t stage_bytes(uint32_t H, uint32_t pad) { return (((32u + H) * S + pad + 127u) / 128u) * 128u; }
+    __host__ __device__ static constexpr uint32_t warp_bytes(uint32_t H, uint32_t pad) { return ((SPEC_STAGES * stage_bytes(H, pad) + (2u * NL_LIST + NL_HALO) * 2u + 127u) / 128u) * 128u; }
 };
 
-template <int CH, int W>
+template <int POLICY, int CH, int W>
 __host__ __device__ inline size_t spec_smem_bytes(uint32_t H, uint32_t hist_entries) {
-    return (size_t)W * SpecGeom<CH>::warp_bytes(H) + (size_t)hist_entries * 4;
+    return (size_t)W * SpecGeom<CH>::warp_bytes(H, spec_stage_pad(POLICY)) + (size_t)hist_entries * 4;
 }
 
 __device__ __forceinline__ uint64_t spec_n_ranges(uint64_t beg, uint64_t end, uint64_t own, uint64_t range_bytes, uint64_t& origin0) {
@@ -85,11 +90,13 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     const uint64_t beg = St->beg, end = St->end;
     const bool eof = St->is_last != 0;
     const uint32_t H = P.halo_rows;
-    const uint32_t stage_bytes = G_::stage_bytes(H), warp_bytes = G_::warp_bytes(H), load_bytes = (32u + H) * S;
+    constexpr bool FLEX = policy_is_flex(POLICY);
+    constexpr uint32_t PAD = spec_stage_pad(POLICY);
+    const uint32_t stage_bytes = G_::stage_bytes(H, PAD), warp_bytes = G_::warp_bytes(H, PAD), load_bytes = (32u + H) * S;
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem + (size_t)W * warp_bytes);
     if (St->spec_off || end <= beg) return;                            // (a sample whose speculation failed once stays on the exact kernel)
 
-    if (POLICY == POLICY_GENERIC)
+    if (POLICY == POLICY_GENERIC || FLEX)
         for (uint32_t i = tid; i < sizeof(GenericCfg) / 4; i += blockDim.x)
             reinterpret_cast<uint32_t*>(&s_G)[i] = reinterpret_cast<const uint32_t*>(Gp)[i];
     if (P.hist_smem) for (uint32_t i = tid; i < T.n_keys; i += blockDim.x) hist[i] = 0;
@@ -100,11 +107,16 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     if (tid == 0) s_qn = 0;
     __syncthreads();
 
-    const GenericCfg& G = (POLICY == POLICY_GENERIC) ? s_G : *Gp;
+    const GenericCfg& G = (POLICY == POLICY_GENERIC || FLEX) ? s_G : *Gp;
     Fast1Ctx F;
     F.init(Gp);
     F.hist = P.hist_smem ? hist : nullptr; F.myq = P.queue + (size_t)blockIdx.x * P.seg_cap; F.seg_cap = P.seg_cap; F.s_qn = &s_qn;
     F.gqueue = P.gqueue; F.St = St; F.X = X;
+    FlexCtx FX;
+    FX.myq = reinterpret_cast<FlexQ*>(P.queue) + (size_t)blockIdx.x * P.seg_cap;
+    FX.mylog = reinterpret_cast<unsigned long long*>(P.queue) + (size_t)blockIdx.x * P.seg_cap;
+    FX.seg_cap = P.seg_cap; FX.s_qn = &s_qn; FX.hist = P.hist_smem ? hist : nullptr; FX.gqueue = P.gqueue; FX.St = St;
+    FX.mode = Gp->c.mode; FX.miss = Gp->c.miss;
     Acc acc{0, 0, 0, 0, 0, 0};
     unsigned long long gst[F2Q_N_STATS] = {0, 0, 0, 0, 0};
     Fast1Counts cn{0, 0, 0, 0, 0};
@@ -212,7 +224,8 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 bool valid = j < total_own;
                 if (valid && j + 3 >= total_all) {
                     // the read's last newline is not in the loaded rows (a long record, or the end of the chunk)
-                    slow_record(buf, pbase + nlA[j], end, eof, G, X, acc, gst);
+                    if constexpr (FLEX) slow_record_defer(buf, pbase + nlA[j], end, eof, P.gqueue, St, acc);
+                    else slow_record(buf, pbase + nlA[j], end, eof, G, X, acc, gst);
                     valid = false;
                 }
                 uint32_t s0 = 0, e0 = 0, s3 = 0, e3 = 0;
@@ -226,6 +239,9 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                         const uint8_t* Rp = ptile + s0; const uint8_t* Qp = ptile + s3;
                         g_process_read(G, X->T, X->E, X->O, Rp, g_rstrip(Rp, (int)(e0 - s0)), Qp, g_rstrip(Qp, (int)(e3 - s3)), gst);
                     }
+                } else if constexpr (FLEX) {
+                    __syncwarp();
+                    flex_read_warp<policy_pw(POLICY), policy_k(POLICY)>(FX, G, valid, ptile, s0, e0, s3, e3, buf + pbase + s0, buf + pbase + s3, T, O, cn, lane);
                 } else {
                     __syncwarp();
                     if (j0 != jf) fast1_warp_commit(F, pend, T, O, cn, lane);          // (a second pass over the same tile: rare)
@@ -234,7 +250,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 }
             }
         };
-        if (POLICY == POLICY_GENERIC) passes(std::integral_constant<int, 0>{});
+        if (POLICY == POLICY_GENERIC || FLEX) passes(std::integral_constant<int, 0>{});
         else switch (ord_words) {
             case 4: passes(std::integral_constant<int, 4>{}); break;
             case 5: passes(std::integral_constant<int, 5>{}); break;

@@ -37,7 +37,12 @@
 
 namespace f2q {
 
-enum { POLICY_GENERIC = 0, POLICY_FAST1 = 1 };
+// per-read code of the fused kernels: byte-wise generic | one fixed window, packed (fast1) | bit-parallel search sequences /
+// several windows (flex.cuh): planes of 96 positions and <= 1 mismatch per search sequence | 160 positions and <= 3
+enum { POLICY_GENERIC = 0, POLICY_FAST1 = 1, POLICY_FLEX_S = 2, POLICY_FLEX_B = 3 };
+__host__ __device__ constexpr bool policy_is_flex(int p) { return p == POLICY_FLEX_S || p == POLICY_FLEX_B; }
+__host__ __device__ constexpr int policy_pw(int p) { return p == POLICY_FLEX_B ? 5 : 3; }
+__host__ __device__ constexpr int policy_k(int p) { return p == POLICY_FLEX_B ? 3 : 1; }
 
 struct TileParams {
     const uint8_t* buf;        // 128-byte aligned base of the chunk buffer
@@ -263,6 +268,31 @@ __device__ __noinline__ void slow_record(const uint8_t* buf, uint64_t hdr_end, u
     acc.last_end = acc.last_end > le ? acc.last_end : le;
     const uint8_t* Rp = buf + pos[0] + 1; const uint8_t* Qp = buf + pos[2] + 1;
     g_process_read(G, X->T, X->E, X->O, Rp, g_rstrip(Rp, (int)(pos[1] - pos[0] - 1)), Qp, g_rstrip(Qp, (int)(pos[3] - pos[2] - 1)), gst);
+}
+
+// the same geometry, but the read is only QUEUED for the generic kernel (k_generic_queue runs after the speculation was
+// verified): the flex policies use it, because an Extract+Count insert done here could not be taken back
+__device__ __noinline__ void slow_record_defer(const uint8_t* buf, uint64_t hdr_end, uint64_t end, bool eof, GEntry* gqueue, DevState* St, Acc& acc) {
+    uint64_t pos[4];
+    pos[0] = hdr_end;
+    uint64_t from = hdr_end + 1;
+    for (int k = 1; k < 4; k++) {
+        const uint64_t p = find_newline_global(buf, from, end);
+        if (p >= end) {
+            if (k == 3 && eof && from < end) { pos[3] = end; break; }
+            return;
+        }
+        pos[k] = p; from = p + 1;
+    }
+    acc.reads++;
+    const unsigned long long le = (unsigned long long)(pos[3] + 1 < end ? pos[3] + 1 : end);
+    acc.last_end = acc.last_end > le ? acc.last_end : le;
+    GEntry ge;
+    ge.seq_addr = (uint64_t)(buf + pos[0] + 1); ge.seq_len = (uint32_t)(pos[1] - pos[0] - 1);
+    ge.qual_addr = (uint64_t)(buf + pos[2] + 1); ge.qual_len = (uint32_t)(pos[3] - pos[2] - 1);
+    const uint32_t slot = atomicAdd(&St->g_count, 1u);
+    if (slot < St->g_cap) gqueue[slot] = ge;
+    else St->spec_fail = 1u;
 }
 
 // @region fast1_read

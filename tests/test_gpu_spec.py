@@ -21,7 +21,7 @@ def gu():
 
 
 def counter_cases():
-    return [c for c in G.kat() + G.fuzz() if c["params"]["mode"] == "C"]
+    return G.kat() + G.fuzz()        # (Extract+Count cases too: their inserts go through the insert log of the flex policy)
 
 
 @pytest.mark.parametrize("opts", [dict(spec=0), dict(spec=0, tile_threads=128), dict(spec_range_tiles=1), dict(spec_range_tiles=2, spec_warps=12),
@@ -167,3 +167,105 @@ def test_ordinary_read_code_with_whitespace_tails_and_short_lines(gu, oracle, le
     for opts in (dict(), dict(spec_range_tiles=2), dict(spec=0)):
         c, s, _ = _run(gu, params, keys, data, **opts)
         assert s == want_s and np.array_equal(c, want_c), (length, start, opts)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the bit-parallel (flex) policies of the streaming kernel: search sequences with mismatches, several windows per read,
+# Extract+Count through the insert log.  Every golden / fuzz case that is not "one fixed window, Counter" runs on them
+# by default; here every side path: the byte-wise generic kernels instead, overflowing queues, every resolver group size
+# ------------------------------------------------------------------------------------------------------------------
+def flex_cases():
+    out = []
+    for c in G.kat() + G.fuzz():
+        p = c["params"]
+        single_fixed = p["upstream"] is None and p["downstream"] is None and "," not in str(p["start"])
+        if p["mode"] == "EC" or not single_fixed:
+            out.append(c)
+    return out
+
+
+@pytest.mark.parametrize("opts", [dict(flex=0), dict(spec=0), dict(spec_range_tiles=1), dict(queue_entries=16), dict(queue_entries=16, generic_entries=3),
+                                  dict(resolve_group=1), dict(resolve_group=8), dict(resolve_group=32), dict(row_chunks=5, spec_range_tiles=2)], ids=str)
+def test_flex_cases_every_path(gu, opts):
+    cs = flex_cases()
+    assert len(cs) > 150
+    for c in cs:
+        gu.check_case(c, c["fastq"], **opts)
+    for c in cs[::4]:
+        gu.check_case(c, c["fastq"], 777, **opts)
+
+
+def _shaped_workload(config, n_reads, first=0):
+    synth = importlib.import_module("2fast2q_b200.synth")
+    spec = synth.shape_spec(config)
+    if config == "4":
+        guides = synth.random_kmers(4, 20_000, 20)
+        params = dict(mode="EC", upstream=synth.BARSEQ_US.decode(), downstream=synth.BARSEQ_DS.decode(), miss_search_up=1, miss_search_down=1)
+        return params, None, synth.shaped_reads(guides, first, n_reads, **spec)
+    names, keys, xs, ys = synth.dual_keys(3000)
+    params = dict(mode="C", miss=1, start="0,30") if config == "5a" else dict(mode="C", miss=1, upstream="ACCGGT,GGATCC", downstream="TTGACA,CAATTG")
+    return params, keys, synth.shaped_reads(xs + ys, first, n_reads, **spec)
+
+
+@pytest.mark.parametrize("config", ["4", "5a", "5b"])
+def test_flex_workloads_are_committed_and_exact(gu, oracle, config):
+    """the bench's config-4 / 5a / 5b streams (K0 shapes 1-3), 300k reads: the streaming kernel must commit every chunk (this
+    is the path the bench measures) and equal the oracle; then the same through odd host chunks, tiny queues and flex off"""
+    params, keys, data = _shaped_workload(config, 300_000)
+    ocfg = oracle.make_config(**params)
+    if keys is None:
+        want, want_s = oracle.extract_count(ocfg, data)
+    else:
+        want, want_s = oracle.count(ocfg, keys, data)
+    cfg = gu.lib.make_config(**params)
+    for chunk, opts in ((None, {}), (5_000_011, {}), (None, dict(queue_entries=1000)), (None, dict(flex=0)), (1_000_003, dict(spec=0))):
+        with gu.lib.Engine(cfg, 0, None, **opts) as e:
+            if keys is not None:
+                e.set_library(keys)
+            counts, stats = e.run(data, chunk)
+            got = e.ec_items() if keys is None else counts
+            committed, fell_back = e.spec_counts()
+        assert stats == want_s, (config, chunk, opts)
+        if keys is None:
+            assert got == want, (config, chunk, opts)
+        else:
+            assert np.array_equal(got, want), (config, chunk, opts)
+        if opts.get("spec", 1) and opts.get("flex", 1):
+            assert fell_back == 0 and committed >= 1, (config, chunk, opts, committed, fell_back)
+
+
+def test_extract_count_tables_grow_on_the_device(gu, oracle):
+    """every read a new key: the packed table starts small and is rehashed on the device several times; a second sample on
+    the same context starts from empty tables again"""
+    synth = importlib.import_module("2fast2q_b200.synth")
+    r = synth.SM64(4242)
+    recs = []
+    for i in range(120_000):
+        bc = r.dna(24) if i % 7 else r.dna(23) + b"N"                   # every 7th key goes to the byte-arena table
+        s = b"GGATCCAA" + bc + b"TTGACACC" + r.dna(6)
+        recs.append(b"@g%d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    data = b"".join(recs)
+    params = dict(mode="EC", upstream="GGATCCAA", downstream="TTGACACC")
+    want, want_s = oracle.extract_count(oracle.make_config(**params), data)
+    cfg = gu.lib.make_config(**params)
+    with gu.lib.Engine(cfg, 0, None, stage_bytes=1 << 20) as e:
+        for rep in range(2):
+            counts, stats = e.run(data, 3_000_000)
+            assert stats == want_s and e.ec_items() == want, rep
+
+
+def test_extract_count_large_resident_chunk_is_sub_chunked(gu, oracle):
+    """a multi-GB f2q_submit_device in Extract+Count mode must not reserve worst-case tables; 1.3 GB here"""
+    params, _, piece = _shaped_workload("4", 1_000_000)
+    want, want_s = oracle.extract_count(oracle.make_config(**params), piece)
+    reps = 8
+    cfg = gu.lib.make_config(**params)
+    with gu.lib.Engine(cfg) as e:
+        d = e.device_alloc(piece.size * reps)
+        for k in range(reps):
+            e.h2d(d + k * piece.size, piece)
+        e.begin(); e.submit_device(d, piece.size * reps, True); counts, stats = e.end()
+        got = e.ec_items()
+        e.device_free(d)
+    assert stats == {k: v * reps for k, v in want_s.items()}
+    assert got == {k: v * reps for k, v in want.items()}
