@@ -88,6 +88,7 @@ struct f2q_ctx {
     unsigned long long* ec_meta_host = nullptr;      // pinned ring of EC_RING x 4 words
     uint64_t ec_ring_next = 0;
     unsigned long long ec_known[4] = {0, 0, 0, 0};   // newest counters seen: arena bytes, arena keys, packed keys, spec_off
+    int flex_warps = 12;                             // option "flex_warps": warps per CTA of the streaming kernel's flex policies
     int fx_group = 1, fx_group_opt = 0;              // lanes per key of the flex resolver (auto from the seed index / option)
     size_t q_entry = 0;                              // bytes per entry the queue buffer was sized for
     int64_t opt_generic_entries = 0;
@@ -312,10 +313,14 @@ int launch_spec(f2q_ctx* c, const SpecParams& P, Outputs O) {
 int launch_spec_dyn(f2q_ctx* c, const SpecParams& P, Outputs O) {
     int rc12;
     if (is_flex(c)) {
-        // the flex code keeps a read's planes in registers: 12 warps per CTA (170 registers per thread)
+        // the flex code keeps a read's planes in registers: 12 warps per CTA (170 registers per thread) or 16 (128)
         const int ch = c->ch == 3 ? 5 : c->ch;
-        if (c->policy == POLICY_FLEX_S) rc12 = ch == 5 ? launch_spec<POLICY_FLEX_S, 5, 12>(c, P, O) : launch_spec<POLICY_FLEX_S, 7, 12>(c, P, O);
-        else rc12 = ch == 5 ? launch_spec<POLICY_FLEX_B, 5, 12>(c, P, O) : launch_spec<POLICY_FLEX_B, 7, 12>(c, P, O);
+        int rc16 = 1;
+        if (c->policy == POLICY_FLEX_S) {
+            if (c->flex_warps == 16) rc16 = ch == 5 ? launch_spec<POLICY_FLEX_S, 5, 16>(c, P, O) : launch_spec<POLICY_FLEX_S, 7, 16>(c, P, O);
+            if (rc16 != 1) return rc16;
+            rc12 = ch == 5 ? launch_spec<POLICY_FLEX_S, 5, 12>(c, P, O) : launch_spec<POLICY_FLEX_S, 7, 12>(c, P, O);
+        } else rc12 = ch == 5 ? launch_spec<POLICY_FLEX_B, 5, 12>(c, P, O) : launch_spec<POLICY_FLEX_B, 7, 12>(c, P, O);
         return rc12 == 1 ? fail(c, F2Q_EINTERNAL, "speculative kernel does not fit on an SM") : rc12;
     }
     const bool f = c->policy == POLICY_FAST1;
@@ -412,6 +417,7 @@ void ec_bind(f2q_ctx* c) {
 void ec_fold_done(f2q_ctx* c, bool wait_oldest) {
     while (!c->ec_pend.empty()) {
         f2q_ctx::EcPend& p = c->ec_pend.front();
+        if (!p.ev) { c->ec_pend.pop_front(); continue; }               // (a chunk that failed before its counters were queued)
         if (wait_oldest) { cudaEventSynchronize(p.ev); wait_oldest = false; }
         else if (cudaEventQuery(p.ev) != cudaSuccess) { cudaGetLastError(); break; }
         for (int k = 0; k < 3; k++) c->ec_known[k] = p.host[k];
@@ -553,9 +559,10 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     const int spec_ch = flex && c->ch == 3 ? 5 : c->ch;
     const uint64_t spec_own = 512ull * spec_ch;
     uint64_t spec_range_tiles = 0;
+    if (flex) grid = (unsigned)c->sm_count;                            // (the exact kernel runs the generic code: no queue segments of its own)
     if (use_spec) {
         grid = std::max<unsigned>(grid, (unsigned)c->sm_count);        // one queue segment per CTA of either kernel
-        const uint64_t tiles = (delta + n) / spec_own + 1, streams = (uint64_t)c->sm_count * (flex ? 12 : c->spec_warps);
+        const uint64_t tiles = (delta + n) / spec_own + 1, streams = (uint64_t)c->sm_count * (flex ? c->flex_warps : c->spec_warps);
         spec_range_tiles = c->spec_range_tiles > 0 ? (uint64_t)c->spec_range_tiles : std::min<uint64_t>(64, std::max<uint64_t>(8, tiles / (streams * 4)));
         const uint64_t n_rec = (delta + n) / (spec_range_tiles * spec_own) + 2;
         if ((rc = dev_alloc(c, c->spec_rec, n_rec))) return rc;
@@ -569,6 +576,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     if (flex && ec && c->opt_queue_entries <= 0) want_q = std::max<uint64_t>(1 << 16, (c->rec_bytes ? 3 * n / (2 * c->rec_bytes) : n / 48) + 4096);
     want_q = std::min<uint64_t>(want_q, 0x7FFFFFFFull);
     if (c->policy == POLICY_GENERIC) want_q = grid;
+    if (flex) want_q = ((want_q + FX_BLOCK - 1) / FX_BLOCK + (c->opt_queue_entries > 0 ? 0 : (uint64_t)c->sm_count * 16)) * FX_BLOCK;   // + one open block per warp
     if (want_q > c->q_cap || grid != c->n_segs || entry != c->q_entry) {
         want_q = std::max<uint64_t>(want_q, c->q_cap);
         if ((rc = dev_alloc(c, c->queue, want_q * entry))) return rc;
@@ -583,8 +591,9 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         if (use_spec) {
             // the streaming kernel can insert at most its log + its generic queue; the stitched record adds one
             const uint64_t gq = (uint64_t)c->g_cap + 4;
-            rc = ec_reserve(c, (uint64_t)c->seg_cap * c->n_segs + gq, gq, std::min<uint64_t>(worst_bytes, gq * 1024ull * (uint64_t)c->cfg.n_iter));
-        } else rc = ec_reserve(c, worst, worst, worst_bytes);           // exact kernel: every record could be 4 bytes and every key new
+            rc = ec_reserve(c, (uint64_t)c->q_cap + gq, gq, std::min<uint64_t>(worst_bytes, gq * 1024ull * (uint64_t)c->cfg.n_iter));
+        } else if (n == 0) rc = ec_reserve(c, 4, 4, (uint64_t)c->cfg.n_iter * c->carry_cap + 64);     // only the carried last record is left
+        else rc = ec_reserve(c, worst, worst, worst_bytes);             // exact kernel: every record could be 4 bytes and every key new
         if (rc) return rc;
     }
 
@@ -621,7 +630,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         SpecParams Q{};
         Q.buf = base; Q.S = c->dS; Q.ticket = c->d_tickets + 2; Q.rec = reinterpret_cast<uint8_t*>(c->spec_rec.p);
         Q.range_bytes = spec_range_tiles * spec_own;
-        Q.queue = P.queue; Q.seg_count = P.seg_count; Q.seg_cap = c->policy != POLICY_GENERIC ? c->seg_cap : 0; Q.gqueue = P.gqueue;
+        Q.queue = P.queue; Q.seg_count = P.seg_count; Q.seg_cap = flex ? c->q_cap : c->policy != POLICY_GENERIC ? c->seg_cap : 0; Q.gqueue = P.gqueue;
         Q.halo_rows = (uint32_t)std::min<int>(c->halo_rows, (int)SPEC_MAX_HALO);
         Outputs O2 = O;
         O2.counts = reinterpret_cast<unsigned long long*>(c->spec_scratch.p); O2.stats = O2.counts + c->n_keys;
@@ -638,8 +647,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         if (flex && ec) {
             // the verified chunk's insert log -> the packed key table
             cudaEvent_t t4 = timing_begin(c);
-            k_ec_commit<<<dim3(8, c->n_segs), 256, 0, c->stream>>>(c->dS, c->E, O, reinterpret_cast<const unsigned long long*>(c->queue.p),
-                                                                 P.seg_count, c->seg_cap, c->n_segs);
+            k_ec_commit<<<(unsigned)c->sm_count * 8, 256, 0, c->stream>>>(c->dS, c->E, O, reinterpret_cast<const unsigned long long*>(c->queue.p), c->q_cap);
             c->launches++;
             timing_end(c, t4, 1);
         }
@@ -676,10 +684,10 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         cudaEvent_t t1 = timing_begin(c);
         const FlexQ* fq = reinterpret_cast<const FlexQ*>(c->queue.p);
         const int G = c->fx_group_opt ? c->fx_group_opt : c->fx_group;
-        const dim3 rg(c->n_segs, 8);
-        if (G == 32) k_resolve_flex<32><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, fq, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
-        else if (G == 8) k_resolve_flex<8><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, fq, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
-        else k_resolve_flex<1><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, fq, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
+        const unsigned rg = (unsigned)c->sm_count * 8;
+        if (G == 32) k_resolve_flex<32><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, c->dS, fq, c->q_cap, O.counts, O.stats);
+        else if (G == 8) k_resolve_flex<8><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, c->dS, fq, c->q_cap, O.counts, O.stats);
+        else k_resolve_flex<1><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, c->dS, fq, c->q_cap, O.counts, O.stats);
         timing_end(c, t1, 1);
         c->launches++;
     }
@@ -774,7 +782,8 @@ F2Q_EXPORT int f2q_create(const f2q_config* cfg, int device, void* stream, f2q_c
     decide_policy(c);
     if (cfg->mode == F2Q_MODE_EXTRACT_COUNT) {
         // no library in this mode: results are [stats 5]
-        if ((rc = dev_alloc(c, c->result, 5 * 8))) return bail(rc, "");
+        if ((rc = dev_alloc(c, c->result, 5 * 8)) || (rc = dev_alloc(c, c->spec_scratch, 5 * 8))) return bail(rc, "");
+        cudaMemset(c->spec_scratch.p, 0, 5 * 8);
         std::vector<uint32_t> gh(16, 0); std::vector<uint64_t> ko(1, 0); std::vector<uint8_t> kb(1, 0);
         if ((rc = upload(c, gh, &c->T.ghash)) || (rc = upload(c, ko, &c->T.key_off)) || (rc = upload(c, kb, &c->T.key_bytes))) return bail(rc, "");
         c->T.ghash_mask = 15; c->lib_set = true;
@@ -827,6 +836,7 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "debug_waits") c->debug_waits = value != 0;
     else if (n == "spec") c->spec = value != 0;
     else if (n == "spec_warps") { if (value != 12 && value != 16) return fail(c, F2Q_EINVAL, "spec_warps must be 12 or 16"); c->spec_warps = (int)value; }
+    else if (n == "flex_warps") { if (value != 12 && value != 16) return fail(c, F2Q_EINVAL, "flex_warps must be 12 or 16"); c->flex_warps = (int)value; }
     else if (n == "spec_range_tiles") { if (value < 0 || value > (1 << 20)) return fail(c, F2Q_EINVAL, "spec_range_tiles out of range"); c->spec_range_tiles = (int)value; }
     else if (n == "force_generic") { c->force_generic = value != 0; decide_policy(c); c->n_segs = 0; c->q_cap = 0; }
     else if (n == "flex") { c->no_flex = value == 0; decide_policy(c); c->n_segs = 0; c->q_cap = 0; }

@@ -94,24 +94,36 @@ __device__ __noinline__ FlexPiece fx_fix_case(const uint8_t* seq, FlexPiece p) {
 constexpr uint32_t EC_PK_MAX_LEN = 29;
 __host__ __device__ __forceinline__ unsigned long long ec_pk_tag(uint64_t codes, uint32_t len) { return ((codes << 6) | len) + 1ull; }
 
-// what the streaming kernel needs for the flex policies
+// what the streaming kernel needs for the flex policies.  Queue (Counter: FlexQ) and insert log (Extract+Count: u64) are ONE
+// array for the whole grid; a warp takes blocks of FX_BLOCK entries from a global counter (DevState::q_count) and fills the
+// rest of its last block with empty entries, so that the consumers see [0, min(q_count, capacity)) fully written.  How the
+// reads spread over the CTAs (a small chunk is parsed by a few of them) therefore never matters.
+constexpr uint32_t FX_BLOCK = 128, FX_NOBLOCK = 0xFFFFFFFFu;
 struct FlexCtx {
-    FlexQ* myq;                        // Counter: this CTA's queue segment
-    unsigned long long* mylog;         // Extract+Count: this CTA's insert log segment
-    uint32_t seg_cap;
-    uint32_t* s_qn;                    // shared fill count of the segment (queue or log)
+    FlexQ* q;                          // Counter: the queue
+    unsigned long long* log;           // Extract+Count: the insert log
+    uint32_t q_cap;                    // entries (multiple of FX_BLOCK)
     uint32_t* hist;                    // shared-memory histogram or nullptr
     GEntry* gqueue;
     DevState* St;
     int mode, miss;
 };
+struct FlexWarp { uint32_t base, used; };                               // the warp's current block (uniform over its lanes)
+
+__device__ __forceinline__ void fx_block_fill(const FlexCtx& F, const FlexWarp& W, uint32_t lane) {
+    if (W.base == FX_NOBLOCK) return;
+    for (uint32_t i = W.used + lane; i < FX_BLOCK; i += 32u) {
+        if (F.mode == F2Q_MODE_COUNT) { FlexQ e; e.lo = 0; e.bad = 0; e.hi = 0; e.sig = 0; e.pad0 = 0; e.pad1 = 0; F.q[W.base + i] = e; }
+        else F.log[W.base + i] = 0ull;
+    }
+}
 
 // one read of a CONVERGED warp (every lane calls it; `valid` lanes hold a read).  tile = the stage in shared memory,
 // [s0, e0) / [s3, e3) the sequence / quality line before rstrip, gseq / gqual their global addresses.
 template <int PW, int K>
 __device__ __forceinline__ void flex_read_warp(const FlexCtx& F, const GenericCfg& G, bool valid, const uint8_t* tile, uint32_t s0, uint32_t e0,
                                                uint32_t s3, uint32_t e3, const uint8_t* gseq, const uint8_t* gqual, const LibTables& T,
-                                               const Outputs& O, Fast1Counts& n, uint32_t lane) {
+                                               const Outputs& O, Fast1Counts& n, FlexWarp& W, uint32_t lane) {
     if (!valid) { s0 = e0 = s3 = e3 = 0; }
     else {
         if (is_py_space(tile[e0 - 1])) while (e0 > s0 && is_py_space(tile[e0 - 1])) e0--;
@@ -129,7 +141,14 @@ __device__ __forceinline__ void flex_read_warp(const FlexCtx& F, const GenericCf
     int np = flex_pieces<PW, K>(G.flex, sw, live ? r : 0u, qw, live ? q : 0u, pc);
     if (!live) np = -1;
     n.qfail += (live && np == -1) ? 1u : 0u;
-    generic = generic || (live && np == -2);
+    if (live && np <= -2) {
+        // a piece longer than 32 symbols.  Counter: nothing can align when the library has no key of the key's byte length
+        // (the usual case: a search sequence that also occurs by chance elsewhere in the read); otherwise the generic code
+        const uint32_t pieces = (uint32_t)(-np - 1);
+        const uint32_t bl = pc[0].len + (pieces > 1 ? pc[1].len + 1u : 0u);
+        if (F.mode == F2Q_MODE_COUNT && (bl > FX_MAX_BYTELEN || __ldg(T.fx_len_sig + bl) == 0)) n.nonal++;
+        else generic = true;
+    }
     bool keyed = live && np >= 1;
     if (keyed && ((pc[0].notok | (np > 1 ? pc[1].notok : 0u)) != 0u)) {                  // rare: lower case / N inside the key
         pc[0] = fx_fix_case(tile + s0, pc[0]);
@@ -161,18 +180,26 @@ __device__ __forceinline__ void flex_read_warp(const FlexCtx& F, const GenericCf
             else generic = true;
         }
     }
-    // queue / log slots of the warp: one atomic per warp
+    // queue / log slots of the warp
     const uint32_t mq = __ballot_sync(0xffffffffu, to_queue);
     if (mq) {
-        uint32_t sl = 0;
-        if (lane == 0) sl = atomicAdd(F.s_qn, (uint32_t)__popc(mq));
-        sl = __shfl_sync(0xffffffffu, sl, 0) + (uint32_t)__popc(mq & ((1u << lane) - 1u));
-        if (to_queue) {
-            if (sl < F.seg_cap) {
-                if (F.mode == F2Q_MODE_COUNT) { FlexQ e; e.lo = k.lo; e.bad = k.bad; e.hi = k.hi; e.sig = k.sig; e.pad0 = 0; e.pad1 = 0; F.myq[sl] = e; }
-                else { F.mylog[sl] = ec_pk_tag(pc[0].codes, pc[0].len); n.perfect++; }
-            } else generic = true;                                     // segment full: the generic queue takes the read
+        const uint32_t cnt = (uint32_t)__popc(mq);
+        if (W.used + cnt > FX_BLOCK) {                                 // (uniform) next block: one global atomic per FX_BLOCK entries
+            fx_block_fill(F, W, lane);
+            uint32_t nb = 0;
+            if (lane == 0) nb = atomicAdd(&F.St->q_count, FX_BLOCK);
+            nb = __shfl_sync(0xffffffffu, nb, 0);
+            W.base = (nb <= F.q_cap - FX_BLOCK && F.q_cap >= FX_BLOCK) ? nb : FX_NOBLOCK;
+            W.used = 0;
         }
+        if (to_queue) {
+            if (W.base != FX_NOBLOCK) {
+                const uint32_t sl = W.base + W.used + (uint32_t)__popc(mq & ((1u << lane) - 1u));
+                if (F.mode == F2Q_MODE_COUNT) { FlexQ e; e.lo = k.lo; e.bad = k.bad; e.hi = k.hi; e.sig = k.sig; e.pad0 = 0; e.pad1 = 0; F.q[sl] = e; }
+                else { F.log[sl] = ec_pk_tag(pc[0].codes, pc[0].len); n.perfect++; }
+            } else generic = true;                                     // no room left: the generic queue takes the read
+        }
+        if (W.base != FX_NOBLOCK) W.used += cnt;
     }
     if (__any_sync(0xffffffffu, generic)) {
         if (generic) {
@@ -208,19 +235,18 @@ __device__ __forceinline__ void ec_pk_insert(const EcTable& E, const Outputs& O,
 
 // the insert log of a chunk -> the packed table, when the chunk's speculation verified (DevState::spec_ok).  One thread per
 // entry; equal tags inside a warp are added once (bar-seq abundances are heavy-tailed: the hot keys would serialise)
-__global__ void __launch_bounds__(256) k_ec_commit(const DevState* St, EcTable E, Outputs O, const unsigned long long* __restrict__ log,
-                                                   const uint32_t* __restrict__ seg_count, uint32_t seg_cap, uint32_t n_segs) {
+__device__ __forceinline__ uint32_t fx_queue_fill(const DevState* St, uint32_t q_cap) {
+    const uint32_t full = q_cap - q_cap % FX_BLOCK;
+    return min(St->q_count, full);
+}
+__global__ void __launch_bounds__(256) k_ec_commit(const DevState* St, EcTable E, Outputs O, const unsigned long long* __restrict__ log, uint32_t q_cap) {
     if (!St->spec_ok) return;
-    for (uint32_t seg = blockIdx.y; seg < n_segs; seg += gridDim.y) {
-        const uint32_t n = min(seg_count[seg], seg_cap);
-        const unsigned long long* __restrict__ L = log + (size_t)seg * seg_cap;
-        for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-            const uint32_t i = base + threadIdx.x;
-            const bool act = i < n;
-            const unsigned long long tag = act ? L[i] : 0ull;
-            const uint32_t peers = __match_any_sync(0xffffffffu, tag);
-            if (act && (uint32_t)(__ffs((int)peers) - 1) == (threadIdx.x & 31u)) ec_pk_insert(E, O, tag, (unsigned long long)__popc(peers));
-        }
+    const uint32_t n = fx_queue_fill(St, q_cap);
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        const unsigned long long tag = i < n ? log[i] : 0ull;
+        const uint32_t peers = __match_any_sync(0xffffffffu, tag);
+        if (tag && (uint32_t)(__ffs((int)peers) - 1) == (threadIdx.x & 31u)) ec_pk_insert(E, O, tag, (unsigned long long)__popc(peers));
     }
 }
 
@@ -338,24 +364,22 @@ __device__ __forceinline__ uint32_t fx_resolve_group(const LibTables& T, int m, 
 }
 
 template <int G>
-__global__ void __launch_bounds__(256) k_resolve_flex(LibTables T, int m, const FlexQ* __restrict__ queue, const uint32_t* __restrict__ seg_count,
-                                                      uint32_t seg_cap, uint32_t n_segs, unsigned long long* counts, unsigned long long* stats) {
+__global__ void __launch_bounds__(256) k_resolve_flex(LibTables T, int m, const DevState* St, const FlexQ* __restrict__ q, uint32_t q_cap,
+                                                      unsigned long long* counts, unsigned long long* stats) {
     const uint32_t gl = threadIdx.x % G, grp = threadIdx.x / G, groups = blockDim.x / G;
     uint32_t imperfect = 0, nonal = 0;
-    for (uint32_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
-        const uint32_t n = min(seg_count[seg], seg_cap);
-        const FlexQ* __restrict__ q = queue + (size_t)seg * seg_cap;
-        // (every thread of a warp runs the same number of rounds: the shuffles inside need the whole warp)
-        const uint32_t per_round = gridDim.y * groups;
-        for (uint32_t base = 0; base < n; base += per_round) {
-            const uint32_t i = base + blockIdx.y * groups + grp;
-            const bool act = i < n;
-            FlexQ e;
-            e.lo = 0; e.bad = ~0ull; e.hi = 0; e.sig = 0; e.pad0 = 0; e.pad1 = 0;     // (inactive: too many bad symbols, no work)
-            if (act) e = q[i];
-            const uint32_t r = fx_resolve_group<G>(T, m, e, gl);
-            if (act && gl == 0) { if (r != RES_NONE) { atomicAdd(counts + r, 1ull); imperfect++; } else nonal++; }
-        }
+    const uint32_t n = St->spec_ok ? fx_queue_fill(St, q_cap) : 0u;     // (a chunk the exact kernel re-parsed left nothing valid here)
+    // (every thread of a warp runs the same number of rounds: the shuffles inside need the whole warp)
+    const uint32_t per_round = gridDim.x * groups;
+    for (uint32_t base = 0; base < n; base += per_round) {
+        const uint32_t i = base + blockIdx.x * groups + grp;
+        FlexQ e;
+        e.lo = 0; e.bad = 0; e.hi = 0; e.sig = 0; e.pad0 = 0; e.pad1 = 0;
+        if (i < n) e = q[i];
+        const bool act = e.sig != 0;                                    // (sig 0: the unused rest of a warp's block)
+        if (!act) e.bad = ~0ull;                                        // too many bad symbols: no work
+        const uint32_t r = fx_resolve_group<G>(T, m, e, gl);
+        if (act && gl == 0) { if (r != RES_NONE) { atomicAdd(counts + r, 1ull); imperfect++; } else nonal++; }
     }
     imperfect = __reduce_add_sync(0xffffffffu, imperfect);
     nonal = __reduce_add_sync(0xffffffffu, nonal);

@@ -66,14 +66,23 @@ F2Q_HD void flex_load(const uint8_t* base, uint32_t o, uint32_t (&w)[NW]) {
     for (int i = 0; i < NW; i++) w[i] = F2Q_FSHR(r[i], r[i + 1], sh);
 }
 
+// bits [0, left) of one word: 0 for left <= 0, all ones for left >= 32.  Device: the PTX shift clamps its amount at 32
+// (1 << 32 = 0), so this is max, shift, subtract
+F2Q_HD uint32_t flex_ones_below(int32_t left) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("{\n\t.reg .u32 t;\n\tmax.s32 t, %1, 0;\n\tshl.b32 t, 1, t;\n\tsub.u32 %0, t, 1;\n\t}" : "=r"(r) : "r"(left));
+    return r;
+#else
+    return left >= 32 ? 0xFFFFFFFFu : left <= 0 ? 0u : ((1u << left) - 1u);
+#endif
+}
+
 // bits [0, n) of a PW-word plane (n <= 32 * PW)
 template <int PW>
 F2Q_HD void flex_prefix_mask(uint32_t n, uint32_t (&m)[PW]) {
 #pragma unroll
-    for (int j = 0; j < PW; j++) {
-        const int32_t left = (int32_t)n - 32 * j;
-        m[j] = left >= 32 ? 0xFFFFFFFFu : left <= 0 ? 0u : ((1u << left) - 1u);
-    }
+    for (int j = 0; j < PW; j++) m[j] = flex_ones_below((int32_t)n - 32 * j);
 }
 
 // 8 flag bits (bit k = byte k of the pair w0|w1 has `bit` set, scaled by `bit`'s value) placed at plane bit 8 * g
@@ -299,7 +308,8 @@ F2Q_HD void flex_lowq(const uint32_t* qw_dummy, uint32_t fmax, uint32_t& add_ge,
 
 // sw / qw: the sequence / quality line as words (flex_load), r / q their lengths after rstrip (both <= 32 * PW).
 // Returns the number of pieces (>= 0; the key is their ':'-join), -1 when every iteration was flagged (quality_failed,
-// fast2q.py:389-390), -2 when a piece is longer than FLEX_MAX_PIECE (the caller takes the generic path).
+// fast2q.py:389-390), -(pieces + 1) <= -2 when a piece is longer than FLEX_MAX_PIECE (pc[] then holds every piece's length
+// and offset, but codes only for the short ones).
 template <int PW, int K>
 F2Q_HD int flex_pieces(const FlexCfg& C, const uint32_t (&sw)[8 * PW], uint32_t r, const uint32_t (&qw)[8 * PW], uint32_t q,
                        FlexPiece (&pc)[FLEX_ITER]) {
@@ -373,14 +383,15 @@ F2Q_HD int flex_pieces(const FlexCfg& C, const uint32_t (&sw)[8 * PW], uint32_t 
         if (flex_any<PW>(lq, qlo, qhi)) continue;
         any = true;
         const uint32_t n = (uint32_t)(hi - lo);
-        if (n > (uint32_t)FLEX_MAX_PIECE) { slow = true; continue; }
         FlexPiece p;
-        flex_cut<PW>(b0, b1, ok, (uint32_t)lo, n, p.codes, p.notok);
+        p.codes = 0; p.notok = 0;
+        if (n > (uint32_t)FLEX_MAX_PIECE) slow = true;                 // (its length is still reported: the caller may need no more)
+        else flex_cut<PW>(b0, b1, ok, (uint32_t)lo, n, p.codes, p.notok);
         p.len = n; p.off = (uint32_t)lo;
         pc[np] = p;
         np++;
     }
-    if (slow) return -2;
+    if (slow) return -(np + 1);
     return any ? np : -1;
 }
 

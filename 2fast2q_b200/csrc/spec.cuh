@@ -113,10 +113,11 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     F.hist = P.hist_smem ? hist : nullptr; F.myq = P.queue + (size_t)blockIdx.x * P.seg_cap; F.seg_cap = P.seg_cap; F.s_qn = &s_qn;
     F.gqueue = P.gqueue; F.St = St; F.X = X;
     FlexCtx FX;
-    FX.myq = reinterpret_cast<FlexQ*>(P.queue) + (size_t)blockIdx.x * P.seg_cap;
-    FX.mylog = reinterpret_cast<unsigned long long*>(P.queue) + (size_t)blockIdx.x * P.seg_cap;
-    FX.seg_cap = P.seg_cap; FX.s_qn = &s_qn; FX.hist = P.hist_smem ? hist : nullptr; FX.gqueue = P.gqueue; FX.St = St;
+    FX.q = reinterpret_cast<FlexQ*>(P.queue); FX.log = reinterpret_cast<unsigned long long*>(P.queue);
+    FX.q_cap = P.seg_cap;                                              // (flex: P.seg_cap is the capacity of the whole array)
+    FX.hist = P.hist_smem ? hist : nullptr; FX.gqueue = P.gqueue; FX.St = St;
     FX.mode = Gp->c.mode; FX.miss = Gp->c.miss;
+    FlexWarp FW{FX_NOBLOCK, FX_BLOCK};
     Acc acc{0, 0, 0, 0, 0, 0};
     unsigned long long gst[F2Q_N_STATS] = {0, 0, 0, 0, 0};
     Fast1Counts cn{0, 0, 0, 0, 0};
@@ -241,7 +242,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                     }
                 } else if constexpr (FLEX) {
                     __syncwarp();
-                    flex_read_warp<policy_pw(POLICY), policy_k(POLICY)>(FX, G, valid, ptile, s0, e0, s3, e3, buf + pbase + s0, buf + pbase + s3, T, O, cn, lane);
+                    flex_read_warp<policy_pw(POLICY), policy_k(POLICY)>(FX, G, valid, ptile, s0, e0, s3, e3, buf + pbase + s0, buf + pbase + s3, T, O, cn, FW, lane);
                 } else {
                     __syncwarp();
                     if (j0 != jf) fast1_warp_commit(F, pend, T, O, cn, lane);          // (a second pass over the same tile: rare)
@@ -388,10 +389,11 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         gs = s; pre = nxt_pre; cur = nxt;
     }
     if (POLICY == POLICY_FAST1) fast1_warp_commit(F, pend, T, O, cn, lane);
+    if constexpr (FLEX) fx_block_fill(FX, FW, lane);
 
     // @region spec_epilogue
     __syncthreads();
-    if (tid == 0 && P.seg_cap) P.seg_count[blockIdx.x] = min(s_qn, P.seg_cap);
+    if (tid == 0 && P.seg_cap && !FLEX) P.seg_count[blockIdx.x] = min(s_qn, P.seg_cap);
     if (P.hist_smem)
         for (uint32_t i = tid; i < T.n_keys; i += blockDim.x) { const uint32_t v = hist[i]; if (v) atomicAdd(O.counts + i, (unsigned long long)v); }
     acc.reads += cn.reads; acc.perfect += cn.perfect; acc.imperfect += cn.imperfect; acc.nonal += cn.nonal; acc.qfail += cn.qfail;
@@ -446,7 +448,7 @@ __global__ void __launch_bounds__(SPEC_VERIFY_THREADS) k_spec_verify(DevState* S
     if (tid == 0) {
         St->spec_ok = ok ? 1u : 0u;
         if (ok) { if (end > beg) { St->nl_total = total & 3u; St->spec_commits++; } }
-        else { St->last_rec_end = 0; St->g_count = 0; St->spec_off = 1u; St->spec_fallbacks++; }
+        else { St->last_rec_end = 0; St->g_count = 0; St->q_count = 0; St->spec_off = 1u; St->spec_fallbacks++; }
     }
     if (!ok) for (uint32_t i = tid; i < n_segs; i += SPEC_VERIFY_THREADS) seg_count[i] = 0;
 }

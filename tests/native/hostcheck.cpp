@@ -33,7 +33,7 @@ int flex_key_t(const f2q::FlexCfg& C, const uint8_t* read, int r, const uint8_t*
     f2q::flex_load<8 * PW>(qb.data(), qo, qw);
     f2q::FlexPiece pc[f2q::FLEX_ITER];
     const int np = f2q::flex_pieces<PW, K>(C, sw, (uint32_t)r, qw, (uint32_t)q, pc);
-    if (np < 0) return np;
+    if (np < 0) return np < -2 ? -2 : np;
     int n = 0;
     for (int p = 0; p < np; p++) {
         if (p) out[n++] = ':';
