@@ -84,6 +84,7 @@ SYMBOLS = {
     "f2q_launch_count": (C.c_uint64, [_VP]),
     "f2q_kernel_times": (C.c_int, [_VP, C.POINTER(C.c_double), _U64P]),
     "f2q_spec_counts": (C.c_int, [_VP, _U64P, _U64P]),
+    "f2q_memo_counts": (C.c_int, [_VP, _U64P, _U64P]),
 }
 
 _lib = None
@@ -355,6 +356,12 @@ class Engine:
         """(chunks committed by the speculative kernel, chunks parsed by the exact kernel) of the last finished sample"""
         a, b = C.c_uint64(), C.c_uint64()
         self._ck(self.L.f2q_spec_counts(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def memo_counts(self):
+        """(lookups, hits) of the device memo of resolved non-exact keys during the last finished sample"""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.f2q_memo_counts(self.h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
     def kernel_times(self):

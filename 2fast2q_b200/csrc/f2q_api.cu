@@ -88,7 +88,11 @@ struct f2q_ctx {
     unsigned long long* ec_meta_host = nullptr;      // pinned ring of EC_RING x 4 words
     uint64_t ec_ring_next = 0;
     unsigned long long ec_known[4] = {0, 0, 0, 0};   // newest counters seen: arena bytes, arena keys, packed keys, spec_off
-    int flex_warps = 12;                             // option "flex_warps": warps per CTA of the streaming kernel's flex policies
+    int flex_warps = 16;                             // option "flex_warps": warps per CTA of the streaming kernel's flex policies
+    int seed_group = 1;                              // lanes per key of the fast1 seed resolver (auto)
+    int64_t memo_entries = -1;                       // option "memo_entries": -1 auto (2^20 when m >= 2), 0 off
+    DevBuf memo;
+    uint64_t memo_counts[2] = {0, 0};                // last finished sample: memo lookups / hits
     int fx_group = 1, fx_group_opt = 0;              // lanes per key of the flex resolver (auto from the seed index / option)
     size_t q_entry = 0;                              // bytes per entry the queue buffer was sized for
     int64_t opt_generic_entries = 0;
@@ -304,7 +308,7 @@ int launch_spec(f2q_ctx* c, const SpecParams& P, Outputs O) {
         CU(c, cudaFuncSetAttribute(k_spec<POLICY, CH, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMEM_BYTES - sizeof(GenericCfg) - SPEC_SMEM_MARGIN)));
         ready = 1;
     }
-    k_spec<POLICY, CH, W><<<(unsigned)c->sm_count, W * 32, smem, c->stream>>>(p, c->dG, c->T, c->E, O, reinterpret_cast<const SlowArgs*>(c->slow_args.p) + 1);
+    k_spec<POLICY, CH, W><<<(unsigned)c->sm_count, W * 32, smem, c->stream>>>(p, c->dG, c->T, c->E, O, reinterpret_cast<const SlowArgs*>(c->slow_args.p) + 1, c->hG.flex);
     c->launches++;
     CU(c, cudaGetLastError());
     return F2Q_OK;
@@ -313,7 +317,7 @@ int launch_spec(f2q_ctx* c, const SpecParams& P, Outputs O) {
 int launch_spec_dyn(f2q_ctx* c, const SpecParams& P, Outputs O) {
     int rc12;
     if (is_flex(c)) {
-        // the flex code keeps a read's planes in registers: 12 warps per CTA (170 registers per thread) or 16 (128)
+        // 16 warps per CTA (128 registers per thread; measured 5-10 % faster than 12 warps with 168), 12 when the stages do not fit
         const int ch = c->ch == 3 ? 5 : c->ch;
         int rc16 = 1;
         if (c->policy == POLICY_FLEX_S) {
@@ -674,7 +678,16 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
             if (res == 2 && c->cfg.miss > 32) res = 3;
             cudaEvent_t t1 = timing_begin(c);
             if (res == 1) k_resolve_probe<<<c->n_segs, 256, 0, c->stream>>>(c->T, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
-            else if (res == 2) k_resolve_seed<<<dim3(c->n_segs, 8), 256, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
+            else if (res == 2) {
+                // pigeonhole seed index; lanes per key from the mean bucket size (option "resolve_group"); the memo sits in front
+                const int G = c->fx_group_opt ? c->fx_group_opt : c->seed_group;
+                unsigned long long* ms = &c->dS->memo_lookups;
+                const dim3 rg(c->n_segs, 8);
+                if (G == 32) k_resolve_seed_g<32><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats, ms);
+                else if (G == 8) k_resolve_seed_g<8><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats, ms);
+                else if (c->T.memo) k_resolve_seed_g<1><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats, ms);
+                else k_resolve_seed<<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
+            }
             else k_resolve_scan<<<c->n_segs, SCAN_THREADS, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
             timing_end(c, t1, 1);
             c->launches++;
@@ -685,9 +698,9 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         const FlexQ* fq = reinterpret_cast<const FlexQ*>(c->queue.p);
         const int G = c->fx_group_opt ? c->fx_group_opt : c->fx_group;
         const unsigned rg = (unsigned)c->sm_count * 8;
-        if (G == 32) k_resolve_flex<32><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, c->dS, fq, c->q_cap, O.counts, O.stats);
-        else if (G == 8) k_resolve_flex<8><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, c->dS, fq, c->q_cap, O.counts, O.stats);
-        else k_resolve_flex<1><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, c->dS, fq, c->q_cap, O.counts, O.stats);
+        if (G == 32) k_resolve_flex<32><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, c->dS, fq, c->q_cap, O.counts, O.stats, &c->dS->memo_lookups);
+        else if (G == 8) k_resolve_flex<8><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, c->dS, fq, c->q_cap, O.counts, O.stats, &c->dS->memo_lookups);
+        else k_resolve_flex<1><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, c->dS, fq, c->q_cap, O.counts, O.stats, &c->dS->memo_lookups);
         timing_end(c, t1, 1);
         c->launches++;
     }
@@ -799,7 +812,7 @@ F2Q_EXPORT void f2q_destroy(f2q_ctx* c) {
     for (auto& b : c->lib_bufs) b.release();
     c->result.release(); c->carry.release(); c->status.release(); c->status_stitch.release(); c->queue.release(); c->gqueue.release();
     c->seg_count.release(); c->spec_rec.release(); c->spec_scratch.release(); c->slow_args.release(); c->synth_guides.release();
-    c->ec_slots.release(); c->ec_counts.release(); c->ec_arena.release(); c->ec_meta.release(); c->ec_pk.release(); c->ec_compact.release();
+    c->ec_slots.release(); c->ec_counts.release(); c->ec_arena.release(); c->ec_meta.release(); c->ec_pk.release(); c->ec_compact.release(); c->memo.release();
     for (auto& p : c->ec_pend) if (p.ev) cudaEventDestroy(p.ev);
     for (auto e : c->ec_events) cudaEventDestroy(e);
     if (c->ec_meta_host) cudaFreeHost(c->ec_meta_host);
@@ -836,6 +849,7 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "debug_waits") c->debug_waits = value != 0;
     else if (n == "spec") c->spec = value != 0;
     else if (n == "spec_warps") { if (value != 12 && value != 16) return fail(c, F2Q_EINVAL, "spec_warps must be 12 or 16"); c->spec_warps = (int)value; }
+    else if (n == "memo_entries") { if (value < -1 || value > (1ll << 28) || (value > 0 && (value & (value - 1)))) return fail(c, F2Q_EINVAL, "memo_entries must be -1 (auto), 0 (off) or a power of two"); c->memo_entries = value; if (c->lib_set) return fail(c, F2Q_ESTATE, "memo_entries must be set before f2q_set_library"); }
     else if (n == "flex_warps") { if (value != 12 && value != 16) return fail(c, F2Q_EINVAL, "flex_warps must be 12 or 16"); c->flex_warps = (int)value; }
     else if (n == "spec_range_tiles") { if (value < 0 || value > (1 << 20)) return fail(c, F2Q_EINVAL, "spec_range_tiles out of range"); c->spec_range_tiles = (int)value; }
     else if (n == "force_generic") { c->force_generic = value != 0; decide_policy(c); c->n_segs = 0; c->q_cap = 0; }
@@ -1130,6 +1144,23 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
             c->T.fx_mask = fcap - 1; c->T.fxs_mask = (uint32_t)fs_slots.size() - 1; c->T.fxs_parts = fparts;
         }
     }
+    {
+        // lanes per key of the fast1 seed resolver, from the mean number of candidates a probe returns (weighted by bucket size)
+        double w = 0, tot = 0;
+        for (const uint4& sl : seed_slots) if (sl.x | sl.y) { w += (double)sl.w * (double)sl.w; tot += (double)sl.w; }
+        const double mean = tot > 0 ? w / tot : 0;
+        c->seed_group = mean >= 16 ? 32 : mean >= 3 ? 8 : 1;
+    }
+    {
+        // memo of resolved keys: emptied with every new library
+        const int64_t want = c->memo_entries < 0 ? (c->cfg.miss >= 2 ? (1ll << 20) : 0) : c->memo_entries;
+        c->memo.release();
+        if (want > 0 && c->cfg.miss > 0) {
+            if ((rc = dev_alloc(c, c->memo, (size_t)want * 16))) return rc;
+            CU(c, cudaMemset(c->memo.p, 0, (size_t)want * 16));
+            c->T.memo = reinterpret_cast<uint4*>(c->memo.p); c->T.memo_mask = (uint32_t)want - 1;
+        }
+    }
     if ((rc = upload(c, seed_slots, &c->T.seed_slots)) || (rc = upload(c, seed_recs, &c->T.seed_recs))) return rc;
     c->T.seed_mask = (uint32_t)seed_slots.size() - 1; c->T.seed_parts = parts;
     if ((rc = upload(c, slots, &c->T.slots)) || (rc = upload(c, fk, &c->T.fast_keys)) || (rc = upload(c, fl, &c->T.fast_lens)) ||
@@ -1258,6 +1289,7 @@ F2Q_EXPORT int f2q_end_sample(f2q_ctx* c, uint64_t* counts, uint64_t* stats) {
     CU(c, cudaMemcpy(&hs, c->dS, sizeof(hs), cudaMemcpyDeviceToHost));
     err |= hs.error;
     c->spec_counts[0] = hs.spec_commits; c->spec_counts[1] = hs.spec_fallbacks;
+    c->memo_counts[0] = hs.memo_lookups; c->memo_counts[1] = hs.memo_hits;
     if (c->debug_waits)
         fprintf(stderr, "f2q debug: wait Mcycles  empty(loader) %llu  full(lookback) %llu agg(lookback) %llu  in-lookback %llu | full(consumers) %llu  p0(consumers) %llu | respins %llu | consumer warp Mcycles %llu\n",
                 hs.dbg[0] >> 20, hs.dbg[7] >> 20, hs.dbg[1] >> 20, hs.dbg[4] >> 20, hs.dbg[2] >> 20, hs.dbg[3] >> 20, hs.dbg[5], hs.dbg[6] >> 20);
@@ -1407,6 +1439,12 @@ F2Q_EXPORT uint64_t f2q_launch_count(const f2q_ctx* c) { return c ? c->launches 
 F2Q_EXPORT int f2q_spec_counts(const f2q_ctx* c, uint64_t* committed, uint64_t* fell_back) {
     if (!c || !committed || !fell_back) return F2Q_EINVAL;
     *committed = c->spec_counts[0]; *fell_back = c->spec_counts[1];
+    return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_memo_counts(const f2q_ctx* c, uint64_t* lookups, uint64_t* hits) {
+    if (!c || !lookups || !hits) return F2Q_EINVAL;
+    *lookups = c->memo_counts[0]; *hits = c->memo_counts[1];
     return F2Q_OK;
 }
 

@@ -89,6 +89,11 @@ struct LibTables {
     uint32_t fxs_mask;
     const uint4* fxs_recs;     // {lo.x, lo.y, hi, feature index} grouped by seed slot
     uint32_t fxs_parts;        // miss + 1
+    // memo of resolved non-exact keys (the device analogue of passed_reads / failed_reads, fast2q.py:724-731, 741, 748):
+    // direct-mapped, lossy, 16-byte entries {key lo, key hi, shape, result + 1}; lives as long as the library (across chunks
+    // AND samples of the context).  A key's result is a function of key, library and m, so a hit never changes a count
+    uint4* memo;
+    uint32_t memo_mask;        // entries - 1; memo == nullptr: off
 };
 
 // entry of the deferred non-exact key queue (filled by the tile kernel, drained by the resolver kernel)
@@ -128,6 +133,7 @@ struct DevState {
     uint32_t spec_ok;              // k_spec_verify: every speculated phase was right, the scratch results are committed
     uint32_t spec_off;             // sticky per sample: a speculation failed, later chunks go straight to the exact kernel
     uint32_t spec_commits, spec_fallbacks;   // chunks of this sample whose speculation held / that the exact kernel parsed
+    unsigned long long memo_lookups, memo_hits;
     unsigned long long dbg[8];     // diagnostics (F2Q_DEBUG=1): failed mbarrier tries per wait site, look-back rounds / spins
 };
 
@@ -172,6 +178,31 @@ __host__ __device__ __forceinline__ bool base_code(uint32_t c, uint32_t& code) {
 }
 
 #ifdef __CUDACC__
+// 16-byte single-copy-atomic accesses (PTX .b128 with memory-model semantics; SASS LDG/STG.E.128.STRONG.GPU): a memo entry is
+// read and written as a whole, whoever races
+__device__ __forceinline__ void st_b128(uint4* p, uint4 v) {
+    asm volatile("{\n\t.reg .b128 q;\n\tmov.b128 q, {%1, %2};\n\tst.relaxed.gpu.global.b128 [%0], q;\n\t}"
+                 :: "l"(p), "l"(((uint64_t)v.y << 32) | v.x), "l"(((uint64_t)v.w << 32) | v.z) : "memory");
+}
+__device__ __forceinline__ uint4 ld_b128(const uint4* p) {
+    uint64_t lo, hi;
+    asm volatile("{\n\t.reg .b128 q;\n\tld.relaxed.gpu.global.b128 q, [%2];\n\tmov.b128 {%0, %1}, q;\n\t}" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+    return make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+}
+__device__ __forceinline__ uint32_t memo_slot(const LibTables& T, uint32_t x, uint32_t y, uint32_t z) {
+    uint64_t h = ((((uint64_t)y << 32) | x) ^ ((uint64_t)z * 0x9E3779B97F4A7C15ull)) * 0xD6E8FEB86659FD93ull;
+    h ^= h >> 32;
+    return (uint32_t)h & T.memo_mask;
+}
+// stored result + 1 of the key (x, y, z), or 0 when the memo does not hold it
+__device__ __forceinline__ uint32_t memo_lookup(const LibTables& T, uint32_t x, uint32_t y, uint32_t z) {
+    const uint4 e = ld_b128(T.memo + memo_slot(T, x, y, z));
+    return (e.x == x && e.y == y && e.z == z) ? e.w : 0u;
+}
+__device__ __forceinline__ void memo_store(const LibTables& T, uint32_t x, uint32_t y, uint32_t z, uint32_t result_plus_1) {
+    st_b128(T.memo + memo_slot(T, x, y, z), make_uint4(x, y, z, result_plus_1));
+}
+
 // swizzled address of the byte at tile offset o (see the tile geometry above)
 __device__ __forceinline__ uint32_t swz(uint32_t o) { return o ^ ((o >> 3) & 0x70u); }
 

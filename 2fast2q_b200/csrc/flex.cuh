@@ -119,9 +119,10 @@ __device__ __forceinline__ void fx_block_fill(const FlexCtx& F, const FlexWarp& 
 }
 
 // one read of a CONVERGED warp (every lane calls it; `valid` lanes hold a read).  tile = the stage in shared memory,
-// [s0, e0) / [s3, e3) the sequence / quality line before rstrip, gseq / gqual their global addresses.
+// [s0, e0) / [s3, e3) the sequence / quality line before rstrip, gseq / gqual their global addresses.  FC: the kernel's own
+// parameter copy of the configuration (constant bank: the search-sequence loops run on uniform registers).
 template <int PW, int K>
-__device__ __forceinline__ void flex_read_warp(const FlexCtx& F, const GenericCfg& G, bool valid, const uint8_t* tile, uint32_t s0, uint32_t e0,
+__device__ __forceinline__ void flex_read_warp(const FlexCtx& F, const FlexCfg& FC, bool valid, const uint8_t* tile, uint32_t s0, uint32_t e0,
                                                uint32_t s3, uint32_t e3, const uint8_t* gseq, const uint8_t* gqual, const LibTables& T,
                                                const Outputs& O, Fast1Counts& n, FlexWarp& W, uint32_t lane) {
     if (!valid) { s0 = e0 = s3 = e3 = 0; }
@@ -132,13 +133,12 @@ __device__ __forceinline__ void flex_read_warp(const FlexCtx& F, const GenericCf
     const uint32_t r = e0 - s0, q = e3 - s3;
     bool generic = valid && (r > 32u * PW || q > 32u * PW);           // longer than the planes: byte-wise code
     const bool live = valid && !generic;
-    uint32_t sw[8 * PW], qw[8 * PW];
-    flex_load<8 * PW>(tile, live ? s0 : 0u, sw);
-    flex_load<8 * PW>(tile, live ? s3 : 0u, qw);
     FlexPiece pc[FLEX_ITER];
     pc[0].codes = 0; pc[0].notok = 0; pc[0].len = 0; pc[0].off = 0;
     pc[1] = pc[0];
-    int np = flex_pieces<PW, K>(G.flex, sw, live ? r : 0u, qw, live ? q : 0u, pc);
+    // (the planes are built only for the 8-byte groups the longest line of the warp reaches)
+    const uint32_t maxlen = __reduce_max_sync(0xffffffffu, live ? max(r, q) : 0u);
+    int np = flex_pieces<PW, K>(FC, tile, live ? s0 : 0u, live ? r : 0u, tile, live ? s3 : 0u, live ? q : 0u, maxlen, pc);
     if (!live) np = -1;
     n.qfail += (live && np == -1) ? 1u : 0u;
     if (live && np <= -2) {
@@ -365,7 +365,7 @@ __device__ __forceinline__ uint32_t fx_resolve_group(const LibTables& T, int m, 
 
 template <int G>
 __global__ void __launch_bounds__(256) k_resolve_flex(LibTables T, int m, const DevState* St, const FlexQ* __restrict__ q, uint32_t q_cap,
-                                                      unsigned long long* counts, unsigned long long* stats) {
+                                                      unsigned long long* counts, unsigned long long* stats, unsigned long long* memo_stats) {
     const uint32_t gl = threadIdx.x % G, grp = threadIdx.x / G, groups = blockDim.x / G;
     uint32_t imperfect = 0, nonal = 0;
     const uint32_t n = St->spec_ok ? fx_queue_fill(St, q_cap) : 0u;     // (a chunk the exact kernel re-parsed left nothing valid here)
@@ -377,8 +377,17 @@ __global__ void __launch_bounds__(256) k_resolve_flex(LibTables T, int m, const 
         e.lo = 0; e.bad = 0; e.hi = 0; e.sig = 0; e.pad0 = 0; e.pad1 = 0;
         if (i < n) e = q[i];
         const bool act = e.sig != 0;                                    // (sig 0: the unused rest of a warp's block)
-        if (!act) e.bad = ~0ull;                                        // too many bad symbols: no work
-        const uint32_t r = fx_resolve_group<G>(T, m, e, gl);
+        // memo first (keys without bad symbols): entry = {lo.x, lo.y, hi | sig << 16, result + 2}
+        const uint32_t mz = e.hi | (e.sig << 16);
+        const bool memo_ok = act && T.memo && e.bad == 0;
+        uint32_t cached = 0;
+        if (memo_ok && gl == 0) cached = memo_lookup(T, (uint32_t)e.lo, (uint32_t)(e.lo >> 32), mz);
+        if (G > 1) cached = __shfl_sync(0xffffffffu, cached, (threadIdx.x & 31u) - gl);
+        if (memo_ok && gl == 0) { atomicAdd(memo_stats, 1ull); if (cached) atomicAdd(memo_stats + 1, 1ull); }
+        if (!act || cached) e.bad = ~0ull;                              // too many bad symbols: no work
+        uint32_t r = fx_resolve_group<G>(T, m, e, gl);
+        if (cached) r = cached - 2u;
+        else if (memo_ok && gl == 0) memo_store(T, (uint32_t)e.lo, (uint32_t)(e.lo >> 32), mz, r + 2u);
         if (act && gl == 0) { if (r != RES_NONE) { atomicAdd(counts + r, 1ull); imperfect++; } else nonal++; }
     }
     imperfect = __reduce_add_sync(0xffffffffu, imperfect);

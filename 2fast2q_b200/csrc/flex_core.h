@@ -48,6 +48,17 @@ inline uint32_t f2q_fshr_host(uint32_t lo, uint32_t hi, uint32_t s) {
 #define F2Q_FFS(x) __builtin_ffs((int)(x))
 #endif
 
+// a + b issued as a multiply-add on the device (a * one + b, `one` an opaque register holding 1): the byte-parallel loops
+// are bound by the integer ALU pipe (logic, shifts, adds: one warp instruction per 2 cycles); multiply-adds run on the
+// FMA pipe next to it
+#if defined(__CUDA_ARCH__)
+F2Q_HD uint32_t flex_one() { uint32_t r; asm volatile("mov.u32 %0, 1;" : "=r"(r)); return r; }
+F2Q_HD uint32_t flex_add(uint32_t a, uint32_t b, uint32_t one) { uint32_t r; asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(one), "r"(b)); return r; }
+#else
+inline uint32_t flex_one() { return 1u; }
+inline uint32_t flex_add(uint32_t a, uint32_t b, uint32_t one) { return a * one + b; }
+#endif
+
 // search sequence, prepared by the host: pos[c] = bit i set iff symbol i has base code c
 struct FlexDelim {
     uint32_t pos[4];
@@ -55,13 +66,14 @@ struct FlexDelim {
     int32_t k;               // allowed mismatches, 0 .. FLEX_MAX_K
 };
 
-// NW = 8 * PW words starting at byte offset o of `base` (4-byte aligned base address): NW + 1 aligned loads, NW funnel shifts
+// NW = 8 * PW words starting at byte offset o of `base` (4-byte aligned base address): aligned loads + funnel shifts.
+// Only the first 2 * ng words (ng groups of 8 bytes, uniform over the warp) are loaded; the others read as 0
 template <int NW>
-F2Q_HD void flex_load(const uint8_t* base, uint32_t o, uint32_t (&w)[NW]) {
+F2Q_HD void flex_load(const uint8_t* base, uint32_t o, uint32_t ng, uint32_t (&w)[NW]) {
     const uint32_t a = o & ~3u, sh = (o & 3u) * 8u;
     uint32_t r[NW + 1];
 #pragma unroll
-    for (int i = 0; i <= NW; i++) r[i] = *reinterpret_cast<const uint32_t*>(base + a + 4 * i);
+    for (int i = 0; i <= NW; i++) r[i] = ((uint32_t)i <= 2u * ng) ? *reinterpret_cast<const uint32_t*>(base + a + 4 * i) : 0u;
 #pragma unroll
     for (int i = 0; i < NW; i++) w[i] = F2Q_FSHR(r[i], r[i + 1], sh);
 }
@@ -96,11 +108,13 @@ F2Q_HD void flex_insert(uint32_t& word, uint32_t r, int scale_log2) {
 // sequence line -> code planes b0, b1 and the raw-validity plane ok (bits at positions >= len are 0 in ok; b0/b1 are
 // don't-care there).  w = the line's bytes as NW = 8 * PW words
 template <int PW>
-F2Q_HD void flex_seq_planes(const uint32_t (&w)[8 * PW], uint32_t len, uint32_t (&b0)[PW], uint32_t (&b1)[PW], uint32_t (&ok)[PW]) {
+F2Q_HD void flex_seq_planes(const uint32_t (&w)[8 * PW], uint32_t len, uint32_t ng, uint32_t (&b0)[PW], uint32_t (&b1)[PW], uint32_t (&ok)[PW]) {
 #pragma unroll
     for (int j = 0; j < PW; j++) { b0[j] = 0; b1[j] = 0; ok[j] = 0; }
+    const uint32_t one = flex_one();
 #pragma unroll
     for (int g = 0; g < 4 * PW; g++) {
+        if ((uint32_t)g >= ng) break;                                   // (uniform: no line of the warp reaches this group)
         const uint32_t w0 = w[2 * g], w1 = w[2 * g + 1];
         const uint32_t r0 = F2Q_DP4A(w0 & 0x02020202u, 0x08040201u, F2Q_DP4A(w1 & 0x02020202u, 0x80402010u, 0u));     // 2 * flags
         const uint32_t r1 = F2Q_DP4A(w0 & 0x04040404u, 0x08040201u, F2Q_DP4A(w1 & 0x04040404u, 0x80402010u, 0u));     // 4 * flags
@@ -112,7 +126,7 @@ F2Q_HD void flex_seq_planes(const uint32_t (&w)[8 * PW], uint32_t len, uint32_t 
             const uint32_t x = h ? w1 : w0;
             const uint32_t t = (x >> 2) & ~(x >> 1) & 0x01010101u;
             const uint32_t d = x ^ (0x41414141u | (x & 0x06060606u)) ^ (t * 0x11u);
-            nz[h] = (((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;                                            // 0x80 per non-zero byte
+            nz[h] = (flex_add(d & 0x7F7F7F7Fu, 0x7F7F7F7Fu, one) | d) & 0x80808080u;                                            // 0x80 per non-zero byte
         }
         const uint32_t rn = F2Q_DP4A(nz[0], 0x08040201u, F2Q_DP4A(nz[1], 0x80402010u, 0u));                           // 128 * flags
         switch (g & 3) {
@@ -131,16 +145,18 @@ F2Q_HD void flex_seq_planes(const uint32_t (&w)[8 * PW], uint32_t len, uint32_t 
 // quality line -> lq: bit p set iff 33 <= byte p <= fmax and p < len.  add_ge / add_gt as in Fast1Ctx (tile.cuh):
 // (0x80 - 33) and (0x80 - (fmax + 1)) replicated; fmax == 0 (empty fail set) must be handled by the caller (lq = 0)
 template <int PW>
-F2Q_HD void flex_lowq_plane(const uint32_t (&w)[8 * PW], uint32_t len, uint32_t add_ge, uint32_t add_gt, uint32_t (&lq)[PW]) {
+F2Q_HD void flex_lowq_plane(const uint32_t (&w)[8 * PW], uint32_t len, uint32_t ng, uint32_t add_ge, uint32_t add_gt, uint32_t (&lq)[PW]) {
 #pragma unroll
     for (int j = 0; j < PW; j++) lq[j] = 0;
+    const uint32_t one = flex_one();
 #pragma unroll
     for (int g = 0; g < 4 * PW; g++) {
+        if ((uint32_t)g >= ng) break;
         uint32_t f[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const uint32_t x = w[2 * g + h], lo7 = x & 0x7F7F7F7Fu;
-            f[h] = (lo7 + add_ge) & ~(lo7 + add_gt) & ~x & 0x80808080u;                                              // 0x80 per failing byte
+            f[h] = flex_add(lo7, add_ge, one) & ~flex_add(lo7, add_gt, one) & ~x & 0x80808080u;                                              // 0x80 per failing byte
         }
         const uint32_t r = F2Q_DP4A(f[0], 0x08040201u, F2Q_DP4A(f[1], 0x80402010u, 0u));
         switch (g & 3) {
@@ -181,37 +197,45 @@ F2Q_HD void flex_shr_small(const uint32_t (&p)[PW], uint32_t i, uint32_t (&out)[
 
 // positions where the search sequence D matches with <= D.k mismatches: out bit p set iff Hamming(D, R[p : p + len)) <= k,
 // counting every position (also those that overlap the end of the read: the caller restricts p to <= r - len).
-// M[c] = positions whose byte is base c (0 elsewhere).  K = compile-time bound on D.k
-template <int PW, int K>
-F2Q_HD void flex_search(const uint32_t (&M)[4][PW], const FlexDelim& D, uint32_t (&out)[PW]) {
-    uint32_t th[K + 1][PW];                                            // th[e] = at most e mismatches so far
+// M[c] = positions whose byte is base c (0 elsewhere).  KK = the exact k of this instance, RW = result words wanted (the
+// higher ones read as 0: no position up there can be returned)
+template <int PW, int KK, int RW>
+F2Q_HD void flex_search_k(const uint32_t (&M)[4][PW], const FlexDelim& D, uint32_t (&out)[PW]) {
+    uint32_t th[KK + 1][RW];                                           // th[e] = at most e mismatches so far
 #pragma unroll
-    for (int e = 0; e <= K; e++)
+    for (int e = 0; e <= KK; e++)
 #pragma unroll
-        for (int j = 0; j < PW; j++) th[e][j] = 0xFFFFFFFFu;
+        for (int j = 0; j < RW; j++) th[e][j] = 0xFFFFFFFFu;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         uint32_t todo = D.pos[c];
-        while (todo) {                                                 // (uniform: the search sequence is the same for every thread)
+        while (todo) {                                                 // (uniform: the search sequence is a kernel parameter)
             const uint32_t i = (uint32_t)F2Q_FFS(todo) - 1u;
             todo &= todo - 1u;
-            uint32_t m[PW];
-            flex_shr_small<PW>(M[c], i, m);
+            uint32_t m[RW];
 #pragma unroll
-            for (int e = K; e >= 1; e--)
+            for (int j = 0; j < RW; j++) m[j] = F2Q_FSHR(M[c][j], j + 1 < PW ? M[c][j + 1] : 0u, i);
 #pragma unroll
-                for (int j = 0; j < PW; j++) th[e][j] = (th[e][j] & m[j]) | th[e - 1][j];
+            for (int e = KK; e >= 1; e--)
 #pragma unroll
-            for (int j = 0; j < PW; j++) th[0][j] &= m[j];
+                for (int j = 0; j < RW; j++) th[e][j] = (th[e][j] & m[j]) | th[e - 1][j];
+#pragma unroll
+            for (int j = 0; j < RW; j++) th[0][j] &= m[j];
         }
     }
 #pragma unroll
-    for (int j = 0; j < PW; j++) {
-        uint32_t v = th[0][j];
-#pragma unroll
-        for (int e = 1; e <= K; e++) if (D.k >= e) v = th[e][j];
-        out[j] = v;
-    }
+    for (int j = 0; j < PW; j++) out[j] = j < RW ? th[KK][j] : 0u;
+}
+
+// K = compile-time bound on D.k; rw = result words the caller needs (uniform)
+template <int PW, int K>
+F2Q_HD void flex_search(const uint32_t (&M)[4][PW], const FlexDelim& D, uint32_t rw, uint32_t (&out)[PW]) {
+    constexpr int LOW = PW > 1 ? PW - 1 : 1;
+    const bool low = rw <= (uint32_t)LOW;
+    if (D.k <= 0) { if (low) flex_search_k<PW, 0, LOW>(M, D, out); else flex_search_k<PW, 0, PW>(M, D, out); }
+    else if (K >= 1 && D.k == 1) { if (low) flex_search_k<PW, (K >= 1 ? 1 : 0), LOW>(M, D, out); else flex_search_k<PW, (K >= 1 ? 1 : 0), PW>(M, D, out); }
+    else if (K >= 2 && D.k == 2) { if (low) flex_search_k<PW, (K >= 2 ? 2 : 0), LOW>(M, D, out); else flex_search_k<PW, (K >= 2 ? 2 : 0), PW>(M, D, out); }
+    else { if (low) flex_search_k<PW, K, LOW>(M, D, out); else flex_search_k<PW, K, PW>(M, D, out); }
 }
 
 // lowest set bit of plane p inside [from, to) (to <= 32 * PW), or -1
@@ -306,28 +330,29 @@ F2Q_HD void flex_lowq(const uint32_t* qw_dummy, uint32_t fmax, uint32_t& add_ge,
     add_gt = (0x80u - (fmax + 1u)) * 0x01010101u;
 }
 
-// sw / qw: the sequence / quality line as words (flex_load), r / q their lengths after rstrip (both <= 32 * PW).
+// Search-sequence modes.  sw / qw: the sequence / quality line as words (flex_load), r / q their lengths after rstrip (both
+// <= 32 * PW), maxlen = the longest line of the warp (uniform; planes are built for its 8-byte groups only).
 // Returns the number of pieces (>= 0; the key is their ':'-join), -1 when every iteration was flagged (quality_failed,
 // fast2q.py:389-390), -(pieces + 1) <= -2 when a piece is longer than FLEX_MAX_PIECE (pc[] then holds every piece's length
 // and offset, but codes only for the short ones).
 template <int PW, int K>
-F2Q_HD int flex_pieces(const FlexCfg& C, const uint32_t (&sw)[8 * PW], uint32_t r, const uint32_t (&qw)[8 * PW], uint32_t q,
-                       FlexPiece (&pc)[FLEX_ITER]) {
+F2Q_HD int flex_pieces_delim(const FlexCfg& C, const uint32_t (&sw)[8 * PW], uint32_t r, const uint32_t (&qw)[8 * PW], uint32_t q, uint32_t maxlen,
+                             FlexPiece (&pc)[FLEX_ITER]) {
+    const uint32_t ng = (maxlen + 7u) >> 3;
     uint32_t b0[PW], b1[PW], ok[PW], lq[PW], lqu[PW], lqd[PW];
-    flex_seq_planes<PW>(sw, r, b0, b1, ok);
+    flex_seq_planes<PW>(sw, r, ng, b0, b1, ok);
     uint32_t age, agt;
     flex_lowq(nullptr, C.fmax_ph, age, agt);
-    flex_lowq_plane<PW>(qw, q, age, agt, lq);
+    flex_lowq_plane<PW>(qw, q, ng, age, agt, lq);
     if (C.fmax_ph == 0) {
 #pragma unroll
         for (int j = 0; j < PW; j++) lq[j] = 0;
     }
-    const bool delim = C.has_up || C.has_down;
 #pragma unroll
     for (int j = 0; j < PW; j++) { lqu[j] = lq[j]; lqd[j] = lq[j]; }
     if (C.has_up && C.fmax_up != C.fmax_ph) {                          // (uniform; the three thresholds are normally equal)
         flex_lowq(nullptr, C.fmax_up, age, agt);
-        flex_lowq_plane<PW>(qw, q, age, agt, lqu);
+        flex_lowq_plane<PW>(qw, q, ng, age, agt, lqu);
         if (C.fmax_up == 0) {
 #pragma unroll
             for (int j = 0; j < PW; j++) lqu[j] = 0;
@@ -335,7 +360,7 @@ F2Q_HD int flex_pieces(const FlexCfg& C, const uint32_t (&sw)[8 * PW], uint32_t 
     }
     if (C.has_down && C.fmax_down != C.fmax_ph) {
         flex_lowq(nullptr, C.fmax_down, age, agt);
-        flex_lowq_plane<PW>(qw, q, age, agt, lqd);
+        flex_lowq_plane<PW>(qw, q, ng, age, agt, lqd);
         if (C.fmax_down == 0) {
 #pragma unroll
             for (int j = 0; j < PW; j++) lqd[j] = 0;
@@ -354,28 +379,26 @@ F2Q_HD int flex_pieces(const FlexCfg& C, const uint32_t (&sw)[8 * PW], uint32_t 
         if (i >= C.n_iter) break;
         int start, end;
         bool found = true;
-        if (!delim) { start = C.starts[i]; end = start + C.length; }
-        else {
-            int u = 0, d = 0;
-            const int ul = C.up[i].len, dl = C.down[i].len;
-            if (C.has_up) {
-                uint32_t hit[PW];
-                flex_search<PW, K>(M, C.up[i], hit);
-                u = flex_first<PW>(hit, 0, (int)r - ul + 1);
-                found = u >= 0;
-            }
-            if (C.has_down) {
-                uint32_t hit[PW];
-                flex_search<PW, K>(M, C.down[i], hit);
-                d = flex_first<PW>(hit, C.has_up ? u + ul : 0, (int)r - dl + 1);
-                found = found && d >= 0;
-            }
-            if (found && C.has_up && flex_any<PW>(lqu, u, u + ul)) found = false;
-            if (found && C.has_down && flex_any<PW>(lqd, d, d + dl)) found = false;
-            if (C.has_up && C.has_down) { start = u + ul; end = d; }
-            else if (C.has_up) { start = u + ul; end = start + C.length; }
-            else { start = d - C.length; end = d; }
+        int u = 0, d = 0;
+        const int ul = C.up[i].len, dl = C.down[i].len;
+        if (C.has_up) {
+            // a match starts at p <= longest line - ul: result words beyond that are never looked at
+            uint32_t hit[PW];
+            flex_search<PW, K>(M, C.up[i], maxlen >= (uint32_t)ul ? ((maxlen - (uint32_t)ul) >> 5) + 1u : 1u, hit);
+            u = flex_first<PW>(hit, 0, (int)r - ul + 1);
+            found = u >= 0;
         }
+        if (C.has_down) {
+            uint32_t hit[PW];
+            flex_search<PW, K>(M, C.down[i], maxlen >= (uint32_t)dl ? ((maxlen - (uint32_t)dl) >> 5) + 1u : 1u, hit);
+            d = flex_first<PW>(hit, C.has_up ? u + ul : 0, (int)r - dl + 1);
+            found = found && d >= 0;
+        }
+        if (found && C.has_up && flex_any<PW>(lqu, u, u + ul)) found = false;
+        if (found && C.has_down && flex_any<PW>(lqd, d, d + dl)) found = false;
+        if (C.has_up && C.has_down) { start = u + ul; end = d; }
+        else if (C.has_up) { start = u + ul; end = start + C.length; }
+        else { start = d - C.length; end = d; }
         if (!found || end < start) continue;
         int lo, hi, qlo, qhi;
         flex_py_slice((int)r, start, end, lo, hi);
@@ -393,6 +416,62 @@ F2Q_HD int flex_pieces(const FlexCfg& C, const uint32_t (&sw)[8 * PW], uint32_t 
     }
     if (slow) return -(np + 1);
     return any ? np : -1;
+}
+
+// Fixed windows (--st a,b --l n, fast2q.py:349-360): no planes of the whole line, each window is loaded by itself.
+// seq / qual: addresses such that the lines start at seq[so], qual[qo] (4-byte aligned base, see flex_load); a window is
+// at most 32 symbols (flex_prepare checks C.length).  Same return convention as flex_pieces_delim.
+template <int DUMMY>
+F2Q_HD int flex_pieces_fixed(const FlexCfg& C, const uint8_t* seq, uint32_t so, uint32_t r, const uint8_t* qual, uint32_t qo, uint32_t q,
+                             FlexPiece (&pc)[FLEX_ITER]) {
+    const uint32_t ngw = ((uint32_t)C.length + 7u) >> 3;               // groups of a window (uniform)
+    uint32_t age, agt;
+    flex_lowq(nullptr, C.fmax_ph, age, agt);
+    int np = 0;
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < FLEX_ITER; i++) {
+        if (i >= C.n_iter) break;
+        const int start = C.starts[i], end = start + C.length;
+        int lo, hi, qlo, qhi;
+        flex_py_slice((int)r, start, end, lo, hi);
+        flex_py_slice((int)q, start, end, qlo, qhi);
+        uint32_t w[8], lq[1] = {0u};
+        if (C.fmax_ph != 0) {
+            flex_load<8>(qual, qo + (uint32_t)qlo, ngw, w);
+            flex_lowq_plane<1>(w, (uint32_t)(qhi - qlo), ngw, age, agt, lq);
+        }
+        flex_load<8>(seq, so + (uint32_t)lo, ngw, w);
+        uint32_t b0[1], b1[1], ok[1];
+        const uint32_t n = (uint32_t)(hi - lo);
+        flex_seq_planes<1>(w, n, ngw, b0, b1, ok);
+        if (lq[0]) continue;                                           // the window's quality slice holds a failing byte
+        any = true;
+        const uint32_t keep = flex_ones_below((int32_t)n);
+        FlexPiece p;
+        p.notok = ~ok[0] & keep;
+        const uint32_t v0 = b0[0] & keep & ~p.notok, v1 = b1[0] & keep & ~p.notok;
+        const uint32_t clo = flex_spread16(v0 & 0xFFFFu) | (flex_spread16(v1 & 0xFFFFu) << 1);
+        const uint32_t chi = flex_spread16(v0 >> 16) | (flex_spread16(v1 >> 16) << 1);
+        p.codes = ((uint64_t)chi << 32) | clo;
+        p.len = n; p.off = (uint32_t)lo;
+        pc[np] = p;
+        np++;
+    }
+    return any ? np : -1;
+}
+
+// one read: fixed windows or search sequences.  seq / qual: 4-byte aligned base addresses, the lines start at seq[so] and
+// qual[qo]; maxlen >= max(r, q) is uniform over the warp
+template <int PW, int K>
+F2Q_HD int flex_pieces(const FlexCfg& C, const uint8_t* seq, uint32_t so, uint32_t r, const uint8_t* qual, uint32_t qo, uint32_t q, uint32_t maxlen,
+                       FlexPiece (&pc)[FLEX_ITER]) {
+    if (!(C.has_up || C.has_down)) return flex_pieces_fixed<0>(C, seq, so, r, qual, qo, q, pc);
+    const uint32_t ng = (maxlen + 7u) >> 3;
+    uint32_t sw[8 * PW], qw[8 * PW];
+    flex_load<8 * PW>(seq, so, ng, sw);
+    flex_load<8 * PW>(qual, qo, ng, qw);
+    return flex_pieces_delim<PW, K>(C, sw, r, qw, q, maxlen, pc);
 }
 
 // host side: can this configuration run on the bit-parallel path?  (search sequences pure ACGT, 1..32 symbols, <= FLEX_MAX_K

@@ -253,6 +253,99 @@ __global__ void __launch_bounds__(256) k_resolve_seed(LibTables T, int m, const 
         if (nonal) atomicAdd(stats + F2Q_STAT_NON_ALIGNED, (unsigned long long)nonal);
     }
 }
+
+// ---- the same pigeonhole resolution, G lanes per key: they share the bucket probes, split the candidates and merge
+// (min distance, how many attain it, which) with shuffles.  With 100 000 guides and m = 2 a key meets ~36 candidates: one
+// thread per key walks them one dependent 16-byte load after the other, eight lanes take four or five each.  Resolved keys
+// without bad symbols go through the memo (LibTables::memo) first.
+template <int G>
+__device__ __forceinline__ uint32_t resolve_seed_group(const LibTables& T, int m, uint64_t key, uint32_t bad, uint32_t len, bool act,
+                                                       const uint8_t* bounds, uint32_t gl, unsigned long long* memo_stats) {
+    const uint32_t klo = (uint32_t)key, khi = (uint32_t)(key >> 32);
+    const bool memo_ok = act && T.memo && bad == 0;
+    uint32_t cached = 0;
+    if (memo_ok && gl == 0) cached = memo_lookup(T, klo, khi, len);
+    if (G > 1) cached = __shfl_sync(0xffffffffu, cached, (threadIdx.x & 31u) - gl);
+    if (memo_ok && gl == 0 && memo_stats) { atomicAdd(memo_stats, 1ull); if (cached) atomicAdd(memo_stats + 1, 1ull); }
+    const int nbad = __popc(bad);
+    Best b{m + 1, 0, 0};
+    if (act && !cached && m > 0 && nbad <= m) {
+        const uint32_t parts = T.seed_parts;
+        const uint64_t lenmask = even_range(0, len), badeven = spread_even(bad) & lenmask;
+        const uint8_t* bl = bounds + len * SEED_BOUND_STRIDE;
+        for (uint32_t s = 0; s < parts; s++) {
+            const uint32_t b0 = bl[s], b1 = bl[s + 1];
+            const uint64_t seg = even_range(b0, b1);
+            if (badeven & seg) continue;
+            const uint64_t v = (key >> (2 * b0)) & ((seg | (seg << 1)) >> (2 * b0));
+            const uint64_t tag = seed_tag(len, s, v);
+            uint32_t h = seed_hash(tag) & T.seed_mask, start = 0, count = 0;
+            for (;;) {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(T.seed_slots) + h);
+                const uint64_t t = ((uint64_t)raw.y << 32) | raw.x;
+                if (t == 0) break;
+                if (t == tag) { start = raw.z; count = raw.w; break; }
+                h = (h + 1) & T.seed_mask;
+            }
+            for (uint32_t c = gl; c < count; c += (uint32_t)G) {
+                const uint4 it = __ldg(T.seed_recs + start + c);
+                const uint64_t x = key ^ (((uint64_t)it.y << 32) | it.x);
+                const uint64_t diff = (((x | (x >> 1)) & lenmask) | badeven);
+                bool dup = false;
+                for (uint32_t s2 = 0; s2 < s; s2++)
+                    if ((diff & even_range(bl[s2], bl[s2 + 1])) == 0) { dup = true; break; }
+                if (dup) continue;
+                b.add(__popcll(diff), it.z, m);
+            }
+        }
+    }
+    #pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) {
+        const int od = __shfl_xor_sync(0xffffffffu, b.d, o);
+        const uint32_t on = __shfl_xor_sync(0xffffffffu, b.n, o), oi = __shfl_xor_sync(0xffffffffu, b.idx, o);
+        if (od < b.d) { b.d = od; b.n = on; b.idx = oi; }
+        else if (od == b.d) b.n += on;
+    }
+    uint32_t r = (b.d <= m && b.n == 1) ? b.idx : RES_NONE;
+    if (cached) r = cached - 2u;                                        // stored: 1 = not aligned (RES_NONE = 1 - 2), idx + 2
+    else if (memo_ok && gl == 0) memo_store(T, klo, khi, len, r + 2u);
+    return r;
+}
+
+template <int G>
+__global__ void __launch_bounds__(256) k_resolve_seed_g(LibTables T, int m, const QEntry* __restrict__ queue, const uint32_t* __restrict__ seg_count,
+                                                        uint32_t seg_cap, uint32_t n_segs, unsigned long long* counts, unsigned long long* stats,
+                                                        unsigned long long* memo_stats) {
+    __shared__ uint8_t s_bounds[33 * SEED_BOUND_STRIDE];
+    for (uint32_t i = threadIdx.x; i < 33u * SEED_BOUND_STRIDE; i += blockDim.x) {
+        const uint32_t len = i / SEED_BOUND_STRIDE, sg = i % SEED_BOUND_STRIDE;
+        s_bounds[i] = (uint8_t)(min(sg, T.seed_parts) * len / T.seed_parts);
+    }
+    __syncthreads();
+    const uint32_t gl = threadIdx.x % G, grp = threadIdx.x / G, groups = blockDim.x / G;
+    uint32_t imperfect = 0, nonal = 0;
+    for (uint32_t seg = blockIdx.x; seg < n_segs; seg += gridDim.x) {
+        const uint32_t n = min(seg_count[seg], seg_cap);
+        const QEntry* __restrict__ q = queue + (size_t)seg * seg_cap;
+        const uint32_t per_round = gridDim.y * groups;                  // (uniform trip count: the shuffles need whole warps)
+        for (uint32_t base = 0; base < n; base += per_round) {
+            const uint32_t i = base + blockIdx.y * groups + grp;
+            const bool act = i < n;
+            QEntry e; e.key = 0; e.bad = 0; e.len = 0;
+            if (act) e = q[i];
+            const bool ok = act && e.len <= 32;
+            uint32_t r = resolve_seed_group<G>(T, m, e.key, e.bad, min(e.len, 32u), ok, s_bounds, gl, memo_stats);
+            if (act && !ok) r = resolve_seed_thread(T, m, e.key, e.bad, e.len);
+            if (act && gl == 0) { if (r != RES_NONE) { atomicAdd(counts + r, 1ull); imperfect++; } else nonal++; }
+        }
+    }
+    imperfect = __reduce_add_sync(0xffffffffu, imperfect);
+    nonal = __reduce_add_sync(0xffffffffu, nonal);
+    if ((threadIdx.x & 31) == 0) {
+        if (imperfect) atomicAdd(stats + F2Q_STAT_IMPERFECT, (unsigned long long)imperfect);
+        if (nonal) atomicAdd(stats + F2Q_STAT_NON_ALIGNED, (unsigned long long)nonal);
+    }
+}
 #endif  // __CUDACC__
 
 }  // namespace f2q

@@ -77,7 +77,8 @@ __device__ __forceinline__ uint64_t spec_n_ranges(uint64_t beg, uint64_t end, ui
 // @region spec_kernel
 template <int POLICY, int CH, int W>
 __global__ void __launch_bounds__(W * 32, 1)
-k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, Outputs O, const SlowArgs* __restrict__ X) {
+k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, Outputs O, const SlowArgs* __restrict__ X,
+       const __grid_constant__ FlexCfg FC) {
     using G_ = SpecGeom<CH>;
     constexpr int S = G_::S, OWN = G_::OWN, NS = SPEC_STAGES, CAP = SPEC_CAP, MW = G_::MW;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -242,7 +243,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                     }
                 } else if constexpr (FLEX) {
                     __syncwarp();
-                    flex_read_warp<policy_pw(POLICY), policy_k(POLICY)>(FX, G, valid, ptile, s0, e0, s3, e3, buf + pbase + s0, buf + pbase + s3, T, O, cn, FW, lane);
+                    flex_read_warp<policy_pw(POLICY), policy_k(POLICY)>(FX, FC, valid, ptile, s0, e0, s3, e3, buf + pbase + s0, buf + pbase + s3, T, O, cn, FW, lane);
                 } else {
                     __syncwarp();
                     if (j0 != jf) fast1_warp_commit(F, pend, T, O, cn, lane);          // (a second pass over the same tile: rare)

@@ -118,6 +118,14 @@ const char* f2q_last_error(const f2q_ctx* ctx);   /* ctx may be NULL: last creat
  *                     falls back to the exact look-back kernel when its line-phase guesses do not verify | 0: exact only
  *   "spec_warps"      12 | 16: warps per CTA of the streaming kernel (one CTA per SM)
  *   "spec_range_tiles" 0 auto | tiles (32 rows each) per speculated range
+ *   "flex"            1 (default): search sequences / several windows per read / Extract+Count run on the bit-parallel
+ *                     policies of the streaming kernel when the configuration allows | 0: byte-wise generic kernels
+ *   "flex_warps"      12 | 16: warps per CTA of the streaming kernel's bit-parallel policies
+ *   "resolve_group"   0 auto | 1 | 8 | 32: lanes that resolve one non-exact key together (seed-index resolvers)
+ *   "memo_entries"    -1 auto (2^20 when m >= 2) | 0 off | power of two: entries of the device memo of resolved non-exact
+ *                     keys; set before f2q_set_library
+ *   "generic_entries" capacity of the queue of reads handed to the byte-wise generic kernel (default: derived)
+ *   "ec_slots"        minimum capacity of the Extract+Count packed key table (default: grown on demand)
  */
 int f2q_set_option(f2q_ctx* ctx, const char* name, int64_t value);
 
@@ -236,6 +244,11 @@ uint64_t f2q_launch_count(const f2q_ctx* ctx);
 /* last finished sample: number of chunks whose speculative parse verified and was committed, and number of chunks the
  * exact look-back kernel had to parse instead (always 0 / every chunk with option "spec" = 0) */
 int f2q_spec_counts(const f2q_ctx* ctx, uint64_t* committed, uint64_t* fell_back);
+
+/* last finished sample (f2q_end_sample): lookups of non-exact keys in the device memo of resolved keys and how many of them
+ * hit.  The memo is the device analogue of the reference's passed_reads / failed_reads (fast2q.py:724-731, 741, 748): it
+ * lives with the library — across chunks and samples of the context — and never changes a count (option "memo_entries"). */
+int f2q_memo_counts(const f2q_ctx* ctx, uint64_t* lookups, uint64_t* hits);
 
 /* device time of the last finished sample per kernel class, measured with CUDA events on the context's stream
  * (needs option "time_kernels" = 1): [0] fused tile kernel over the chunk (the streaming kernel when "spec" is on),

@@ -23,16 +23,14 @@ void hc_synth(const f2q_synth_spec* sp, const uint8_t* guides, uint64_t first, u
 
 namespace {
 template <int PW, int K>
-int flex_key_t(const f2q::FlexCfg& C, const uint8_t* read, int r, const uint8_t* qual, int q, uint8_t* out, int* out_len) {
+int flex_key_t(const f2q::FlexCfg& C, const uint8_t* read, int r, const uint8_t* qual, int q, int extra, uint8_t* out, int* out_len) {
     // the lines sit at odd offsets of padded buffers, as they do inside a tile
     std::vector<uint8_t> sb(32 * PW + 64, '\n'), qb(32 * PW + 64, '\n');
     const uint32_t so = 5, qo = 11;
     memcpy(sb.data() + so, read, r); memcpy(qb.data() + qo, qual, q);
-    uint32_t sw[8 * PW], qw[8 * PW];
-    f2q::flex_load<8 * PW>(sb.data(), so, sw);
-    f2q::flex_load<8 * PW>(qb.data(), qo, qw);
     f2q::FlexPiece pc[f2q::FLEX_ITER];
-    const int np = f2q::flex_pieces<PW, K>(C, sw, (uint32_t)r, qw, (uint32_t)q, pc);
+    const uint32_t maxlen = (uint32_t)((r > q ? r : q) + extra);       // (a warp's longest line may be longer than this one)
+    const int np = f2q::flex_pieces<PW, K>(C, sb.data(), so, (uint32_t)r, qb.data(), qo, (uint32_t)q, maxlen > 32u * PW ? 32u * PW : maxlen, pc);
     if (np < 0) return np < -2 ? -2 : np;
     int n = 0;
     for (int p = 0; p < np; p++) {
@@ -61,14 +59,13 @@ int hc_flex_eligible(const f2q_config* cfg) {
 // key of one read through flex_pieces: returns np >= 0 (key in out), -1 all iterations flagged, -2 generic path needed,
 // -3 not eligible / read too long for pw planes
 __attribute__((visibility("default")))
-int hc_flex_key(const f2q_config* cfg, int pw, const uint8_t* read, int r, const uint8_t* qual, int q, uint8_t* out, int* out_len) {
+int hc_flex_key(const f2q_config* cfg, int pw, const uint8_t* read, int r, const uint8_t* qual, int q, int extra, uint8_t* out, int* out_len) {
     f2q::FlexCfg C;
     if (!f2q::flex_prepare(*cfg, C)) return -3;
     if (r > 32 * pw || q > 32 * pw) return -3;
-    const int K = C.max_k;
-#define F2Q_HC_CASE(PWV, KV) if (pw == PWV && K == KV) return flex_key_t<PWV, KV>(C, read, r, qual, q, out, out_len);
-    F2Q_HC_CASE(3, 0) F2Q_HC_CASE(3, 1) F2Q_HC_CASE(3, 2) F2Q_HC_CASE(3, 3)
-    F2Q_HC_CASE(5, 0) F2Q_HC_CASE(5, 1) F2Q_HC_CASE(5, 2) F2Q_HC_CASE(5, 3)
+    const int K = C.max_k <= 1 ? 1 : 3;                              // the two instances the kernels have
+#define F2Q_HC_CASE(PWV, KV) if (pw == PWV && K == KV) return flex_key_t<PWV, KV>(C, read, r, qual, q, extra, out, out_len);
+    F2Q_HC_CASE(3, 1) F2Q_HC_CASE(3, 3) F2Q_HC_CASE(5, 1) F2Q_HC_CASE(5, 3)
 #undef F2Q_HC_CASE
     return -3;
 }

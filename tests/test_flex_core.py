@@ -14,12 +14,13 @@ synth = importlib.import_module("2fast2q_b200.synth")
 lib = importlib.import_module("2fast2q_b200._lib")
 
 
-def flex_key(cfg, pw, read, qual):
+def flex_key(cfg, pw, read, qual, extra=0):
+    """extra: how much longer the longest line of the (imagined) warp is than this read's lines"""
     H = hostcheck.lib()
-    H.hc_flex_key.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_int)]
+    H.hc_flex_key.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_int)]
     out = C.create_string_buffer(256)
     n = C.c_int()
-    rc = H.hc_flex_key(C.byref(cfg), pw, read, len(read), qual, len(qual), out, C.byref(n))
+    rc = H.hc_flex_key(C.byref(cfg), pw, read, len(read), qual, len(qual), extra, out, C.byref(n))
     return rc, (out.raw[:n.value] if rc >= 0 else None)
 
 
@@ -92,8 +93,8 @@ def test_flex_extraction_equals_oracle_key(k, oracle):
     n_keys = n_fail = 0
     for s, q in fuzz_reads(1000 + k, 4000, kw):
         want = oracle.build_key(ocfg, s, q)
-        for pw in (3, 5):
-            rc, got = flex_key(cfg, pw, s, q)
+        for pw, extra in ((3, 0), (5, 0), (3, 13), (5, 40)):
+            rc, got = flex_key(cfg, pw, s, q, extra)
             if rc == -2:                                # a piece longer than 32 symbols: the kernels hand the read to the generic code
                 assert want is not None and max(len(p) for p in want.split(b":")) > 32 or len(want) > 32, (kw, s, q, want)
                 continue
@@ -102,7 +103,7 @@ def test_flex_extraction_equals_oracle_key(k, oracle):
                 assert rc == -1, (kw, s, q, got)
                 n_fail += 1
             else:
-                assert rc >= 0 and got == want, (kw, pw, s, q, got, want)
+                assert rc >= 0 and got == want, (kw, pw, extra, s, q, got, want)
                 n_keys += 1
     assert n_keys > 100 and n_fail > 20, (n_keys, n_fail)
 

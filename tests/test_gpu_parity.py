@@ -243,3 +243,37 @@ def test_end_sample_async_back_to_back(gu, oracle):
             oc, os_ = oracle.count(oracle.make_config(miss=1), keys, d)
             assert s == os_ and np.array_equal(c, oc)
             b.free()
+
+
+@pytest.mark.parametrize("name", ["config2_slice", "config3_slice", "config3_m3", "config5a_dual_fixed", "config5b_dual_delim"])
+@pytest.mark.parametrize("opts", [dict(memo_entries=0), dict(memo_entries=1 << 12), dict(memo_entries=1 << 20, resolve_group=8),
+                                  dict(resolve_group=32), dict(resolve_group=1, memo_entries=1 << 16)], ids=str)
+def test_resolvers_agree_with_memo_and_groups(gu, name, opts):
+    """the seed-index resolvers with 1 / 8 / 32 lanes per key, the device memo of resolved keys off, tiny (constant eviction)
+    and large: always the reference's counts (fast2q.py:692-750 — the memo never changes an outcome)"""
+    c = [x for x in G.shaped() if x["name"] == name][0]
+    params, lib, data = cases.shaped_inputs(name)
+    gu.check_case(dict(c, library=lib), data, **opts)
+    gu.check_case(dict(c, library=lib), data, 300007, **opts)
+
+
+def test_memo_is_reused_across_chunks_and_samples(gu, oracle):
+    """the same non-exact keys again and again (what real screens do): the first sample fills the memo, the
+    second one — another f2q_begin_sample on the same context — resolves nothing itself, and both equal the oracle"""
+    synth = importlib.import_module("2fast2q_b200.synth")
+    spec = synth.default_spec(3)
+    names, keys = synth.make_library(3, 20_000, 20)
+    block = synth.fixed_reads(keys, 0, 20_000, **spec)
+    data = np.tile(block, 6)
+    want_c, want_s = oracle.count(oracle.make_config(miss=2), keys, data)
+    cfg = gu.lib.make_config(miss=2)
+    with gu.lib.Engine(cfg, 0, None, memo_entries=1 << 20) as e:
+        e.set_library(keys)
+        c1, s1 = e.run(data, block.size)                 # one chunk per repetition
+        look1, hit1 = e.memo_counts()
+        c2, s2 = e.run(data)
+        look2, hit2 = e.memo_counts()
+    assert s1 == want_s and s2 == want_s and np.array_equal(c1, want_c) and np.array_equal(c2, want_c)
+    assert look1 > 10_000 and hit1 >= look1 * 4 // 6      # repetitions 2..6 of the first sample hit
+    assert look2 >= look1 and hit2 >= look2 * 99 // 100   # the second sample finds (nearly) everything: entries survive f2q_begin_sample
+    # (look1 < look2: the first sample's small chunks overflow their queue segments, those keys are resolved in place)
