@@ -651,7 +651,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         if (flex && ec) {
             // the verified chunk's insert log -> the packed key table
             cudaEvent_t t4 = timing_begin(c);
-            k_ec_commit<<<(unsigned)c->sm_count * 8, 256, 0, c->stream>>>(c->dS, c->E, O, reinterpret_cast<const unsigned long long*>(c->queue.p), c->q_cap);
+            k_ec_commit<<<(unsigned)c->sm_count * 16, 256, 0, c->stream>>>(c->dS, c->E, O, reinterpret_cast<const unsigned long long*>(c->queue.p), c->q_cap);
             c->launches++;
             timing_end(c, t4, 1);
         }

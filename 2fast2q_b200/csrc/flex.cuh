@@ -242,11 +242,31 @@ __device__ __forceinline__ uint32_t fx_queue_fill(const DevState* St, uint32_t q
 __global__ void __launch_bounds__(256) k_ec_commit(const DevState* St, EcTable E, Outputs O, const unsigned long long* __restrict__ log, uint32_t q_cap) {
     if (!St->spec_ok) return;
     const uint32_t n = fx_queue_fill(St, q_cap);
-    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + threadIdx.x;
-        const unsigned long long tag = i < n ? log[i] : 0ull;
-        const uint32_t peers = __match_any_sync(0xffffffffu, tag);
-        if (tag && (uint32_t)(__ffs((int)peers) - 1) == (threadIdx.x & 31u)) ec_pk_insert(E, O, tag, (unsigned long long)__popc(peers));
+    constexpr int U = 4;                                               // entries per thread and round: U independent probes in flight
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += stride * U) {
+        unsigned long long tag[U], cur[U];
+        uint64_t slot[U];
+        uint32_t add[U];
+        #pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t i = base + u * stride + threadIdx.x;
+            tag[u] = i < n ? log[i] : 0ull;
+        }
+        #pragma unroll
+        for (int u = 0; u < U; u++) {
+            // equal tags inside a warp are added once
+            const uint32_t peers = __match_any_sync(0xffffffffu, tag[u]);
+            add[u] = (tag[u] && (uint32_t)(__ffs((int)peers) - 1) == (threadIdx.x & 31u)) ? (uint32_t)__popc(peers) : 0u;
+            slot[u] = ec_pk_hash(tag[u]) & E.pk_mask;
+            cur[u] = add[u] ? *(volatile unsigned long long*)(E.pk_slots + 2 * slot[u]) : 0ull;
+        }
+        #pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!add[u]) continue;
+            if (cur[u] == tag[u]) atomicAdd(E.pk_slots + 2 * slot[u] + 1, (unsigned long long)add[u]);      // the usual case: the key is there, at its home slot
+            else ec_pk_insert(E, O, tag[u], (unsigned long long)add[u]);
+        }
     }
 }
 

@@ -67,15 +67,15 @@ struct FlexDelim {
 };
 
 // NW = 8 * PW words starting at byte offset o of `base` (4-byte aligned base address): aligned loads + funnel shifts.
-// Only the first 2 * ng words (ng groups of 8 bytes, uniform over the warp) are loaded; the others read as 0
-template <int NW>
-F2Q_HD void flex_load(const uint8_t* base, uint32_t o, uint32_t ng, uint32_t (&w)[NW]) {
+// Only the first 2 * NG words (NG groups of 8 bytes) are loaded; the others read as 0
+template <int NW, int NG>
+F2Q_HD void flex_load(const uint8_t* base, uint32_t o, uint32_t (&w)[NW]) {
     const uint32_t a = o & ~3u, sh = (o & 3u) * 8u;
     uint32_t r[NW + 1];
 #pragma unroll
-    for (int i = 0; i <= NW; i++) r[i] = ((uint32_t)i <= 2u * ng) ? *reinterpret_cast<const uint32_t*>(base + a + 4 * i) : 0u;
+    for (int i = 0; i <= NW; i++) r[i] = (i <= 2 * NG) ? *reinterpret_cast<const uint32_t*>(base + a + 4 * i) : 0u;
 #pragma unroll
-    for (int i = 0; i < NW; i++) w[i] = F2Q_FSHR(r[i], r[i + 1], sh);
+    for (int i = 0; i < NW; i++) w[i] = (i < 2 * NG) ? F2Q_FSHR(r[i], r[i + 1], sh) : 0u;
 }
 
 // bits [0, left) of one word: 0 for left <= 0, all ones for left >= 32.  Device: the PTX shift clamps its amount at 32
@@ -107,14 +107,13 @@ F2Q_HD void flex_insert(uint32_t& word, uint32_t r, int scale_log2) {
 
 // sequence line -> code planes b0, b1 and the raw-validity plane ok (bits at positions >= len are 0 in ok; b0/b1 are
 // don't-care there).  w = the line's bytes as NW = 8 * PW words
-template <int PW>
-F2Q_HD void flex_seq_planes(const uint32_t (&w)[8 * PW], uint32_t len, uint32_t ng, uint32_t (&b0)[PW], uint32_t (&b1)[PW], uint32_t (&ok)[PW]) {
+template <int PW, int NG>
+F2Q_HD void flex_seq_planes(const uint32_t (&w)[8 * PW], uint32_t len, uint32_t (&b0)[PW], uint32_t (&b1)[PW], uint32_t (&ok)[PW]) {
 #pragma unroll
     for (int j = 0; j < PW; j++) { b0[j] = 0; b1[j] = 0; ok[j] = 0; }
     const uint32_t one = flex_one();
 #pragma unroll
-    for (int g = 0; g < 4 * PW; g++) {
-        if ((uint32_t)g >= ng) break;                                   // (uniform: no line of the warp reaches this group)
+    for (int g = 0; g < NG; g++) {                                     // (NG: the groups the longest line of the warp reaches)
         const uint32_t w0 = w[2 * g], w1 = w[2 * g + 1];
         const uint32_t r0 = F2Q_DP4A(w0 & 0x02020202u, 0x08040201u, F2Q_DP4A(w1 & 0x02020202u, 0x80402010u, 0u));     // 2 * flags
         const uint32_t r1 = F2Q_DP4A(w0 & 0x04040404u, 0x08040201u, F2Q_DP4A(w1 & 0x04040404u, 0x80402010u, 0u));     // 4 * flags
@@ -144,14 +143,13 @@ F2Q_HD void flex_seq_planes(const uint32_t (&w)[8 * PW], uint32_t len, uint32_t 
 
 // quality line -> lq: bit p set iff 33 <= byte p <= fmax and p < len.  add_ge / add_gt as in Fast1Ctx (tile.cuh):
 // (0x80 - 33) and (0x80 - (fmax + 1)) replicated; fmax == 0 (empty fail set) must be handled by the caller (lq = 0)
-template <int PW>
-F2Q_HD void flex_lowq_plane(const uint32_t (&w)[8 * PW], uint32_t len, uint32_t ng, uint32_t add_ge, uint32_t add_gt, uint32_t (&lq)[PW]) {
+template <int PW, int NG>
+F2Q_HD void flex_lowq_plane(const uint32_t (&w)[8 * PW], uint32_t len, uint32_t add_ge, uint32_t add_gt, uint32_t (&lq)[PW]) {
 #pragma unroll
     for (int j = 0; j < PW; j++) lq[j] = 0;
     const uint32_t one = flex_one();
 #pragma unroll
-    for (int g = 0; g < 4 * PW; g++) {
-        if ((uint32_t)g >= ng) break;
+    for (int g = 0; g < NG; g++) {
         uint32_t f[2];
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -331,19 +329,18 @@ F2Q_HD void flex_lowq(const uint32_t* qw_dummy, uint32_t fmax, uint32_t& add_ge,
 }
 
 // Search-sequence modes.  sw / qw: the sequence / quality line as words (flex_load), r / q their lengths after rstrip (both
-// <= 32 * PW), maxlen = the longest line of the warp (uniform; planes are built for its 8-byte groups only).
+// <= 32 * PW), maxlen = the longest line of the warp (uniform), NG >= ceil(maxlen / 8) the 8-byte groups the planes are built for.
 // Returns the number of pieces (>= 0; the key is their ':'-join), -1 when every iteration was flagged (quality_failed,
 // fast2q.py:389-390), -(pieces + 1) <= -2 when a piece is longer than FLEX_MAX_PIECE (pc[] then holds every piece's length
 // and offset, but codes only for the short ones).
-template <int PW, int K>
+template <int PW, int K, int NG>
 F2Q_HD int flex_pieces_delim(const FlexCfg& C, const uint32_t (&sw)[8 * PW], uint32_t r, const uint32_t (&qw)[8 * PW], uint32_t q, uint32_t maxlen,
                              FlexPiece (&pc)[FLEX_ITER]) {
-    const uint32_t ng = (maxlen + 7u) >> 3;
     uint32_t b0[PW], b1[PW], ok[PW], lq[PW], lqu[PW], lqd[PW];
-    flex_seq_planes<PW>(sw, r, ng, b0, b1, ok);
+    flex_seq_planes<PW, NG>(sw, r, b0, b1, ok);
     uint32_t age, agt;
     flex_lowq(nullptr, C.fmax_ph, age, agt);
-    flex_lowq_plane<PW>(qw, q, ng, age, agt, lq);
+    flex_lowq_plane<PW, NG>(qw, q, age, agt, lq);
     if (C.fmax_ph == 0) {
 #pragma unroll
         for (int j = 0; j < PW; j++) lq[j] = 0;
@@ -352,7 +349,7 @@ F2Q_HD int flex_pieces_delim(const FlexCfg& C, const uint32_t (&sw)[8 * PW], uin
     for (int j = 0; j < PW; j++) { lqu[j] = lq[j]; lqd[j] = lq[j]; }
     if (C.has_up && C.fmax_up != C.fmax_ph) {                          // (uniform; the three thresholds are normally equal)
         flex_lowq(nullptr, C.fmax_up, age, agt);
-        flex_lowq_plane<PW>(qw, q, ng, age, agt, lqu);
+        flex_lowq_plane<PW, NG>(qw, q, age, agt, lqu);
         if (C.fmax_up == 0) {
 #pragma unroll
             for (int j = 0; j < PW; j++) lqu[j] = 0;
@@ -360,7 +357,7 @@ F2Q_HD int flex_pieces_delim(const FlexCfg& C, const uint32_t (&sw)[8 * PW], uin
     }
     if (C.has_down && C.fmax_down != C.fmax_ph) {
         flex_lowq(nullptr, C.fmax_down, age, agt);
-        flex_lowq_plane<PW>(qw, q, ng, age, agt, lqd);
+        flex_lowq_plane<PW, NG>(qw, q, age, agt, lqd);
         if (C.fmax_down == 0) {
 #pragma unroll
             for (int j = 0; j < PW; j++) lqd[j] = 0;
@@ -420,11 +417,10 @@ F2Q_HD int flex_pieces_delim(const FlexCfg& C, const uint32_t (&sw)[8 * PW], uin
 
 // Fixed windows (--st a,b --l n, fast2q.py:349-360): no planes of the whole line, each window is loaded by itself.
 // seq / qual: addresses such that the lines start at seq[so], qual[qo] (4-byte aligned base, see flex_load); a window is
-// at most 32 symbols (flex_prepare checks C.length).  Same return convention as flex_pieces_delim.
-template <int DUMMY>
+// at most 32 symbols (flex_prepare checks C.length) = NGW <= 4 groups of 8.  Same return convention as flex_pieces_delim.
+template <int NGW>
 F2Q_HD int flex_pieces_fixed(const FlexCfg& C, const uint8_t* seq, uint32_t so, uint32_t r, const uint8_t* qual, uint32_t qo, uint32_t q,
                              FlexPiece (&pc)[FLEX_ITER]) {
-    const uint32_t ngw = ((uint32_t)C.length + 7u) >> 3;               // groups of a window (uniform)
     uint32_t age, agt;
     flex_lowq(nullptr, C.fmax_ph, age, agt);
     int np = 0;
@@ -438,13 +434,13 @@ F2Q_HD int flex_pieces_fixed(const FlexCfg& C, const uint8_t* seq, uint32_t so, 
         flex_py_slice((int)q, start, end, qlo, qhi);
         uint32_t w[8], lq[1] = {0u};
         if (C.fmax_ph != 0) {
-            flex_load<8>(qual, qo + (uint32_t)qlo, ngw, w);
-            flex_lowq_plane<1>(w, (uint32_t)(qhi - qlo), ngw, age, agt, lq);
+            flex_load<8, NGW>(qual, qo + (uint32_t)qlo, w);
+            flex_lowq_plane<1, NGW>(w, (uint32_t)(qhi - qlo), age, agt, lq);
         }
-        flex_load<8>(seq, so + (uint32_t)lo, ngw, w);
+        flex_load<8, NGW>(seq, so + (uint32_t)lo, w);
         uint32_t b0[1], b1[1], ok[1];
         const uint32_t n = (uint32_t)(hi - lo);
-        flex_seq_planes<1>(w, n, ngw, b0, b1, ok);
+        flex_seq_planes<1, NGW>(w, n, b0, b1, ok);
         if (lq[0]) continue;                                           // the window's quality slice holds a failing byte
         any = true;
         const uint32_t keep = flex_ones_below((int32_t)n);
@@ -466,12 +462,21 @@ F2Q_HD int flex_pieces_fixed(const FlexCfg& C, const uint8_t* seq, uint32_t so, 
 template <int PW, int K>
 F2Q_HD int flex_pieces(const FlexCfg& C, const uint8_t* seq, uint32_t so, uint32_t r, const uint8_t* qual, uint32_t qo, uint32_t q, uint32_t maxlen,
                        FlexPiece (&pc)[FLEX_ITER]) {
-    if (!(C.has_up || C.has_down)) return flex_pieces_fixed<0>(C, seq, so, r, qual, qo, q, pc);
-    const uint32_t ng = (maxlen + 7u) >> 3;
+    if (!(C.has_up || C.has_down)) {
+        // (uniform) a window of <= 24 symbols needs three 8-byte groups, longer ones four
+        if (C.length <= 24) return flex_pieces_fixed<3>(C, seq, so, r, qual, qo, q, pc);
+        return flex_pieces_fixed<4>(C, seq, so, r, qual, qo, q, pc);
+    }
     uint32_t sw[8 * PW], qw[8 * PW];
-    flex_load<8 * PW>(seq, so, ng, sw);
-    flex_load<8 * PW>(qual, qo, ng, qw);
-    return flex_pieces_delim<PW, K>(C, sw, r, qw, q, maxlen, pc);
+    constexpr int NGS = 4 * PW - 2;                                    // (75 bp reads: 10 groups of the 96-position planes)
+    if (maxlen <= 8u * NGS) {
+        flex_load<8 * PW, NGS>(seq, so, sw);
+        flex_load<8 * PW, NGS>(qual, qo, qw);
+        return flex_pieces_delim<PW, K, NGS>(C, sw, r, qw, q, maxlen, pc);
+    }
+    flex_load<8 * PW, 4 * PW>(seq, so, sw);
+    flex_load<8 * PW, 4 * PW>(qual, qo, qw);
+    return flex_pieces_delim<PW, K, 4 * PW>(C, sw, r, qw, q, maxlen, pc);
 }
 
 // host side: can this configuration run on the bit-parallel path?  (search sequences pure ACGT, 1..32 symbols, <= FLEX_MAX_K
