@@ -71,6 +71,14 @@ SYMBOLS = {
     "f2q_result_device": (C.c_int, [_VP, C.POINTER(_VP), _U64P]),
     "f2q_ec_size": (C.c_int, [_VP, _U64P, _U64P]),
     "f2q_ec_drain": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "f2q_comm_load": (C.c_int, [C.c_char_p]),
+    "f2q_comm_unique_id": (C.c_int, [_VP]),
+    "f2q_comm_init_rank": (C.c_int, [_VP, _VP, C.c_int, C.c_int]),
+    "f2q_comm_init": (C.c_int, [C.POINTER(_VP), C.c_int]),
+    "f2q_comm_destroy": (C.c_int, [_VP]),
+    "f2q_comm_share": (C.c_int, [_VP, _VP]),
+    "f2q_allreduce_counts": (C.c_int, [C.POINTER(_VP), C.c_int]),
+    "f2q_ec_merge": (C.c_int, [C.POINTER(_VP), C.c_int]),
     "f2q_host_alloc": (C.c_int, [C.POINTER(_VP), C.c_uint64]),
     "f2q_host_free": (C.c_int, [_VP]),
     "f2q_border_finder": (C.c_int, [C.c_int, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_int32, C.c_int32, _I32P]),
@@ -170,6 +178,56 @@ def pack_keys(keys):
         off[1:] = np.cumsum([len(b) for b in bs], dtype=np.uint64)
     blob = np.frombuffer(b"".join(bs) + b"\0", dtype=np.uint8).copy()
     return blob, off
+
+
+def nccl_library_path():
+    """libnccl.so.2 of the nvidia-nccl wheel beside torch, or None (libf2q then uses F2Q_NCCL_LIB / the default search)"""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (spec.submodule_search_locations or []) if spec else []:
+            p = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(p):
+                return p
+    except Exception:
+        pass
+    return None
+
+
+def comm_load():
+    L = load()
+    p = nccl_library_path()
+    rc = L.f2q_comm_load(p.encode() if p else None)
+    if rc:
+        raise F2QError(rc, L.f2q_last_error(None).decode())
+
+
+def comm_unique_id() -> bytes:
+    comm_load()
+    buf = (C.c_uint8 * 128)()
+    rc = load().f2q_comm_unique_id(buf)
+    if rc:
+        raise F2QError(rc, load().f2q_last_error(None).decode())
+    return bytes(buf)
+
+
+def comm_init(engines):
+    """one process, several engines on distinct devices: one communicator over all of them"""
+    comm_load()
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    rc = load().f2q_comm_init(arr, len(engines))
+    if rc:
+        raise F2QError(rc, load().f2q_last_error(engines[0].h).decode() or load().f2q_last_error(None).decode())
+
+
+def allreduce_counts(engines):
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    engines[0]._ck(load().f2q_allreduce_counts(arr, len(engines)))
+
+
+def ec_merge(engines):
+    arr = (C.c_void_p * len(engines))(*[e.h for e in engines])
+    engines[0]._ck(load().f2q_ec_merge(arr, len(engines)))
 
 
 class PinnedBuffer:
@@ -291,6 +349,24 @@ class Engine:
         if int(v[self.n_keys + 5]):
             raise F2QError(-8, f"device-side failure, flags={int(v[self.n_keys + 5]):#x}")
         return v[:self.n_keys].copy(), dict(zip(STAT_NAMES, (int(x) for x in v[self.n_keys:self.n_keys + 5])))
+
+    # -- several GPUs, one process per GPU (f2q_comm_*)
+    def comm_init_rank(self, unique_id: bytes, nranks: int, rank: int):
+        comm_load()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self.L.f2q_comm_init_rank(self.h, buf, nranks, rank))
+
+    def comm_share(self, other: "Engine"):
+        """use `other`'s communicator (same device; `other` must stay open while this engine uses it)"""
+        self._ck(self.L.f2q_comm_share(self.h, other.h))
+
+    def allreduce_counts(self):
+        """sum [counts | stats] over all ranks in place (stream-ordered); then end() / end_async() as usual"""
+        allreduce_counts([self])
+
+    def ec_merge(self):
+        """Extract+Count: every rank's key table becomes the merged table of all ranks (call after end())"""
+        ec_merge([self])
 
     def result_device(self):
         p, n = C.c_void_p(), C.c_uint64()

@@ -8,6 +8,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <dlfcn.h>
+#include <map>
 #include <mutex>
 #include <string>
 #include <unordered_set>
@@ -89,6 +91,10 @@ struct f2q_ctx {
     uint64_t ec_ring_next = 0;
     unsigned long long ec_known[4] = {0, 0, 0, 0};   // newest counters seen: arena bytes, arena keys, packed keys, spec_off
     int flex_warps = 16;                             // option "flex_warps": warps per CTA of the streaming kernel's flex policies
+    // multi-GPU (NCCL): the communicator this context is a rank of
+    void* comm = nullptr; int comm_rank = 0, comm_size = 1; bool comm_owner = false;
+    bool ec_merged = false;                          // f2q_ec_merge ran for this sample: the packed table holds every rank's keys,
+    std::vector<uint8_t> ec_extra_keys; std::vector<uint64_t> ec_extra_off, ec_extra_cnt;   // ... and these the merged byte-arena keys
     int seed_group = 1;                              // lanes per key of the fast1 seed resolver (auto)
     int64_t memo_entries = -1;                       // option "memo_entries": -1 auto (2^20 when m >= 2), 0 off
     DevBuf memo;
@@ -805,6 +811,8 @@ F2Q_EXPORT int f2q_create(const f2q_config* cfg, int device, void* stream, f2q_c
     return F2Q_OK;
 }
 
+F2Q_EXPORT int f2q_comm_destroy(f2q_ctx* c);
+
 F2Q_EXPORT void f2q_destroy(f2q_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
@@ -816,6 +824,7 @@ F2Q_EXPORT void f2q_destroy(f2q_ctx* c) {
     for (auto& p : c->ec_pend) if (p.ev) cudaEventDestroy(p.ev);
     for (auto e : c->ec_events) cudaEventDestroy(e);
     if (c->ec_meta_host) cudaFreeHost(c->ec_meta_host);
+    f2q_comm_destroy(c);
     for (auto p : c->d_stage) cudaFree(p);
     for (auto e : c->ev_copied) cudaEventDestroy(e);
     for (auto e : c->ev_free) cudaEventDestroy(e);
@@ -1205,7 +1214,7 @@ F2Q_EXPORT int f2q_begin_sample(f2q_ctx* c) {
         if (c->ec_meta.p) CU(c, cudaMemsetAsync(c->ec_meta.p, 0, 32, c->stream));
         if (c->ec_slots.p) { CU(c, cudaMemsetAsync(c->ec_slots.p, 0, c->ec_cap * 8, c->stream)); CU(c, cudaMemsetAsync(c->ec_counts.p, 0, c->ec_cap * 8, c->stream)); }
         if (c->ec_pk.p) CU(c, cudaMemsetAsync(c->ec_pk.p, 0, c->ec_pk_cap * 16, c->stream));
-        c->ec_drained = false;
+        c->ec_drained = false; c->ec_merged = false;
     }
     c->in_sample = true; c->closed = false; c->sample_failed = F2Q_OK;
     return F2Q_OK;
@@ -1357,7 +1366,14 @@ static int ec_fetch(f2q_ctx* c) {
             c->ec_drain_cnt.push_back(pairs[2 * i + 1]);
         }
     }
-    if (c->ec_cap) {
+    if (c->ec_merged) {
+        // f2q_ec_merge ran: the byte-arena keys of every rank were merged on the host
+        for (size_t k = 0; k < c->ec_extra_cnt.size(); k++) {
+            c->ec_drain_keys.insert(c->ec_drain_keys.end(), c->ec_extra_keys.begin() + c->ec_extra_off[k], c->ec_extra_keys.begin() + c->ec_extra_off[k + 1]);
+            c->ec_drain_off.push_back(c->ec_drain_keys.size());
+            c->ec_drain_cnt.push_back(c->ec_extra_cnt[k]);
+        }
+    } else if (c->ec_cap) {
         unsigned long long meta[4];
         CU(c, cudaMemcpy(meta, c->ec_meta.p, 32, cudaMemcpyDeviceToHost));
         if (meta[1]) {
@@ -1396,6 +1412,298 @@ F2Q_EXPORT int f2q_ec_drain(f2q_ctx* c, uint8_t* key_bytes, uint64_t* key_offset
     if (!c->ec_drain_keys.empty()) memcpy(key_bytes, c->ec_drain_keys.data(), c->ec_drain_keys.size());
     memcpy(key_offsets, c->ec_drain_off.data(), c->ec_drain_off.size() * 8);
     if (!c->ec_drain_cnt.empty()) memcpy(counts, c->ec_drain_cnt.data(), c->ec_drain_cnt.size() * 8);
+    return F2Q_OK;
+}
+
+
+// ---- multi-GPU: NCCL over NVLink / NVSwitch ---------------------------------------------------------------------------
+// The path shards by reads with no data-path collective; what crosses GPUs is the RESULT, once per sample:
+//   Counter        [counts | stats] summed by one ncclAllReduce(sum, uint64) — merge_feature_dicts, fast2q.py:439-445, 487-495
+//   Extract+Count  every rank's key table gathered on every rank (ncclBroadcast per rank inside one group = all-gather of
+//                  unequal pieces) and merged on the device into the rank's own packed table (hash insert with count
+//                  addition — dict addition again); the few keys of the byte-arena table are merged on the host
+// libnccl is loaded at run time (dlopen), so the library itself has no link-time dependency on it: a single-GPU user never
+// needs NCCL.  Works for one process per GPU (f2q_comm_unique_id + f2q_comm_init_rank, the id travels by any means the host
+// has: MPI, torch.distributed, a file) and for one process driving several contexts (f2q_comm_init).
+namespace {
+
+typedef struct f2q_ncclComm* nccl_comm_t;
+struct nccl_uid { char internal[128]; };
+enum { NCCL_UINT8 = 1, NCCL_UINT64 = 5, NCCL_SUM = 0 };
+struct Nccl {
+    void* h = nullptr;
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_uid, int) = nullptr;
+    int (*CommInitAll)(nccl_comm_t*, int, const int*) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+} g_nccl;
+std::mutex g_nccl_mu;
+
+int nccl_load(const char* path) {
+    std::lock_guard<std::mutex> l(g_nccl_mu);
+    if (g_nccl.h) return F2Q_OK;
+    void* h = nullptr;
+    if (path && *path) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) if (const char* e = getenv("F2Q_NCCL_LIB")) h = dlopen(e, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(nullptr, F2Q_EUNSUPPORTED, std::string("libnccl could not be loaded (pass its path to f2q_comm_load or set F2Q_NCCL_LIB): ") + (dlerror() ? dlerror() : ""));
+    bool ok = true;
+    auto sym = [&](const char* n) { void* p = dlsym(h, n); if (!p) ok = false; return p; };
+    g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(sym("ncclGetUniqueId"));
+    g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(sym("ncclCommInitRank"));
+    g_nccl.CommInitAll = reinterpret_cast<decltype(g_nccl.CommInitAll)>(sym("ncclCommInitAll"));
+    g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(sym("ncclCommDestroy"));
+    g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(sym("ncclAllReduce"));
+    g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(sym("ncclAllGather"));
+    g_nccl.Broadcast = reinterpret_cast<decltype(g_nccl.Broadcast)>(sym("ncclBroadcast"));
+    g_nccl.GroupStart = reinterpret_cast<decltype(g_nccl.GroupStart)>(sym("ncclGroupStart"));
+    g_nccl.GroupEnd = reinterpret_cast<decltype(g_nccl.GroupEnd)>(sym("ncclGroupEnd"));
+    g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(sym("ncclGetErrorString"));
+    if (!ok) { dlclose(h); return fail(nullptr, F2Q_EUNSUPPORTED, "libnccl lacks a symbol this library needs"); }
+    g_nccl.h = h;
+    return F2Q_OK;
+}
+
+#define NC(ctx, call)                                                                                              \
+    do {                                                                                                           \
+        int r__ = (call);                                                                                          \
+        if (r__ != 0) return fail(ctx, F2Q_ECUDA, std::string(#call) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r__) : "NCCL error")); \
+    } while (0)
+
+int comm_check(f2q_ctx** ctxs, int n) {
+    if (!ctxs || n < 1) return F2Q_EINVAL;
+    for (int i = 0; i < n; i++) {
+        if (!ctxs[i]) return F2Q_EINVAL;
+        if (ctxs[i]->sticky) return ctxs[i]->sticky;
+        if (!ctxs[i]->comm) return fail(ctxs[i], F2Q_ESTATE, "the context has no communicator (f2q_comm_init / f2q_comm_init_rank first)");
+    }
+    return F2Q_OK;
+}
+
+// merged pairs (tag, count) of every rank -> this rank's packed table (emptied first)
+__global__ void __launch_bounds__(256) k_ec_merge_pairs(EcTable E, Outputs O, const unsigned long long* __restrict__ pairs, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long tag = pairs[2 * i];
+        if (tag) ec_pk_insert(E, O, tag, pairs[2 * i + 1]);
+    }
+}
+
+}  // namespace
+
+F2Q_EXPORT int f2q_comm_load(const char* libnccl_path) { return nccl_load(libnccl_path); }
+
+F2Q_EXPORT int f2q_comm_unique_id(uint8_t* id128) {
+    if (!id128) return fail(nullptr, F2Q_EINVAL, "null argument");
+    int rc = nccl_load(nullptr); if (rc) return rc;
+    nccl_uid u;
+    NC(nullptr, g_nccl.GetUniqueId(&u));
+    memcpy(id128, u.internal, 128);
+    return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_comm_init_rank(f2q_ctx* c, const uint8_t* id128, int nranks, int rank) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(c, F2Q_EINVAL, "bad communicator arguments");
+    if (c->comm) return fail(c, F2Q_ESTATE, "the context already has a communicator");
+    if ((rc = nccl_load(nullptr))) return fail(c, rc, f2q_last_error(nullptr));
+    nccl_uid u;
+    memcpy(u.internal, id128, 128);
+    nccl_comm_t comm = nullptr;
+    NC(c, g_nccl.CommInitRank(&comm, nranks, u, rank));
+    c->comm = comm; c->comm_rank = rank; c->comm_size = nranks; c->comm_owner = true;
+    return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_comm_init(f2q_ctx** ctxs, int n) {
+    if (!ctxs || n < 1) return fail(nullptr, F2Q_EINVAL, "bad communicator arguments");
+    int rc = nccl_load(nullptr); if (rc) return rc;
+    std::vector<int> devs(n);
+    for (int i = 0; i < n; i++) {
+        if (!ctxs[i] || ctxs[i]->comm) return fail(ctxs[i], F2Q_ESTATE, "null context, or the context already has a communicator");
+        devs[i] = ctxs[i]->device;
+        for (int j = 0; j < i; j++) if (devs[j] == devs[i]) return fail(ctxs[i], F2Q_EINVAL, "f2q_comm_init needs one context per device");
+    }
+    std::vector<nccl_comm_t> comms(n, nullptr);
+    NC(ctxs[0], g_nccl.CommInitAll(comms.data(), n, devs.data()));
+    for (int i = 0; i < n; i++) { ctxs[i]->comm = comms[i]; ctxs[i]->comm_rank = i; ctxs[i]->comm_size = n; ctxs[i]->comm_owner = true; }
+    return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_comm_destroy(f2q_ctx* c) {
+    if (!c) return F2Q_EINVAL;
+    if (c->comm && c->comm_owner && g_nccl.CommDestroy) { cudaSetDevice(c->device); if (c->stream) cudaStreamSynchronize(c->stream); g_nccl.CommDestroy(static_cast<nccl_comm_t>(c->comm)); }
+    c->comm = nullptr; c->comm_size = 1; c->comm_rank = 0; c->comm_owner = false;
+    return F2Q_OK;
+}
+
+// another context of the same device and process uses `from`'s communicator (which must outlive it): creating a communicator
+// costs a rendezvous, a process that runs several configurations needs only one
+F2Q_EXPORT int f2q_comm_share(f2q_ctx* c, f2q_ctx* from) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (!from || !from->comm) return fail(c, F2Q_ESTATE, "the source context has no communicator");
+    if (c->comm) return fail(c, F2Q_ESTATE, "the context already has a communicator");
+    if (c->device != from->device) return fail(c, F2Q_EINVAL, "a communicator can only be shared by contexts of one device");
+    c->comm = from->comm; c->comm_rank = from->comm_rank; c->comm_size = from->comm_size; c->comm_owner = false;
+    return F2Q_OK;
+}
+
+// in-place sum over all ranks of [counts[n_keys] | stats[5]], stream-ordered on each context's stream (call it after the
+// last submit of the sample and before f2q_end_sample / f2q_end_sample_async)
+F2Q_EXPORT int f2q_allreduce_counts(f2q_ctx** ctxs, int n) {
+    int rc = comm_check(ctxs, n); if (rc) return rc;
+    for (int i = 0; i < n; i++) {
+        f2q_ctx* c = ctxs[i];
+        if (!c->in_sample) return fail(c, F2Q_ESTATE, "f2q_allreduce_counts outside a sample");
+        if (!c->closed) { cudaSetDevice(c->device); if ((rc = process_device_chunk(c, nullptr, 0, 1))) return rc; }      // flush a carried final record first
+    }
+    NC(ctxs[0], g_nccl.GroupStart());
+    for (int i = 0; i < n; i++) {
+        f2q_ctx* c = ctxs[i];
+        cudaSetDevice(c->device);
+        const int r = g_nccl.AllReduce(c->result.p, c->result.p, (size_t)c->n_keys + 5, NCCL_UINT64, NCCL_SUM, static_cast<nccl_comm_t>(c->comm), c->stream);
+        if (r != 0) { g_nccl.GroupEnd(); return fail(c, F2Q_ECUDA, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r)); }
+        c->launches++;
+    }
+    NC(ctxs[0], g_nccl.GroupEnd());
+    return F2Q_OK;
+}
+
+// Extract+Count: after it every rank's tables hold the keys of ALL ranks with summed counts (f2q_ec_size / f2q_ec_drain then
+// return the merged table everywhere).  The five statistics are NOT touched: f2q_allreduce_counts sums them.
+F2Q_EXPORT int f2q_ec_merge(f2q_ctx** ctxs, int n) {
+    int rc = comm_check(ctxs, n); if (rc) return rc;
+    const int W = ctxs[0]->comm_size;
+    struct Local { uint64_t npk = 0; std::vector<uint8_t> blob; };     // blob: arena keys as [len u32 | count u64 | bytes]...
+    std::vector<Local> L(n);
+    std::vector<DevBuf> sizes_d(n), gathered(n), blob_d(n), blobs_all(n);
+    std::vector<std::vector<unsigned long long>> sizes_h(n, std::vector<unsigned long long>(2 * (size_t)W, 0));
+    auto cleanup = [&]() { for (int i = 0; i < n; i++) { cudaSetDevice(ctxs[i]->device); sizes_d[i].release(); gathered[i].release(); blob_d[i].release(); blobs_all[i].release(); } };
+    // 1. local tables: packed keys compacted on the device, arena keys packed into a blob on the host (they are few)
+    for (int i = 0; i < n; i++) {
+        f2q_ctx* c = ctxs[i];
+        if (c->cfg.mode != F2Q_MODE_EXTRACT_COUNT) return fail(c, F2Q_ESTATE, "not in Extract+Count mode");
+        if (c->comm_size != W) return fail(c, F2Q_EINVAL, "contexts of different communicators");
+        cudaSetDevice(c->device);
+        if (c->in_sample && !c->closed && (rc = process_device_chunk(c, nullptr, 0, 1))) return rc;
+        CU(c, cudaStreamSynchronize(c->stream));
+        if ((rc = ec_compact_packed(c, &L[i].npk))) return rc;
+        if (c->ec_cap && c->ec_meta.p) {
+            unsigned long long meta[4];
+            CU(c, cudaMemcpy(meta, c->ec_meta.p, 32, cudaMemcpyDeviceToHost));
+            if (meta[1]) {
+                std::vector<unsigned long long> hs(c->ec_cap), hc(c->ec_cap);
+                std::vector<uint8_t> ar(meta[0] + 1);
+                CU(c, cudaMemcpy(hs.data(), c->ec_slots.p, c->ec_cap * 8, cudaMemcpyDeviceToHost));
+                CU(c, cudaMemcpy(hc.data(), c->ec_counts.p, c->ec_cap * 8, cudaMemcpyDeviceToHost));
+                if (meta[0]) CU(c, cudaMemcpy(ar.data(), c->ec_arena.p, meta[0], cudaMemcpyDeviceToHost));
+                for (uint64_t k = 0; k < c->ec_cap; k++) {
+                    if (!hs[k]) continue;
+                    const uint64_t off = (hs[k] - 1) >> 24; const uint32_t len = (uint32_t)((hs[k] - 1) & 0xFFFFFF);
+                    const uint64_t cnt = hc[k];
+                    const uint8_t* p4 = reinterpret_cast<const uint8_t*>(&len); const uint8_t* p8 = reinterpret_cast<const uint8_t*>(&cnt);
+                    L[i].blob.insert(L[i].blob.end(), p4, p4 + 4); L[i].blob.insert(L[i].blob.end(), p8, p8 + 8);
+                    L[i].blob.insert(L[i].blob.end(), ar.begin() + off, ar.begin() + off + len);
+                }
+            }
+        }
+    }
+    // 2. sizes of every rank's pieces (two words per rank: packed pairs, blob bytes)
+    for (int i = 0; i < n; i++) {
+        f2q_ctx* c = ctxs[i];
+        cudaSetDevice(c->device);
+        if ((rc = dev_alloc(c, sizes_d[i], 16 * (size_t)W + 16))) { cleanup(); return rc; }
+        unsigned long long mine[2] = {L[i].npk, L[i].blob.size()};
+        CU(c, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(sizes_d[i].p) + 16 * (size_t)W, mine, 16, cudaMemcpyHostToDevice, c->stream));
+    }
+    NC(ctxs[0], g_nccl.GroupStart());
+    for (int i = 0; i < n; i++) {
+        f2q_ctx* c = ctxs[i];
+        cudaSetDevice(c->device);
+        g_nccl.AllGather(reinterpret_cast<uint8_t*>(sizes_d[i].p) + 16 * (size_t)W, sizes_d[i].p, 2, NCCL_UINT64, static_cast<nccl_comm_t>(c->comm), c->stream);
+        c->launches++;
+    }
+    NC(ctxs[0], g_nccl.GroupEnd());
+    for (int i = 0; i < n; i++) {
+        f2q_ctx* c = ctxs[i];
+        cudaSetDevice(c->device);
+        CU(c, cudaMemcpyAsync(sizes_h[i].data(), sizes_d[i].p, 16 * (size_t)W, cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    }
+    // 3. the pieces themselves: rank r broadcasts its piece into everybody's buffer at r's offset (one NCCL group)
+    std::vector<uint64_t> tot_pk(n, 0), tot_blob(n, 0);
+    for (int i = 0; i < n; i++) {
+        f2q_ctx* c = ctxs[i];
+        cudaSetDevice(c->device);
+        for (int r = 0; r < W; r++) { tot_pk[i] += sizes_h[i][2 * r]; tot_blob[i] += sizes_h[i][2 * r + 1]; }
+        if ((rc = dev_alloc(c, gathered[i], (tot_pk[i] + 1) * 16)) || (rc = dev_alloc(c, blob_d[i], L[i].blob.size() + 16)) ||
+            (rc = dev_alloc(c, blobs_all[i], tot_blob[i] + 16))) { cleanup(); return rc; }
+        if (!L[i].blob.empty()) CU(c, cudaMemcpyAsync(blob_d[i].p, L[i].blob.data(), L[i].blob.size(), cudaMemcpyHostToDevice, c->stream));
+    }
+    NC(ctxs[0], g_nccl.GroupStart());
+    for (int i = 0; i < n; i++) {
+        f2q_ctx* c = ctxs[i];
+        cudaSetDevice(c->device);
+        uint64_t opk = 0, ob = 0;
+        for (int r = 0; r < W; r++) {
+            const uint64_t npk = sizes_h[i][2 * r], nb = sizes_h[i][2 * r + 1];
+            const void* send_pk = reinterpret_cast<const uint8_t*>(c->ec_compact.p) + 16;      // (only read on the root)
+            if (npk) g_nccl.Broadcast(r == c->comm_rank ? send_pk : reinterpret_cast<uint8_t*>(gathered[i].p) + opk * 16, reinterpret_cast<uint8_t*>(gathered[i].p) + opk * 16, npk * 2, NCCL_UINT64, r,
+                                      static_cast<nccl_comm_t>(c->comm), c->stream);
+            if (nb) g_nccl.Broadcast(r == c->comm_rank ? blob_d[i].p : reinterpret_cast<uint8_t*>(blobs_all[i].p) + ob, reinterpret_cast<uint8_t*>(blobs_all[i].p) + ob, nb, NCCL_UINT8, r,
+                                     static_cast<nccl_comm_t>(c->comm), c->stream);
+            opk += npk; ob += nb;
+            c->launches++;
+        }
+    }
+    NC(ctxs[0], g_nccl.GroupEnd());
+    // 4. merge: the packed table is emptied and every gathered pair inserted (counts add); the arena blobs merge on the host
+    for (int i = 0; i < n; i++) {
+        f2q_ctx* c = ctxs[i];
+        cudaSetDevice(c->device);
+        // room for every gathered key (nothing is in flight: the counters are exact)
+        while (!c->ec_pend.empty()) { if (c->ec_pend.front().ev) { cudaEventSynchronize(c->ec_pend.front().ev); c->ec_events.push_back(c->ec_pend.front().ev); } c->ec_pend.pop_front(); }
+        if (c->ec_meta.p) {
+            CU(c, cudaStreamSynchronize(c->stream));
+            if (c->ec_pk.p) CU(c, cudaMemsetAsync(c->ec_pk.p, 0, c->ec_pk_cap * 16, c->stream));
+            CU(c, cudaMemsetAsync(reinterpret_cast<uint8_t*>(c->ec_meta.p) + 16, 0, 8, c->stream));
+            unsigned long long meta[4];
+            CU(c, cudaMemcpyAsync(meta, c->ec_meta.p, 32, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            c->ec_known[0] = meta[0]; c->ec_known[1] = meta[1]; c->ec_known[2] = 0;
+        }
+        if ((rc = ec_reserve(c, tot_pk[i], 0, 0))) { cleanup(); return rc; }
+        if (tot_pk[i]) {
+            k_ec_merge_pairs<<<(unsigned)std::min<uint64_t>((tot_pk[i] + 255) / 256, (uint64_t)c->sm_count * 16), 256, 0, c->stream>>>(
+                c->E, outputs_of(c), reinterpret_cast<const unsigned long long*>(gathered[i].p), tot_pk[i]);
+            c->launches++;
+        }
+        if ((rc = ec_after_chunk(c))) { cleanup(); return rc; }
+        std::vector<uint8_t> all(tot_blob[i] + 1);
+        if (tot_blob[i]) CU(c, cudaMemcpyAsync(all.data(), blobs_all[i].p, tot_blob[i], cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        std::map<std::string, uint64_t> extra;                         // (ordered: every rank gets the same table)
+        for (uint64_t p = 0; p + 12 <= tot_blob[i];) {
+            uint32_t len; uint64_t cnt;
+            memcpy(&len, all.data() + p, 4); memcpy(&cnt, all.data() + p + 4, 8);
+            extra[std::string(reinterpret_cast<const char*>(all.data() + p + 12), len)] += cnt;
+            p += 12 + len;
+        }
+        c->ec_extra_keys.clear(); c->ec_extra_off.assign(1, 0); c->ec_extra_cnt.clear();
+        for (auto& kv : extra) {
+            c->ec_extra_keys.insert(c->ec_extra_keys.end(), kv.first.begin(), kv.first.end());
+            c->ec_extra_off.push_back(c->ec_extra_keys.size());
+            c->ec_extra_cnt.push_back(kv.second);
+        }
+        c->ec_merged = true; c->ec_drained = false;
+    }
+    cleanup();
     return F2Q_OK;
 }
 

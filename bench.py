@@ -20,7 +20,7 @@ roofline.frac / e2e and a parity block (GPU == oracle on a >= 1 M-read slice of 
   north_star  50 bp reads vs 100 000 guides, m = 1 (the target shape of BASELINE.json's north_star), weak
   config3     1e9 x 75 bp reads vs 100 000 guides, m = 2, STRONG-scaled (1e9 / N reads per GPU), generated per chunk by K0
   config4     Extract + Count Bar-seq, 500 M x 75 bp reads between --us/--ds with 1 mismatch each, STRONG-scaled; at N > 1
-              the per-rank key tables are merged (all-gather + sort-merge) inside the timed step
+              the per-rank key tables are merged (f2q_ec_merge: all-gather over NCCL + merge on the device) inside the timed step
   config5a/b  48 samples x 1.5 M x 75 bp, 10 000 'X:Y' dual keys + their singles, m = 1: fixed positions / delimiters;
               samples over GPUs, no collective
 --impl reference times the reference's CPU algorithm (the oracle port on all host threads, file-parallel like the reference's
@@ -349,10 +349,8 @@ def run_workload(w, env):
     if w.keys is not None:
         eng.set_library(w.keys)
     n_keys = len(w.keys) if w.keys is not None else 0
-    result_t = None
-    if world > 1 and not w.ec:
-        rptr, rwords = eng.result_device()
-        result_t = torch.as_tensor(_DevArr(rptr, rwords), device=dev)
+    if world > 1:
+        eng.comm_share(env["comm"])                                          # the rank's NCCL communicator (libf2q's own C-ABI collectives)
 
     def barrier():
         if world > 1:
@@ -360,23 +358,13 @@ def run_workload(w, env):
         torch.cuda.synchronize(dev)
 
     def merge_counts():
-        if result_t is not None:
-            with torch.cuda.stream(stream):
-                multi.merge_results(result_t)
+        if world > 1:
+            eng.allreduce_counts()                                           # f2q_allreduce_counts: ncclAllReduce(sum, uint64) on the engine's stream
 
     def merge_ec():
-        """(keys, counts) of this rank's Extract+Count table merged over all ranks (all-gather + sort-merge)"""
-        items = eng.ec_items()
-        if world == 1:
-            return items
-        ks = list(items.keys())
-        off = np.zeros(len(ks) + 1, dtype=np.uint64)
-        if ks:
-            off[1:] = np.cumsum([len(k) for k in ks], dtype=np.uint64)
-        blob = np.frombuffer(b"".join(ks) + b"\0", dtype=np.uint8)
-        with torch.cuda.stream(stream):
-            mk, mc = multi.merge_ec_tables(blob, off, np.array([items[k] for k in ks], dtype=np.uint64))
-        return dict(zip(mk, mc))
+        """Extract+Count: every rank's key table becomes the merged table (f2q_ec_merge: all-gather + device merge)"""
+        if world > 1:
+            eng.ec_merge()
 
     # ---- this rank's reads ----
     if w.n_samples > 1:
@@ -432,12 +420,12 @@ def run_workload(w, env):
             eng.submit(shard, False)
         eng.submit(b"", True)
         if w.ec:
-            _c, st_local = eng.end()
-            st = torch.tensor([st_local[k] for k in lib.STAT_NAMES], dtype=torch.int64, device=dev)
-            dist.all_reduce(st)
-            merged = merge_ec()
+            merge_counts()                                                   # the five statistics
+            _c, st_all = eng.end()
+            merge_ec()
+            merged = eng.ec_items()
             if rank == 0:
-                assert dict(zip(lib.STAT_NAMES, (int(x) for x in st.tolist()))) == want_s, (w.name, "sharded stats differ")
+                assert st_all == want_s, (w.name, "sharded stats differ")
                 assert merged == want_ec, (w.name, "sharded Extract+Count tables differ")
         else:
             merge_counts()
@@ -495,9 +483,9 @@ def run_workload(w, env):
         if w.ec:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
+            merge_counts()
             eng.end()
-            if world > 1:
-                merge_ec()
+            merge_ec()
             e1.record(stream)
             evs.append((e0, e1))
         eng.sync()
@@ -547,10 +535,9 @@ def run_workload(w, env):
             for k, (f, m) in enumerate(use):
                 eng.submit_ptr(pin.ptr.value, min(m, chunks[0][1]) * rec, k == len(use) - 1)
                 done += min(m, chunks[0][1])
-            if not w.ec:
-                merge_counts()
+            merge_counts()
             eng.end()
-            if w.ec and world > 1:
+            if w.ec:
                 merge_ec()
             return done
 
@@ -628,6 +615,13 @@ def run_gpu(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     stream = torch.cuda.Stream(device=dev)
     want = set(args.configs.split(","))
+    comm_eng = None
+    if world > 1:
+        # one NCCL communicator per rank for libf2q's own collectives (f2q_comm_*); the 128-byte id travels over torch.distributed
+        comm_eng = lib.Engine(lib.make_config(), local_rank, stream.cuda_stream)
+        box = [lib.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm_eng.comm_init_rank(box[0], world, rank)
     clocks = ClockSampler(local_rank, gpu_uuid)
     windows = []
     out = None
@@ -649,13 +643,12 @@ def run_gpu(args, rank, local_rank, world):
         eng.set_library(keys)
         data = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         eng.synth(data.data_ptr(), keys, rank * n_reads, n_reads, **spec)      # every rank owns its own contiguous read range
-        rptr, rwords = eng.result_device()
-        result_t = torch.as_tensor(_DevArr(rptr, rwords), device=dev) if world > 1 else None
+        if world > 1:
+            eng.comm_share(comm_eng)
 
         def merge():
             if world > 1:
-                with torch.cuda.stream(stream):
-                    multi.merge_results(result_t)        # ncclAllReduce(sum) of [counts | stats] over NVLink (merge_feature_dicts)
+                eng.allreduce_counts()                   # f2q_allreduce_counts: ncclAllReduce(sum, uint64) of [counts | stats] over NVLink
 
         def step_resident():
             eng.begin()
@@ -758,7 +751,7 @@ def run_gpu(args, rank, local_rank, world):
                 "config": {"workload": WORKLOAD,
                            "reads_per_gpu": n_reads, "bytes_per_read": REC, "input_bytes_per_gpu": nbytes,
                            "l2": "inputs (%.1f GB/GPU) are far larger than the 126 MB L2; no flush needed" % (nbytes / 1e9),
-                           "parallelism": f"reads sharded by contiguous range over {world} GPU(s); counts merged by NCCL all-reduce",
+                           "parallelism": f"reads sharded by contiguous range over {world} GPU(s); counts merged by f2q_allreduce_counts (ncclAllReduce, uint64 sum)",
                            "host_placement": placement},
                 "e2e": e2e,
                 "gpu_launches": launches,
@@ -791,7 +784,7 @@ def run_gpu(args, rank, local_rank, world):
     others = {}
     if want - {"headline"}:
         env = dict(lib=lib, multi=multi, host=host_mod, rank=rank, world=world, dev=dev, stream=stream, local_rank=local_rank,
-                   args=args, windows=windows)
+                   args=args, windows=windows, comm=comm_eng)
         for name, w in build_workloads(args).items():
             t0 = time.perf_counter()
             r = run_workload(w, env)
@@ -803,6 +796,8 @@ def run_gpu(args, rank, local_rank, world):
         out["other_configs"] = others
         out["clocks"] = clocks.stop(windows)
         emit(out)
+    if comm_eng is not None:
+        comm_eng.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -189,6 +189,29 @@ int f2q_ec_size(f2q_ctx* ctx, uint64_t* n_keys, uint64_t* key_bytes);
 /* copy out keys (concatenated), offsets[n_keys+1] and counts[n_keys]; order unspecified */
 int f2q_ec_drain(f2q_ctx* ctx, uint8_t* key_bytes, uint64_t* key_offsets, uint64_t* counts);
 
+/* ---- several GPUs (NCCL over NVLink / NVSwitch) --------------------------------------------------
+ * Reads shard over GPUs with no data-path collective (every rank parses its own byte range / its own record-aligned
+ * shards); what is exchanged is the per-sample RESULT.  Replaces merge_feature_dicts and the statistics additions of the
+ * reference's chunked mode (fast2q.py:439-445, 487-495) and the per-file pool of fast2q.py:1646-1655.
+ * libnccl is loaded at run time: f2q_comm_load(path) (or NULL: F2Q_NCCL_LIB, then the default library search).
+ * One process per GPU: rank 0 calls f2q_comm_unique_id, ships the 128 bytes to the other ranks by any means, every rank
+ * calls f2q_comm_init_rank.  One process, several contexts on distinct devices: f2q_comm_init(ctxs, n).
+ * Collective calls take the contexts of THIS process that take part (n = 1 with one process per GPU).
+ *   f2q_allreduce_counts  in-place sum over all ranks of [counts | stats], stream-ordered; call it after the last submit of
+ *                         the sample, then f2q_end_sample / f2q_end_sample_async as usual (every rank gets the totals)
+ *   f2q_ec_merge          Extract+Count: the key tables of all ranks are gathered on every rank and merged on the device
+ *                         (counts of equal keys add); f2q_ec_size / f2q_ec_drain then return the merged table on every rank.
+ *                         Call it after f2q_end_sample (statistics: sum them with f2q_allreduce_counts before that). */
+int f2q_comm_load(const char* libnccl_path);
+int f2q_comm_unique_id(uint8_t id128[128]);
+int f2q_comm_init_rank(f2q_ctx* ctx, const uint8_t id128[128], int nranks, int rank);
+int f2q_comm_init(f2q_ctx** ctxs, int n);
+int f2q_comm_destroy(f2q_ctx* ctx);
+/* ctx (same device, same process) uses `from`'s communicator, which must outlive it */
+int f2q_comm_share(f2q_ctx* ctx, f2q_ctx* from);
+int f2q_allreduce_counts(f2q_ctx** ctxs, int n);
+int f2q_ec_merge(f2q_ctx** ctxs, int n);
+
 /* ---- pinned host memory for f2q_submit ------------------------------------------------------ */
 int f2q_host_alloc(void** ptr, uint64_t nbytes);
 int f2q_host_free(void* ptr);
