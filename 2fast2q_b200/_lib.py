@@ -80,6 +80,7 @@ SYMBOLS = {
     "f2q_allreduce_counts": (C.c_int, [C.POINTER(_VP), C.c_int]),
     "f2q_ec_merge": (C.c_int, [C.POINTER(_VP), C.c_int]),
     "f2q_host_alloc": (C.c_int, [C.POINTER(_VP), C.c_uint64]),
+    "f2q_host_alloc_near": (C.c_int, [C.POINTER(_VP), C.c_uint64, C.c_int, C.c_int, _I32P]),
     "f2q_host_free": (C.c_int, [_VP]),
     "f2q_border_finder": (C.c_int, [C.c_int, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32, C.c_int32, C.c_int32, _I32P]),
     "f2q_sequence_tinder": (C.c_int, [C.c_int, C.POINTER(Config), C.c_int32, C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32,
@@ -233,9 +234,16 @@ def ec_merge(engines):
 class PinnedBuffer:
     """page-locked host memory from f2q_host_alloc, exposed as a writable numpy uint8 array / memoryview"""
 
-    def __init__(self, nbytes: int):
+    def __init__(self, nbytes: int, device: int | None = None, write_combined: bool = False):
+        """device: allocate near that GPU (its NUMA node, when the platform shows several; f2q_host_alloc_near)"""
         self.ptr = C.c_void_p()
-        rc = load().f2q_host_alloc(C.byref(self.ptr), nbytes)
+        self.numa_node = -1
+        if device is None and not write_combined:
+            rc = load().f2q_host_alloc(C.byref(self.ptr), nbytes)
+        else:
+            node = C.c_int32(-1)
+            rc = load().f2q_host_alloc_near(C.byref(self.ptr), nbytes, device or 0, 1 if write_combined else 0, C.byref(node))
+            self.numa_node = node.value
         if rc:
             raise F2QError(rc, load().f2q_last_error(None).decode())
         self.nbytes = nbytes

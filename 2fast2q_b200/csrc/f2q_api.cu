@@ -9,6 +9,10 @@
 #include <cstring>
 #include <deque>
 #include <dlfcn.h>
+#include <sys/mman.h>
+#include <sys/syscall.h>
+#include <unistd.h>
+#include <cctype>
 #include <map>
 #include <mutex>
 #include <string>
@@ -1714,7 +1718,82 @@ F2Q_EXPORT int f2q_host_alloc(void** ptr, uint64_t nbytes) {
     if (e != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return fail(nullptr, F2Q_ENOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
     return F2Q_OK;
 }
-F2Q_EXPORT int f2q_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); return F2Q_OK; }
+
+namespace {
+std::mutex g_near_mu;
+std::map<void*, size_t> g_near;                                        // buffers of f2q_host_alloc_near that were mmap'ed + registered
+
+// NUMA node of a CUDA device from sysfs (-1: unknown / the platform shows a single node, as VMs do)
+int device_numa_node(int device) {
+    char bdf[32] = {0};
+    if (cudaDeviceGetPCIBusId(bdf, sizeof(bdf), device) != cudaSuccess) { cudaGetLastError(); return -1; }
+    for (char* p = bdf; *p; p++) *p = (char)tolower(*p);
+    const std::string path = std::string("/sys/bus/pci/devices/") + bdf + "/numa_node";
+    FILE* f = fopen(path.c_str(), "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+int numa_nodes_visible() {
+    int n = 0;
+    for (int k = 0; k < 64; k++) {
+        const std::string p = "/sys/devices/system/node/node" + std::to_string(k);
+        if (access(p.c_str(), F_OK) == 0) n++;
+    }
+    return n;
+}
+}  // namespace
+
+// page-locked host memory for the chunks of ONE device: on the NUMA node of that device when the platform shows more than
+// one node (mmap + mbind(MPOL_BIND) + first touch + cudaHostRegister), else plain cudaHostAlloc.  flags bit 0: write-combined
+// (the CPU only writes the buffer, the GPU's DMA reads it without snooping the CPU caches).  *numa_node = the node used, -1 none
+F2Q_EXPORT int f2q_host_alloc_near(void** ptr, uint64_t nbytes, int device, int flags, int* numa_node) {
+    if (!ptr) return F2Q_EINVAL;
+    *ptr = nullptr;
+    if (numa_node) *numa_node = -1;
+    const int node = device_numa_node(device);
+    const size_t len = ((nbytes ? nbytes : 1) + 4095) & ~(size_t)4095;
+    if (node >= 0 && node < 64 && numa_nodes_visible() > 1 && !(flags & 1)) {
+        void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        if (p != MAP_FAILED) {
+            unsigned long mask = 1ul << node;
+            const long r = syscall(SYS_mbind, p, len, 2 /*MPOL_BIND*/, &mask, 65ul, 0u);
+            if (r == 0) {
+                memset(p, 0, len);                                     // first touch on the bound node
+                if (cudaHostRegister(p, len, cudaHostRegisterDefault) == cudaSuccess) {
+                    std::lock_guard<std::mutex> l(g_near_mu);
+                    g_near[p] = len;
+                    *ptr = p;
+                    if (numa_node) *numa_node = node;
+                    return F2Q_OK;
+                }
+                cudaGetLastError();
+            }
+            munmap(p, len);
+        }
+    }
+    cudaError_t e = cudaHostAlloc(ptr, len, (flags & 1) ? cudaHostAllocWriteCombined : cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); *ptr = nullptr; return fail(nullptr, F2Q_ENOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+    return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_host_free(void* ptr) {
+    if (!ptr) return F2Q_OK;
+    {
+        std::lock_guard<std::mutex> l(g_near_mu);
+        auto it = g_near.find(ptr);
+        if (it != g_near.end()) {
+            cudaHostUnregister(ptr);
+            munmap(ptr, it->second);
+            g_near.erase(it);
+            return F2Q_OK;
+        }
+    }
+    cudaFreeHost(ptr);
+    return F2Q_OK;
+}
 
 F2Q_EXPORT int f2q_device_alloc(f2q_ctx* c, void** dptr, uint64_t nbytes) {
     int rc = check_ctx(c); if (rc) return rc;

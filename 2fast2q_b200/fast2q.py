@@ -302,9 +302,9 @@ def _raw_blocks(path, want=None):
 class _PinnedRing:
     """a few page-locked buffers a feeder cycles through (f2q_host_alloc)"""
 
-    def __init__(self, n=3, nbytes=None):
+    def __init__(self, n=3, nbytes=None, device=None):
         nbytes = nbytes or CHUNK_BYTES
-        self.bufs = [_lib.PinnedBuffer(nbytes) for _ in range(n)]
+        self.bufs = [_lib.PinnedBuffer(nbytes, device) for _ in range(n)]       # on the NUMA node of the GPU they feed
         self.k = 0
         self.nbytes = nbytes
 
@@ -402,7 +402,7 @@ def _engine_for(param, features, device):
         eng = _lib.Engine(cfg, device)
         if keys is not None:
             eng.set_library(keys)
-        cache[sig] = (eng, _PinnedRing())
+        cache[sig] = (eng, _PinnedRing(device=device))
     return cache[sig]
 
 

@@ -514,12 +514,12 @@ def run_workload(w, env):
     e2e = None
     if not env["args"].no_e2e and my_reads:
         if w.n_samples > 1:
-            pin = lib.PinnedBuffer(len(my_samples) * w.reads * rec)
+            pin = lib.PinnedBuffer(len(my_samples) * w.reads * rec, local_rank)
             eng._ck(eng.L.f2q_memcpy_d2h(eng.h, pin.ptr, dptr, pin.nbytes))
         else:
             if not resident_once:
                 gen(*chunks[0])
-            pin = lib.PinnedBuffer(chunks[0][1] * rec)
+            pin = lib.PinnedBuffer(chunks[0][1] * rec, local_rank)
             eng._ck(eng.L.f2q_memcpy_d2h(eng.h, pin.ptr, dptr, pin.nbytes))
 
         def e2e_pass(limit=None):
@@ -698,7 +698,7 @@ def run_gpu(args, rank, local_rank, world):
         # ---- end-to-end leg: host (pinned) buffers through f2q_submit ----
         e2e = None
         if not args.no_e2e:
-            pin = lib.PinnedBuffer(nbytes)
+            pin = lib.PinnedBuffer(nbytes, local_rank, write_combined=args.pinned == "wc")      # near this rank's GPU (f2q_host_alloc_near)
             eng._ck(eng.L.f2q_memcpy_d2h(eng.h, pin.ptr, data.data_ptr(), nbytes))
 
             def step_e2e():
@@ -735,6 +735,7 @@ def run_gpu(args, rank, local_rank, world):
             e2e = {"value": world * n_reads / (ms2 / 1e3) / 1e6, "unit": "M reads/s", "h2d_bytes_per_step": nbytes,
                    "d2h_bytes_per_step": (len(keys) + 5) * 8, "ms_per_step": ms2, "wall_ms_per_step": wall,
                    "h2d_gbs_per_gpu": nbytes / (ms2 / 1e3) / 1e9, "pcie_copy_gbs_measured": pcie,
+                   "pinned_numa_node": pin.numa_node, "pinned_kind": args.pinned,
                    "pcie_frac": (nbytes / (ms2 / 1e3) / 1e9) / pcie if pcie else None}
             pin.free()
 
@@ -752,7 +753,7 @@ def run_gpu(args, rank, local_rank, world):
                            "reads_per_gpu": n_reads, "bytes_per_read": REC, "input_bytes_per_gpu": nbytes,
                            "l2": "inputs (%.1f GB/GPU) are far larger than the 126 MB L2; no flush needed" % (nbytes / 1e9),
                            "parallelism": f"reads sharded by contiguous range over {world} GPU(s); counts merged by f2q_allreduce_counts (ncclAllReduce, uint64 sum)",
-                           "host_placement": placement},
+                           "host_placement": placement, "host_topology": host_topology()},
                 "e2e": e2e,
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -822,6 +823,21 @@ def cpu_baseline_and_parity(eng, dptr, n, keys):
     return base, {"reads": n, "ok": True, "stats": got_s, "checker": "oracle/f2q_oracle.c, bit-exact counts + stats of the first reads of the benchmarked stream"}
 
 
+def host_topology():
+    """what the box shows about host memory placement (a VM usually shows ONE node, whatever the hardware below it has)"""
+    import glob
+    nodes = sorted(glob.glob("/sys/devices/system/node/node[0-9]*"))
+    gpus = {}
+    for d in glob.glob("/sys/bus/pci/devices/*"):
+        try:
+            if open(os.path.join(d, "class")).read().startswith("0x0302"):
+                gpus[os.path.basename(d)] = int(open(os.path.join(d, "numa_node")).read())
+        except (OSError, ValueError):
+            pass
+    return {"numa_nodes_visible": len(nodes), "gpu_numa_node": gpus, "cpus": os.cpu_count(),
+            "cpus_allowed": len(os.sched_getaffinity(0))}
+
+
 def numa_bind(gpu_uuid, gpu_index):
     """run this rank (and first-touch its pinned buffers) on the CPUs nearest to its GPU, when the container allows it"""
     try:
@@ -863,6 +879,7 @@ def main():
     ap.add_argument("--real-ref-reads", type=int, default=1_600_000)
     ap.add_argument("--no-real-reference", action="store_true")
     ap.add_argument("--tile-threads", type=int, default=0)
+    ap.add_argument("--pinned", default="default", choices=["default", "wc"], help="pinned host memory of the end-to-end leg: default | write-combined")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -214,6 +214,11 @@ int f2q_ec_merge(f2q_ctx** ctxs, int n);
 
 /* ---- pinned host memory for f2q_submit ------------------------------------------------------ */
 int f2q_host_alloc(void** ptr, uint64_t nbytes);
+/* the same for the chunks of ONE device: on that device's NUMA node (/sys/bus/pci/devices/<bdf>/numa_node; mmap + mbind +
+ * cudaHostRegister) when the platform shows more than one node — eight GPUs fed from one socket's memory share that socket's
+ * bandwidth.  flags bit 0: write-combined.  *numa_node (may be NULL) = the node the buffer was bound to, -1 when none was
+ * (single-node platforms such as VMs).  Free with f2q_host_free. */
+int f2q_host_alloc_near(void** ptr, uint64_t nbytes, int device, int flags, int* numa_node);
 int f2q_host_free(void* ptr);
 
 /* ---- primitives with public reference counterparts (README.md:259-298; tests/test_mainfunctions.py) ----

@@ -98,3 +98,17 @@ def test_comm_errors():
             lib.ec_merge([e])                                  # Counter mode context
     finally:
         e.close()
+
+
+def test_host_alloc_near_device():
+    """pinned memory on the GPU's NUMA node where the platform shows several nodes, plain pinned memory otherwise (VMs)"""
+    for wc in (False, True):
+        b = lib.PinnedBuffer(1 << 20, device=0, write_combined=wc)
+        assert b.numa_node >= -1
+        b.array[:] = 7
+        with lib.Engine(lib.make_config(mode="EC", upstream="ACGT", downstream="TTTT"), 0) as e:
+            e.begin()
+            b.array[:22] = np.frombuffer(b"@r\nACGTGGTTTT\n+\nIIIIIIIIII\n"[:22], dtype=np.uint8)
+            e.submit_ptr(b.ptr.value, 0, True)
+            e.end()
+        b.free()
