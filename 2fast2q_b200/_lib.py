@@ -64,6 +64,7 @@ SYMBOLS = {
     "f2q_begin_sample": (C.c_int, [_VP]),
     "f2q_submit": (C.c_int, [_VP, _VP, C.c_uint64, C.c_int]),
     "f2q_submit_device": (C.c_int, [_VP, _VP, C.c_uint64, C.c_int]),
+    "f2q_submit_file": (C.c_int, [_VP, C.c_char_p, C.c_int, C.c_uint64, C.c_int, _I32P, _U64P]),
     "f2q_sync": (C.c_int, [_VP]),
     "f2q_sync_copies": (C.c_int, [_VP]),
     "f2q_end_sample": (C.c_int, [_VP, _VP, _VP]),
@@ -328,6 +329,13 @@ class Engine:
 
     def submit_ptr(self, host_ptr: int, nbytes: int, is_last: bool | int = False):
         self._ck(self.L.f2q_submit(self.h, C.c_void_p(host_ptr), nbytes, int(is_last)))
+
+    def submit_file(self, path: str, gzip: bool, limit_lines: int = 0, threads: int = 1):
+        """one sequencing file -> the current sample, read / inflated natively into pinned ring buffers (f2q_submit_file).
+        Returns (complete, uncompressed bytes); complete is False for a gzip stream that broke off before its end."""
+        ok, nb = C.c_int32(1), C.c_uint64(0)
+        self._ck(self.L.f2q_submit_file(self.h, os.fsencode(path), int(bool(gzip)), int(limit_lines), int(threads), C.byref(ok), C.byref(nb)))
+        return bool(ok.value), int(nb.value)
 
     def submit_device(self, dptr: int, nbytes: int, is_last: bool | int = False):
         self._ck(self.L.f2q_submit_device(self.h, C.c_void_p(dptr), nbytes, int(is_last)))

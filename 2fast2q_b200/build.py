@@ -14,7 +14,7 @@ HEADERS = ["f2q_dev.cuh", "generic.cuh", "resolve.cuh", "stream.cuh", "tile.cuh"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "--extended-lambda", "-split-compile", "0",
-    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "-shared", "-cudart", "static", "-lz",
 ]
 
 

@@ -9,6 +9,9 @@
 #include <cstring>
 #include <deque>
 #include <dlfcn.h>
+#include <zlib.h>
+#include <thread>
+#include <cerrno>
 #include <sys/mman.h>
 #include <sys/syscall.h>
 #include <unistd.h>
@@ -39,6 +42,16 @@ thread_local std::string g_create_err;
 struct DevBuf {
     void* p = nullptr; size_t n = 0;
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+// page-locked ring of f2q_submit_file: the file is read / inflated straight into these, the copy engine drains them
+struct FileRing {
+    static constexpr int N = 3;
+    uint8_t* buf[N] = {nullptr, nullptr, nullptr};
+    cudaEvent_t done[N] = {nullptr, nullptr, nullptr};
+    bool used[N] = {false, false, false};
+    size_t bytes = 0;
+    int next = 0;
 };
 
 }  // namespace
@@ -95,12 +108,13 @@ struct f2q_ctx {
     uint64_t ec_ring_next = 0;
     unsigned long long ec_known[4] = {0, 0, 0, 0};   // newest counters seen: arena bytes, arena keys, packed keys, spec_off
     int flex_warps = 16;                             // option "flex_warps": warps per CTA of the streaming kernel's flex policies
+    FileRing* file_ring = nullptr;                   // page-locked ring of f2q_submit_file (allocated on first use)
     // multi-GPU (NCCL): the communicator this context is a rank of
     void* comm = nullptr; int comm_rank = 0, comm_size = 1; bool comm_owner = false;
     bool ec_merged = false;                          // f2q_ec_merge ran for this sample: the packed table holds every rank's keys,
     std::vector<uint8_t> ec_extra_keys; std::vector<uint64_t> ec_extra_off, ec_extra_cnt;   // ... and these the merged byte-arena keys
     int seed_group = 1;                              // lanes per key of the fast1 seed resolver (auto)
-    int64_t memo_entries = -1;                       // option "memo_entries": -1 auto (2^20 when m >= 2), 0 off
+    int64_t memo_entries = -1;                       // option "memo_entries": -1 / 0 off, else a power of two
     DevBuf memo;
     uint64_t memo_counts[2] = {0, 0};                // last finished sample: memo lookups / hits
     int fx_group = 1, fx_group_opt = 0;              // lanes per key of the flex resolver (auto from the seed index / option)
@@ -119,7 +133,7 @@ struct f2q_ctx {
     int spec = 1;                      // 0: always the exact look-back kernel
     int spec_warps = 16;               // warps per CTA (one CTA per SM): 12 or 16
     int spec_range_tiles = 0;          // 0 auto | tiles per range
-    int spec_ready[4][8][2] = {{{0}}}; // function attributes set for (policy, ch, warps == 16)
+    int spec_ready[4][8][4] = {{{0}}}; // function attributes set for (policy, ch, warps / 4 - 3)
     DevBuf spec_rec, spec_scratch;
     DevBuf synth_guides; size_t synth_guide_bytes = 0;   // guide table of the last f2q_synth_fastq call (K0, bench / tests)
     // [0] tables + result outputs, [1] tables + scratch outputs, in device memory (SlowArgs, generic.cuh); re-uploaded when they change
@@ -313,7 +327,7 @@ int launch_spec(f2q_ctx* c, const SpecParams& P, Outputs O) {
     p.hist_smem = hist;
     const size_t smem = spec_smem_bytes<POLICY, CH, W>(H, hist ? c->n_keys : 0);
     if (smem + sizeof(GenericCfg) + SPEC_SMEM_MARGIN > SM_SMEM_BYTES) return 1;        // does not fit with W warps: the caller retries with fewer
-    int& ready = c->spec_ready[POLICY][CH][W == 16];
+    int& ready = c->spec_ready[POLICY][CH][W / 4 - 3];
     if (!ready) {
         CU(c, cudaFuncSetAttribute(k_spec<POLICY, CH, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_SMEM_BYTES - sizeof(GenericCfg) - SPEC_SMEM_MARGIN)));
         ready = 1;
@@ -340,12 +354,19 @@ int launch_spec_dyn(f2q_ctx* c, const SpecParams& P, Outputs O) {
     const bool f = c->policy == POLICY_FAST1;
 #define F2Q_SPEC_CASE(CHV)                                                                                         \
     case CHV:                                                                                                      \
-        if (c->spec_warps == 16) {                                                                                 \
+        if (c->spec_warps >= 16) {                                                                                 \
             const int rc16 = f ? launch_spec<POLICY_FAST1, CHV, 16>(c, P, O) : launch_spec<POLICY_GENERIC, CHV, 16>(c, P, O); \
             if (rc16 != 1) return rc16;                                                                            \
         }                                                                                                          \
         rc12 = f ? launch_spec<POLICY_FAST1, CHV, 12>(c, P, O) : launch_spec<POLICY_GENERIC, CHV, 12>(c, P, O);      \
         return rc12 == 1 ? fail(c, F2Q_EINTERNAL, "speculative kernel does not fit on an SM") : rc12;
+    if (f && c->spec_warps > 16) {
+        // 20 / 24 warps with a two-stage ring (the fast1 policy only)
+        int rcw = 1;
+        if (c->spec_warps == 24) rcw = c->ch == 3 ? launch_spec<POLICY_FAST1, 3, 24>(c, P, O) : c->ch == 5 ? launch_spec<POLICY_FAST1, 5, 24>(c, P, O) : launch_spec<POLICY_FAST1, 7, 24>(c, P, O);
+        if (rcw == 1) rcw = c->ch == 3 ? launch_spec<POLICY_FAST1, 3, 20>(c, P, O) : c->ch == 5 ? launch_spec<POLICY_FAST1, 5, 20>(c, P, O) : launch_spec<POLICY_FAST1, 7, 20>(c, P, O);
+        if (rcw != 1) return rcw;
+    }
     switch (c->ch) {
         F2Q_SPEC_CASE(3)
         F2Q_SPEC_CASE(5)
@@ -816,6 +837,8 @@ F2Q_EXPORT int f2q_create(const f2q_config* cfg, int device, void* stream, f2q_c
 }
 
 F2Q_EXPORT int f2q_comm_destroy(f2q_ctx* c);
+F2Q_EXPORT int f2q_host_free(void* ptr);
+F2Q_EXPORT int f2q_host_alloc_near(void** ptr, uint64_t nbytes, int device, int flags, int* numa_node);
 
 F2Q_EXPORT void f2q_destroy(f2q_ctx* c) {
     if (!c) return;
@@ -828,6 +851,10 @@ F2Q_EXPORT void f2q_destroy(f2q_ctx* c) {
     for (auto& p : c->ec_pend) if (p.ev) cudaEventDestroy(p.ev);
     for (auto e : c->ec_events) cudaEventDestroy(e);
     if (c->ec_meta_host) cudaFreeHost(c->ec_meta_host);
+    if (c->file_ring) {
+        for (int k = 0; k < FileRing::N; k++) { if (c->file_ring->buf[k]) f2q_host_free(c->file_ring->buf[k]); if (c->file_ring->done[k]) cudaEventDestroy(c->file_ring->done[k]); }
+        delete c->file_ring; c->file_ring = nullptr;
+    }
     f2q_comm_destroy(c);
     for (auto p : c->d_stage) cudaFree(p);
     for (auto e : c->ev_copied) cudaEventDestroy(e);
@@ -861,7 +888,7 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "time_kernels") c->time_kernels = value != 0;
     else if (n == "debug_waits") c->debug_waits = value != 0;
     else if (n == "spec") c->spec = value != 0;
-    else if (n == "spec_warps") { if (value != 12 && value != 16) return fail(c, F2Q_EINVAL, "spec_warps must be 12 or 16"); c->spec_warps = (int)value; }
+    else if (n == "spec_warps") { if (value != 12 && value != 16 && value != 20 && value != 24) return fail(c, F2Q_EINVAL, "spec_warps must be 12, 16, 20 or 24"); c->spec_warps = (int)value; }
     else if (n == "memo_entries") { if (value < -1 || value > (1ll << 28) || (value > 0 && (value & (value - 1)))) return fail(c, F2Q_EINVAL, "memo_entries must be -1 (auto), 0 (off) or a power of two"); c->memo_entries = value; if (c->lib_set) return fail(c, F2Q_ESTATE, "memo_entries must be set before f2q_set_library"); }
     else if (n == "flex_warps") { if (value != 12 && value != 16) return fail(c, F2Q_EINVAL, "flex_warps must be 12 or 16"); c->flex_warps = (int)value; }
     else if (n == "spec_range_tiles") { if (value < 0 || value > (1 << 20)) return fail(c, F2Q_EINVAL, "spec_range_tiles out of range"); c->spec_range_tiles = (int)value; }
@@ -1149,7 +1176,8 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
                 double w = 0, tot = 0;
                 for (size_t i = 0; i < ent.size();) { size_t e = i; while (e < ent.size() && ent[e].first == ent[i].first) e++; w += (double)(e - i) * (double)(e - i); tot += (double)(e - i); i = e; }
                 const double mean = tot > 0 ? w / tot : 0;
-                c->fx_group = mean >= 16 ? 32 : mean >= 3 ? 8 : 1;
+                (void)mean;
+                c->fx_group = 1;                                       // (as for the fast1 resolver: one thread per key)
             }
             if ((rc = upload(c, fslots, &c->T.fx_slots)) || (rc = upload(c, len_sig, &c->T.fx_len_sig)) ||
                 (rc = upload(c, fs_slots, &c->T.fxs_slots)) || (rc = upload(c, fs_recs, &c->T.fxs_recs)))
@@ -1162,11 +1190,13 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
         double w = 0, tot = 0;
         for (const uint4& sl : seed_slots) if (sl.x | sl.y) { w += (double)sl.w * (double)sl.w; tot += (double)sl.w; }
         const double mean = tot > 0 ? w / tot : 0;
-        c->seed_group = mean >= 16 ? 32 : mean >= 3 ? 8 : 1;
+        (void)mean;
+        c->seed_group = 1;        // measured (config 3: 250 M queued keys, ~36 candidates each): one thread per key 46 ms, 8 / 32 lanes 104 ms — with
+                                  // millions of keys in flight the GPU hides the candidate loads' latency itself; lanes per key only add instructions
     }
     {
         // memo of resolved keys: emptied with every new library
-        const int64_t want = c->memo_entries < 0 ? (c->cfg.miss >= 2 ? (1ll << 20) : 0) : c->memo_entries;
+        const int64_t want = c->memo_entries < 0 ? 0 : c->memo_entries;     // (off unless asked for: a stream without repeated non-exact keys only pays for it)
         c->memo.release();
         if (want > 0 && c->cfg.miss > 0) {
             if ((rc = dev_alloc(c, c->memo, (size_t)want * 16))) return rc;
@@ -1242,12 +1272,10 @@ F2Q_EXPORT int f2q_submit_device(f2q_ctx* c, const void* dptr, uint64_t nbytes, 
     return F2Q_OK;
 }
 
-F2Q_EXPORT int f2q_submit(f2q_ctx* c, const uint8_t* host_chunk, uint64_t nbytes, int is_last) {
-    int rc = check_ctx(c); if (rc) return rc;
-    if (!c->in_sample) return fail(c, F2Q_ESTATE, "f2q_submit outside a sample");
-    if (c->sample_failed) return c->sample_failed;
-    if (c->closed) return fail(c, F2Q_ESTATE, "stream already closed with is_last");
-    if (nbytes && !host_chunk) return fail(c, F2Q_EINVAL, "null chunk");
+// host chunk -> staging slots -> kernels.  `host_done` (optional) is recorded on the copy stream behind the last copy out of
+// host_chunk: the caller may refill the host buffer once it has completed
+static int submit_host(f2q_ctx* c, const uint8_t* host_chunk, uint64_t nbytes, int is_last, cudaEvent_t host_done) {
+    int rc;
     if ((rc = ensure_staging(c))) return rc;
     if (!c->ch_decided && nbytes) { decide_ch(c, host_chunk, (size_t)std::min<uint64_t>(nbytes, 4096)); c->ch_from_device = false; }
     uint64_t done = 0;
@@ -1260,11 +1288,254 @@ F2Q_EXPORT int f2q_submit(f2q_ctx* c, const uint8_t* host_chunk, uint64_t nbytes
         CU(c, cudaEventRecord(c->ev_copied[s], c->copy_stream));
         CU(c, cudaStreamWaitEvent(c->stream, c->ev_copied[s], 0));
         done += len;
+        if (done == nbytes && host_done) CU(c, cudaEventRecord(host_done, c->copy_stream));
         rc = process_device_chunk(c, c->d_stage[s], len, is_last && done == nbytes);
         CU(c, cudaEventRecord(c->ev_free[s], c->stream));               // (also on failure: kernels already queued may still read the slot)
         if (rc) { if (!c->sticky) c->sample_failed = rc; return rc; }
     } while (done < nbytes);
     return F2Q_OK;
+}
+
+F2Q_EXPORT int f2q_submit(f2q_ctx* c, const uint8_t* host_chunk, uint64_t nbytes, int is_last) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (!c->in_sample) return fail(c, F2Q_ESTATE, "f2q_submit outside a sample");
+    if (c->sample_failed) return c->sample_failed;
+    if (c->closed) return fail(c, F2Q_ESTATE, "stream already closed with is_last");
+    if (nbytes && !host_chunk) return fail(c, F2Q_EINVAL, "null chunk");
+    return submit_host(c, host_chunk, nbytes, is_last, nullptr);
+}
+
+// ---- native file ingest ------------------------------------------------------------------------------------------------
+// One sequencing file -> the current sample, on host threads and without a copy in between: the file is read (.fastq) or
+// inflated (.gz) straight INTO page-locked ring buffers near the GPU, which f2q_submit's copy engine drains.
+// Replaces the open / gzip.open + `for line in current` of reads_counter and fastq_parser (fast2q.py:566-578, 324).
+//   .fastq   read(2) into the ring, chunks cut anywhere (the device carries the partial record)
+//   .gz      zlib inflate into the ring; multi-member files and zero padding between members as Python's gzip module reads
+//            them.  Only WHOLE LINES are submitted while the stream is open, so that a stream that breaks off ends exactly
+//            like the reference's line iterator: every complete line before the break is parsed, the partial one is dropped
+//            and *complete = 0 (the reference's EOFError, fast2q.py:405-407)
+//   BGZF     (bgzip: gzip members of <= 64 KiB that carry their compressed size in an extra field and their uncompressed
+//            size in their trailer) blocks are independent: `threads` workers inflate a ring buffer's worth of blocks in
+//            parallel, each straight to its final offset (BGZF-aware parallel host inflate)
+namespace {
+
+int ring_get(f2q_ctx* c, FileRing& R, uint8_t** out, int* idx) {
+    const int k = R.next; R.next = (R.next + 1) % FileRing::N;
+    if (R.used[k]) CU(c, cudaEventSynchronize(R.done[k]));              // the copy out of this buffer (N submits ago) has finished
+    *out = R.buf[k]; *idx = k;
+    return F2Q_OK;
+}
+
+int ring_submit(f2q_ctx* c, FileRing& R, int idx, uint64_t n, int last) {
+    R.used[idx] = true;
+    return submit_host(c, R.buf[idx], n, last, R.done[idx]);
+}
+
+const uint8_t* last_newline(const uint8_t* p, size_t n) { return static_cast<const uint8_t*>(memrchr(p, '\n', n)); }
+
+// BGZF block at p (>= 18 bytes available): total block size, or 0 when this is not a BGZF member header
+size_t bgzf_block_size(const uint8_t* p, size_t avail) {
+    if (avail < 18 || p[0] != 0x1f || p[1] != 0x8b || p[2] != 8 || p[3] != 4) return 0;
+    if (p[12] != 'B' || p[13] != 'C' || p[14] != 2 || p[15] != 0 || (unsigned)(p[10] | p[11] << 8) < 6) return 0;
+    return (size_t)(p[16] | p[17] << 8) + 1;
+}
+
+}  // namespace
+
+F2Q_EXPORT int f2q_submit_file(f2q_ctx* c, const char* path, int is_gzip, uint64_t limit_lines, int threads, int* complete, uint64_t* bytes_out) {
+    int rc = check_ctx(c); if (rc) return rc;
+    if (!c->in_sample) return fail(c, F2Q_ESTATE, "f2q_submit_file outside a sample");
+    if (c->sample_failed) return c->sample_failed;
+    if (c->closed) return fail(c, F2Q_ESTATE, "stream already closed with is_last");
+    if (!path) return fail(c, F2Q_EINVAL, "null path");
+    if (complete) *complete = 1;
+    if (bytes_out) *bytes_out = 0;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(c, F2Q_EINVAL, std::string("cannot open ") + path + ": " + strerror(errno));
+    setvbuf(f, nullptr, _IONBF, 0);
+    // the ring lives with the context
+    if (!c->file_ring) c->file_ring = new FileRing();
+    FileRing& R = *c->file_ring;
+    if (!R.buf[0]) {
+        R.bytes = 32u << 20;
+        for (int k = 0; k < FileRing::N; k++) {
+            void* p = nullptr;
+            if ((rc = f2q_host_alloc_near(&p, R.bytes + 65536, c->device, 0, nullptr))) { fclose(f); return fail(c, rc, f2q_last_error(nullptr)); }
+            R.buf[k] = static_cast<uint8_t*>(p);
+            if (cudaEventCreateWithFlags(&R.done[k], cudaEventDisableTiming) != cudaSuccess) { fclose(f); return fail(c, F2Q_ECUDA, "cudaEventCreate failed"); }
+        }
+    }
+    if ((rc = ensure_staging(c))) { fclose(f); return rc; }
+    uint64_t total = 0, lines_left = limit_lines;
+    bool stop = false;                                                 // preprocess mode: the line limit was reached
+    // cut `n` bytes at the line limit; returns the bytes to submit
+    auto apply_limit = [&](const uint8_t* p, uint64_t n) -> uint64_t {
+        if (!limit_lines) return n;
+        const uint8_t* q = p; const uint8_t* e = p + n;
+        while (q < e) {
+            const uint8_t* nl = static_cast<const uint8_t*>(memchr(q, '\n', (size_t)(e - q)));
+            if (!nl) break;
+            q = nl + 1;
+            if (--lines_left == 0) { stop = true; return (uint64_t)(q - p); }
+        }
+        return n;
+    };
+    int idx = 0; uint8_t* buf = nullptr;
+    if (!is_gzip) {
+        for (;;) {
+            if ((rc = ring_get(c, R, &buf, &idx))) break;
+            const size_t n = fread(buf, 1, R.bytes, f);
+            const bool eof = n < R.bytes;
+            const uint64_t m = apply_limit(buf, n);
+            total += m;
+            if ((rc = ring_submit(c, R, idx, m, (eof || stop) ? 1 : 0)) || eof || stop) break;
+        }
+        fclose(f);
+        if (bytes_out) *bytes_out = total;
+        return rc;
+    }
+    // ---- gzip ----
+    std::vector<uint8_t> in(8u << 20);
+    size_t in_len = fread(in.data(), 1, in.size(), f), in_pos = 0;
+    bool in_eof = in_len < in.size();
+    auto refill = [&]() {                                              // keep the unread input, append more
+        if (in_pos) { memmove(in.data(), in.data() + in_pos, in_len - in_pos); in_len -= in_pos; in_pos = 0; }
+        if (!in_eof && in_len < in.size()) { const size_t g = fread(in.data() + in_len, 1, in.size() - in_len, f); if (g < in.size() - in_len) in_eof = true; in_len += g; }
+    };
+    size_t tail = 0;                                                   // bytes behind the last newline, carried at the start of `buf`
+    bool truncated = false, corrupt = false;
+    if ((rc = ring_get(c, R, &buf, &idx))) { fclose(f); return rc; }
+    size_t fill = 0;                                                   // bytes in buf (the tail included)
+    // submit buf[0, cut) (whole lines) and carry the rest into the next ring buffer
+    auto flush_lines = [&](bool final_ok) -> int {
+        size_t cut = fill;
+        if (!final_ok) { const uint8_t* nl = fill ? last_newline(buf, fill) : nullptr; cut = nl ? (size_t)(nl - buf) + 1 : 0; }
+        const uint64_t m = apply_limit(buf, cut);
+        uint8_t* nb; int nidx;
+        int r2 = ring_get(c, R, &nb, &nidx); if (r2) return r2;
+        tail = fill - cut;
+        if (tail) memcpy(nb, buf + cut, tail);
+        total += m;
+        if (m || stop) r2 = ring_submit(c, R, idx, m, stop ? 1 : 0);
+        buf = nb; idx = nidx; fill = tail;
+        return r2;
+    };
+    const bool bgzf = threads > 1 && bgzf_block_size(in.data(), in_len) != 0;
+    if (bgzf) {
+        struct Blk { const uint8_t* src; uint32_t csize, isize; size_t dst; };
+        std::vector<Blk> blks;
+        bool fell_back = false;
+        while (!stop && !rc) {
+            // gather whole blocks while they fit into the ring buffer
+            blks.clear();
+            size_t out = fill;
+            for (;;) {
+                if (in_len - in_pos < 18 || bgzf_block_size(in.data() + in_pos, in_len - in_pos) > in_len - in_pos) {
+                    if (in_eof || !blks.empty()) break;
+                    refill();
+                    if (in_len - in_pos < 18 && in_eof) break;
+                    continue;
+                }
+                const size_t bs = bgzf_block_size(in.data() + in_pos, in_len - in_pos);
+                if (!bs) { fell_back = true; break; }                   // a foreign member: the serial reader takes over
+                const uint8_t* p = in.data() + in_pos;
+                const uint32_t xlen = (uint32_t)(p[10] | p[11] << 8);
+                if (bs < 12u + xlen + 8u) { corrupt = true; break; }
+                uint32_t isize; memcpy(&isize, p + bs - 4, 4);
+                if (isize > 65536u) { corrupt = true; break; }
+                if (out + isize > R.bytes + 65536) break;
+                blks.push_back({p + 12 + xlen, (uint32_t)(bs - 12 - xlen - 8), isize, out});
+                out += isize; in_pos += bs;
+                if (out >= R.bytes) break;
+            }
+            if (corrupt) break;
+            if (blks.empty()) {
+                if (fell_back) break;
+                if (in_eof) { if (in_len - in_pos) fell_back = true; break; }      // a partial block at the end: the serial reader delivers its decodable part
+                continue;
+            }
+            // inflate them in parallel, each to its final place
+            const int T = std::max(1, std::min<int>(threads, (int)blks.size()));
+            std::vector<int> bad(T, 0);
+            auto work = [&](int t) {
+                z_stream z; memset(&z, 0, sizeof(z));
+                if (inflateInit2(&z, -15) != Z_OK) { bad[t] = 1; return; }
+                for (size_t k = t; k < blks.size(); k += T) {
+                    inflateReset(&z);
+                    z.next_in = const_cast<Bytef*>(blks[k].src); z.avail_in = blks[k].csize;
+                    z.next_out = buf + blks[k].dst; z.avail_out = blks[k].isize;
+                    const int zr = inflate(&z, Z_FINISH);
+                    if (zr != Z_STREAM_END || z.avail_out != 0) { bad[t] = 1; break; }
+                }
+                inflateEnd(&z);
+            };
+            std::vector<std::thread> pool;
+            for (int t = 1; t < T; t++) pool.emplace_back(work, t);
+            work(0);
+            for (auto& th : pool) th.join();
+            for (int t = 0; t < T; t++) if (bad[t]) corrupt = true;
+            if (corrupt) break;
+            fill = out;
+            rc = flush_lines(false);
+            refill();
+        }
+        if (fell_back && !corrupt && !rc && !stop) { /* continue below with the serial reader on the remaining input */ }
+        else {
+            fclose(f);
+            if (rc) return rc;
+            if (corrupt) { if (complete) *complete = 0; return fail(c, F2Q_EINVAL, std::string(path) + ": corrupted gzip data"); }
+            if (!stop) {
+                // the last line: complete streams keep an unterminated final line, truncated ones drop it
+                if (truncated) { fill = 0; if (complete) *complete = 0; }
+                total += fill;
+                rc = ring_submit(c, R, idx, fill, 1);
+            }
+            if (bytes_out) *bytes_out = total;
+            return rc;
+        }
+    }
+    {
+        z_stream z; memset(&z, 0, sizeof(z));
+        if (inflateInit2(&z, 15 + 16) != Z_OK) { fclose(f); return fail(c, F2Q_ENOMEM, "inflateInit2 failed"); }
+        bool fresh = true;                                             // at a member boundary, nothing consumed yet
+        while (!stop && !rc) {
+            if (in_pos == in_len) {
+                refill();
+                if (in_pos == in_len) { if (!fresh) truncated = true; break; }
+            }
+            if (fresh) {
+                while (in_pos < in_len && in[in_pos] == 0) in_pos++;   // zero padding between members (gzip module behaviour)
+                if (in_pos == in_len) continue;
+                fresh = false;
+            }
+            if (fill >= R.bytes) { if ((rc = flush_lines(false))) break; if (fill >= R.bytes) { rc = fail(c, F2Q_ETOOLONG, "a line longer than the ingest buffer"); break; } }
+            z.next_in = in.data() + in_pos; z.avail_in = (uInt)std::min<size_t>(in_len - in_pos, 1u << 30);
+            z.next_out = buf + fill; z.avail_out = (uInt)(R.bytes - fill);
+            const uInt in0 = z.avail_in, out0 = z.avail_out;
+            const int zr = inflate(&z, Z_NO_FLUSH);
+            in_pos += in0 - z.avail_in; fill += out0 - z.avail_out;
+            if (zr == Z_STREAM_END) { inflateReset(&z); fresh = true; }
+            else if (zr != Z_OK && zr != Z_BUF_ERROR) { corrupt = true; break; }
+            else if (zr == Z_BUF_ERROR && z.avail_in == 0 && in_eof && in_pos == in_len) { truncated = true; break; }
+        }
+        inflateEnd(&z);
+    }
+    fclose(f);
+    if (rc) return rc;
+    if (corrupt) { if (complete) *complete = 0; return fail(c, F2Q_EINVAL, std::string(path) + ": corrupted gzip data"); }
+    if (!stop) {
+        if (truncated) {
+            // every complete line before the break is parsed, the partial one is dropped (fast2q.py:405-407)
+            const uint8_t* nl = fill ? last_newline(buf, fill) : nullptr;
+            fill = nl ? (size_t)(nl - buf) + 1 : 0;
+            if (complete) *complete = 0;
+        }
+        const uint64_t m = apply_limit(buf, fill);
+        total += m;
+        rc = ring_submit(c, R, idx, m, 1);
+    }
+    if (bytes_out) *bytes_out = total;
+    return rc;
 }
 
 F2Q_EXPORT int f2q_sync(f2q_ctx* c) {

@@ -30,7 +30,9 @@
 
 namespace f2q {
 
-constexpr int SPEC_STAGES = 3;
+// stages of a warp's ring: three (scan tile i+1 and parse tile i while tile i+2 lands) up to 16 warps per CTA; with 20 or 24
+// warps two stages — the other warps hide the exposed part of a warp's own load latency, and the shared memory fits
+__host__ __device__ constexpr int spec_stages(int W) { return W > 16 ? 2 : 3; }
 constexpr int SPEC_CAP = 6 * 32;                     // newline positions kept per tile (its 32 own rows)
 constexpr uint32_t SPEC_MAX_HALO = 16;
 
@@ -60,12 +62,12 @@ struct SpecGeom {
     static constexpr int NL_LIST = SPEC_CAP + 8;                       // u16 entries of one position list
     static constexpr int NL_HALO = 6 * (int)16 + 8;                    // ... of the list of a range's last read-ahead rows (SPEC_MAX_HALO rows)
     __host__ __device__ static constexpr uint32_t stage_bytes(uint32_t H, uint32_t pad) { return (((32u + H) * S + pad + 127u) / 128u) * 128u; }
-    __host__ __device__ static constexpr uint32_t warp_bytes(uint32_t H, uint32_t pad) { return ((SPEC_STAGES * stage_bytes(H, pad) + (2u * NL_LIST + NL_HALO) * 2u + 127u) / 128u) * 128u; }
+    __host__ __device__ static constexpr uint32_t warp_bytes(uint32_t H, uint32_t pad, uint32_t ns) { return ((ns * stage_bytes(H, pad) + (2u * NL_LIST + NL_HALO) * 2u + 127u) / 128u) * 128u; }
 };
 
 template <int POLICY, int CH, int W>
 __host__ __device__ inline size_t spec_smem_bytes(uint32_t H, uint32_t hist_entries) {
-    return (size_t)W * SpecGeom<CH>::warp_bytes(H, spec_stage_pad(POLICY)) + (size_t)hist_entries * 4;
+    return (size_t)W * SpecGeom<CH>::warp_bytes(H, spec_stage_pad(POLICY), spec_stages(W)) + (size_t)hist_entries * 4;
 }
 
 __device__ __forceinline__ uint64_t spec_n_ranges(uint64_t beg, uint64_t end, uint64_t own, uint64_t range_bytes, uint64_t& origin0) {
@@ -80,7 +82,7 @@ __global__ void __launch_bounds__(W * 32, 1)
 k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, Outputs O, const SlowArgs* __restrict__ X,
        const __grid_constant__ FlexCfg FC) {
     using G_ = SpecGeom<CH>;
-    constexpr int S = G_::S, OWN = G_::OWN, NS = SPEC_STAGES, CAP = SPEC_CAP, MW = G_::MW;
+    constexpr int S = G_::S, OWN = G_::OWN, NS = spec_stages(W), CAP = SPEC_CAP, MW = G_::MW;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar_full[W][NS];
     __shared__ uint32_t s_qn;
@@ -93,7 +95,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
     const uint32_t H = P.halo_rows;
     constexpr bool FLEX = policy_is_flex(POLICY);
     constexpr uint32_t PAD = spec_stage_pad(POLICY);
-    const uint32_t stage_bytes = G_::stage_bytes(H, PAD), warp_bytes = G_::warp_bytes(H, PAD), load_bytes = (32u + H) * S;
+    const uint32_t stage_bytes = G_::stage_bytes(H, PAD), warp_bytes = G_::warp_bytes(H, PAD, NS), load_bytes = (32u + H) * S;
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem + (size_t)W * warp_bytes);
     if (St->spec_off || end <= beg) return;                            // (a sample whose speculation failed once stays on the exact kernel)
 
@@ -317,10 +319,14 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                     // (bounded in time: a copy that never lands fails the speculation — the exact kernel then redoes the
                     // chunk — and this warp stops taking work; nothing traps, see WAIT_CYCLE_LIMIT in tile.cuh)
                     if (!mbar_try_wait(&bars[s], (par_bits >> s) & 1u)) {
-                        const long long tw = clock64();
+                        long long tw = 0;                               // (the clock is read only after 1024 failed tries: never on the ordinary path)
                         uint32_t spins = 0;
-                        while (!mbar_try_wait(&bars[s], (par_bits >> s) & 1u))
-                            if ((++spins & 1023u) == 0u && clock64() - tw > WAIT_CYCLE_LIMIT) { dead = true; break; }
+                        while (!mbar_try_wait(&bars[s], (par_bits >> s) & 1u)) {
+                            if ((++spins & 1023u) != 0u) continue;
+                            const long long now = clock64();
+                            if (tw == 0) tw = now;
+                            else if (now - tw > WAIT_CYCLE_LIMIT) { dead = true; break; }
+                        }
                         if (dead) { if (lane == 0) St->spec_fail = 1u; F2Q_TIMEOUT_TRAP(); break; }
                     }
                     par_bits ^= 1u << s;

@@ -119,6 +119,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // bounded wait: a protocol bug must not hang the GPU.  gerr = the sample's error word (DevState::error)
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, volatile uint32_t* abort, uint32_t* gerr, unsigned long long* dbg = nullptr) {
     if (*abort) return false;
+    if (mbar_try_wait(bar, parity)) return true;                        // (the ordinary case reads no clock)
     const long long t0 = clock64();
     for (uint32_t spins = 0;; spins++) {
         if (mbar_try_wait(bar, parity)) { if (dbg && (threadIdx.x & 31) == 0) atomicAdd(dbg, (unsigned long long)(clock64() - t0)); return true; }

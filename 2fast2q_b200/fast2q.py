@@ -300,18 +300,24 @@ def _raw_blocks(path, want=None):
 
 
 class _PinnedRing:
-    """a few page-locked buffers a feeder cycles through (f2q_host_alloc)"""
+    """a few page-locked buffers a feeder cycles through (f2q_host_alloc_near: on the NUMA node of the GPU they feed);
+    allocated on first use — the file mode streams through libf2q's own ring (f2q_submit_file) and never needs them"""
 
     def __init__(self, n=3, nbytes=None, device=None):
-        nbytes = nbytes or CHUNK_BYTES
-        self.bufs = [_lib.PinnedBuffer(nbytes, device) for _ in range(n)]       # on the NUMA node of the GPU they feed
+        self.nbytes = nbytes or CHUNK_BYTES
+        self.n, self.device = n, device
+        self.bufs = []
         self.k = 0
-        self.nbytes = nbytes
 
     def next(self):
+        if not self.bufs:
+            self.bufs = [_lib.PinnedBuffer(self.nbytes, self.device) for _ in range(self.n)]
         b = self.bufs[self.k % len(self.bufs)]
         self.k += 1
         return b
+
+    def __len__(self):
+        return self.n
 
     def free(self):
         for b in self.bufs:
@@ -320,54 +326,21 @@ class _PinnedRing:
 
 
 def _stream_file(engine, ring, raw, limit_lines=None):
-    """feeds one file through engine.submit; returns False when the gzip stream was truncated.
-    Only whole lines are submitted while the stream is open, so that a truncated gzip ends exactly like the
-    reference's line iterator does: every complete line before the break is parsed, the partial one is dropped."""
+    """feeds one file through the engine; returns False when the gzip stream was truncated.
+    The work is native (f2q_submit_file): the file is read, or inflated with zlib — bgzip files block-parallel on host
+    threads — straight into page-locked ring buffers near the GPU; no byte passes through a Python object.  While a gzip
+    stream is open only whole lines are submitted, so a truncated stream ends exactly like the reference's line iterator:
+    every complete line before the break is parsed, the partial one is dropped (fast2q.py:405-407)."""
     gz = os.path.splitext(raw)[1] == ".gz"
-    blocks = _inflate_blocks(raw) if gz else _raw_blocks(raw)
-    tail = b""
-    ok = True
-    lines_left = limit_lines
-    submits = 0
-
-    def push(piece, last):
-        """one or more submits (a piece may be longer than a ring buffer when a long unfinished line was carried)"""
-        nonlocal submits
-        cap = ring.nbytes
-        n_sub = max(1, -(-len(piece) // cap))
-        for k in range(n_sub):
-            part = piece[k * cap:(k + 1) * cap]
-            buf = ring.next()
-            if submits >= len(ring.bufs):
-                engine.sync_copies()                        # the copy out of this buffer (ring size submits ago) is done
-            if part:
-                buf.array[:len(part)] = np.frombuffer(part, dtype=np.uint8)
-            engine.submit_ptr(buf.ptr.value, len(part), last and k == n_sub - 1)
-            submits += 1
-
     try:
-        for block in blocks:
-            if lines_left is not None:
-                have = block.count(b"\n")
-                if have >= lines_left:                      # preprocess mode: stop after limit_lines lines
-                    pos = -1
-                    for _ in range(lines_left):
-                        pos = block.find(b"\n", pos + 1)
-                    push(tail + block[:pos + 1], True)
-                    return True
-                lines_left -= have
-            cut = block.rfind(b"\n") + 1
-            if cut == 0:
-                tail += block
-                continue
-            piece = tail + block[:cut] if tail else (block[:cut] if cut < len(block) else block)
-            tail = block[cut:]
-            push(piece, False)
-    except TruncatedGzip:
-        ok = False
-        tail = b""                                          # the unfinished line is never seen by the reference's loop
-    push(tail, True)                                        # a final line without '\n' still counts (fast2q.py:324-328)
-    return ok
+        complete, _ = engine.submit_file(raw, gz, limit_lines or 0, _INFLATE_WORKERS)
+    except _lib.F2QError as e:
+        if e.code == -1 and "corrupted gzip" in str(e):
+            raise zlib.error(str(e)) from None
+        if e.code == -1 and "cannot open" in str(e):
+            raise OSError(str(e)) from None
+        raise
+    return complete
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -399,7 +372,8 @@ def _engine_for(param, features, device):
         for old in cache.values():
             old[0].close(); old[1].free()
         cache.clear()
-        eng = _lib.Engine(cfg, device)
+        # the device memo of resolved non-exact keys (the reference's passed_reads / failed_reads): real screens repeat them
+        eng = _lib.Engine(cfg, device, memo_entries=1 << 20) if keys is not None else _lib.Engine(cfg, device)
         if keys is not None:
             eng.set_library(keys)
         cache[sig] = (eng, _PinnedRing(device=device))
@@ -768,7 +742,7 @@ def split_file_counter(raw, features, param, n_gpus):
                 for o in range(0, max(len(item), 1), ring.nbytes):
                     piece = item[o:o + ring.nbytes]
                     buf = ring.next()
-                    if n >= len(ring.bufs):
+                    if n >= len(ring):
                         engine.sync_copies()
                     buf.array[:len(piece)] = np.frombuffer(piece, dtype=np.uint8)
                     engine.submit_ptr(buf.ptr.value, len(piece), False)

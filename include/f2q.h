@@ -122,8 +122,9 @@ const char* f2q_last_error(const f2q_ctx* ctx);   /* ctx may be NULL: last creat
  *                     policies of the streaming kernel when the configuration allows | 0: byte-wise generic kernels
  *   "flex_warps"      12 | 16: warps per CTA of the streaming kernel's bit-parallel policies
  *   "resolve_group"   0 auto | 1 | 8 | 32: lanes that resolve one non-exact key together (seed-index resolvers)
- *   "memo_entries"    -1 auto (2^20 when m >= 2) | 0 off | power of two: entries of the device memo of resolved non-exact
- *                     keys; set before f2q_set_library
+ *   "memo_entries"    0 off (default) | power of two: entries of the device memo of resolved non-exact keys; set before
+ *                     f2q_set_library.  Worth it when the stream repeats its erroneous keys (real screens do; the host layer
+ *                     2fast2q_b200/fast2q.py switches it on), pure overhead when it does not (the synthetic bench streams)
  *   "generic_entries" capacity of the queue of reads handed to the byte-wise generic kernel (default: derived)
  *   "ec_slots"        minimum capacity of the Extract+Count packed key table (default: grown on demand)
  */
@@ -149,6 +150,18 @@ int f2q_begin_sample(f2q_ctx* ctx);
  * is_last != 0 marks end of stream (a final unterminated 4th line still completes a record).
  */
 int f2q_submit(f2q_ctx* ctx, const uint8_t* host_chunk, uint64_t nbytes, int is_last);
+
+/*
+ * One sequencing file -> the current sample, natively: the file is read (is_gzip == 0) or inflated with zlib (is_gzip != 0;
+ * multi-member and zero-padded files as Python's gzip module reads them; bgzip/BGZF files block-parallel on `threads` host
+ * threads) straight into page-locked ring buffers near the GPU and submitted from there; the stream is closed (is_last).
+ * Replaces the open / gzip.open + `for line in current` of reads_counter / fastq_parser (fast2q.py:566-578, 324).
+ * limit_lines > 0 stops after that many lines (preprocess mode parses 10 000 reads = 40 000 lines, fast2q.py:398-400).
+ * *complete (may be NULL) = 0 when a gzip stream broke off before its end: every complete line before the break has been
+ * parsed and the partial one dropped, as the reference's line iterator does before its EOFError (fast2q.py:405-407).
+ * Corrupted deflate data -> F2Q_EINVAL (the reference crashes with zlib.error).  *bytes_out = uncompressed bytes submitted.
+ */
+int f2q_submit_file(f2q_ctx* ctx, const char* path, int is_gzip, uint64_t limit_lines, int threads, int* complete, uint64_t* bytes_out);
 
 /* Same, but the chunk already lives in device memory of this context's GPU (resident mode).  The buffer
  * must stay valid and unmodified until the next f2q_end_sample/f2q_sync returns. */
