@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <deque>
 #include <dlfcn.h>
@@ -593,7 +594,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
     const bool use_spec = c->spec && n && (!ec || flex) && !spec_seen_off;
     const int spec_ch = flex && c->ch == 3 ? 5 : c->ch;
     const uint64_t spec_own = 512ull * spec_ch;
-    uint64_t spec_range_tiles = 0;
+    uint64_t spec_range_tiles = 0, n_spec_rec = 0;
     if (flex) grid = (unsigned)c->sm_count;                            // (the exact kernel runs the generic code: no queue segments of its own)
     if (use_spec) {
         grid = std::max<unsigned>(grid, (unsigned)c->sm_count);        // one queue segment per CTA of either kernel
@@ -601,7 +602,7 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         spec_range_tiles = c->spec_range_tiles > 0 ? (uint64_t)c->spec_range_tiles : std::min<uint64_t>(64, std::max<uint64_t>(8, tiles / (streams * 4)));
         const uint64_t n_rec = (delta + n) / (spec_range_tiles * spec_own) + 2;
         if ((rc = dev_alloc(c, c->spec_rec, n_rec))) return rc;
-        CU(c, cudaMemsetAsync(c->spec_rec.p, 0, n_rec, c->stream));
+        n_spec_rec = n_rec;
     }
     // queues sized for the chunk.  fast1: one entry per 64 bytes covers every non-exact read of ordinary FASTQ; flex Counter
     // the same; flex Extract+Count: the insert log takes EVERY read's key (1.5 x the reads the sniffed record length
@@ -632,12 +633,13 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         if (rc) return rc;
     }
 
-    CU(c, cudaMemsetAsync(c->status.p, 0, n_tiles + 64, c->stream));
-    CU(c, cudaMemsetAsync(c->status_stitch.p, 0, stitch_tiles + 64, c->stream));
-    CU(c, cudaMemsetAsync(c->seg_count.p, 0, (size_t)c->n_segs * 4, c->stream));
+    // (zeroing: the big look-back status array only when the exact kernel really parses the chunk — behind a speculation
+    // k_spec_verify clears it on failure; the small per-chunk arrays inside k_prepare)
+    if (!use_spec) CU(c, cudaMemsetAsync(c->status.p, 0, n_tiles + 64, c->stream));
+    PrepClear Z{reinterpret_cast<uint8_t*>(c->status_stitch.p), (uint32_t)(stitch_tiles + 64), reinterpret_cast<uint8_t*>(c->spec_rec.p), (uint32_t)n_spec_rec,
+                reinterpret_cast<uint32_t*>(c->seg_count.p), c->n_segs};
     k_prepare<<<1, PREP_THREADS, 0, c->stream>>>(c->dS, base, delta, n, is_last ? 1u : 0u, reinterpret_cast<uint8_t*>(c->carry.p),
-                                                 c->carry_cap, c->d_tickets, c->q_cap, c->g_cap);
-    CU(c, cudaMemsetAsync(c->d_tickets + 2, 0, 4, c->stream));
+                                                 c->carry_cap, c->d_tickets, c->q_cap, c->g_cap, Z);
     c->launches++;
     Outputs O = outputs_of(c);
     {
@@ -674,7 +676,8 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
         timing_end(c, t0, 0);
         if (rc) return rc;
         cudaEvent_t t3 = timing_begin(c);
-        k_spec_verify<<<1, SPEC_VERIFY_THREADS, 0, c->stream>>>(c->dS, Q.rec, Q.range_bytes, (uint32_t)spec_own, P.seg_count, c->n_segs);
+        k_spec_verify<<<1, SPEC_VERIFY_THREADS, 0, c->stream>>>(c->dS, Q.rec, Q.range_bytes, (uint32_t)spec_own, P.seg_count, c->n_segs,
+                                                                reinterpret_cast<uint8_t*>(c->status.p), n_tiles + 64);
         const uint64_t nres = (uint64_t)c->n_keys + 5;
         k_spec_merge<<<(unsigned)std::min<uint64_t>((nres + 255) / 256, (uint64_t)c->sm_count * 8), 256, 0, c->stream>>>(c->dS, O2.counts, O.counts, nres);
         c->launches += 2;
@@ -1238,10 +1241,13 @@ F2Q_EXPORT int f2q_begin_sample(f2q_ctx* c) {
     if ((rc = dev_alloc(c, c->carry, c->carry_cap + 256))) return rc;
     if ((rc = dev_alloc(c, c->status_stitch, c->carry_cap / (64 * 16 * 3) + 2 + 64))) return rc;
     if (!c->ch_from_device) c->ch_decided = false;
-    CU(c, cudaMemsetAsync(c->result.p, 0, ((size_t)c->n_keys + 5) * 8, c->stream));
-    if (c->spec_scratch.p) CU(c, cudaMemsetAsync(c->spec_scratch.p, 0, ((size_t)c->n_keys + 5) * 8, c->stream));
-    CU(c, cudaMemsetAsync(c->d_error, 0, 4, c->stream));
-    CU(c, cudaMemsetAsync(c->dS, 0, sizeof(DevState), c->stream));
+    {
+        const uint64_t nw = (uint64_t)c->n_keys + 5;
+        k_begin<<<(unsigned)std::min<uint64_t>((nw + 255) / 256, (uint64_t)c->sm_count), 256, 0, c->stream>>>(
+            reinterpret_cast<unsigned long long*>(c->result.p), reinterpret_cast<unsigned long long*>(c->spec_scratch.p), nw, c->d_error, c->dS);
+        c->launches++;
+        CU(c, cudaGetLastError());
+    }
     if (c->cfg.mode == F2Q_MODE_EXTRACT_COUNT) {
         while (!c->ec_pend.empty()) { if (c->ec_pend.front().ev) { cudaEventSynchronize(c->ec_pend.front().ev); c->ec_events.push_back(c->ec_pend.front().ev); } c->ec_pend.pop_front(); }
         for (int k = 0; k < 4; k++) c->ec_known[k] = 0;
@@ -1602,6 +1608,18 @@ F2Q_EXPORT int f2q_end_sample_async(f2q_ctx* c, uint64_t* pinned_out) {
 }
 
 // ---- Extract+Count results ---------------------------------------------------------------------------
+// compacts one of the two Extract+Count tables on the device: (tag, count) pairs of its `n` keys land in c->ec_compact behind
+// a 16-byte header
+static int ec_compact_table(f2q_ctx* c, const unsigned long long* tags, uint32_t ts, const unsigned long long* counts, uint32_t cs, uint64_t cap, uint64_t n) {
+    int rc = dev_alloc(c, c->ec_compact, (n + 1) * 16 + 16); if (rc) return rc;
+    unsigned long long* d_n = reinterpret_cast<unsigned long long*>(c->ec_compact.p);
+    CU(c, cudaMemsetAsync(d_n, 0, 16, c->stream));
+    k_ec_compact<<<(unsigned)std::min<uint64_t>((cap + 1023) / 1024, (uint64_t)c->sm_count * 32), 256, 0, c->stream>>>(tags, ts, counts, cs, cap, d_n + 2, d_n);
+    c->launches++;
+    CU(c, cudaStreamSynchronize(c->stream));
+    return F2Q_OK;
+}
+
 // number of keys of the packed table and their compacted (tag, count) pairs in c->ec_compact (device)
 static int ec_compact_packed(f2q_ctx* c, uint64_t* n_out) {
     *n_out = 0;
@@ -1610,14 +1628,28 @@ static int ec_compact_packed(f2q_ctx* c, uint64_t* n_out) {
     CU(c, cudaMemcpy(meta, c->ec_meta.p, 32, cudaMemcpyDeviceToHost));
     const uint64_t n = meta[2];
     if (!n) return F2Q_OK;
-    int rc = dev_alloc(c, c->ec_compact, (n + 1) * 16 + 16); if (rc) return rc;
-    unsigned long long* d_n = reinterpret_cast<unsigned long long*>(c->ec_compact.p);
-    CU(c, cudaMemsetAsync(d_n, 0, 16, c->stream));
-    k_ec_compact<<<(unsigned)std::min<uint64_t>((c->ec_pk_cap + 255) / 256, (uint64_t)c->sm_count * 32), 256, 0, c->stream>>>(
-        reinterpret_cast<const unsigned long long*>(c->ec_pk.p), c->ec_pk_cap, d_n + 2, d_n);
-    c->launches++;
-    CU(c, cudaStreamSynchronize(c->stream));
+    const unsigned long long* pk = reinterpret_cast<const unsigned long long*>(c->ec_pk.p);
+    int rc = ec_compact_table(c, pk, 2, pk + 1, 2, c->ec_pk_cap, n); if (rc) return rc;
     *n_out = n;
+    return F2Q_OK;
+}
+
+// the byte-arena table on the host: (slot word, count) pairs of its keys and the arena bytes in use.  The table is sized for
+// what a chunk COULD insert (millions of slots), its keys are few: compacted on the device, only they cross the bus.
+// NOTE: overwrites c->ec_compact
+static int ec_arena_fetch(f2q_ctx* c, std::vector<unsigned long long>& pairs, std::vector<uint8_t>& arena) {
+    pairs.clear(); arena.assign(1, 0);
+    if (!c->ec_cap || !c->ec_meta.p) return F2Q_OK;
+    unsigned long long meta[4];
+    CU(c, cudaMemcpy(meta, c->ec_meta.p, 32, cudaMemcpyDeviceToHost));
+    if (!meta[1]) return F2Q_OK;
+    int rc = ec_compact_table(c, reinterpret_cast<const unsigned long long*>(c->ec_slots.p), 1, reinterpret_cast<const unsigned long long*>(c->ec_counts.p), 1,
+                              c->ec_cap, meta[1]);
+    if (rc) return rc;
+    pairs.resize(2 * meta[1]);
+    CU(c, cudaMemcpy(pairs.data(), reinterpret_cast<const uint8_t*>(c->ec_compact.p) + 16, meta[1] * 16, cudaMemcpyDeviceToHost));
+    arena.resize(meta[0] + 1);
+    if (meta[0]) CU(c, cudaMemcpy(arena.data(), c->ec_arena.p, meta[0], cudaMemcpyDeviceToHost));
     return F2Q_OK;
 }
 
@@ -1648,22 +1680,14 @@ static int ec_fetch(f2q_ctx* c) {
             c->ec_drain_off.push_back(c->ec_drain_keys.size());
             c->ec_drain_cnt.push_back(c->ec_extra_cnt[k]);
         }
-    } else if (c->ec_cap) {
-        unsigned long long meta[4];
-        CU(c, cudaMemcpy(meta, c->ec_meta.p, 32, cudaMemcpyDeviceToHost));
-        if (meta[1]) {
-            std::vector<unsigned long long> hs(c->ec_cap), hc(c->ec_cap);
-            std::vector<uint8_t> ar(meta[0] + 1);
-            CU(c, cudaMemcpy(hs.data(), c->ec_slots.p, c->ec_cap * 8, cudaMemcpyDeviceToHost));
-            CU(c, cudaMemcpy(hc.data(), c->ec_counts.p, c->ec_cap * 8, cudaMemcpyDeviceToHost));
-            if (meta[0]) CU(c, cudaMemcpy(ar.data(), c->ec_arena.p, meta[0], cudaMemcpyDeviceToHost));
-            for (uint64_t i = 0; i < c->ec_cap; i++) {
-                if (!hs[i]) continue;
-                const uint64_t off = (hs[i] - 1) >> 24, len = (hs[i] - 1) & 0xFFFFFF;
-                c->ec_drain_keys.insert(c->ec_drain_keys.end(), ar.begin() + off, ar.begin() + off + len);
-                c->ec_drain_off.push_back(c->ec_drain_keys.size());
-                c->ec_drain_cnt.push_back(hc[i]);
-            }
+    } else {
+        std::vector<unsigned long long> ap; std::vector<uint8_t> ar;
+        if ((rc = ec_arena_fetch(c, ap, ar))) return rc;
+        for (size_t k = 0; k + 1 < ap.size(); k += 2) {
+            const uint64_t off = (ap[k] - 1) >> 24, len = (ap[k] - 1) & 0xFFFFFF;
+            c->ec_drain_keys.insert(c->ec_drain_keys.end(), ar.begin() + off, ar.begin() + off + len);
+            c->ec_drain_off.push_back(c->ec_drain_keys.size());
+            c->ec_drain_cnt.push_back(ap[k + 1]);
         }
     }
     c->ec_drained = true;
@@ -1855,6 +1879,10 @@ F2Q_EXPORT int f2q_allreduce_counts(f2q_ctx** ctxs, int n) {
 F2Q_EXPORT int f2q_ec_merge(f2q_ctx** ctxs, int n) {
     int rc = comm_check(ctxs, n); if (rc) return rc;
     const int W = ctxs[0]->comm_size;
+    const bool dbg = getenv("F2Q_DEBUG_MERGE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tp = now();
+    auto lap = [&](const char* what) { if (dbg) { for (int i = 0; i < n; i++) { cudaSetDevice(ctxs[i]->device); cudaStreamSynchronize(ctxs[i]->stream); } const double t = now(); fprintf(stderr, "f2q_ec_merge: %-28s %8.2f ms\n", what, t - tp); tp = t; } };
     struct Local { uint64_t npk = 0; std::vector<uint8_t> blob; };     // blob: arena keys as [len u32 | count u64 | bytes]...
     std::vector<Local> L(n);
     std::vector<DevBuf> sizes_d(n), gathered(n), blob_d(n), blobs_all(n);
@@ -1868,27 +1896,20 @@ F2Q_EXPORT int f2q_ec_merge(f2q_ctx** ctxs, int n) {
         cudaSetDevice(c->device);
         if (c->in_sample && !c->closed && (rc = process_device_chunk(c, nullptr, 0, 1))) return rc;
         CU(c, cudaStreamSynchronize(c->stream));
-        if ((rc = ec_compact_packed(c, &L[i].npk))) return rc;
-        if (c->ec_cap && c->ec_meta.p) {
-            unsigned long long meta[4];
-            CU(c, cudaMemcpy(meta, c->ec_meta.p, 32, cudaMemcpyDeviceToHost));
-            if (meta[1]) {
-                std::vector<unsigned long long> hs(c->ec_cap), hc(c->ec_cap);
-                std::vector<uint8_t> ar(meta[0] + 1);
-                CU(c, cudaMemcpy(hs.data(), c->ec_slots.p, c->ec_cap * 8, cudaMemcpyDeviceToHost));
-                CU(c, cudaMemcpy(hc.data(), c->ec_counts.p, c->ec_cap * 8, cudaMemcpyDeviceToHost));
-                if (meta[0]) CU(c, cudaMemcpy(ar.data(), c->ec_arena.p, meta[0], cudaMemcpyDeviceToHost));
-                for (uint64_t k = 0; k < c->ec_cap; k++) {
-                    if (!hs[k]) continue;
-                    const uint64_t off = (hs[k] - 1) >> 24; const uint32_t len = (uint32_t)((hs[k] - 1) & 0xFFFFFF);
-                    const uint64_t cnt = hc[k];
-                    const uint8_t* p4 = reinterpret_cast<const uint8_t*>(&len); const uint8_t* p8 = reinterpret_cast<const uint8_t*>(&cnt);
-                    L[i].blob.insert(L[i].blob.end(), p4, p4 + 4); L[i].blob.insert(L[i].blob.end(), p8, p8 + 8);
-                    L[i].blob.insert(L[i].blob.end(), ar.begin() + off, ar.begin() + off + len);
-                }
+        {
+            std::vector<unsigned long long> ap; std::vector<uint8_t> ar;
+            if ((rc = ec_arena_fetch(c, ap, ar))) return rc;           // (first: it uses the compaction buffer the packed keys stay in)
+            for (size_t k = 0; k + 1 < ap.size(); k += 2) {
+                const uint64_t off = (ap[k] - 1) >> 24; const uint32_t len = (uint32_t)((ap[k] - 1) & 0xFFFFFF);
+                const uint64_t cnt = ap[k + 1];
+                const uint8_t* p4 = reinterpret_cast<const uint8_t*>(&len); const uint8_t* p8 = reinterpret_cast<const uint8_t*>(&cnt);
+                L[i].blob.insert(L[i].blob.end(), p4, p4 + 4); L[i].blob.insert(L[i].blob.end(), p8, p8 + 8);
+                L[i].blob.insert(L[i].blob.end(), ar.begin() + off, ar.begin() + off + len);
             }
         }
+        if ((rc = ec_compact_packed(c, &L[i].npk))) return rc;
     }
+    lap("local tables");
     // 2. sizes of every rank's pieces (two words per rank: packed pairs, blob bytes)
     for (int i = 0; i < n; i++) {
         f2q_ctx* c = ctxs[i];
@@ -1911,6 +1932,7 @@ F2Q_EXPORT int f2q_ec_merge(f2q_ctx** ctxs, int n) {
         CU(c, cudaMemcpyAsync(sizes_h[i].data(), sizes_d[i].p, 16 * (size_t)W, cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
     }
+    lap("sizes all-gather");
     // 3. the pieces themselves: rank r broadcasts its piece into everybody's buffer at r's offset (one NCCL group)
     std::vector<uint64_t> tot_pk(n, 0), tot_blob(n, 0);
     for (int i = 0; i < n; i++) {
@@ -1938,6 +1960,7 @@ F2Q_EXPORT int f2q_ec_merge(f2q_ctx** ctxs, int n) {
         }
     }
     NC(ctxs[0], g_nccl.GroupEnd());
+    lap("pieces broadcast");
     // 4. merge: the packed table is emptied and every gathered pair inserted (counts add); the arena blobs merge on the host
     for (int i = 0; i < n; i++) {
         f2q_ctx* c = ctxs[i];
@@ -1978,7 +2001,9 @@ F2Q_EXPORT int f2q_ec_merge(f2q_ctx** ctxs, int n) {
         }
         c->ec_merged = true; c->ec_drained = false;
     }
+    lap("device merge");
     cleanup();
+    lap("free");
     return F2Q_OK;
 }
 

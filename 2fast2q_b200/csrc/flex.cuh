@@ -284,14 +284,41 @@ __global__ void __launch_bounds__(256) k_ec_rehash(const unsigned long long* __r
     }
 }
 
-// compacts the packed table into (tag, count) pairs for f2q_ec_drain / f2q_ec_merge; out_n counts them
-__global__ void __launch_bounds__(256) k_ec_compact(const unsigned long long* __restrict__ slots, uint64_t cap, unsigned long long* __restrict__ out,
-                                                    unsigned long long* out_n) {
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < cap; i += (uint64_t)gridDim.x * blockDim.x) {
-        const unsigned long long tag = slots[2 * i];
-        if (!tag) continue;
-        const unsigned long long o = atomicAdd(out_n, 1ull);
-        out[2 * o] = tag; out[2 * o + 1] = slots[2 * i + 1];
+// compacts the packed table into (tag, count) pairs for f2q_ec_drain / f2q_ec_merge; out_n counts them.  A block takes 1024
+// slots per round and reserves the room for their keys with ONE atomic (an atomic with a return value per key — all on one
+// address — ran at 20 M keys/s: 70 ms for the 1.4 M keys of the Bar-seq workload)
+// (tags at tags[i * ts], counts at counts[i * cs]: the packed table interleaves them, the byte-arena table has two arrays)
+__global__ void __launch_bounds__(256) k_ec_compact(const unsigned long long* __restrict__ tags, uint32_t ts, const unsigned long long* __restrict__ counts,
+                                                    uint32_t cs, uint64_t cap, unsigned long long* __restrict__ out, unsigned long long* out_n) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ unsigned long long s_base;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    for (uint64_t base = (uint64_t)blockIdx.x * 1024u; base < cap; base += (uint64_t)gridDim.x * 1024u) {
+        unsigned long long tag[4], cnt[4];
+        uint32_t mine = 0;
+        #pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint64_t i = base + (uint64_t)k * 256u + threadIdx.x;
+            tag[k] = i < cap ? tags[i * ts] : 0ull;
+            cnt[k] = tag[k] ? counts[i * cs] : 0ull;
+            mine += tag[k] ? 1u : 0u;
+        }
+        uint32_t incl = mine;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += y; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+        #pragma unroll
+        for (int w = 0; w < 8; w++) { const uint32_t v = s_warp[w]; if ((uint32_t)w < warp) before += v; total += v; }
+        if (threadIdx.x == 0 && total) s_base = atomicAdd(out_n, (unsigned long long)total);
+        __syncthreads();
+        if (mine) {
+            unsigned long long o = s_base + before + incl - mine;
+            #pragma unroll
+            for (int k = 0; k < 4; k++) if (tag[k]) { out[2 * o] = tag[k]; out[2 * o + 1] = cnt[k]; o++; }
+        }
+        __syncthreads();
     }
 }
 #endif  // __CUDACC__

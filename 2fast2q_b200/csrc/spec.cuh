@@ -316,18 +316,19 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 uint8_t* const tile = wsm + s * stage_bytes;
                 const uint64_t base = rb + (uint64_t)ti * OWN;
                 if (ti >= t_lo && ti < t_hi) {
-                    // (bounded in time: a copy that never lands fails the speculation — the exact kernel then redoes the
-                    // chunk — and this warp stops taking work; nothing traps, see WAIT_CYCLE_LIMIT in tile.cuh)
-                    if (!mbar_try_wait(&bars[s], (par_bits >> s) & 1u)) {
+                    // (bounded in time: a copy that never lands fails the speculation — the exact kernel then redoes the chunk.
+                    // Nothing traps and nothing leaves the loop early: the warp stops WAITING (`dead`), runs through the rest
+                    // of its range on whatever the stage holds, takes no further range (take_range sees spec_fail), and all it
+                    // counted is dropped with the failed speculation; see WAIT_CYCLE_LIMIT in tile.cuh)
+                    if (!dead && !mbar_try_wait(&bars[s], (par_bits >> s) & 1u)) {
                         long long tw = 0;                               // (the clock is read only after 1024 failed tries: never on the ordinary path)
                         uint32_t spins = 0;
                         while (!mbar_try_wait(&bars[s], (par_bits >> s) & 1u)) {
                             if ((++spins & 1023u) != 0u) continue;
                             const long long now = clock64();
                             if (tw == 0) tw = now;
-                            else if (now - tw > WAIT_CYCLE_LIMIT) { dead = true; break; }
+                            else if (now - tw > WAIT_CYCLE_LIMIT) { dead = true; if (lane == 0) St->spec_fail = 1u; F2Q_TIMEOUT_TRAP(); break; }
                         }
-                        if (dead) { if (lane == 0) St->spec_fail = 1u; F2Q_TIMEOUT_TRAP(); break; }
                     }
                     par_bits ^= 1u << s;
                 } else {
@@ -391,7 +392,6 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
             }
             if (own) { prev_total = total; sp = s; s = (s == (uint32_t)NS - 1u) ? 0u : s + 1u; }
         }
-        if (dead) break;                                               // (its range stays unpublished: the verification fails)
         if (lane == 0) P.rec[r] = (uint8_t)(0x80u | (spec_p0 << 2) | (range_cnt & 3u));
         gs = s; pre = nxt_pre; cur = nxt;
     }
@@ -425,7 +425,8 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
 // finished and guessed exactly that.  On failure everything the speculative kernel left behind is reset.
 constexpr int SPEC_VERIFY_THREADS = 1024;
 __global__ void __launch_bounds__(SPEC_VERIFY_THREADS) k_spec_verify(DevState* St, const uint8_t* __restrict__ rec, uint64_t range_bytes,
-                                                                    uint32_t own_bytes, uint32_t* seg_count, uint32_t n_segs) {
+                                                                    uint32_t own_bytes, uint32_t* seg_count, uint32_t n_segs,
+                                                                    uint8_t* status, uint64_t n_status) {
     __shared__ uint32_t s_sum[SPEC_VERIFY_THREADS];
     __shared__ uint32_t s_bad, s_total;
     const uint32_t tid = threadIdx.x;
@@ -457,7 +458,12 @@ __global__ void __launch_bounds__(SPEC_VERIFY_THREADS) k_spec_verify(DevState* S
         if (ok) { if (end > beg) { St->nl_total = total & 3u; St->spec_commits++; } }
         else { St->last_rec_end = 0; St->g_count = 0; St->q_count = 0; St->spec_off = 1u; St->spec_fallbacks++; }
     }
-    if (!ok) for (uint32_t i = tid; i < n_segs; i += SPEC_VERIFY_THREADS) seg_count[i] = 0;
+    if (!ok) {
+        for (uint32_t i = tid; i < n_segs; i += SPEC_VERIFY_THREADS) seg_count[i] = 0;
+        // the exact kernel is about to parse the chunk: its look-back status bytes start from zero (no memset per chunk for
+        // the ordinary case, in which that kernel returns at once)
+        for (uint64_t i = tid; i < n_status; i += SPEC_VERIFY_THREADS) status[i] = 0;
+    }
 }
 
 // commit (or drop) the scratch count vector of the speculative kernel; scratch is left zeroed for the next chunk
