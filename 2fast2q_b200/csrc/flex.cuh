@@ -156,7 +156,13 @@ __device__ __forceinline__ void flex_read_warp(const FlexCtx& F, const FlexCfg& 
     }
     FlexKey k;
     k.lo = 0; k.hi = 0; k.sig = 0; k.bad = 0;
-    if (keyed && !fx_assemble(pc, np, k)) { keyed = false; generic = true; }
+    if (keyed && !fx_assemble(pc, np, k)) {
+        // more than 40 symbols in all: Counter mode needs the generic code only when the library has keys of that byte length
+        keyed = false;
+        const uint32_t bl = pc[0].len + (np > 1 ? pc[1].len + 1u : 0u);
+        if (F.mode == F2Q_MODE_COUNT && (bl > FX_MAX_BYTELEN || __ldg(T.fx_len_sig + bl) == 0)) n.nonal++;
+        else generic = true;
+    }
     bool to_queue = false;
     if (F.mode == F2Q_MODE_COUNT) {
         uint32_t v = FX_EMPTY;
