@@ -1388,9 +1388,41 @@ F2Q_EXPORT int f2q_submit_file(f2q_ctx* c, const char* path, int is_gzip, uint64
     };
     int idx = 0; uint8_t* buf = nullptr;
     if (!is_gzip) {
+        // plain file: `threads` readers pread() the parts of a ring buffer in parallel (one reader copies ~3 GB/s out of the
+        // page cache, far below what the link and the kernels take)
+        const int fd = fileno(f);
+        const int T = std::max(1, std::min(threads, 8));
+        uint64_t off = 0;
         for (;;) {
             if ((rc = ring_get(c, R, &buf, &idx))) break;
-            const size_t n = fread(buf, 1, R.bytes, f);
+            size_t n = 0;
+            if (T == 1) {
+                const ssize_t g = pread(fd, buf, R.bytes, (off_t)off);
+                n = g > 0 ? (size_t)g : 0;
+            } else {
+                const size_t part = (R.bytes / T + 4095) & ~(size_t)4095;
+                std::vector<size_t> got(T, 0);
+                auto rd = [&](int t) {
+                    const size_t lo = (size_t)t * part, want = lo < R.bytes ? std::min(part, R.bytes - lo) : 0;
+                    size_t have = 0;
+                    while (have < want) {
+                        const ssize_t g = pread(fd, buf + lo + have, want - have, (off_t)(off + lo + have));
+                        if (g <= 0) break;
+                        have += (size_t)g;
+                    }
+                    got[t] = have;
+                };
+                std::vector<std::thread> pool;
+                for (int t = 1; t < T; t++) pool.emplace_back(rd, t);
+                rd(0);
+                for (auto& th : pool) th.join();
+                for (int t = 0; t < T; t++) {                         // bytes are contiguous up to the first short part
+                    n += got[t];
+                    const size_t lo = (size_t)t * part, want = lo < R.bytes ? std::min(part, R.bytes - lo) : 0;
+                    if (got[t] < want) break;
+                }
+            }
+            off += n;
             const bool eof = n < R.bytes;
             const uint64_t m = apply_limit(buf, n);
             total += m;

@@ -432,10 +432,15 @@ def reads_counter(i, raw, features, param, reads_stats, preprocess=False):
     10 000 reads (fast2q.py:398-400)."""
     _derive_positions(param)
     device = int(param.get("device", 0))
+    t_a = time.perf_counter()
     engine, ring = _engine_for(param, features, device)
+    t_b = time.perf_counter()
     engine.begin()
     try:
         complete = _stream_file(engine, ring, raw, limit_lines=40000 if preprocess else None)
+        if os.environ.get("F2Q_CLI_TIMING"):
+            engine.sync()
+            print(f" [timing] {os.path.basename(raw)}: engine {t_b - t_a:.3f} s, stream {time.perf_counter() - t_b:.3f} s", flush=True)
     except (zlib.error, gzip.BadGzipFile, EOFError) as e:     # (other I/O errors surface, as in the reference: fast2q.py:580)
         try:
             engine.end()
@@ -922,12 +927,17 @@ def run_stats(headers, sentences, param):
 
 
 def main(argv=None):
+    t0 = time.perf_counter()
     param = file_sizer_split(initializer(input_parser(argv)))
     features = {}
     if param['Running Mode'] == 'C':
         features = features_loader(param["feature"])
+    t1 = time.perf_counter()
     aligner_mp_dispenser(features, param)
+    t2 = time.perf_counter()
     compiling(param)
+    if os.environ.get("F2Q_CLI_TIMING"):
+        print(f" [timing] parameters + features {t1 - t0:.2f} s, samples {t2 - t1:.2f} s, compiling {time.perf_counter() - t2:.2f} s", flush=True)
 
 
 if __name__ == "__main__":
