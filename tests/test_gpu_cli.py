@@ -44,8 +44,11 @@ def test_cli_matches_reference_outputs(name, tmp_path):
 
 
 @pytest.mark.parametrize("name", ["cli_counter", "cli_ec", "cli_truncated_gz"])
-def test_cli_file_split_mode_same_counts(name, tmp_path):
-    """--fs: every file is cut into record-aligned shards (one stream per GPU); counts must not change"""
+@pytest.mark.parametrize("native", [True, False])
+def test_cli_file_split_mode_same_counts(name, native, tmp_path, monkeypatch):
+    """--fs: every file is cut into record-aligned shards (one stream per GPU) — or, on one GPU, streamed through the native
+    ingest; counts must not change"""
+    monkeypatch.setattr(fq, "SPLIT_NATIVE_SINGLE_GPU", native)
     c = CG.case(name)
     got = run_cli(c, tmp_path, extra=["--fs"])
     want = dict(c["outputs"])
@@ -58,6 +61,7 @@ def test_cli_file_split_mode_same_counts(name, tmp_path):
 def test_small_shards_over_streams(tmp_path, monkeypatch):
     """force many tiny shards and chunks through the split path"""
     monkeypatch.setattr(fq, "CHUNK_BYTES", 50_000)
+    monkeypatch.setattr(fq, "SPLIT_NATIVE_SINGLE_GPU", False)
     c = CG.case("cli_single_split")
     check_outputs(c, run_cli(c, tmp_path))
 
