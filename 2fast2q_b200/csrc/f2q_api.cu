@@ -14,6 +14,7 @@
 #include <thread>
 #include <cerrno>
 #include <sys/mman.h>
+#include <sys/stat.h>
 #include <sys/syscall.h>
 #include <unistd.h>
 #include <cctype>
@@ -109,6 +110,12 @@ struct f2q_ctx {
     uint64_t ec_ring_next = 0;
     unsigned long long ec_known[4] = {0, 0, 0, 0};   // newest counters seen: arena bytes, arena keys, packed keys, spec_off
     int flex_warps = 16;                             // option "flex_warps": warps per CTA of the streaming kernel's flex policies
+    // GPU inflate of bgzip input (option "gpu_inflate"): two compressed staging buffers, two output buffers, block tables
+    bool gpu_inflate = false;                        // (off by default: see DESIGN.md §5 for the measurements)
+    DevBuf gz_comp[2], gz_out[2], gz_tab[2];
+    BgzfBlock* gz_tab_host[2] = {nullptr, nullptr};
+    cudaEvent_t gz_copied[2] = {nullptr, nullptr}, gz_free[2] = {nullptr, nullptr};
+    uint64_t gz_blocks = 0;                          // blocks inflated on the device by the last f2q_submit_file
     FileRing* file_ring = nullptr;                   // page-locked ring of f2q_submit_file (allocated on first use)
     // multi-GPU (NCCL): the communicator this context is a rank of
     void* comm = nullptr; int comm_rank = 0, comm_size = 1; bool comm_owner = false;
@@ -854,6 +861,12 @@ F2Q_EXPORT void f2q_destroy(f2q_ctx* c) {
     for (auto& p : c->ec_pend) if (p.ev) cudaEventDestroy(p.ev);
     for (auto e : c->ec_events) cudaEventDestroy(e);
     if (c->ec_meta_host) cudaFreeHost(c->ec_meta_host);
+    for (int k = 0; k < 2; k++) {
+        c->gz_comp[k].release(); c->gz_out[k].release(); c->gz_tab[k].release();
+        if (c->gz_tab_host[k]) cudaFreeHost(c->gz_tab_host[k]);
+        if (c->gz_copied[k]) cudaEventDestroy(c->gz_copied[k]);
+        if (c->gz_free[k]) cudaEventDestroy(c->gz_free[k]);
+    }
     if (c->file_ring) {
         for (int k = 0; k < FileRing::N; k++) { if (c->file_ring->buf[k]) f2q_host_free(c->file_ring->buf[k]); if (c->file_ring->done[k]) cudaEventDestroy(c->file_ring->done[k]); }
         delete c->file_ring; c->file_ring = nullptr;
@@ -893,6 +906,7 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "spec") c->spec = value != 0;
     else if (n == "spec_warps") { if (value != 12 && value != 16 && value != 20 && value != 24) return fail(c, F2Q_EINVAL, "spec_warps must be 12, 16, 20 or 24"); c->spec_warps = (int)value; }
     else if (n == "memo_entries") { if (value < -1 || value > (1ll << 28) || (value > 0 && (value & (value - 1)))) return fail(c, F2Q_EINVAL, "memo_entries must be -1 (auto), 0 (off) or a power of two"); c->memo_entries = value; if (c->lib_set) return fail(c, F2Q_ESTATE, "memo_entries must be set before f2q_set_library"); }
+    else if (n == "gpu_inflate") c->gpu_inflate = value != 0;
     else if (n == "flex_warps") { if (value != 12 && value != 16) return fail(c, F2Q_EINVAL, "flex_warps must be 12 or 16"); c->flex_warps = (int)value; }
     else if (n == "spec_range_tiles") { if (value < 0 || value > (1 << 20)) return fail(c, F2Q_EINVAL, "spec_range_tiles out of range"); c->spec_range_tiles = (int)value; }
     else if (n == "force_generic") { c->force_generic = value != 0; decide_policy(c); c->n_segs = 0; c->q_cap = 0; }
@@ -1348,6 +1362,102 @@ size_t bgzf_block_size(const uint8_t* p, size_t avail) {
 
 }  // namespace
 
+namespace {
+
+constexpr size_t GZ_COMP_BYTES = 256u << 20, GZ_OUT_BYTES = 1u << 30, GZ_MAX_BLOCKS = 1u << 16;
+const uint8_t BGZF_EOF[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+
+// bgzip file -> the sample, inflated ON THE DEVICE: compressed pieces are read into the pinned ring, their block headers and
+// trailers are walked on the host (sizes only), the pieces go to a device staging buffer on the copy stream, and one launch
+// of k_inflate_bgzf per batch (<= 256 MiB compressed, <= 1 GiB of output, <= 65 536 blocks) writes the FASTQ text straight
+// into the buffer process_device_chunk parses.  Two staging / output buffers: the next batch is read and copied while the
+// previous one is inflated and parsed.  Stops at the first thing that is not a whole BGZF block (a foreign gzip member, a
+// truncated block) and reports the file offset there: the host reader takes over from that offset.
+int submit_bgzf_gpu(f2q_ctx* c, FILE* f, FileRing& R, uint64_t* total, uint64_t* resume_off, bool* finished) {
+    int rc;
+    for (int k = 0; k < 2; k++) {
+        if ((rc = dev_alloc(c, c->gz_comp[k], GZ_COMP_BYTES + 65536)) || (rc = dev_alloc(c, c->gz_out[k], GZ_OUT_BYTES + 65536 + 256)) ||
+            (rc = dev_alloc(c, c->gz_tab[k], GZ_MAX_BLOCKS * sizeof(BgzfBlock)))) return rc;
+        if (!c->gz_tab_host[k]) CU(c, cudaHostAlloc(reinterpret_cast<void**>(&c->gz_tab_host[k]), GZ_MAX_BLOCKS * sizeof(BgzfBlock), cudaHostAllocDefault));
+        if (!c->gz_copied[k]) { CU(c, cudaEventCreateWithFlags(&c->gz_copied[k], cudaEventDisableTiming)); CU(c, cudaEventCreateWithFlags(&c->gz_free[k], cudaEventDisableTiming)); }
+    }
+    const int fd = fileno(f);
+    uint64_t off = 0;                                                  // file offset of the next unread byte
+    std::vector<uint8_t> carry;                                        // the head of a block whose rest is in the next piece
+    bool eof = false, stop = false;
+    int batch = 0;
+    *finished = false;
+    c->gz_blocks = 0;
+    while (!eof && !stop) {
+        const int k = batch & 1;
+        // batch k: the copy engine may overwrite its staging buffer only after the previous inflate out of it has finished
+        CU(c, cudaStreamWaitEvent(c->copy_stream, c->gz_free[k], 0));
+        BgzfBlock* tab = c->gz_tab_host[k];
+        // (the host table of batch k-2 was consumed by an H2D copy that completed before gz_free[k] did)
+        CU(c, cudaEventSynchronize(c->gz_free[k]));                    // (returns at once for an event that was never recorded)
+        uint32_t nb = 0;
+        size_t comp_fill = 0, out_fill = 0;
+        uint64_t batch_start = off - carry.size();
+        while (!eof && !stop && comp_fill + R.bytes + 65536 <= GZ_COMP_BYTES && out_fill + 4 * R.bytes <= GZ_OUT_BYTES && nb + 4096 < GZ_MAX_BLOCKS) {
+            uint8_t* buf; int idx;
+            if ((rc = ring_get(c, R, &buf, &idx))) return rc;
+            size_t have = carry.size();
+            if (have) memcpy(buf, carry.data(), have);
+            carry.clear();
+            if (have < R.bytes) {
+                const ssize_t g = pread(fd, buf + have, R.bytes - have, (off_t)off);
+                if (g <= 0) eof = true; else { have += (size_t)g; off += (size_t)g; }
+            }
+            // whole blocks of this piece
+            size_t p = 0;
+            while (have - p >= 18) {
+                const size_t bs = bgzf_block_size(buf + p, have - p);
+                if (!bs) { stop = true; break; }                        // not a BGZF member: the host reader continues from here
+                if (bs > have - p) break;
+                const uint32_t xlen = (uint32_t)(buf[p + 10] | buf[p + 11] << 8);
+                uint32_t isize; memcpy(&isize, buf + p + bs - 4, 4);
+                if (bs < 12u + xlen + 8u || isize > 65536u) { stop = true; break; }
+                if (out_fill + isize > GZ_OUT_BYTES || nb >= GZ_MAX_BLOCKS) break;
+                if (isize) { tab[nb++] = BgzfBlock{(uint32_t)(comp_fill + p + 12 + xlen), (uint32_t)(bs - 12 - xlen - 8), (uint32_t)out_fill, isize}; out_fill += isize; }
+                p += bs;
+            }
+            // copy the whole blocks to the device staging buffer; what is left (a partial block) is carried
+            if (p) CU(c, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->gz_comp[k].p) + comp_fill, buf, p, cudaMemcpyHostToDevice, c->copy_stream));
+            R.used[idx] = true;
+            CU(c, cudaEventRecord(R.done[idx], c->copy_stream));
+            comp_fill += p;
+            if (stop) { off = batch_start + comp_fill; carry.clear(); break; }
+            if (have > p) {
+                if (eof) { stop = true; off = off - (have - p); break; }    // a truncated last block: the host reader delivers its decodable part
+                carry.assign(buf + p, buf + have);
+            }
+            batch_start = off - carry.size() - comp_fill;
+        }
+        if (stop && !carry.empty()) carry.clear();
+        if (nb) {
+            CU(c, cudaMemcpyAsync(c->gz_tab[k].p, tab, (size_t)nb * sizeof(BgzfBlock), cudaMemcpyHostToDevice, c->copy_stream));
+            CU(c, cudaEventRecord(c->gz_copied[k], c->copy_stream));
+            CU(c, cudaStreamWaitEvent(c->stream, c->gz_copied[k], 0));
+            // (the output buffer of batch k-2 was parsed by kernels earlier on this same stream)
+            k_inflate_bgzf<<<(nb + INFLATE_THREADS - 1) / INFLATE_THREADS, INFLATE_THREADS, 0, c->stream>>>(
+                reinterpret_cast<const uint8_t*>(c->gz_comp[k].p), reinterpret_cast<const BgzfBlock*>(c->gz_tab[k].p), nb,
+                reinterpret_cast<uint8_t*>(c->gz_out[k].p), c->d_error);
+            c->launches++;
+            CU(c, cudaGetLastError());
+            CU(c, cudaEventRecord(c->gz_free[k], c->stream));
+            c->gz_blocks += nb;
+            *total += out_fill;
+            if ((rc = process_device_chunk(c, reinterpret_cast<const uint8_t*>(c->gz_out[k].p), out_fill, 0))) { if (!c->sticky) c->sample_failed = rc; return rc; }
+            batch++;
+        } else if (!stop && !eof) return fail(c, F2Q_EINTERNAL, "bgzip batch without a block");
+    }
+    *resume_off = off;
+    *finished = eof && !stop;
+    return F2Q_OK;
+}
+
+}  // namespace
+
 F2Q_EXPORT int f2q_submit_file(f2q_ctx* c, const char* path, int is_gzip, uint64_t limit_lines, int threads, int* complete, uint64_t* bytes_out) {
     int rc = check_ctx(c); if (rc) return rc;
     if (!c->in_sample) return fail(c, F2Q_ESTATE, "f2q_submit_file outside a sample");
@@ -1458,7 +1568,32 @@ F2Q_EXPORT int f2q_submit_file(f2q_ctx* c, const char* path, int is_gzip, uint64
         buf = nb; idx = nidx; fill = tail;
         return r2;
     };
-    const bool bgzf = threads > 1 && bgzf_block_size(in.data(), in_len) != 0;
+    bool bgzf = threads > 1 && bgzf_block_size(in.data(), in_len) != 0;
+    if (bgzf_block_size(in.data(), in_len) != 0 && c->gpu_inflate && !limit_lines) {
+        // a bgzip file that ends with its end-of-file block is inflated on the device; whatever is not a whole BGZF block
+        // (a foreign member behind the blocks, a truncated file) is left to the host reader below, from the offset it starts at
+        uint8_t tailb[28];
+        struct stat sb;
+        if (fstat(fileno(f), &sb) == 0 && sb.st_size >= 28 && pread(fileno(f), tailb, 28, sb.st_size - 28) == 28 && memcmp(tailb, BGZF_EOF, 28) == 0) {
+            uint64_t resume = 0; bool finished = false;
+            if ((rc = submit_bgzf_gpu(c, f, R, &total, &resume, &finished))) { fclose(f); return rc; }
+            if (finished) {
+                fclose(f);
+                rc = ring_get(c, R, &buf, &idx);
+                if (!rc) rc = ring_submit(c, R, idx, 0, 1);            // close the stream
+                if (bytes_out) *bytes_out = total;
+                return rc;
+            }
+            // continue on the host from `resume` (with a ring buffer of our own again: the device path cycled through them)
+            if ((rc = ring_get(c, R, &buf, &idx))) { fclose(f); return rc; }
+            in_len = 0; in_pos = 0; in_eof = false;
+            const ssize_t g = pread(fileno(f), in.data(), in.size(), (off_t)resume);
+            in_len = g > 0 ? (size_t)g : 0;
+            in_eof = in_len < in.size();
+            if (fseek(f, (long)(resume + in_len), SEEK_SET) != 0) { fclose(f); return fail(c, F2Q_EINVAL, "seek failed"); }
+            bgzf = threads > 1 && bgzf_block_size(in.data(), in_len) != 0;
+        }
+    }
     if (bgzf) {
         struct Blk { const uint8_t* src; uint32_t csize, isize; size_t dst; };
         std::vector<Blk> blks;
@@ -1617,6 +1752,7 @@ F2Q_EXPORT int f2q_end_sample(f2q_ctx* c, uint64_t* counts, uint64_t* stats) {
                 hs.dbg[0] >> 20, hs.dbg[7] >> 20, hs.dbg[1] >> 20, hs.dbg[4] >> 20, hs.dbg[2] >> 20, hs.dbg[3] >> 20, hs.dbg[5], hs.dbg[6] >> 20);
     if (err & ERR_RECORD_TOO_LONG) return fail(c, F2Q_ETOOLONG, "a FASTQ record is longer than carry_bytes; raise it with f2q_set_option");
     if (err & ERR_LOOKBACK_TIMEOUT) return fail(c, F2Q_EINTERNAL, "a device-side wait timed out; this sample's counts are invalid (the context stays usable)");
+    if (err & ERR_INFLATE) return fail(c, F2Q_EINVAL, "corrupted gzip data (a bgzip block did not inflate to its promised size on the device)");
     if (err & ERR_EC_FULL) return fail(c, F2Q_EINTERNAL, "an Extract+Count table overflowed (a chunk whose line structure defeated the speculation held more keys than were reserved): rerun with option spec = 0");
     if (err) return fail(c, F2Q_EINTERNAL, "device-side failure, flags=" + std::to_string(err));
     if (counts && c->n_keys) CU(c, cudaMemcpy(counts, c->result.p, (size_t)c->n_keys * 8, cudaMemcpyDeviceToHost));

@@ -7,6 +7,7 @@
 #pragma once
 
 #include "f2q_dev.cuh"
+#include "inflate_core.h"
 #include "synth_gen.h"
 
 namespace f2q {
@@ -107,6 +108,22 @@ __global__ void __launch_bounds__(PREP_THREADS) k_carry(DevState* S, const uint8
     if (tlen > carry_cap) { if (tid == 0) { atomicOr(&S->error, ERR_RECORD_TOO_LONG); S->tail_len = 0; S->tail_nl = 0; } return; }
     for (uint64_t i = tid; i < tlen; i += PREP_THREADS) carry[i] = buf[tb + i];
     if (tid == 0) { S->tail_len = (uint32_t)tlen; S->tail_nl = nl; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// GPU inflate of bgzip (BGZF) input: one thread per block (inflate_core.h).  The blocks of a chunk are independent, their
+// compressed sizes come from the headers and their output offsets from the trailers, so thousands decode at once straight
+// into the buffer the streaming kernel parses; only the COMPRESSED bytes cross PCIe.
+// ------------------------------------------------------------------------------------------------
+struct BgzfBlock { uint32_t src, csize, dst, isize; };
+constexpr int INFLATE_THREADS = 64;
+
+__global__ void __launch_bounds__(INFLATE_THREADS) k_inflate_bgzf(const uint8_t* __restrict__ comp, const BgzfBlock* __restrict__ blk, uint32_t n,
+                                                                  uint8_t* __restrict__ out, uint32_t* error) {
+    for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
+        const BgzfBlock B = blk[b];
+        if (inflate_raw(comp + B.src, B.csize, out + B.dst, B.isize) != 0) atomicOr(error, ERR_INFLATE);
+    }
 }
 
 // start of a sample: result vector, scratch vector, error word and the stream state in ONE launch

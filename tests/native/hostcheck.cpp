@@ -71,3 +71,11 @@ int hc_flex_key(const f2q_config* cfg, int pw, const uint8_t* read, int r, const
 }
 
 }
+
+// ---- inflate_core.h: the per-block DEFLATE decoder of k_inflate_bgzf, against zlib --------------------------------------
+#include "../../2fast2q_b200/csrc/inflate_core.h"
+
+extern "C" {
+__attribute__((visibility("default")))
+int hc_inflate_raw(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len) { return f2q::inflate_raw(in, in_len, out, out_len); }
+}

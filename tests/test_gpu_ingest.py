@@ -103,3 +103,43 @@ def test_line_limit_and_corruption(world, tmp_path):
     with pytest.raises(lib.F2QError):
         e.submit_file(str(tmp_path / "missing.fastq"), False)
     e.close()
+
+
+def test_bgzf_inflated_on_the_device(world, tmp_path, oracle):
+    """bgzip input is inflated by k_inflate_bgzf (one thread per block, only compressed bytes cross PCIe): same counts as the
+    host path and the oracle; a foreign gzip member behind the blocks is picked up by the host reader at the right offset; a
+    corrupted block is reported, never mis-counted"""
+    body, check = world
+    blob = _bgzf(body, level=1)
+    g = tmp_path / "x.fastq.gz"
+    g.write_bytes(blob)
+    check(g, body, True, threads=6)                                   # the fixture engine: host threads (the default)
+    spec = synth.default_spec(2)
+    names, keys = synth.make_library(2, 400, 20)
+    want_c, want_s = oracle.count(oracle.make_config(miss=1), keys, body)
+    for opt in (1, 0):
+        with lib.Engine(lib.make_config(miss=1), 0, None, gpu_inflate=opt) as e:
+            e.set_library(keys)
+            e.begin(); ok, nb = e.submit_file(str(g), True, 0, 6); c, s = e.end()
+            assert ok and nb == len(body) and s == want_s and np.array_equal(c, want_c), opt
+    # blocks + an ordinary gzip member + the bgzip end-of-file block
+    a, b = body[:3_000_000], body[3_000_000:]
+    g.write_bytes(_bgzf(a)[:-28] + _gz(b) + _bgzf(b"")[-28:])
+    want, ok = _py_gzip_lines(g)
+    assert ok and want == body
+    check(g, body, True, threads=6)
+    with lib.Engine(lib.make_config(miss=1), 0, None, gpu_inflate=1) as e:
+        e.set_library(keys)
+        e.begin(); ok, nb = e.submit_file(str(g), True, 0, 6); c, s = e.end()
+        assert ok and nb == len(body) and s == want_s and np.array_equal(c, want_c)
+    # a flipped byte inside a block's payload
+    bad = bytearray(blob)
+    bad[len(bad) // 2] ^= 0x5A
+    g.write_bytes(bytes(bad))
+    with lib.Engine(lib.make_config(miss=1), 0, None, gpu_inflate=1) as e:
+        e.set_library(keys)
+        e.begin()
+        with pytest.raises(lib.F2QError) as err:
+            e.submit_file(str(g), True, 0, 6)
+            e.end()
+        assert "corrupted gzip" in str(err.value)

@@ -1,0 +1,73 @@
+"""
+CPU: the DEFLATE decoder the GPU inflate kernel runs per BGZF block (2fast2q_b200/csrc/inflate_core.h, compiled here with g++)
+against zlib: stored, fixed-Huffman and dynamic-Huffman blocks, every compression level, FASTQ text, random bytes, long
+matches, empty input, and corrupted / truncated streams (which must be refused, never mis-decoded silently).
+"""
+import ctypes as C
+import importlib
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+import hostcheck
+
+synth = importlib.import_module("2fast2q_b200.synth")
+
+
+def infl(comp: bytes, out_len: int):
+    H = hostcheck.lib()
+    H.hc_inflate_raw.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32]
+    out = C.create_string_buffer(max(out_len, 1))
+    rc = H.hc_inflate_raw(comp, len(comp), out, out_len)
+    return rc, out.raw[:out_len]
+
+
+def raw_deflate(data, level=6, strategy=zlib.Z_DEFAULT_STRATEGY):
+    c = zlib.compressobj(level, zlib.DEFLATED, -15, 9, strategy)
+    return c.compress(data) + c.flush()
+
+
+def payloads():
+    rnd = random.Random(3)
+    spec = synth.default_spec(3)
+    _, keys = synth.make_library(3, 300, 20)
+    fastq = synth.fixed_reads(keys, 0, 380, **spec).tobytes()          # ~64 KB of FASTQ text: one BGZF block's worth
+    yield "fastq", fastq
+    yield "fastq_short", fastq[:777]
+    yield "empty", b""
+    yield "one_byte", b"A"
+    yield "random", bytes(rnd.randrange(256) for _ in range(30000))
+    yield "runs", b"A" * 40000 + b"CG" * 10000 + b"\n" * 300
+    yield "text", (b"the quick brown fox jumps over the lazy dog\n" * 1400)[:65280]
+
+
+@pytest.mark.parametrize("name,data", list(payloads()), ids=[n for n, _ in payloads()])
+def test_decoder_equals_zlib(name, data):
+    for level in (0, 1, 4, 6, 9):
+        for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+            comp = raw_deflate(data, level, strategy)
+            rc, out = infl(comp, len(data))
+            assert rc == 0 and out == data, (name, level, strategy)
+
+
+def test_corrupted_and_truncated_streams_are_refused():
+    data = next(d for n, d in payloads() if n == "fastq")
+    comp = raw_deflate(data, 6)
+    assert infl(comp, len(data))[0] == 0
+    assert infl(comp, len(data) - 1)[0] != 0                 # produces more than the trailer promised
+    assert infl(comp, len(data) + 1)[0] != 0                 # produces less
+    for cut in (0, 1, 10, len(comp) // 2, len(comp) - 1):
+        assert infl(comp[:cut], len(data))[0] != 0, cut
+    rnd = random.Random(9)
+    bad = 0
+    for _ in range(200):
+        b = bytearray(comp)
+        p = rnd.randrange(len(b))
+        b[p] ^= 1 << rnd.randrange(8)
+        rc, out = infl(bytes(b), len(data))
+        if rc != 0 or out != data:
+            bad += 1
+        assert rc != 0 or len(out) == len(data)
+    assert bad > 150                                         # (a flipped bit may leave a valid stream of the same length; that is what the CRC is for)
