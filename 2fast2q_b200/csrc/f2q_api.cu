@@ -111,7 +111,9 @@ struct f2q_ctx {
     unsigned long long ec_known[4] = {0, 0, 0, 0};   // newest counters seen: arena bytes, arena keys, packed keys, spec_off
     int flex_warps = 16;                             // option "flex_warps": warps per CTA of the streaming kernel's flex policies
     // GPU inflate of bgzip input (option "gpu_inflate"): two compressed staging buffers, two output buffers, block tables
-    bool gpu_inflate = false;                        // (off by default: see DESIGN.md §5 for the measurements)
+    bool gpu_inflate = true;                         // bgzip input is inflated on the device (DESIGN.md §5 has the measurements)
+    int gpu_inflate_mode = 1;                        // 1 lock-step lanes | 2 free-running threads (cross-check)
+    bool gz_attr = false;
     DevBuf gz_comp[2], gz_out[2], gz_tab[2];
     BgzfBlock* gz_tab_host[2] = {nullptr, nullptr};
     cudaEvent_t gz_copied[2] = {nullptr, nullptr}, gz_free[2] = {nullptr, nullptr};
@@ -906,7 +908,7 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "spec") c->spec = value != 0;
     else if (n == "spec_warps") { if (value != 12 && value != 16 && value != 20 && value != 24) return fail(c, F2Q_EINVAL, "spec_warps must be 12, 16, 20 or 24"); c->spec_warps = (int)value; }
     else if (n == "memo_entries") { if (value < -1 || value > (1ll << 28) || (value > 0 && (value & (value - 1)))) return fail(c, F2Q_EINVAL, "memo_entries must be -1 (auto), 0 (off) or a power of two"); c->memo_entries = value; if (c->lib_set) return fail(c, F2Q_ESTATE, "memo_entries must be set before f2q_set_library"); }
-    else if (n == "gpu_inflate") c->gpu_inflate = value != 0;
+    else if (n == "gpu_inflate") { if (value < 0 || value > 2) return fail(c, F2Q_EINVAL, "gpu_inflate must be 0, 1 or 2"); c->gpu_inflate = value != 0; c->gpu_inflate_mode = value == 2 ? 2 : 1; }
     else if (n == "flex_warps") { if (value != 12 && value != 16) return fail(c, F2Q_EINVAL, "flex_warps must be 12 or 16"); c->flex_warps = (int)value; }
     else if (n == "spec_range_tiles") { if (value < 0 || value > (1 << 20)) return fail(c, F2Q_EINVAL, "spec_range_tiles out of range"); c->spec_range_tiles = (int)value; }
     else if (n == "force_generic") { c->force_generic = value != 0; decide_policy(c); c->n_segs = 0; c->q_cap = 0; }
@@ -1351,6 +1353,36 @@ int ring_submit(f2q_ctx* c, FileRing& R, int idx, uint64_t n, int last) {
     return submit_host(c, R.buf[idx], n, last, R.done[idx]);
 }
 
+// read [off, off + want) of fd into buf with T readers (one reader copies ~3 GB/s out of the page cache, far below what the
+// link and the kernels take); returns the contiguous bytes read from `off` (short at the end of the file)
+size_t pread_parallel(int fd, uint8_t* buf, size_t want, uint64_t off, int T) {
+    if (want == 0) return 0;
+    if (T <= 1 || want < ((size_t)1 << 20)) {
+        size_t have = 0;
+        while (have < want) { const ssize_t g = pread(fd, buf + have, want - have, (off_t)(off + have)); if (g <= 0) break; have += (size_t)g; }
+        return have;
+    }
+    const size_t part = (want / T + 4095) & ~(size_t)4095;
+    std::vector<size_t> got(T, 0);
+    auto rd = [&](int t) {
+        const size_t lo = (size_t)t * part, w = lo < want ? std::min(part, want - lo) : 0;
+        size_t have = 0;
+        while (have < w) { const ssize_t g = pread(fd, buf + lo + have, w - have, (off_t)(off + lo + have)); if (g <= 0) break; have += (size_t)g; }
+        got[t] = have;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; t++) pool.emplace_back(rd, t);
+    rd(0);
+    for (auto& th : pool) th.join();
+    size_t n = 0;
+    for (int t = 0; t < T; t++) {                                      // bytes are contiguous up to the first short part
+        n += got[t];
+        const size_t lo = (size_t)t * part, w = lo < want ? std::min(part, want - lo) : 0;
+        if (got[t] < w) break;
+    }
+    return n;
+}
+
 const uint8_t* last_newline(const uint8_t* p, size_t n) { return static_cast<const uint8_t*>(memrchr(p, '\n', n)); }
 
 // BGZF block at p (>= 18 bytes available): total block size, or 0 when this is not a BGZF member header
@@ -1373,8 +1405,9 @@ const uint8_t BGZF_EOF[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06,
 // into the buffer process_device_chunk parses.  Two staging / output buffers: the next batch is read and copied while the
 // previous one is inflated and parsed.  Stops at the first thing that is not a whole BGZF block (a foreign gzip member, a
 // truncated block) and reports the file offset there: the host reader takes over from that offset.
-int submit_bgzf_gpu(f2q_ctx* c, FILE* f, FileRing& R, uint64_t* total, uint64_t* resume_off, bool* finished) {
+int submit_bgzf_gpu(f2q_ctx* c, FILE* f, FileRing& R, int threads, uint64_t* total, uint64_t* resume_off, bool* finished) {
     int rc;
+    const int T = std::max(1, std::min(threads, 8));
     for (int k = 0; k < 2; k++) {
         if ((rc = dev_alloc(c, c->gz_comp[k], GZ_COMP_BYTES + 65536)) || (rc = dev_alloc(c, c->gz_out[k], GZ_OUT_BYTES + 65536 + 256)) ||
             (rc = dev_alloc(c, c->gz_tab[k], GZ_MAX_BLOCKS * sizeof(BgzfBlock)))) return rc;
@@ -1405,8 +1438,9 @@ int submit_bgzf_gpu(f2q_ctx* c, FILE* f, FileRing& R, uint64_t* total, uint64_t*
             if (have) memcpy(buf, carry.data(), have);
             carry.clear();
             if (have < R.bytes) {
-                const ssize_t g = pread(fd, buf + have, R.bytes - have, (off_t)off);
-                if (g <= 0) eof = true; else { have += (size_t)g; off += (size_t)g; }
+                const size_t want = R.bytes - have, g = pread_parallel(fd, buf + have, want, off, T);
+                if (g < want) eof = true;
+                have += g; off += g;
             }
             // whole blocks of this piece
             size_t p = 0;
@@ -1439,9 +1473,16 @@ int submit_bgzf_gpu(f2q_ctx* c, FILE* f, FileRing& R, uint64_t* total, uint64_t*
             CU(c, cudaEventRecord(c->gz_copied[k], c->copy_stream));
             CU(c, cudaStreamWaitEvent(c->stream, c->gz_copied[k], 0));
             // (the output buffer of batch k-2 was parsed by kernels earlier on this same stream)
-            k_inflate_bgzf<<<(nb + INFLATE_THREADS - 1) / INFLATE_THREADS, INFLATE_THREADS, 0, c->stream>>>(
-                reinterpret_cast<const uint8_t*>(c->gz_comp[k].p), reinterpret_cast<const BgzfBlock*>(c->gz_tab[k].p), nb,
-                reinterpret_cast<uint8_t*>(c->gz_out[k].p), c->d_error);
+            if (c->gpu_inflate_mode == 2)
+                k_inflate_bgzf<<<(nb + INFLATE_THREADS - 1) / INFLATE_THREADS, INFLATE_THREADS, 0, c->stream>>>(
+                    reinterpret_cast<const uint8_t*>(c->gz_comp[k].p), reinterpret_cast<const BgzfBlock*>(c->gz_tab[k].p), nb,
+                    reinterpret_cast<uint8_t*>(c->gz_out[k].p), c->d_error);
+            else {
+                if (!c->gz_attr) { CU(c, cudaFuncSetAttribute(k_inflate_bgzf_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INFLATE_SMEM)); c->gz_attr = true; }
+                k_inflate_bgzf_lanes<<<(nb + INFLATE_THREADS - 1) / INFLATE_THREADS, INFLATE_THREADS, INFLATE_SMEM, c->stream>>>(
+                    reinterpret_cast<const uint8_t*>(c->gz_comp[k].p), reinterpret_cast<const BgzfBlock*>(c->gz_tab[k].p), nb,
+                    reinterpret_cast<uint8_t*>(c->gz_out[k].p), c->d_error);
+            }
             c->launches++;
             CU(c, cudaGetLastError());
             CU(c, cudaEventRecord(c->gz_free[k], c->stream));
@@ -1498,40 +1539,13 @@ F2Q_EXPORT int f2q_submit_file(f2q_ctx* c, const char* path, int is_gzip, uint64
     };
     int idx = 0; uint8_t* buf = nullptr;
     if (!is_gzip) {
-        // plain file: `threads` readers pread() the parts of a ring buffer in parallel (one reader copies ~3 GB/s out of the
-        // page cache, far below what the link and the kernels take)
+        // plain file: `threads` readers pread() the parts of a ring buffer in parallel
         const int fd = fileno(f);
         const int T = std::max(1, std::min(threads, 8));
         uint64_t off = 0;
         for (;;) {
             if ((rc = ring_get(c, R, &buf, &idx))) break;
-            size_t n = 0;
-            if (T == 1) {
-                const ssize_t g = pread(fd, buf, R.bytes, (off_t)off);
-                n = g > 0 ? (size_t)g : 0;
-            } else {
-                const size_t part = (R.bytes / T + 4095) & ~(size_t)4095;
-                std::vector<size_t> got(T, 0);
-                auto rd = [&](int t) {
-                    const size_t lo = (size_t)t * part, want = lo < R.bytes ? std::min(part, R.bytes - lo) : 0;
-                    size_t have = 0;
-                    while (have < want) {
-                        const ssize_t g = pread(fd, buf + lo + have, want - have, (off_t)(off + lo + have));
-                        if (g <= 0) break;
-                        have += (size_t)g;
-                    }
-                    got[t] = have;
-                };
-                std::vector<std::thread> pool;
-                for (int t = 1; t < T; t++) pool.emplace_back(rd, t);
-                rd(0);
-                for (auto& th : pool) th.join();
-                for (int t = 0; t < T; t++) {                         // bytes are contiguous up to the first short part
-                    n += got[t];
-                    const size_t lo = (size_t)t * part, want = lo < R.bytes ? std::min(part, R.bytes - lo) : 0;
-                    if (got[t] < want) break;
-                }
-            }
+            const size_t n = pread_parallel(fd, buf, R.bytes, off, T);
             off += n;
             const bool eof = n < R.bytes;
             const uint64_t m = apply_limit(buf, n);
@@ -1576,7 +1590,7 @@ F2Q_EXPORT int f2q_submit_file(f2q_ctx* c, const char* path, int is_gzip, uint64
         struct stat sb;
         if (fstat(fileno(f), &sb) == 0 && sb.st_size >= 28 && pread(fileno(f), tailb, 28, sb.st_size - 28) == 28 && memcmp(tailb, BGZF_EOF, 28) == 0) {
             uint64_t resume = 0; bool finished = false;
-            if ((rc = submit_bgzf_gpu(c, f, R, &total, &resume, &finished))) { fclose(f); return rc; }
+            if ((rc = submit_bgzf_gpu(c, f, R, threads, &total, &resume, &finished))) { fclose(f); return rc; }
             if (finished) {
                 fclose(f);
                 rc = ring_get(c, R, &buf, &idx);

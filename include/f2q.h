@@ -125,8 +125,9 @@ const char* f2q_last_error(const f2q_ctx* ctx);   /* ctx may be NULL: last creat
  *   "memo_entries"    0 off (default) | power of two: entries of the device memo of resolved non-exact keys; set before
  *                     f2q_set_library.  Worth it when the stream repeats its erroneous keys (real screens do; the host layer
  *                     2fast2q_b200/fast2q.py switches it on), pure overhead when it does not (the synthetic bench streams)
- *   "gpu_inflate"     1: f2q_submit_file inflates bgzip (BGZF) files ON THE DEVICE (k_inflate_bgzf: only the compressed bytes
- *                     cross PCIe) | 0 (default): on host threads, block-parallel
+ *   "gpu_inflate"     1 (default): f2q_submit_file inflates bgzip (BGZF) files ON THE DEVICE (k_inflate_bgzf_lanes: the 32
+ *                     lanes of a warp inflate 32 blocks in lock step; only the compressed bytes cross PCIe) | 0: on host
+ *                     threads, block-parallel | 2: on the device, one free-running thread per block (cross-check, slow)
  *   "generic_entries" capacity of the queue of reads handed to the byte-wise generic kernel (default: derived)
  *   "ec_slots"        minimum capacity of the Extract+Count packed key table (default: grown on demand)
  */

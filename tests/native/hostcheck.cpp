@@ -78,4 +78,17 @@ int hc_flex_key(const f2q_config* cfg, int pw, const uint8_t* read, int r, const
 extern "C" {
 __attribute__((visibility("default")))
 int hc_inflate_raw(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len) { return f2q::inflate_raw(in, in_len, out, out_len); }
+
+// the lock-step state machine, one lane; `in` must be readable 8 bytes past in_len (as in the kernel's staging buffer)
+__attribute__((visibility("default")))
+int hc_inflate_lane(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len) {
+    static thread_local uint16_t lut[1 << f2q::INFL_LUT_BITS], dlut[1 << f2q::INFL_DLUT_BITS];
+    f2q::InflLane L;
+    f2q::infl_lane_init(L, in, in_len, out, out_len);
+    for (uint64_t it = 0; L.state != f2q::INFL_ST_DONE; it++) {
+        if (it > (1ull << 28)) return 9;
+        f2q::infl_step(L, lut, dlut, 1);
+    }
+    return f2q::infl_lane_result(L);
+}
 }

@@ -117,7 +117,7 @@ def test_bgzf_inflated_on_the_device(world, tmp_path, oracle):
     spec = synth.default_spec(2)
     names, keys = synth.make_library(2, 400, 20)
     want_c, want_s = oracle.count(oracle.make_config(miss=1), keys, body)
-    for opt in (1, 0):
+    for opt in (1, 2, 0):
         with lib.Engine(lib.make_config(miss=1), 0, None, gpu_inflate=opt) as e:
             e.set_library(keys)
             e.begin(); ok, nb = e.submit_file(str(g), True, 0, 6); c, s = e.end()

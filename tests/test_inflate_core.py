@@ -16,11 +16,12 @@ import hostcheck
 synth = importlib.import_module("2fast2q_b200.synth")
 
 
-def infl(comp: bytes, out_len: int):
+def infl(comp: bytes, out_len: int, fn="hc_inflate_raw"):
     H = hostcheck.lib()
-    H.hc_inflate_raw.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32]
-    out = C.create_string_buffer(max(out_len, 1))
-    rc = H.hc_inflate_raw(comp, len(comp), out, out_len)
+    f = getattr(H, fn)
+    f.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_uint32]
+    out = C.create_string_buffer(max(out_len, 1) + 16)
+    rc = f(comp + b"\xAA" * 16, len(comp), out, out_len)              # (readable slack behind the stream, as in the staging buffer)
     return rc, out.raw[:out_len]
 
 
@@ -48,18 +49,20 @@ def test_decoder_equals_zlib(name, data):
     for level in (0, 1, 4, 6, 9):
         for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
             comp = raw_deflate(data, level, strategy)
-            rc, out = infl(comp, len(data))
-            assert rc == 0 and out == data, (name, level, strategy)
+            for fn in ("hc_inflate_raw", "hc_inflate_lane"):
+                rc, out = infl(comp, len(data), fn)
+                assert rc == 0 and out == data, (name, level, strategy, fn)
 
 
 def test_corrupted_and_truncated_streams_are_refused():
     data = next(d for n, d in payloads() if n == "fastq")
     comp = raw_deflate(data, 6)
-    assert infl(comp, len(data))[0] == 0
-    assert infl(comp, len(data) - 1)[0] != 0                 # produces more than the trailer promised
-    assert infl(comp, len(data) + 1)[0] != 0                 # produces less
-    for cut in (0, 1, 10, len(comp) // 2, len(comp) - 1):
-        assert infl(comp[:cut], len(data))[0] != 0, cut
+    for fn in ("hc_inflate_raw", "hc_inflate_lane"):
+        assert infl(comp, len(data), fn)[0] == 0
+        assert infl(comp, len(data) - 1, fn)[0] != 0         # produces more than the trailer promised
+        assert infl(comp, len(data) + 1, fn)[0] != 0         # produces less
+        for cut in (0, 1, 10, len(comp) // 2, len(comp) - 1):
+            assert infl(comp[:cut], len(data), fn)[0] != 0, (fn, cut)
     rnd = random.Random(9)
     bad = 0
     for _ in range(200):
@@ -67,6 +70,8 @@ def test_corrupted_and_truncated_streams_are_refused():
         p = rnd.randrange(len(b))
         b[p] ^= 1 << rnd.randrange(8)
         rc, out = infl(bytes(b), len(data))
+        rc2, out2 = infl(bytes(b), len(data), "hc_inflate_lane")
+        assert (rc == 0) == (rc2 == 0) and (rc != 0 or out == out2)      # both decoders accept / refuse the same streams
         if rc != 0 or out != data:
             bad += 1
         assert rc != 0 or len(out) == len(data)

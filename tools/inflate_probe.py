@@ -32,7 +32,7 @@ if __name__ == "__main__":
     comp = os.path.getsize(path)
     unc = n * 118
     print(f"file: {comp / 1e9:.2f} GB compressed, {unc / 1e9:.2f} GB uncompressed (ratio {unc / comp:.2f}), written in {time.perf_counter() - t0:.0f} s", flush=True)
-    for opt, threads in ((1, 16), (0, 16), (0, 1)):
+    for opt, threads in ((1, 16), (2, 16), (0, 16), (0, 1)):
         with lib.Engine(lib.make_config(miss=1), 0, None, gpu_inflate=opt, time_kernels=1) as e:
             e.set_library(keys)
             for it in range(2):
