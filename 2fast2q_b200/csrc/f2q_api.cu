@@ -114,6 +114,7 @@ struct f2q_ctx {
     bool gpu_inflate = true;                         // bgzip input is inflated on the device (DESIGN.md §5 has the measurements)
     int gpu_inflate_mode = 1;                        // 1 lock-step lanes | 2 free-running threads (cross-check)
     bool gz_attr = false;
+    int gpu_inflate_bits = 0;                        // 0 auto | 8 | 9: index bits of the literal/length lookup table (developer option)
     DevBuf gz_comp[2], gz_out[2], gz_tab[2];
     BgzfBlock* gz_tab_host[2] = {nullptr, nullptr};
     cudaEvent_t gz_copied[2] = {nullptr, nullptr}, gz_free[2] = {nullptr, nullptr};
@@ -908,6 +909,7 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "spec") c->spec = value != 0;
     else if (n == "spec_warps") { if (value != 12 && value != 16 && value != 20 && value != 24) return fail(c, F2Q_EINVAL, "spec_warps must be 12, 16, 20 or 24"); c->spec_warps = (int)value; }
     else if (n == "memo_entries") { if (value < -1 || value > (1ll << 28) || (value > 0 && (value & (value - 1)))) return fail(c, F2Q_EINVAL, "memo_entries must be -1 (auto), 0 (off) or a power of two"); c->memo_entries = value; if (c->lib_set) return fail(c, F2Q_ESTATE, "memo_entries must be set before f2q_set_library"); }
+    else if (n == "gpu_inflate_bits") { if (value != 0 && value != 8 && value != 9) return fail(c, F2Q_EINVAL, "gpu_inflate_bits must be 0, 8 or 9"); c->gpu_inflate_bits = (int)value; }
     else if (n == "gpu_inflate") { if (value < 0 || value > 2) return fail(c, F2Q_EINVAL, "gpu_inflate must be 0, 1 or 2"); c->gpu_inflate = value != 0; c->gpu_inflate_mode = value == 2 ? 2 : 1; }
     else if (n == "flex_warps") { if (value != 12 && value != 16) return fail(c, F2Q_EINVAL, "flex_warps must be 12 or 16"); c->flex_warps = (int)value; }
     else if (n == "spec_range_tiles") { if (value < 0 || value > (1 << 20)) return fail(c, F2Q_EINVAL, "spec_range_tiles out of range"); c->spec_range_tiles = (int)value; }
@@ -1276,22 +1278,28 @@ F2Q_EXPORT int f2q_begin_sample(f2q_ctx* c) {
     return F2Q_OK;
 }
 
+// text already in device memory -> kernels.  Extract+Count: bounded sub-chunks, so that the insert log and the table bounds
+// of one launch stay bounded too
+static int device_range(f2q_ctx* c, const uint8_t* dptr, uint64_t nbytes, int is_last) {
+    const uint64_t sub = c->cfg.mode == F2Q_MODE_EXTRACT_COUNT ? EC_SUBCHUNK_BYTES : ~0ull;
+    uint64_t done = 0;
+    int rc;
+    do {
+        const uint64_t len = std::min<uint64_t>(sub, nbytes - done);
+        rc = process_device_chunk(c, dptr + done, len, is_last && done + len == nbytes);
+        if (rc) { if (!c->sticky) c->sample_failed = rc; return rc; }
+        done += len;
+    } while (done < nbytes);
+    return F2Q_OK;
+}
+
 F2Q_EXPORT int f2q_submit_device(f2q_ctx* c, const void* dptr, uint64_t nbytes, int is_last) {
     int rc = check_ctx(c); if (rc) return rc;
     if (!c->in_sample) return fail(c, F2Q_ESTATE, "f2q_submit_device outside a sample");
     if (c->closed) return fail(c, F2Q_ESTATE, "stream already closed with is_last");
     if (nbytes && !dptr) return fail(c, F2Q_EINVAL, "null chunk");
     if (c->sample_failed) return c->sample_failed;
-    // Extract+Count: bounded sub-chunks, so that the insert log and the table bounds of one launch stay bounded too
-    const uint64_t sub = c->cfg.mode == F2Q_MODE_EXTRACT_COUNT ? EC_SUBCHUNK_BYTES : ~0ull;
-    uint64_t done = 0;
-    do {
-        const uint64_t len = std::min<uint64_t>(sub, nbytes - done);
-        rc = process_device_chunk(c, reinterpret_cast<const uint8_t*>(dptr) + done, len, is_last && done + len == nbytes);
-        if (rc) { if (!c->sticky) c->sample_failed = rc; return rc; }
-        done += len;
-    } while (done < nbytes);
-    return F2Q_OK;
+    return device_range(c, reinterpret_cast<const uint8_t*>(dptr), nbytes, is_last);
 }
 
 // host chunk -> staging slots -> kernels.  `host_done` (optional) is recorded on the copy stream behind the last copy out of
@@ -1396,18 +1404,21 @@ size_t bgzf_block_size(const uint8_t* p, size_t avail) {
 
 namespace {
 
-constexpr size_t GZ_COMP_BYTES = 256u << 20, GZ_OUT_BYTES = 1u << 30, GZ_MAX_BLOCKS = 1u << 16;
+constexpr size_t GZ_COMP_BYTES = 1u << 30, GZ_OUT_BYTES = 3ull << 30, GZ_MAX_BLOCKS = 1u << 16;
 const uint8_t BGZF_EOF[28] = {0x1f, 0x8b, 0x08, 0x04, 0, 0, 0, 0, 0, 0xff, 0x06, 0, 0x42, 0x43, 0x02, 0, 0x1b, 0, 0x03, 0, 0, 0, 0, 0, 0, 0, 0, 0};
 
 // bgzip file -> the sample, inflated ON THE DEVICE: compressed pieces are read into the pinned ring, their block headers and
 // trailers are walked on the host (sizes only), the pieces go to a device staging buffer on the copy stream, and one launch
-// of k_inflate_bgzf per batch (<= 256 MiB compressed, <= 1 GiB of output, <= 65 536 blocks) writes the FASTQ text straight
+// of k_inflate_bgzf_lanes per batch (<= 1 GiB compressed, <= 3 GiB of output, <= 65 536 blocks: tens of thousands of lanes) writes the FASTQ text straight
 // into the buffer process_device_chunk parses.  Two staging / output buffers: the next batch is read and copied while the
 // previous one is inflated and parsed.  Stops at the first thing that is not a whole BGZF block (a foreign gzip member, a
 // truncated block) and reports the file offset there: the host reader takes over from that offset.
 int submit_bgzf_gpu(f2q_ctx* c, FILE* f, FileRing& R, int threads, uint64_t* total, uint64_t* resume_off, bool* finished) {
     int rc;
     const int T = std::max(1, std::min(threads, 8));
+    static const bool debug = getenv("F2Q_DEBUG_INGEST") != nullptr;   // developer lap timers: where the host thread spends its time
+    double t_read = 0, t_ring = 0, t_free = 0, t_walk = 0;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     for (int k = 0; k < 2; k++) {
         if ((rc = dev_alloc(c, c->gz_comp[k], GZ_COMP_BYTES + 65536)) || (rc = dev_alloc(c, c->gz_out[k], GZ_OUT_BYTES + 65536 + 256)) ||
             (rc = dev_alloc(c, c->gz_tab[k], GZ_MAX_BLOCKS * sizeof(BgzfBlock)))) return rc;
@@ -1427,21 +1438,28 @@ int submit_bgzf_gpu(f2q_ctx* c, FILE* f, FileRing& R, int threads, uint64_t* tot
         CU(c, cudaStreamWaitEvent(c->copy_stream, c->gz_free[k], 0));
         BgzfBlock* tab = c->gz_tab_host[k];
         // (the host table of batch k-2 was consumed by an H2D copy that completed before gz_free[k] did)
+        double t0 = now();
         CU(c, cudaEventSynchronize(c->gz_free[k]));                    // (returns at once for an event that was never recorded)
+        t_free += now() - t0;
         uint32_t nb = 0;
         size_t comp_fill = 0, out_fill = 0;
         uint64_t batch_start = off - carry.size();
         while (!eof && !stop && comp_fill + R.bytes + 65536 <= GZ_COMP_BYTES && out_fill + 4 * R.bytes <= GZ_OUT_BYTES && nb + 4096 < GZ_MAX_BLOCKS) {
             uint8_t* buf; int idx;
+            t0 = now();
             if ((rc = ring_get(c, R, &buf, &idx))) return rc;
+            t_ring += now() - t0;
             size_t have = carry.size();
             if (have) memcpy(buf, carry.data(), have);
             carry.clear();
             if (have < R.bytes) {
+                t0 = now();
                 const size_t want = R.bytes - have, g = pread_parallel(fd, buf + have, want, off, T);
+                t_read += now() - t0;
                 if (g < want) eof = true;
                 have += g; off += g;
             }
+            t0 = now();
             // whole blocks of this piece
             size_t p = 0;
             while (have - p >= 18) {
@@ -1455,6 +1473,7 @@ int submit_bgzf_gpu(f2q_ctx* c, FILE* f, FileRing& R, int threads, uint64_t* tot
                 if (isize) { tab[nb++] = BgzfBlock{(uint32_t)(comp_fill + p + 12 + xlen), (uint32_t)(bs - 12 - xlen - 8), (uint32_t)out_fill, isize}; out_fill += isize; }
                 p += bs;
             }
+            t_walk += now() - t0;
             // copy the whole blocks to the device staging buffer; what is left (a partial block) is carried
             if (p) CU(c, cudaMemcpyAsync(reinterpret_cast<uint8_t*>(c->gz_comp[k].p) + comp_fill, buf, p, cudaMemcpyHostToDevice, c->copy_stream));
             R.used[idx] = true;
@@ -1478,20 +1497,34 @@ int submit_bgzf_gpu(f2q_ctx* c, FILE* f, FileRing& R, int threads, uint64_t* tot
                     reinterpret_cast<const uint8_t*>(c->gz_comp[k].p), reinterpret_cast<const BgzfBlock*>(c->gz_tab[k].p), nb,
                     reinterpret_cast<uint8_t*>(c->gz_out[k].p), c->d_error);
             else {
-                if (!c->gz_attr) { CU(c, cudaFuncSetAttribute(k_inflate_bgzf_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INFLATE_SMEM)); c->gz_attr = true; }
-                k_inflate_bgzf_lanes<<<(nb + INFLATE_THREADS - 1) / INFLATE_THREADS, INFLATE_THREADS, INFLATE_SMEM, c->stream>>>(
-                    reinterpret_cast<const uint8_t*>(c->gz_comp[k].p), reinterpret_cast<const BgzfBlock*>(c->gz_tab[k].p), nb,
-                    reinterpret_cast<uint8_t*>(c->gz_out[k].p), c->d_error);
+                const uint32_t grid = (nb + INFLATE_LANES - 1) / INFLATE_LANES;
+                if (!c->gz_attr) {
+                    CU(c, cudaFuncSetAttribute(k_inflate_bgzf_lanes<9, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inflate_smem<9, 7>()));
+                    CU(c, cudaFuncSetAttribute(k_inflate_bgzf_lanes<8, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)inflate_smem<8, 6>()));
+                    c->gz_attr = true;
+                }
+                // 9 + 7 index bits: 5 warps per SM; 8 + 6: 11 — the small tables when the batch can fill those warps
+                const bool small = c->gpu_inflate_bits ? c->gpu_inflate_bits == 8 : grid > 5u * (uint32_t)c->sm_count;
+                if (small)
+                    k_inflate_bgzf_lanes<8, 6><<<grid, INFLATE_LANES, inflate_smem<8, 6>(), c->stream>>>(
+                        reinterpret_cast<const uint8_t*>(c->gz_comp[k].p), reinterpret_cast<const BgzfBlock*>(c->gz_tab[k].p), nb,
+                        reinterpret_cast<uint8_t*>(c->gz_out[k].p), c->d_error);
+                else
+                    k_inflate_bgzf_lanes<9, 7><<<grid, INFLATE_LANES, inflate_smem<9, 7>(), c->stream>>>(
+                        reinterpret_cast<const uint8_t*>(c->gz_comp[k].p), reinterpret_cast<const BgzfBlock*>(c->gz_tab[k].p), nb,
+                        reinterpret_cast<uint8_t*>(c->gz_out[k].p), c->d_error);
             }
             c->launches++;
             CU(c, cudaGetLastError());
             CU(c, cudaEventRecord(c->gz_free[k], c->stream));
             c->gz_blocks += nb;
             *total += out_fill;
-            if ((rc = process_device_chunk(c, reinterpret_cast<const uint8_t*>(c->gz_out[k].p), out_fill, 0))) { if (!c->sticky) c->sample_failed = rc; return rc; }
+            if ((rc = device_range(c, reinterpret_cast<const uint8_t*>(c->gz_out[k].p), out_fill, 0))) return rc;
             batch++;
         } else if (!stop && !eof) return fail(c, F2Q_EINTERNAL, "bgzip batch without a block");
     }
+    if (debug) fprintf(stderr, "[f2q ingest] bgzf on the device: %d batches, %llu blocks; host thread: read %.1f ms, ring wait %.1f ms, batch wait %.1f ms, header walk %.1f ms\n",
+                       batch, (unsigned long long)c->gz_blocks, t_read, t_ring, t_free, t_walk);
     *resume_off = off;
     *finished = eof && !stop;
     return F2Q_OK;

@@ -191,93 +191,128 @@ F2Q_HD int inflate_raw(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_
 // inflate_raw above lets every lane follow its own control flow; measured on the device (ncu: 1.01 active threads per
 // warp instruction) the lanes of a warp then run one after the other.  Here every lane executes the SAME loop body; what a
 // lane does in an iteration depends on its state: read a block header and build its tables (rare, the only part in which
-// lanes wait for each other), decode one literal / length+distance pair through a lookup table, copy up to 8 bytes of a
-// match, copy up to 8 bytes of a stored block.  Codes longer than the table's index are decoded bit-serially from the
-// canonical tables (FASTQ text has none).
+// lanes wait for each other), decode one literal / length+distance pair through a lookup table and copy up to 8 bytes of the
+// match, copy 8 more bytes of a long match, copy up to 4 bytes of a stored block.
+//
+// What the loop is built around (the kernel runs few warps per SM — shared memory bounds them — so it is the latency of one
+// iteration's dependent chain that counts):
+//   * the lane's scalars (InflLane) hold no array and never leave registers; the canonical tables (InflTables, local
+//     memory) are touched by block headers and by codes longer than the lookup index only;
+//   * input arrives in aligned 32-bit words, loaded one refill AHEAD of their use;
+//   * a match loads its 8 source bytes as three aligned words before it stores anything (an overlapping match, distance < 8,
+//     replicates its period in registers), so the loads of a copy never wait for its stores;
+//   * length / distance bases and extra-bit counts are computed, not looked up;
+//   * a code longer than the lookup index resumes the canonical walk at the first uncovered length, on bit-reversed input.
 // lut / dlut: the lane's lookup tables, element i of lane L at lut[i * stride + L] (shared memory on the device: the
 // interleaving makes the lanes' random look-ups hit distinct banks); entry = symbol << 4 | code length, 0 = no short code.
+// The input must be readable 16 bytes past its end and 3 bytes before its start, the output 3 bytes before its start and
+// 16 past its end (aligned word loads; what is read there is never used).
 // ------------------------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+#define F2Q_HD_COLD __host__ __device__ __noinline__
+#else
+#define F2Q_HD_COLD inline
+#endif
+
 constexpr int INFL_LUT_BITS = 9, INFL_DLUT_BITS = 7;
 enum { INFL_ST_HEADER = 0, INFL_ST_SYMBOL = 1, INFL_ST_COPY = 2, INFL_ST_STORED = 3, INFL_ST_DONE = 4 };
 
-struct InflLane {
-    InflState s;
+struct InflTables {
     InflHuff lencode;
     InflHuffD distcode;
-    uint32_t state, last, copy_len, copy_dist;
+    int lfirst, lindex, dfirst, dindex;      // the canonical walk's (first, index) behind the lengths the lookup tables cover
+};
+struct InflLane {
+    const uint8_t* in; uint8_t* out;
+    uint64_t bitbuf;
+    uint32_t ahead;                          // the input word at in_pos, loaded one refill ahead
+    uint32_t bitcnt, in_pos, in_len, out_pos, out_len;
+    uint32_t state, last, copy_len, copy_dist, err;
 };
 
-F2Q_HD uint32_t infl_rev(uint32_t v, int n) {
-    uint32_t r = 0;
-    for (int i = 0; i < n; i++) { r = (r << 1) | (v & 1u); v >>= 1; }
-    return r;
+F2Q_HD uint32_t infl_word(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }   // p is 4-byte aligned
+F2Q_HD uint32_t infl_brev(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __brev(v);
+#else
+    v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+    v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+    v = ((v >> 4) & 0x0F0F0F0Fu) | ((v & 0x0F0F0F0Fu) << 4);
+    return (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24);
+#endif
+}
+// bits [sh, sh + 32) of hi:lo, sh in {0, 8, 16, 24}
+F2Q_HD uint32_t infl_fsr(uint32_t lo, uint32_t hi, uint32_t sh) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> sh);
+#endif
 }
 
 // lookup table of a canonical code: every index whose low `len` bits are the (bit-reversed) code of a symbol of length
-// len <= bits gets symbol << 4 | len
+// len <= bits gets symbol << 4 | len; returns through first / index the state of the canonical walk behind length `bits`
 template <class H>
-F2Q_HD void infl_build_lut(const H& h, int nsym_max, uint16_t* lut, uint32_t stride, int bits) {
+F2Q_HD void infl_build_lut(const H& h, uint16_t* lut, uint32_t stride, int bits, int* first_out, int* index_out) {
     for (uint32_t i = 0; i < (1u << bits); i++) lut[i * stride] = 0;
     uint32_t code = 0, index = 0;
-    for (int len = 1; len <= INFL_MAXBITS; len++) {
+    int first = 0;
+    for (int len = 1; len <= bits; len++) {
         const uint32_t cnt = h.count[len];
-        if (len <= bits) {
-            for (uint32_t k = 0; k < cnt; k++) {
-                const uint32_t sym = h.symbol[index + k], r = infl_rev(code + k, len);
-                for (uint32_t hi = 0; hi < (1u << (bits - len)); hi++) lut[(r | (hi << len)) * stride] = (uint16_t)((sym << 4) | (uint32_t)len);
-            }
+        for (uint32_t k = 0; k < cnt; k++) {
+            const uint32_t sym = h.symbol[index + k], r = infl_brev(code + k) >> (32 - len);
+            for (uint32_t hi = 0; hi < (1u << (bits - len)); hi++) lut[(r | (hi << len)) * stride] = (uint16_t)((sym << 4) | (uint32_t)len);
         }
-        code = (code + cnt) << 1; index += cnt;
+        code = (code + cnt) << 1; index += cnt; first = (first + (int)cnt) << 1;
     }
-    (void)nsym_max;
+    *first_out = first; *index_out = (int)index;
 }
 
-// 4 more input bytes when there is room for them (bytes behind the stream's end read as what follows it in memory: a valid
+// 32 more input bits when there is room for them (words behind the stream's end read as what follows it in memory: a valid
 // stream never uses them, and the final check refuses a stream that did)
-F2Q_HD void infl_refill4(InflState& s) {
-    if (s.bitcnt <= 32u) {
-        const uint8_t* p = s.in + s.in_pos;
-        const uint32_t w = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
-        s.bitbuf |= (uint64_t)w << s.bitcnt; s.bitcnt += 32u; s.in_pos += 4u;
+F2Q_HD void infl_refill4(InflLane& L) {
+    if (L.bitcnt <= 32u) {
+        L.bitbuf |= (uint64_t)L.ahead << L.bitcnt; L.bitcnt += 32u; L.in_pos += 4u;
+        L.ahead = infl_word(L.in + L.in_pos);
     }
 }
-F2Q_HD uint32_t infl_take(InflState& s, uint32_t n) {
-    const uint32_t v = (uint32_t)(s.bitbuf & ((1ull << n) - 1ull));
-    s.bitbuf >>= n; s.bitcnt -= n;
+F2Q_HD uint32_t infl_take(InflLane& L, uint32_t n) {
+    const uint32_t v = (uint32_t)L.bitbuf & ((1u << n) - 1u);          // n <= 16
+    L.bitbuf >>= n; L.bitcnt -= n;
     return v;
 }
-template <class H>
-F2Q_HD int infl_decode_lut(InflState& s, const H& h, const uint16_t* lut, uint32_t stride, int bits) {
-    const uint32_t e = lut[((uint32_t)s.bitbuf & ((1u << bits) - 1u)) * stride];
-    if (e & 15u) { s.bitbuf >>= (e & 15u); s.bitcnt -= (e & 15u); return (int)(e >> 4); }
-    // a code longer than the table's index: bit-serial from the canonical tables (at least 33 bits are buffered)
-    int code = 0, first = 0, index = 0;
-    uint64_t buf = s.bitbuf;
-    for (uint32_t len = 1; len <= (uint32_t)INFL_MAXBITS; len++) {
-        code |= (int)(buf & 1u); buf >>= 1;
-        const int count = h.count[len];
-        if (code - count < first) { s.bitbuf = buf; s.bitcnt -= len; return h.symbol[index + (code - first)]; }
-        index += count; first += count; first <<= 1; code <<= 1;
+// one symbol; at least 33 bits are buffered
+template <int BITS, class H>
+F2Q_HD int infl_decode_lut(InflLane& L, const H& h, const uint16_t* lut, uint32_t stride, int first, int index) {
+    const uint32_t e = lut[((uint32_t)L.bitbuf & ((1u << BITS) - 1u)) * stride];
+    if (e & 15u) { L.bitbuf >>= (e & 15u); L.bitcnt -= (e & 15u); return (int)(e >> 4); }
+    // a code longer than the table's index: the canonical walk, from the first length the table does not cover
+    const uint32_t rev = infl_brev((uint32_t)L.bitbuf);                // the first bit of the code on top
+#pragma unroll
+    for (int len = BITS + 1; len <= INFL_MAXBITS; len++) {
+        const int c = (int)(rev >> (32 - len)), count = h.count[len];
+        if (c - count < first) { L.bitbuf >>= len; L.bitcnt -= (uint32_t)len; return h.symbol[index + (c - first)]; }
+        index += count; first = (first + count) << 1;
     }
-    s.err = s.err ? s.err : 2;
+    L.err = L.err ? L.err : 2u;
     return -1;
 }
 
 // block header of one lane (the divergent part): stored -> INFL_ST_STORED; fixed / dynamic -> tables + INFL_ST_SYMBOL
-F2Q_HD void infl_header(InflLane& L, uint16_t* lut, uint16_t* dlut, uint32_t stride) {
-    InflState& s = L.s;
+template <int LB, int DB>
+F2Q_HD_COLD void infl_header(InflLane& L, InflTables& T, uint16_t* lut, uint16_t* dlut, uint32_t stride) {
     uint8_t lengths[INFL_MAXLCODES + INFL_MAXDCODES + 4];
-    infl_refill4(s);
-    L.last = infl_take(s, 1);
-    const uint32_t type = infl_take(s, 2);
+    infl_refill4(L);
+    L.last = infl_take(L, 1);
+    const uint32_t type = infl_take(L, 2);
     if (type == 0) {
-        const uint32_t drop = s.bitcnt & 7u;
-        s.bitbuf >>= drop; s.bitcnt -= drop;
-        infl_refill4(s);
-        const uint32_t len = infl_take(s, 16), nlen = infl_take(s, 16);
-        if ((len ^ 0xFFFFu) != nlen) { s.err = 2; return; }
-        if (s.out_pos + len > s.out_len) { s.err = 3; return; }
-        L.copy_len = len; L.state = INFL_ST_STORED;
+        const uint32_t drop = L.bitcnt & 7u;
+        L.bitbuf >>= drop; L.bitcnt -= drop;
+        infl_refill4(L);
+        const uint32_t len = infl_take(L, 16), nlen = infl_take(L, 16);
+        if ((len ^ 0xFFFFu) != nlen) { L.err = 2; return; }
+        if (L.out_pos + len > L.out_len) { L.err = 3; return; }
+        L.copy_len = len; L.state = len ? INFL_ST_STORED : (L.last ? INFL_ST_DONE : INFL_ST_HEADER);
         return;
     }
     if (type == 1) {
@@ -286,112 +321,133 @@ F2Q_HD void infl_header(InflLane& L, uint16_t* lut, uint16_t* dlut, uint32_t str
         for (; sym < 256; sym++) lengths[sym] = 9;
         for (; sym < 280; sym++) lengths[sym] = 7;
         for (; sym < INFL_FIXLCODES; sym++) lengths[sym] = 8;
-        infl_construct(L.lencode, lengths, INFL_FIXLCODES);
+        infl_construct(T.lencode, lengths, INFL_FIXLCODES);
         for (sym = 0; sym < INFL_MAXDCODES; sym++) lengths[sym] = 5;
-        infl_construct(L.distcode, lengths, INFL_MAXDCODES);
+        infl_construct(T.distcode, lengths, INFL_MAXDCODES);
     } else if (type == 2) {
         static const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
-        infl_refill4(s);
-        const int nlen = (int)infl_take(s, 5) + 257, ndist = (int)infl_take(s, 5) + 1, ncode = (int)infl_take(s, 4) + 4;
-        if (nlen > INFL_MAXLCODES || ndist > INFL_MAXDCODES) { s.err = 2; return; }
+        infl_refill4(L);
+        const int nlen = (int)infl_take(L, 5) + 257, ndist = (int)infl_take(L, 5) + 1, ncode = (int)infl_take(L, 4) + 4;
+        if (nlen > INFL_MAXLCODES || ndist > INFL_MAXDCODES) { L.err = 2; return; }
         int index = 0;
-        for (; index < ncode; index++) { infl_refill4(s); lengths[order[index]] = (uint8_t)infl_take(s, 3); }
+        for (; index < ncode; index++) { infl_refill4(L); lengths[order[index]] = (uint8_t)infl_take(L, 3); }
         for (; index < 19; index++) lengths[order[index]] = 0;
-        if (infl_construct(L.lencode, lengths, 19) != 0) { s.err = 2; return; }
+        if (infl_construct(T.lencode, lengths, 19) != 0) { L.err = 2; return; }
         index = 0;
         while (index < nlen + ndist) {
-            infl_refill4(s);
-            // (the code-length code has at most 19 symbols of <= 7 bits: the bit-serial decoder, on buffered bits)
+            infl_refill4(L);
+            // (the code-length code has at most 19 symbols of <= 7 bits: the bit-serial walk, on buffered bits)
             int code = 0, first = 0, idx2 = 0, symbol = -1;
             for (uint32_t len = 1; len <= 7u; len++) {
-                code |= (int)(s.bitbuf & 1u); s.bitbuf >>= 1; s.bitcnt -= 1;
-                const int count = L.lencode.count[len];
-                if (code - count < first) { symbol = L.lencode.symbol[idx2 + (code - first)]; break; }
+                code |= (int)(L.bitbuf & 1u); L.bitbuf >>= 1; L.bitcnt -= 1;
+                const int count = T.lencode.count[len];
+                if (code - count < first) { symbol = T.lencode.symbol[idx2 + (code - first)]; break; }
                 idx2 += count; first += count; first <<= 1; code <<= 1;
             }
-            if (symbol < 0) { s.err = 2; return; }
+            if (symbol < 0) { L.err = 2; return; }
             if (symbol < 16) lengths[index++] = (uint8_t)symbol;
             else {
                 int len = 0, rep;
-                if (symbol == 16) { if (index == 0) { s.err = 2; return; } len = lengths[index - 1]; rep = 3 + (int)infl_take(s, 2); }
-                else if (symbol == 17) rep = 3 + (int)infl_take(s, 3);
-                else rep = 11 + (int)infl_take(s, 7);
-                if (index + rep > nlen + ndist) { s.err = 2; return; }
+                if (symbol == 16) { if (index == 0) { L.err = 2; return; } len = lengths[index - 1]; rep = 3 + (int)infl_take(L, 2); }
+                else if (symbol == 17) rep = 3 + (int)infl_take(L, 3);
+                else rep = 11 + (int)infl_take(L, 7);
+                if (index + rep > nlen + ndist) { L.err = 2; return; }
                 while (rep--) lengths[index++] = (uint8_t)len;
             }
         }
-        if (lengths[256] == 0) { s.err = 2; return; }
-        int e = infl_construct(L.lencode, lengths, nlen);
-        if (e < 0 || (e > 0 && nlen - L.lencode.count[0] != 1)) { s.err = 2; return; }
-        e = infl_construct(L.distcode, lengths + nlen, ndist);
-        if (e < 0 || (e > 0 && ndist - L.distcode.count[0] != 1)) { s.err = 2; return; }
-    } else { s.err = 2; return; }
-    infl_build_lut(L.lencode, INFL_FIXLCODES, lut, stride, INFL_LUT_BITS);
-    infl_build_lut(L.distcode, INFL_MAXDCODES, dlut, stride, INFL_DLUT_BITS);
+        if (lengths[256] == 0) { L.err = 2; return; }
+        int e = infl_construct(T.lencode, lengths, nlen);
+        if (e < 0 || (e > 0 && nlen - T.lencode.count[0] != 1)) { L.err = 2; return; }
+        e = infl_construct(T.distcode, lengths + nlen, ndist);
+        if (e < 0 || (e > 0 && ndist - T.distcode.count[0] != 1)) { L.err = 2; return; }
+    } else { L.err = 2; return; }
+    infl_build_lut(T.lencode, lut, stride, LB, &T.lfirst, &T.lindex);
+    infl_build_lut(T.distcode, dlut, stride, DB, &T.dfirst, &T.dindex);
     L.state = INFL_ST_SYMBOL;
 }
 
 F2Q_HD void infl_lane_init(InflLane& L, const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len) {
-    L.s.in = in; L.s.in_len = in_len; L.s.in_pos = 0; L.s.bitbuf = 0; L.s.bitcnt = 0; L.s.out = out; L.s.out_len = out_len; L.s.out_pos = 0; L.s.err = 0;
+    L.in = in; L.in_len = in_len; L.out = out; L.out_len = out_len; L.out_pos = 0; L.err = 0;
+    L.bitbuf = 0; L.bitcnt = 0; L.in_pos = 0; L.ahead = 0;
     L.state = in_len ? INFL_ST_HEADER : INFL_ST_DONE; L.last = 0; L.copy_len = 0; L.copy_dist = 0;
-    if (!in_len && out_len) L.s.err = 2;
+    if (!in_len && out_len) L.err = 2;
+    if (in_len) {
+        // the bytes up to the first aligned word, then aligned words only
+        const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(in) & 3u);
+        L.bitbuf = infl_word(in - mis) >> (8u * mis); L.bitcnt = 32u - 8u * mis; L.in_pos = 4u - mis;
+        L.ahead = infl_word(in + L.in_pos);
+    }
 }
 
 // one iteration of the state machine for one lane; the caller loops while any lane is not INFL_ST_DONE
-F2Q_HD void infl_step(InflLane& L, uint16_t* lut, uint16_t* dlut, uint32_t stride) {
-    static const uint16_t lens[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
-    static const uint8_t lext[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
-    static const uint16_t dists[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
-    static const uint8_t dext[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
-    InflState& s = L.s;
-    if (s.err) { L.state = INFL_ST_DONE; return; }
-    if (L.state == INFL_ST_HEADER) { infl_header(L, lut, dlut, stride); if (s.err) L.state = INFL_ST_DONE; return; }
-    if (L.state == INFL_ST_SYMBOL) {
-        infl_refill4(s);
-        int symbol = infl_decode_lut(s, L.lencode, lut, stride, INFL_LUT_BITS);
-        if (symbol < 0) { L.state = INFL_ST_DONE; return; }
+template <int LB = INFL_LUT_BITS, int DB = INFL_DLUT_BITS>
+F2Q_HD void infl_step(InflLane& L, InflTables& T, uint16_t* lut, uint16_t* dlut, uint32_t stride) {
+    if (L.state == INFL_ST_HEADER) {
+        InflLane t = L;                                                // (the copy's address escapes, the lane's registers do not)
+        infl_header<LB, DB>(t, T, lut, dlut, stride);
+        L = t;
+        if (L.err) L.state = INFL_ST_DONE;
+    } else if (L.state == INFL_ST_SYMBOL) {
+        infl_refill4(L);
+        int symbol = infl_decode_lut<LB>(L, T.lencode, lut, stride, T.lfirst, T.lindex);
         if (symbol < 256) {
-            if (s.out_pos >= s.out_len) { s.err = 3; L.state = INFL_ST_DONE; return; }
-            s.out[s.out_pos++] = (uint8_t)symbol;
+            if (symbol < 0) L.state = INFL_ST_DONE;
+            else if (L.out_pos >= L.out_len) { L.err = 3; L.state = INFL_ST_DONE; }
+            else L.out[L.out_pos++] = (uint8_t)symbol;
         } else if (symbol == 256) L.state = L.last ? INFL_ST_DONE : INFL_ST_HEADER;
         else {
-            symbol -= 257;
-            if (symbol >= 29) { s.err = 2; L.state = INFL_ST_DONE; return; }
-            const uint32_t len = lens[symbol] + infl_take(s, lext[symbol]);
-            infl_refill4(s);
-            const int ds = infl_decode_lut(s, L.distcode, dlut, stride, INFL_DLUT_BITS);
-            if (ds < 0 || ds >= 30) { s.err = 2; L.state = INFL_ST_DONE; return; }
-            const uint32_t dist = dists[ds] + infl_take(s, dext[ds]);
-            if (dist > s.out_pos || s.out_pos + len > s.out_len) { s.err = dist > s.out_pos ? 2 : 3; L.state = INFL_ST_DONE; return; }
-            L.copy_len = len; L.copy_dist = dist; L.state = INFL_ST_COPY;
+            // length 3..258: symbols 257..264 are 3..10, 265..284 carry (sym - 261) / 4 extra bits, 285 is 258
+            const uint32_t sym = (uint32_t)symbol - 257u;
+            const uint32_t lx = (sym < 8u || sym == 28u) ? 0u : (sym - 4u) >> 2;
+            const uint32_t lbase = sym < 8u ? 3u + sym : sym == 28u ? 258u : 3u + ((4u + (sym & 3u)) << lx);
+            const uint32_t len = lbase + infl_take(L, lx);
+            infl_refill4(L);
+            const int ds = infl_decode_lut<DB>(L, T.distcode, dlut, stride, T.dfirst, T.dindex);
+            // distance 1..32768: codes 0..3 are 1..4, the others carry (code - 2) / 2 extra bits
+            const uint32_t d = (uint32_t)ds, dx = d < 4u ? 0u : (d - 2u) >> 1;
+            const uint32_t dbase = d < 4u ? 1u + d : 1u + ((2u + (d & 1u)) << (dx & 15u));
+            const uint32_t dist = dbase + infl_take(L, dx & 15u);
+            if (sym >= 29u || ds < 0 || ds >= 30) { L.err = L.err ? L.err : 2u; L.state = INFL_ST_DONE; }
+            else if (dist > L.out_pos) { L.err = 2; L.state = INFL_ST_DONE; }
+            else if (L.out_pos + len > L.out_len) { L.err = 3; L.state = INFL_ST_DONE; }
+            else { L.copy_len = len; L.copy_dist = dist; L.state = INFL_ST_COPY; }
         }
-        return;
     }
     if (L.state == INFL_ST_COPY) {
+        // up to 8 bytes of the match (a lane that has just decoded it starts the copy in the same iteration)
         const uint32_t n = L.copy_len < 8u ? L.copy_len : 8u;
-        uint8_t* o = s.out + s.out_pos;
+        uint8_t* o = L.out + L.out_pos;
         const uint8_t* f = o - L.copy_dist;
-        for (uint32_t k = 0; k < n; k++) o[k] = f[k];
-        s.out_pos += n; L.copy_len -= n;
+        const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(f) & 3u);
+        const uint32_t w0 = infl_word(f - a), w1 = infl_word(f - a + 4), w2 = infl_word(f - a + 8);
+        uint64_t v = (uint64_t)infl_fsr(w0, w1, 8u * a) | ((uint64_t)infl_fsr(w1, w2, 8u * a) << 32);
+        if (L.copy_dist < 8u) {
+            // the source overlaps what this copy writes: its first `dist` bytes are the period
+            const uint32_t period = 8u * L.copy_dist;
+            v &= (1ull << period) - 1ull;
+            v |= v << period;
+            if (2u * period < 64u) v |= v << (2u * period);
+            if (4u * period < 64u) v |= v << (4u * period);
+        }
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; k++) if (k < n) o[k] = (uint8_t)(v >> (8u * k));
+        L.out_pos += n; L.copy_len -= n;
         if (!L.copy_len) L.state = INFL_ST_SYMBOL;
-        return;
-    }
-    if (L.state == INFL_ST_STORED) {
+    } else if (L.state == INFL_ST_STORED) {
         // the bit buffer holds whole bytes here
-        uint32_t n = L.copy_len < 4u ? L.copy_len : 4u;
-        infl_refill4(s);
-        for (uint32_t k = 0; k < n; k++) s.out[s.out_pos++] = (uint8_t)infl_take(s, 8);
+        const uint32_t n = L.copy_len < 4u ? L.copy_len : 4u;
+        infl_refill4(L);
+        for (uint32_t k = 0; k < n; k++) L.out[L.out_pos++] = (uint8_t)infl_take(L, 8);
         L.copy_len -= n;
         if (!L.copy_len) L.state = L.last ? INFL_ST_DONE : INFL_ST_HEADER;
-        return;
     }
 }
 
 // end of a lane: everything produced, and not a bit taken from behind the stream's end
 F2Q_HD int infl_lane_result(const InflLane& L) {
-    if (L.s.err) return L.s.err;
-    if (L.s.out_pos != L.s.out_len) return 2;
-    if ((uint64_t)L.s.in_pos * 8u - L.s.bitcnt > (uint64_t)L.s.in_len * 8u) return 1;
+    if (L.err) return (int)L.err;
+    if (L.out_pos != L.out_len) return 2;
+    if ((uint64_t)L.in_pos * 8u - L.bitcnt > (uint64_t)L.in_len * 8u) return 1;
     return 0;
 }
 

@@ -130,21 +130,25 @@ __global__ void __launch_bounds__(INFLATE_THREADS) k_inflate_bgzf(const uint8_t*
 
 // lock-step form: the 32 lanes of a warp inflate 32 blocks through the state machine of inflate_core.h — every lane runs the
 // same loop body, so the warp stays converged; the lanes' lookup tables live in shared memory, interleaved by lane (entry i
-// of lane L at [i * 64 + L]: the lanes' random look-ups fall into distinct banks)
-constexpr size_t INFLATE_SMEM = ((size_t)(1 << INFL_LUT_BITS) + (size_t)(1 << INFL_DLUT_BITS)) * INFLATE_THREADS * sizeof(uint16_t);
-__global__ void __launch_bounds__(INFLATE_THREADS) k_inflate_bgzf_lanes(const uint8_t* __restrict__ comp, const BgzfBlock* __restrict__ blk, uint32_t n,
-                                                                        uint8_t* __restrict__ out, uint32_t* error) {
+// of lane L at [i * 32 + L]: the lanes' random look-ups fall into distinct banks).  Shared memory bounds the lanes per SM
+// (1280 B per lane with 9 + 7 index bits, 640 B with 8 + 6), and the kernel is latency-bound: the smaller tables win when
+// the batch has enough blocks to fill the extra warps
+constexpr int INFLATE_LANES = 32;                                   // one warp per CTA: the CTA is the unit shared memory is handed out in
+template <int LB, int DB>
+constexpr size_t inflate_smem() { return ((size_t)(1 << LB) + (size_t)(1 << DB)) * INFLATE_LANES * sizeof(uint16_t); }
+template <int LB, int DB>
+__global__ void __launch_bounds__(INFLATE_LANES) k_inflate_bgzf_lanes(const uint8_t* __restrict__ comp, const BgzfBlock* __restrict__ blk, uint32_t n,
+                                                                      uint8_t* __restrict__ out, uint32_t* error) {
     extern __shared__ __align__(16) uint16_t infl_sm[];
     uint16_t* const lut = infl_sm + threadIdx.x;
-    uint16_t* const dlut = infl_sm + ((size_t)INFLATE_THREADS << INFL_LUT_BITS) + threadIdx.x;
-    for (uint32_t b0 = blockIdx.x * blockDim.x; b0 < n; b0 += gridDim.x * blockDim.x) {
-        const uint32_t b = b0 + threadIdx.x;
-        InflLane L;
-        if (b < n) { const BgzfBlock B = blk[b]; infl_lane_init(L, comp + B.src, B.csize, out + B.dst, B.isize); }
-        else { infl_lane_init(L, comp, 0, out, 0); }
-        while (__any_sync(0xffffffffu, L.state != INFL_ST_DONE)) infl_step(L, lut, dlut, INFLATE_THREADS);
-        if (b < n && infl_lane_result(L) != 0) atomicOr(error, ERR_INFLATE);
-    }
+    uint16_t* const dlut = infl_sm + ((size_t)INFLATE_LANES << LB) + threadIdx.x;
+    const uint32_t b = blockIdx.x * INFLATE_LANES + threadIdx.x;
+    InflLane L;
+    InflTables T;
+    if (b < n) { const BgzfBlock B = blk[b]; infl_lane_init(L, comp + B.src, B.csize, out + B.dst, B.isize); }
+    else { infl_lane_init(L, comp, 0, out, 0); }
+    while (__any_sync(0xffffffffu, L.state != INFL_ST_DONE)) infl_step<LB, DB>(L, T, lut, dlut, INFLATE_LANES);
+    if (b < n && infl_lane_result(L) != 0) atomicOr(error, ERR_INFLATE);
 }
 
 // start of a sample: result vector, scratch vector, error word and the stream state in ONE launch

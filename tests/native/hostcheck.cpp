@@ -75,20 +75,44 @@ int hc_flex_key(const f2q_config* cfg, int pw, const uint8_t* read, int r, const
 // ---- inflate_core.h: the per-block DEFLATE decoder of k_inflate_bgzf, against zlib --------------------------------------
 #include "../../2fast2q_b200/csrc/inflate_core.h"
 
+// (the lock-step decoder reads aligned words around its buffers: the copies here carry the margins its contract asks for)
+template <int LB, int DB>
+static int inflate_lane(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len, uint64_t* stats = nullptr) {
+    static thread_local uint16_t lut[1 << LB], dlut[1 << DB];
+    std::vector<uint8_t> ibuf((size_t)in_len + 64, 0xAA), obuf((size_t)out_len + 64, 0x55);
+    for (int mis = 0; mis < (stats ? 1 : 4); mis++) {                  // every alignment of the input and of the output
+        uint8_t* ip = ibuf.data() + 16 + mis;
+        uint8_t* op = obuf.data() + 16 + ((mis * 3) & 3);
+        memcpy(ip, in, in_len);
+        f2q::InflLane L;
+        f2q::InflTables T;
+        f2q::infl_lane_init(L, ip, in_len, op, out_len);
+        for (uint64_t it = 0; L.state != f2q::INFL_ST_DONE; it++) {
+            if (it > (1ull << 28)) return 9;
+            if (stats) stats[L.state]++;
+            f2q::infl_step<LB, DB>(L, T, lut, dlut, 1);
+        }
+        const int rc = f2q::infl_lane_result(L);
+        if (mis == 0) { memcpy(out, op, out_len); if (rc) return rc; }
+        else if (rc || memcmp(out, op, out_len) != 0) return 8;        // an alignment that decodes differently
+    }
+    return 0;
+}
+
 extern "C" {
 __attribute__((visibility("default")))
 int hc_inflate_raw(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len) { return f2q::inflate_raw(in, in_len, out, out_len); }
 
 // the lock-step state machine, one lane; `in` must be readable 8 bytes past in_len (as in the kernel's staging buffer)
 __attribute__((visibility("default")))
-int hc_inflate_lane(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len) {
-    static thread_local uint16_t lut[1 << f2q::INFL_LUT_BITS], dlut[1 << f2q::INFL_DLUT_BITS];
-    f2q::InflLane L;
-    f2q::infl_lane_init(L, in, in_len, out, out_len);
-    for (uint64_t it = 0; L.state != f2q::INFL_ST_DONE; it++) {
-        if (it > (1ull << 28)) return 9;
-        f2q::infl_step(L, lut, dlut, 1);
-    }
-    return f2q::infl_lane_result(L);
+int hc_inflate_lane(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len) { return inflate_lane<9, 7>(in, in_len, out, out_len); }
+// (the small tables: more codes take the bit-serial path)
+__attribute__((visibility("default")))
+int hc_inflate_lane8(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len) { return inflate_lane<8, 6>(in, in_len, out, out_len); }
 }
+
+// developer statistics: iterations of the lock-step machine by state (HEADER, SYMBOL, COPY, STORED)
+extern "C" __attribute__((visibility("default")))
+int hc_inflate_lane_stats(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_t out_len, uint64_t* stats) {
+    return inflate_lane<9, 7>(in, in_len, out, out_len, stats);
 }

@@ -32,10 +32,10 @@ if __name__ == "__main__":
     comp = os.path.getsize(path)
     unc = n * 118
     print(f"file: {comp / 1e9:.2f} GB compressed, {unc / 1e9:.2f} GB uncompressed (ratio {unc / comp:.2f}), written in {time.perf_counter() - t0:.0f} s", flush=True)
-    for opt, threads in ((1, 16), (2, 16), (0, 16), (0, 1)):
-        with lib.Engine(lib.make_config(miss=1), 0, None, gpu_inflate=opt, time_kernels=1) as e:
+    for opt, bits, threads in ((1, 8, 16), (1, 9, 16), (1, 0, 16), (0, 0, 16)):
+        with lib.Engine(lib.make_config(miss=1), 0, None, gpu_inflate=opt, gpu_inflate_bits=bits) as e:
             e.set_library(keys)
             for it in range(2):
                 e.begin(); t = time.perf_counter(); ok, nb = e.submit_file(path, True, 0, threads); c, s = e.end(); dt = time.perf_counter() - t
-            print(f"gpu_inflate={opt} threads={threads}: {dt * 1e3:8.1f} ms  {unc / dt / 1e9:6.2f} GB/s uncompressed  {n / dt / 1e6:7.1f} M reads/s  reads {s['reads']}", flush=True)
+            print(f"gpu_inflate={opt} bits={bits} threads={threads}: {dt * 1e3:8.1f} ms  {unc / dt / 1e9:6.2f} GB/s uncompressed  {n / dt / 1e6:7.1f} M reads/s  reads {s['reads']}", flush=True)
     os.remove(path)
