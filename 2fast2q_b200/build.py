@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libf2q.so")
 SOURCES = ["f2q_api.cu"]
-HEADERS = ["f2q_dev.cuh", "generic.cuh", "resolve.cuh", "stream.cuh", "tile.cuh", "spec.cuh", "flex.cuh", "flex_core.h", "synth_gen.h",
+HEADERS = ["f2q_dev.cuh", "generic.cuh", "resolve.cuh", "stream.cuh", "tile.cuh", "spec.cuh", "flex.cuh", "flex_core.h", "synth_gen.h", "inflate_core.h",
            os.path.join("..", "..", "include", "f2q.h")]
 
 NVCC_FLAGS = [

@@ -855,8 +855,12 @@ F2Q_EXPORT int f2q_host_alloc_near(void** ptr, uint64_t nbytes, int device, int 
 
 F2Q_EXPORT void f2q_destroy(f2q_ctx* c) {
     if (!c) return;
+    static const bool debug = getenv("F2Q_DEBUG_INGEST") != nullptr;   // developer lap timers
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now(), t1, t2, t3, t4;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    t1 = now();
     for (auto& b : c->lib_bufs) b.release();
     c->result.release(); c->carry.release(); c->status.release(); c->status_stitch.release(); c->queue.release(); c->gqueue.release();
     c->seg_count.release(); c->spec_rec.release(); c->spec_scratch.release(); c->slow_args.release(); c->synth_guides.release();
@@ -864,16 +868,19 @@ F2Q_EXPORT void f2q_destroy(f2q_ctx* c) {
     for (auto& p : c->ec_pend) if (p.ev) cudaEventDestroy(p.ev);
     for (auto e : c->ec_events) cudaEventDestroy(e);
     if (c->ec_meta_host) cudaFreeHost(c->ec_meta_host);
+    t2 = now();
     for (int k = 0; k < 2; k++) {
         c->gz_comp[k].release(); c->gz_out[k].release(); c->gz_tab[k].release();
         if (c->gz_tab_host[k]) cudaFreeHost(c->gz_tab_host[k]);
         if (c->gz_copied[k]) cudaEventDestroy(c->gz_copied[k]);
         if (c->gz_free[k]) cudaEventDestroy(c->gz_free[k]);
     }
+    t3 = now();
     if (c->file_ring) {
         for (int k = 0; k < FileRing::N; k++) { if (c->file_ring->buf[k]) f2q_host_free(c->file_ring->buf[k]); if (c->file_ring->done[k]) cudaEventDestroy(c->file_ring->done[k]); }
         delete c->file_ring; c->file_ring = nullptr;
     }
+    t4 = now();
     f2q_comm_destroy(c);
     for (auto p : c->d_stage) cudaFree(p);
     for (auto e : c->ev_copied) cudaEventDestroy(e);
@@ -887,6 +894,8 @@ F2Q_EXPORT void f2q_destroy(f2q_ctx* c) {
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     cudaGetLastError();
+    if (debug) fprintf(stderr, "[f2q destroy] sync %.1f ms, tables %.1f ms, inflate buffers %.1f ms, file ring %.1f ms, staging + rest %.1f ms\n",
+                       t1 - t0, t2 - t1, t3 - t2, t4 - t3, now() - t4);
     delete c;
 }
 
@@ -1419,13 +1428,30 @@ int submit_bgzf_gpu(f2q_ctx* c, FILE* f, FileRing& R, int threads, uint64_t* tot
     static const bool debug = getenv("F2Q_DEBUG_INGEST") != nullptr;   // developer lap timers: where the host thread spends its time
     double t_read = 0, t_ring = 0, t_free = 0, t_walk = 0;
     auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const int fd = fileno(f);
+    // batches of equal size: the inflate kernel is latency-bound (a launch takes as long as its slowest warp, ~29 ms for 64 KiB
+    // blocks, however few blocks it has), so a small last batch costs as much as a full one.  The staging buffers follow the
+    // file: a 100 MB sample does not take the 8 GB a 10 GB one is given (many contexts may share the GPU)
+    size_t comp_target = GZ_COMP_BYTES;
+    {
+        struct stat sb;
+        if (fstat(fd, &sb) == 0 && sb.st_size > 0) {
+            const size_t usable = GZ_COMP_BYTES - R.bytes - 65536, nbatch = ((size_t)sb.st_size + usable - 1) / usable;
+            comp_target = std::min(GZ_COMP_BYTES, ((size_t)sb.st_size + nbatch - 1) / nbatch + 2 * R.bytes + 65536);
+        }
+    }
+    const size_t out_target = std::min(GZ_OUT_BYTES, std::max<size_t>(6 * comp_target, 8 * R.bytes));
+    const double t_alloc0 = now();
+    if (c->gz_comp[0].p && (c->gz_comp[0].n < comp_target + 65536 || c->gz_out[0].n < out_target + 65536 + 256))
+        CU(c, cudaStreamSynchronize(c->stream));                       // (the buffers grow: nothing may still read the old ones)
     for (int k = 0; k < 2; k++) {
-        if ((rc = dev_alloc(c, c->gz_comp[k], GZ_COMP_BYTES + 65536)) || (rc = dev_alloc(c, c->gz_out[k], GZ_OUT_BYTES + 65536 + 256)) ||
+        if ((rc = dev_alloc(c, c->gz_comp[k], comp_target + 65536)) || (rc = dev_alloc(c, c->gz_out[k], out_target + 65536 + 256)) ||
             (rc = dev_alloc(c, c->gz_tab[k], GZ_MAX_BLOCKS * sizeof(BgzfBlock)))) return rc;
         if (!c->gz_tab_host[k]) CU(c, cudaHostAlloc(reinterpret_cast<void**>(&c->gz_tab_host[k]), GZ_MAX_BLOCKS * sizeof(BgzfBlock), cudaHostAllocDefault));
         if (!c->gz_copied[k]) { CU(c, cudaEventCreateWithFlags(&c->gz_copied[k], cudaEventDisableTiming)); CU(c, cudaEventCreateWithFlags(&c->gz_free[k], cudaEventDisableTiming)); }
     }
-    const int fd = fileno(f);
+    const size_t out_cap = c->gz_out[0].n - 65536 - 256;               // (what the buffers hold: at least the targets)
+    const double t_alloc = now() - t_alloc0;
     uint64_t off = 0;                                                  // file offset of the next unread byte
     std::vector<uint8_t> carry;                                        // the head of a block whose rest is in the next piece
     bool eof = false, stop = false;
@@ -1444,7 +1470,7 @@ int submit_bgzf_gpu(f2q_ctx* c, FILE* f, FileRing& R, int threads, uint64_t* tot
         uint32_t nb = 0;
         size_t comp_fill = 0, out_fill = 0;
         uint64_t batch_start = off - carry.size();
-        while (!eof && !stop && comp_fill + R.bytes + 65536 <= GZ_COMP_BYTES && out_fill + 4 * R.bytes <= GZ_OUT_BYTES && nb + 4096 < GZ_MAX_BLOCKS) {
+        while (!eof && !stop && comp_fill + R.bytes + 65536 <= comp_target && out_fill + 4 * R.bytes <= out_cap && nb + 4096 < GZ_MAX_BLOCKS) {
             uint8_t* buf; int idx;
             t0 = now();
             if ((rc = ring_get(c, R, &buf, &idx))) return rc;
@@ -1469,7 +1495,7 @@ int submit_bgzf_gpu(f2q_ctx* c, FILE* f, FileRing& R, int threads, uint64_t* tot
                 const uint32_t xlen = (uint32_t)(buf[p + 10] | buf[p + 11] << 8);
                 uint32_t isize; memcpy(&isize, buf + p + bs - 4, 4);
                 if (bs < 12u + xlen + 8u || isize > 65536u) { stop = true; break; }
-                if (out_fill + isize > GZ_OUT_BYTES || nb >= GZ_MAX_BLOCKS) break;
+                if (out_fill + isize > out_cap || nb >= GZ_MAX_BLOCKS) break;
                 if (isize) { tab[nb++] = BgzfBlock{(uint32_t)(comp_fill + p + 12 + xlen), (uint32_t)(bs - 12 - xlen - 8), (uint32_t)out_fill, isize}; out_fill += isize; }
                 p += bs;
             }
@@ -1523,8 +1549,8 @@ int submit_bgzf_gpu(f2q_ctx* c, FILE* f, FileRing& R, int threads, uint64_t* tot
             batch++;
         } else if (!stop && !eof) return fail(c, F2Q_EINTERNAL, "bgzip batch without a block");
     }
-    if (debug) fprintf(stderr, "[f2q ingest] bgzf on the device: %d batches, %llu blocks; host thread: read %.1f ms, ring wait %.1f ms, batch wait %.1f ms, header walk %.1f ms\n",
-                       batch, (unsigned long long)c->gz_blocks, t_read, t_ring, t_free, t_walk);
+    if (debug) fprintf(stderr, "[f2q ingest] bgzf on the device: %d batches, %llu blocks; host thread: buffers %.1f ms, read %.1f ms, ring wait %.1f ms, batch wait %.1f ms, header walk %.1f ms\n",
+                       batch, (unsigned long long)c->gz_blocks, t_alloc, t_read, t_ring, t_free, t_walk);
     *resume_off = off;
     *finished = eof && !stop;
     return F2Q_OK;

@@ -199,8 +199,9 @@ F2Q_HD int inflate_raw(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32_
 //   * the lane's scalars (InflLane) hold no array and never leave registers; the canonical tables (InflTables, local
 //     memory) are touched by block headers and by codes longer than the lookup index only;
 //   * input arrives in aligned 32-bit words, loaded one refill AHEAD of their use;
-//   * a match loads its 8 source bytes as three aligned words before it stores anything (an overlapping match, distance < 8,
-//     replicates its period in registers), so the loads of a copy never wait for its stores;
+//   * a match loads its 8 source bytes as three aligned words (an overlapping match, distance < 8, replicates its period in
+//     registers) and stores them ONE ITERATION LATER, behind the next symbol's decode: the decode does not depend on the
+//     copied bytes, so the round trip of the loads (the lane's own output, in L2) is off the chain;
 //   * length / distance bases and extra-bit counts are computed, not looked up;
 //   * a code longer than the lookup index resumes the canonical walk at the first uncovered length, on bit-reversed input.
 // lut / dlut: the lane's lookup tables, element i of lane L at lut[i * stride + L] (shared memory on the device: the
@@ -228,6 +229,7 @@ struct InflLane {
     uint32_t ahead;                          // the input word at in_pos, loaded one refill ahead
     uint32_t bitcnt, in_pos, in_len, out_pos, out_len;
     uint32_t state, last, copy_len, copy_dist, err;
+    uint32_t pw0, pw1, pw2, pend_sh, pend_dist, pend_o, pend_n;   // a copy's source words, loaded but not yet stored
 };
 
 F2Q_HD uint32_t infl_word(const uint8_t* p) { return *reinterpret_cast<const uint32_t*>(p); }   // p is 4-byte aligned
@@ -370,6 +372,7 @@ F2Q_HD void infl_lane_init(InflLane& L, const uint8_t* in, uint32_t in_len, uint
     L.in = in; L.in_len = in_len; L.out = out; L.out_len = out_len; L.out_pos = 0; L.err = 0;
     L.bitbuf = 0; L.bitcnt = 0; L.in_pos = 0; L.ahead = 0;
     L.state = in_len ? INFL_ST_HEADER : INFL_ST_DONE; L.last = 0; L.copy_len = 0; L.copy_dist = 0;
+    L.pw0 = L.pw1 = L.pw2 = 0; L.pend_sh = 0; L.pend_dist = 8; L.pend_o = 0; L.pend_n = 0;
     if (!in_len && out_len) L.err = 2;
     if (in_len) {
         // the bytes up to the first aligned word, then aligned words only
@@ -379,9 +382,32 @@ F2Q_HD void infl_lane_init(InflLane& L, const uint8_t* in, uint32_t in_len, uint
     }
 }
 
-// one iteration of the state machine for one lane; the caller loops while any lane is not INFL_ST_DONE
+// the 8 bytes a copy loaded one iteration ago -> the output
+F2Q_HD void infl_flush(InflLane& L) {
+    if (L.pend_n) {
+        uint64_t v = (uint64_t)infl_fsr(L.pw0, L.pw1, L.pend_sh) | ((uint64_t)infl_fsr(L.pw1, L.pw2, L.pend_sh) << 32);
+        if (L.pend_dist < 8u) {
+            // the source overlaps what this copy writes: its first `dist` bytes are the period
+            const uint32_t period = 8u * L.pend_dist;
+            v &= (1ull << period) - 1ull;
+            v |= v << period;
+            if (2u * period < 64u) v |= v << (2u * period);
+            if (4u * period < 64u) v |= v << (4u * period);
+        }
+        uint8_t* o = L.out + L.pend_o;
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; k++) if (k < L.pend_n) o[k] = (uint8_t)(v >> (8u * k));
+        L.pend_n = 0;
+    }
+}
+
+// one iteration of the state machine for one lane; the caller loops while any lane is not INFL_ST_DONE and calls
+// infl_flush behind the loop.  Three phases, so that the loads of a copy have a whole decode to arrive in:
+//   A  decode (registers, the lookup tables and the input only)   B  store what the copy of the LAST iteration loaded
+//   C  store this iteration's literal, or load (not yet store) the next 8 bytes of a match
 template <int LB = INFL_LUT_BITS, int DB = INFL_DLUT_BITS>
 F2Q_HD void infl_step(InflLane& L, InflTables& T, uint16_t* lut, uint16_t* dlut, uint32_t stride) {
+    int lit = -1;
     if (L.state == INFL_ST_HEADER) {
         InflLane t = L;                                                // (the copy's address escapes, the lane's registers do not)
         infl_header<LB, DB>(t, T, lut, dlut, stride);
@@ -389,11 +415,11 @@ F2Q_HD void infl_step(InflLane& L, InflTables& T, uint16_t* lut, uint16_t* dlut,
         if (L.err) L.state = INFL_ST_DONE;
     } else if (L.state == INFL_ST_SYMBOL) {
         infl_refill4(L);
-        int symbol = infl_decode_lut<LB>(L, T.lencode, lut, stride, T.lfirst, T.lindex);
+        const int symbol = infl_decode_lut<LB>(L, T.lencode, lut, stride, T.lfirst, T.lindex);
         if (symbol < 256) {
             if (symbol < 0) L.state = INFL_ST_DONE;
             else if (L.out_pos >= L.out_len) { L.err = 3; L.state = INFL_ST_DONE; }
-            else L.out[L.out_pos++] = (uint8_t)symbol;
+            else lit = symbol;
         } else if (symbol == 256) L.state = L.last ? INFL_ST_DONE : INFL_ST_HEADER;
         else {
             // length 3..258: symbols 257..264 are 3..10, 265..284 carry (sym - 261) / 4 extra bits, 285 is 258
@@ -413,24 +439,16 @@ F2Q_HD void infl_step(InflLane& L, InflTables& T, uint16_t* lut, uint16_t* dlut,
             else { L.copy_len = len; L.copy_dist = dist; L.state = INFL_ST_COPY; }
         }
     }
-    if (L.state == INFL_ST_COPY) {
-        // up to 8 bytes of the match (a lane that has just decoded it starts the copy in the same iteration)
+    infl_flush(L);
+    if (lit >= 0) L.out[L.out_pos++] = (uint8_t)lit;
+    else if (L.state == INFL_ST_COPY) {
+        // up to 8 bytes of the match (a lane that has just decoded it starts the copy in the same iteration): the three
+        // aligned words that hold them are loaded now and stored by the next iteration's flush
         const uint32_t n = L.copy_len < 8u ? L.copy_len : 8u;
-        uint8_t* o = L.out + L.out_pos;
-        const uint8_t* f = o - L.copy_dist;
+        const uint8_t* f = L.out + L.out_pos - L.copy_dist;
         const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(f) & 3u);
-        const uint32_t w0 = infl_word(f - a), w1 = infl_word(f - a + 4), w2 = infl_word(f - a + 8);
-        uint64_t v = (uint64_t)infl_fsr(w0, w1, 8u * a) | ((uint64_t)infl_fsr(w1, w2, 8u * a) << 32);
-        if (L.copy_dist < 8u) {
-            // the source overlaps what this copy writes: its first `dist` bytes are the period
-            const uint32_t period = 8u * L.copy_dist;
-            v &= (1ull << period) - 1ull;
-            v |= v << period;
-            if (2u * period < 64u) v |= v << (2u * period);
-            if (4u * period < 64u) v |= v << (4u * period);
-        }
-#pragma unroll
-        for (uint32_t k = 0; k < 8u; k++) if (k < n) o[k] = (uint8_t)(v >> (8u * k));
+        L.pw0 = infl_word(f - a); L.pw1 = infl_word(f - a + 4); L.pw2 = infl_word(f - a + 8);
+        L.pend_sh = 8u * a; L.pend_dist = L.copy_dist; L.pend_o = L.out_pos; L.pend_n = n;
         L.out_pos += n; L.copy_len -= n;
         if (!L.copy_len) L.state = INFL_ST_SYMBOL;
     } else if (L.state == INFL_ST_STORED) {

@@ -35,6 +35,7 @@ namespace f2q {
 __host__ __device__ constexpr int spec_stages(int W) { return W > 16 ? 2 : 3; }
 constexpr int SPEC_CAP = 6 * 32;                     // newline positions kept per tile (its 32 own rows)
 constexpr uint32_t SPEC_MAX_HALO = 16;
+constexpr uint32_t SPEC_WAIT_TRIES = 1u << 24;      // failed mbarrier tries after which a warp gives its bulk copy up (the speculation then fails)
 
 struct SpecParams {
     const uint8_t* buf;        // 128-byte aligned base of the chunk buffer
@@ -292,7 +293,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         }
     };
     RangeInfo cur = take_range();
-    bool dead = false;                                                 // a bulk copy of this warp timed out
+    constexpr uint32_t DEAD = 0x80000000u;                             // bit of par_bits: a bulk copy of this warp timed out
     uint32_t pre = 0, gs = 0;                                          // tiles of `cur` already issued; stage of its tile 0
     while (cur.ok) {
         const RangeInfo nxt = take_range();
@@ -307,7 +308,7 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
         for (uint32_t t = pre; t < (uint32_t)NS; t++) issue_seq(t, (gs + t) % NS);
         range_cnt = 0; spec_p0 = 0; phase = 0;                         // (range 0 starts at a record start)
         uint32_t prev_total = 0, s = gs, sp = gs;                      // s = stage of tile ti, sp = stage of tile ti - 1
-        for (uint32_t ti = 0; ti <= nown; ti++) {
+        for (uint32_t ti = 0;; ti++) {                                  // ti = 0 .. nown; left through `own` (a bound of its own, nown + 1, gets spilled)
             const uint32_t par = ti & 1u;
             uint16_t* const nl = nlist + par * G_::NL_LIST;
             uint32_t total = 0, hcnt = 0;
@@ -316,19 +317,15 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 uint8_t* const tile = wsm + s * stage_bytes;
                 const uint64_t base = rb + (uint64_t)ti * OWN;
                 if (ti >= t_lo && ti < t_hi) {
-                    // (bounded in time: a copy that never lands fails the speculation — the exact kernel then redoes the chunk.
-                    // Nothing traps and nothing leaves the loop early: the warp stops WAITING (`dead`), runs through the rest
+                    // (bounded: a copy that never lands fails the speculation — the exact kernel then redoes the chunk.
+                    // Nothing traps and nothing leaves the loop early: the warp stops WAITING (DEAD), runs through the rest
                     // of its range on whatever the stage holds, takes no further range (take_range sees spec_fail), and all it
-                    // counted is dropped with the failed speculation; see WAIT_CYCLE_LIMIT in tile.cuh)
-                    if (!dead && !mbar_try_wait(&bars[s], (par_bits >> s) & 1u)) {
-                        long long tw = 0;                               // (the clock is read only after 1024 failed tries: never on the ordinary path)
-                        uint32_t spins = 0;
-                        while (!mbar_try_wait(&bars[s], (par_bits >> s) & 1u)) {
-                            if ((++spins & 1023u) != 0u) continue;
-                            const long long now = clock64();
-                            if (tw == 0) tw = now;
-                            else if (now - tw > WAIT_CYCLE_LIMIT) { dead = true; if (lane == 0) St->spec_fail = 1u; F2Q_TIMEOUT_TRAP(); break; }
-                        }
+                    // counted is dropped with the failed speculation.  The loop is a bare try + count: anything more — a clock, a
+                    // second flag — costs the tile loop a register, and the compiler then spills the loop bound: measured +4 %)
+                    if (!(par_bits & DEAD)) {
+                        uint32_t spins = 0;                            // (one try suspends the warp for up to the hardware's time limit: the bound is seconds)
+                        while (!mbar_try_wait(&bars[s], (par_bits >> s) & 1u))
+                            if (++spins > SPEC_WAIT_TRIES) { par_bits |= DEAD; if (lane == 0) St->spec_fail = 1u; F2Q_TIMEOUT_TRAP(); break; }
                     }
                     par_bits ^= 1u << s;
                 } else {
@@ -390,7 +387,8 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 phase += prev_total; range_cnt += prev_total;
                 issue_seq(ti - 1 + NS, sp);                            // refill the stage of the parsed tile
             }
-            if (own) { prev_total = total; sp = s; s = (s == (uint32_t)NS - 1u) ? 0u : s + 1u; }
+            if (!own) break;
+            prev_total = total; sp = s; s = (s == (uint32_t)NS - 1u) ? 0u : s + 1u;
         }
         if (lane == 0) P.rec[r] = (uint8_t)(0x80u | (spec_p0 << 2) | (range_cnt & 3u));
         gs = s; pre = nxt_pre; cur = nxt;

@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(INFLATE_LANES) k_inflate_bgzf_lanes(const uint
     if (b < n) { const BgzfBlock B = blk[b]; infl_lane_init(L, comp + B.src, B.csize, out + B.dst, B.isize); }
     else { infl_lane_init(L, comp, 0, out, 0); }
     while (__any_sync(0xffffffffu, L.state != INFL_ST_DONE)) infl_step<LB, DB>(L, T, lut, dlut, INFLATE_LANES);
+    infl_flush(L);
     if (b < n && infl_lane_result(L) != 0) atomicOr(error, ERR_INFLATE);
 }
 

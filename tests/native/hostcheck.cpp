@@ -92,6 +92,7 @@ static int inflate_lane(const uint8_t* in, uint32_t in_len, uint8_t* out, uint32
             if (stats) stats[L.state]++;
             f2q::infl_step<LB, DB>(L, T, lut, dlut, 1);
         }
+        f2q::infl_flush(L);
         const int rc = f2q::infl_lane_result(L);
         if (mis == 0) { memcpy(out, op, out_len); if (rc) return rc; }
         else if (rc || memcmp(out, op, out_len) != 0) return 8;        // an alignment that decodes differently

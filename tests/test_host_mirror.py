@@ -116,6 +116,45 @@ def test_write_sample_reproduces_reference_bytes(name, tmp_path):
         raw = [k for k in c["files"] if fq.sample_name(k) == fn[:-len("_reads.csv")]][0]
         fq.write_sample(str(tmp_path / "in" / raw), sample, stats, p, secs)
         assert (d / fn).read_bytes().decode() == text
+        # the command line's writer (straight from the count vector) produces the same bytes
+        (d / fn).unlink()
+        fq._write_sample_counts(str(tmp_path / "in" / raw), feats, [int(by_name[f.name]) for f in feats.values()], stats, p, secs)
+        assert (d / fn).read_bytes().decode() == text
+
+
+@pytest.mark.parametrize("names", [["10", "9", "-3", "007", "9"], ["b", "a,1", 'q"uote', "B", "a"], ["1", "x", "2"], ["3"]])
+def test_count_vector_writer_equals_write_sample(names, tmp_path):
+    """integer / text / mixed names, duplicates (stable order), names the csv module has to quote"""
+    feats = {f"SEQ{k}": fq.Features(n, 0) for k, n in enumerate(names)}
+    counts = [7 * k + 1 for k in range(len(names))]
+    stats = dict(reads=100, perfect_counter=50, imperfect_counter=10, non_aligned_counter=30, quality_failed=10)
+    outs = []
+    for k, writer in enumerate(("object", "vector")):
+        d = tmp_path / writer
+        d.mkdir()
+        p = {"directory": str(d), "Progress bar": True}
+        if writer == "object":
+            fq.write_sample("/x/s1.fastq.gz", {q: fq.Features(f.name, c) for (q, f), c in zip(feats.items(), counts)}, stats, p, 1.5)
+        else:
+            fq._write_sample_counts("/x/s1.fastq.gz", feats, counts, stats, p, 1.5)
+        outs.append((d / "s1_reads.csv").read_bytes())
+    assert outs[0] == outs[1]
+
+
+def test_input_kind_sniffs_bgzf_and_gzip(tmp_path):
+    text = b"@r\nACGT\n+\nIIII\n" * 50
+    eof = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+    c = zlib.compressobj(6, zlib.DEFLATED, -15)
+    cd = c.compress(text) + c.flush()
+    import struct
+    blk = b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", 18 + len(cd) + 8 - 1) + cd + struct.pack("<II", zlib.crc32(text), len(text))
+    (tmp_path / "a.fastq").write_bytes(text)
+    (tmp_path / "b.fastq.gz").write_bytes(blk + eof)
+    (tmp_path / "c.fastq.gz").write_bytes(gzip.compress(text))
+    (tmp_path / "d.fastq.gz").write_bytes(blk)                          # bgzip blocks without the end-of-file block
+    f = lambda *n: fq._input_kind([str(tmp_path / x) for x in n])
+    assert f("a.fastq") == "plain" and f("a.fastq", "b.fastq.gz") == "bgzf" and f("b.fastq.gz", "c.fastq.gz") == "gzip"
+    assert f("d.fastq.gz") == "gzip" and f("missing.fastq.gz") == "gzip"
 
 
 def test_sample_name_rules():

@@ -11,12 +11,13 @@ from cli_ingest_bench import bgzf_bytes
 from concurrent.futures import ProcessPoolExecutor
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
+level = int(sys.argv[2]) if len(sys.argv) > 2 else 1        # zlib level of the blocks (bgzip's default is 6)
 spec = synth.default_spec(2)
 names, keys = synth.make_library(2, 2000, 20)
 
 
 def part(k):
-    return bgzf_bytes(synth.fixed_reads(keys, k * 500_000, 500_000, **spec).tobytes())[:-28]
+    return bgzf_bytes(synth.fixed_reads(keys, k * 500_000, 500_000, **spec).tobytes(), level)[:-28]
 
 
 if __name__ == "__main__":
@@ -31,7 +32,7 @@ if __name__ == "__main__":
         f.write(bgzf_bytes(b""))
     comp = os.path.getsize(path)
     unc = n * 118
-    print(f"file: {comp / 1e9:.2f} GB compressed, {unc / 1e9:.2f} GB uncompressed (ratio {unc / comp:.2f}), written in {time.perf_counter() - t0:.0f} s", flush=True)
+    print(f"file: {comp / 1e9:.2f} GB compressed, {unc / 1e9:.2f} GB uncompressed (ratio {unc / comp:.2f}, zlib level {level}), written in {time.perf_counter() - t0:.0f} s", flush=True)
     for opt, bits, threads in ((1, 8, 16), (1, 9, 16), (1, 0, 16), (0, 0, 16)):
         with lib.Engine(lib.make_config(miss=1), 0, None, gpu_inflate=opt, gpu_inflate_bits=bits) as e:
             e.set_library(keys)
