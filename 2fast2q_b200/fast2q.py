@@ -1005,10 +1005,17 @@ def compiling(param):
             if len(compiled[entry]) < i + 1:
                 compiled[entry] = compiled[entry] + [0] * (i + 1 - len(compiled[entry]))
 
-    run_stats(headers, sentences, param)
+    table = run_stats(headers, sentences, param)
     final = [[feature] + compiled[feature] for feature in compiled]
     final.insert(0, head)
     csv_writer(os.path.join(param["directory"], f"{param['out_file_name']}.csv"), final)
+    # the four summary plots of the output folder (fast2q.py:1414-1527), drawn by plots.py
+    try:
+        from . import plots
+        if plots.write_all(table, head, compiled, os.path.join(param["directory"], param["out_file_name"])) is None:
+            colourful_errors("WARNING", "Pillow is not installed: the four summary plots were not drawn (the .csv files are complete).")
+    except Exception as e:                                   # noqa: BLE001  (a picture never fails a run whose counts are written)
+        colourful_errors("WARNING", f"The summary plots could not be drawn ({type(e).__name__}: {e}).")
     if param["delete"]:
         for file in ordered_csv:
             os.remove(file)
@@ -1021,8 +1028,8 @@ def compiling(param):
 
 def run_stats(headers, sentences, param):
     """<fn>_stats.csv: the parameter lines, a header row, then per sample the fields of its statistics sentence taken by
-    whitespace-token position exactly as the reference does (fast2q.py:1392-1412).  The four PNG plots of the
-    reference are not produced."""
+    whitespace-token position exactly as the reference does (fast2q.py:1392-1412).  Returns the table (the four PNG
+    plots are drawn from it by plots.py)."""
     table = [[h] for h in headers]
     table.append(["#Sample name", "Running Time", "Running Time unit", "Total number of reads in sample",
                   "Total number of reads that were aligned", "Number of reads that were aligned without mismatches",
@@ -1036,6 +1043,7 @@ def run_stats(headers, sentences, param):
         else:
             table.insert(0, [run])
     csv_writer(os.path.join(param["directory"], f"{param['out_file_name']}_stats.csv"), table)
+    return table
 
 
 def main(argv=None):

@@ -12,6 +12,7 @@ import random
 import re
 import zlib
 
+import numpy as np
 import pytest
 
 import cli_golden as CG
@@ -92,7 +93,8 @@ def test_compiling_reproduces_reference_bytes(name, tmp_path):
     fq.compiling(p)
     assert (d / "compiled.csv").read_bytes().decode() == c["outputs"]["compiled.csv"]
     assert (d / "compiled_stats.csv").read_bytes().decode() == c["outputs"]["compiled_stats.csv"]
-    assert sorted(os.listdir(d)) == ["compiled.csv", "compiled_stats.csv"]    # intermediates removed (fast2q.py:1375-1377)
+    # intermediates removed (fast2q.py:1375-1377); the four summary plots stand beside the two csv files
+    assert sorted(f for f in os.listdir(d) if not f.endswith(".png")) == ["compiled.csv", "compiled_stats.csv"]
 
 
 @pytest.mark.parametrize("name", ["cli_counter", "cli_single_split", "cli_dual_delim"])
@@ -323,3 +325,41 @@ def test_test_mode_data_is_bundled(tmp_path, monkeypatch):
     monkeypatch.chdir(tmp_path)
     p = fq.input_parser(["-c", "-t"])
     assert p["test_mode"] and p["seq_files"] == path and p["feature"] == td.GUIDES and p["out"] == str(tmp_path)
+
+
+def test_output_folder_holds_the_six_files(tmp_path):
+    """the reference's tests/test_cli.py:17-25 counts six files in the output folder: compiled.csv, compiled_stats.csv and
+    the four summary plots (drawn here by 2fast2q_b200/plots.py with Pillow)"""
+    pytest.importorskip("PIL")
+    from PIL import Image
+    c = CG.case("cli_counter")
+    d = tmp_path / "res"
+    d.mkdir()
+    for fn, text in c["outputs"].items():
+        if fn.endswith("_reads.csv"):
+            (d / fn).write_text(text, newline="")
+    p = _param_for(c, tmp_path, d)
+    p["delete"] = True
+    fq.compiling(p)
+    names = sorted(os.listdir(d))
+    fnm = p["out_file_name"]
+    assert names == sorted([f"{fnm}.csv", f"{fnm}_stats.csv", f"{fnm}_reads_plot.png", f"{fnm}_reads_plot_percentage.png",
+                            f"{fnm}_distribution_plot.png", f"{fnm}_distribution_normalized_RPM_plot.png"])
+    for n in names:
+        if n.endswith(".png"):
+            with Image.open(d / n) as im:
+                im.verify()
+            with Image.open(d / n) as im:
+                assert im.size[0] == 1800 and im.size[1] >= 450 and len(np.unique(np.asarray(im))) >= 3      # axes, ink and at least one colour
+    assert (d / f"{fnm}.csv").read_bytes().decode() == c["outputs"][f"{fnm}.csv"]
+
+
+def test_plots_survive_degenerate_samples(tmp_path):
+    """an empty sample (0 reads: the reference divides by zero here), one feature, identical counts"""
+    pytest.importorskip("PIL")
+    plots = importlib.import_module("2fast2q_b200.plots")
+    table = [["#x"], ["#Sample name"] + ["h"] * 8, ["a", "1", "seconds", "0", "0", "0", "0", "0", "0"], ["b", "1", "seconds", "10", "5", "5", "0", "3", "2"]]
+    out = plots.write_all(table, ["#Feature", "a", "b"], {"g1": [0, 5]}, str(tmp_path / "x"))
+    assert len(out) == 4 and all(os.path.getsize(f) > 100 for f in out)
+    out = plots.write_all(table, ["#Feature", "a", "b"], {"g1": [0, 5], "g2": [0, 5], "g3": [0, 5]}, str(tmp_path / "y"))
+    assert all(os.path.getsize(f) > 100 for f in out)
