@@ -35,7 +35,6 @@ namespace f2q {
 __host__ __device__ constexpr int spec_stages(int W) { return W > 16 ? 2 : 3; }
 constexpr int SPEC_CAP = 6 * 32;                     // newline positions kept per tile (its 32 own rows)
 constexpr uint32_t SPEC_MAX_HALO = 16;
-constexpr uint32_t SPEC_WAIT_TRIES = 1u << 24;      // failed mbarrier tries after which a warp gives its bulk copy up (the speculation then fails)
 
 struct SpecParams {
     const uint8_t* buf;        // 128-byte aligned base of the chunk buffer
@@ -317,15 +316,20 @@ k_spec(SpecParams P, const GenericCfg* __restrict__ Gp, LibTables T, EcTable E, 
                 uint8_t* const tile = wsm + s * stage_bytes;
                 const uint64_t base = rb + (uint64_t)ti * OWN;
                 if (ti >= t_lo && ti < t_hi) {
-                    // (bounded: a copy that never lands fails the speculation — the exact kernel then redoes the chunk.
+                    // (bounded in TIME: a copy that never lands fails the speculation — the exact kernel then redoes the chunk.
                     // Nothing traps and nothing leaves the loop early: the warp stops WAITING (DEAD), runs through the rest
                     // of its range on whatever the stage holds, takes no further range (take_range sees spec_fail), and all it
-                    // counted is dropped with the failed speculation.  The loop is a bare try + count: anything more — a clock, a
-                    // second flag — costs the tile loop a register, and the compiler then spills the loop bound: measured +4 %)
-                    if (!(par_bits & DEAD)) {
-                        uint32_t spins = 0;                            // (one try suspends the warp for up to the hardware's time limit: the bound is seconds)
-                        while (!mbar_try_wait(&bars[s], (par_bits >> s) & 1u))
-                            if (++spins > SPEC_WAIT_TRIES) { par_bits |= DEAD; if (lane == 0) St->spec_fail = 1u; F2Q_TIMEOUT_TRAP(); break; }
+                    // counted is dropped with the failed speculation; see WAIT_CYCLE_LIMIT in tile.cuh.  The clock is read
+                    // only after 1024 failed tries: never on the ordinary path)
+                    if (!(par_bits & DEAD) && !mbar_try_wait(&bars[s], (par_bits >> s) & 1u)) {
+                        long long tw = 0;
+                        uint32_t spins = 0;
+                        while (!mbar_try_wait(&bars[s], (par_bits >> s) & 1u)) {
+                            if ((++spins & 1023u) != 0u) continue;
+                            const long long now = clock64();
+                            if (tw == 0) tw = now;
+                            else if (now - tw > WAIT_CYCLE_LIMIT) { par_bits |= DEAD; if (lane == 0) St->spec_fail = 1u; F2Q_TIMEOUT_TRAP(); break; }
+                        }
                     }
                     par_bits ^= 1u << s;
                 } else {

@@ -1,9 +1,11 @@
 #!/bin/bash
-# developer sweep: the command line on 48 config-5a files by compression [and --cp], with its phase timing
+# developer sweep: the command line on 48 config-5a files by compression, with its phase timing
 set -u
-gz=${1:-bgzf}; shift
-for cp in "$@"; do
-  F2Q_CLI_TIMING=1 python tools/cli_ingest_bench.py --config 5a --files 48 --reads 1500000 --gz $gz --cp $cp > /tmp/sweep_$gz.log 2>&1
-  echo "== $gz --cp $cp: $(tail -1 /tmp/sweep_$gz.log | cut -c1-200)"
+for gz in ${@:-bgzf none gzip}; do
+  F2Q_CLI_TIMING=1 F2Q_DEBUG_INGEST=1 python tools/cli_ingest_bench.py --config 5a --files 48 --reads 1500000 --gz $gz > /tmp/sweep_$gz.log 2>&1
+  echo "== $gz: $(tail -1 /tmp/sweep_$gz.log | cut -c1-230)"
   grep "parameters + features" /tmp/sweep_$gz.log
+  grep "released" /tmp/sweep_$gz.log | sort -k8 -n | tail -3
+  grep "f2q destroy" /tmp/sweep_$gz.log | sort -t, -k5 | tail -4
+  grep "timing.*stream" /tmp/sweep_$gz.log | sort -k5 -n | tail -3
 done
