@@ -114,6 +114,7 @@ struct f2q_ctx {
     bool gpu_inflate = true;                         // bgzip input is inflated on the device (DESIGN.md §5 has the measurements)
     int gpu_inflate_mode = 1;                        // 1 lock-step lanes | 2 free-running threads (cross-check)
     bool gz_attr = false;
+    int opt_seed_parts = 0;                          // 0 auto | segments of the seed plan (developer / test option)
     int gpu_inflate_bits = 0;                        // 0 auto | 8 | 9: index bits of the literal/length lookup table (developer option)
     DevBuf gz_comp[2], gz_out[2], gz_tab[2];
     BgzfBlock* gz_tab_host[2] = {nullptr, nullptr};
@@ -727,7 +728,9 @@ int process_device_chunk(f2q_ctx* c, const uint8_t* dptr, uint64_t n, int is_las
                 const int G = c->fx_group_opt ? c->fx_group_opt : c->seed_group;
                 unsigned long long* ms = &c->dS->memo_lookups;
                 const dim3 rg(c->n_segs, 8);
-                if (G == 32) k_resolve_seed_g<32><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats, ms);
+                const bool classic = c->T.seed_ncombo == 0;              // (one-segment seeds for many mismatches: the thread kernel only)
+                if (classic) k_resolve_seed<<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
+                else if (G == 32) k_resolve_seed_g<32><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats, ms);
                 else if (G == 8) k_resolve_seed_g<8><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats, ms);
                 else if (c->T.memo) k_resolve_seed_g<1><<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats, ms);
                 else k_resolve_seed<<<rg, 256, 0, c->stream>>>(c->T, c->cfg.miss, P.queue, P.seg_count, c->seg_cap, c->n_segs, O.counts, O.stats);
@@ -918,6 +921,7 @@ F2Q_EXPORT int f2q_set_option(f2q_ctx* c, const char* name, int64_t value) {
     else if (n == "spec") c->spec = value != 0;
     else if (n == "spec_warps") { if (value != 12 && value != 16 && value != 20 && value != 24) return fail(c, F2Q_EINVAL, "spec_warps must be 12, 16, 20 or 24"); c->spec_warps = (int)value; }
     else if (n == "memo_entries") { if (value < -1 || value > (1ll << 28) || (value > 0 && (value & (value - 1)))) return fail(c, F2Q_EINVAL, "memo_entries must be -1 (auto), 0 (off) or a power of two"); c->memo_entries = value; if (c->lib_set) return fail(c, F2Q_ESTATE, "memo_entries must be set before f2q_set_library"); }
+    else if (n == "seed_parts") { if (value < 0 || value > SEED_MAX_PARTS) return fail(c, F2Q_EINVAL, "seed_parts must be 0 (auto) .. 8"); if (c->lib_set) return fail(c, F2Q_ESTATE, "seed_parts must be set before f2q_set_library"); c->opt_seed_parts = (int)value; }
     else if (n == "gpu_inflate_bits") { if (value != 0 && value != 8 && value != 9) return fail(c, F2Q_EINVAL, "gpu_inflate_bits must be 0, 8 or 9"); c->gpu_inflate_bits = (int)value; }
     else if (n == "gpu_inflate") { if (value < 0 || value > 2) return fail(c, F2Q_EINVAL, "gpu_inflate must be 0, 1 or 2"); c->gpu_inflate = value != 0; c->gpu_inflate_mode = value == 2 ? 2 : 1; }
     else if (n == "flex_warps") { if (value != 12 && value != 16) return fail(c, F2Q_EINVAL, "flex_warps must be 12 or 16"); c->flex_warps = (int)value; }
@@ -1073,17 +1077,46 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
     // pigeonhole seed index for <= miss mismatches (resolve.cuh)
     std::vector<uint4> seed_slots(16, make_uint4(0, 0, 0, 0));
     std::vector<uint4> seed_recs;
-    const uint32_t parts = (uint32_t)std::max(1, std::min(c->cfg.miss, 32) + 1);
+    // seed plan: P segments, seeds = every choice of P - miss of them.  Cost of resolving one key ~ seeds x (1 probe + expected
+    // bucket length); a seed must fit the tag's 32 value bits (<= 16 symbols) for the longest key
+    uint32_t parts = (uint32_t)std::max(1, std::min(c->cfg.miss, 32) + 1);
+    std::vector<uint8_t> combos;
     if (c->cfg.miss > 0 && !fk.empty()) {
+        const uint32_t m = (uint32_t)c->cfg.miss;
+        uint32_t maxlen = 0; double meanlen = 0;
+        for (uint32_t j = 0; j < fk.size(); j++) { maxlen = std::max(maxlen, (uint32_t)fl[j]); meanlen += fl[j]; }
+        meanlen /= (double)fk.size();
+        auto n_choose = [](uint32_t n, uint32_t k) { double r = 1; for (uint32_t i = 0; i < k; i++) r = r * (n - i) / (i + 1); return r; };
+        double best = -1;
+        if (m + 1 <= (uint32_t)SEED_MAX_PARTS)
+            for (uint32_t P = m + 1; P <= (uint32_t)SEED_MAX_PARTS; P++) {
+                const uint32_t K = P - m;
+                const double seeds = n_choose(P, m);
+                if (seeds > SEED_MAX_COMBOS || K * ((maxlen + P - 1) / P) > 16) continue;
+                if (c->opt_seed_parts && (uint32_t)c->opt_seed_parts != P) continue;
+                const double cost = seeds * (1.0 + (double)fk.size() / std::pow(4.0, (double)K * meanlen / P));
+                if (best < 0 || cost < best) { best = cost; parts = P; }
+            }
+        // (more than SEED_MAX_PARTS - 1 mismatches, or no plan that fits: the classic one-segment seeds, miss + 1 of them, no
+        // seed masks — resolve_seed_classic)
+        const bool planned = best >= 0;
+        if (planned) {
+            const uint32_t K = parts - m;
+            for (uint32_t mask = 0; mask < (1u << parts); mask++) if ((uint32_t)__builtin_popcount(mask) == K) combos.push_back((uint8_t)mask);
+        }
         std::vector<std::pair<uint64_t, uint32_t>> ent;
-        ent.reserve(fk.size() * parts);
-        for (uint32_t j = 0; j < fk.size(); j++)
+        ent.reserve(fk.size() * (planned ? combos.size() : parts));
+        for (uint32_t j = 0; j < fk.size(); j++) {
+            uint32_t sv[33] = {0}, sw[33] = {0};
             for (uint32_t sgm = 0; sgm < parts; sgm++) {
                 const uint32_t b0 = sgm * fl[j] / parts, b1 = (sgm + 1) * fl[j] / parts;
                 const uint64_t rng = even_range(b0, b1);
-                const uint64_t v = (fk[j] >> (2 * b0)) & ((rng | (rng << 1)) >> (2 * b0));
-                ent.emplace_back(seed_tag(fl[j], sgm, v), j);
+                sv[sgm] = (uint32_t)((fk[j] >> (2 * b0)) & ((rng | (rng << 1)) >> (2 * b0)));
+                sw[sgm] = 2 * (b1 - b0);
+                if (!planned) ent.emplace_back(seed_tag(fl[j], sgm, (fk[j] >> (2 * b0)) & ((rng | (rng << 1)) >> (2 * b0))), j);
             }
+            for (uint32_t cb = 0; cb < combos.size(); cb++) ent.emplace_back(seed_tag(fl[j], cb, seed_value(combos[cb], sv, sw)), j);
+        }
         std::sort(ent.begin(), ent.end());
         size_t uniq = 0;
         for (size_t i = 0; i < ent.size(); i++) if (i == 0 || ent[i].first != ent[i - 1].first) uniq++;
@@ -1236,6 +1269,9 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
     }
     if ((rc = upload(c, seed_slots, &c->T.seed_slots)) || (rc = upload(c, seed_recs, &c->T.seed_recs))) return rc;
     c->T.seed_mask = (uint32_t)seed_slots.size() - 1; c->T.seed_parts = parts;
+    c->T.seed_ncombo = (uint32_t)combos.size();
+    memset(c->T.seed_combo, 0, sizeof(c->T.seed_combo));
+    for (size_t i = 0; i < combos.size(); i++) c->T.seed_combo[i] = combos[i];
     if ((rc = upload(c, slots, &c->T.slots)) || (rc = upload(c, fk, &c->T.fast_keys)) || (rc = upload(c, fl, &c->T.fast_lens)) ||
         (rc = upload(c, fi, &c->T.fast_idx)) || (rc = upload(c, bytes, &c->T.key_bytes)) || (rc = upload(c, off, &c->T.key_off)) ||
         (rc = upload(c, gh, &c->T.ghash)))

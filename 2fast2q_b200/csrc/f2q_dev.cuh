@@ -76,7 +76,9 @@ struct LibTables {
     const uint4* seed_slots;   // {tag lo, tag hi, start, count}: hash of (len, segment, value) -> range in seed_recs; tag 0 = empty
     uint32_t seed_mask;
     const uint4* seed_recs;    // {packed key lo, hi, feature index, 0} of every (key, segment), grouped by seed slot
-    uint32_t seed_parts;       // miss + 1
+    uint32_t seed_parts;       // P: segments a key is cut into (>= miss + 1)
+    uint32_t seed_ncombo;      // C(P, miss) seeds per key: every choice of P - miss segments (a key within `miss` mismatches agrees on one of them)
+    uint8_t seed_combo[32];    // bit s of entry c: segment s belongs to seed c
     // the same idea over the raw key BYTES of every library entry (generic path: multi-feature 'X:Y' keys, odd alphabets, > 32 symbols)
     const uint4* gseed_slots;  // {tag lo, tag hi, start, count}; tag = 64-bit hash of (key length, segment, segment bytes), 0 = empty
     uint32_t gseed_mask;

@@ -44,6 +44,12 @@ struct Best {
         if (dist < d) { d = dist; n = 1; idx = i; }
         else if (dist == d && dist <= m) n++;
     }
+    // the same for candidate lists in which an entry may show up more than once (seeds that overlap): the one entry that
+    // is alone at the minimum is not counted twice; once two are there the count only has to stay >= 2
+    __host__ __device__ __forceinline__ void add_once(int dist, uint32_t i, int m) {
+        if (dist < d) { d = dist; n = 1; idx = i; }
+        else if (dist == d && dist <= m && !(n == 1 && idx == i)) n++;
+    }
 };
 
 #ifdef __CUDACC__
@@ -175,8 +181,13 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_resolve_scan(LibTables T, int 
         if (nonal) atomicAdd(stats + F2Q_STAT_NON_ALIGNED, (unsigned long long)nonal);
     }
 }
-// ---- pigeonhole seed index: a key within m mismatches of a library entry agrees exactly with it on at least one
-// of m+1 segments.  seed_slots hashes (length, segment, segment value) -> range of seed_recs (candidate keys stored inline, bucket-contiguous).
+// ---- pigeonhole seed index: cut a key into P segments; m mismatches spoil at most m of them, so a key within m mismatches
+// of a library entry agrees exactly with it on some choice of P - m segments.  A SEED is such a choice (a bit mask over the
+// segments); the index hashes (length, seed number, the chosen segments' symbols) -> range of seed_recs (candidate keys stored
+// inline, bucket-contiguous).  P = m + 1 gives the classic one-segment seeds: 3 probes but ~36 candidates per key for 100 000
+// guides at m = 2 (a 6-7 symbol segment has 4 096 - 16 384 values); P = 4 gives 6 seeds of two segments (10 symbols, a
+// million values): 6 probes and ~0.6 candidates.  f2q_set_library picks P from the library's size (seed_plan below).
+constexpr int SEED_MAX_PARTS = 8, SEED_MAX_COMBOS = 32;
 __host__ __device__ __forceinline__ uint64_t seed_tag(uint32_t len, uint32_t seg, uint64_t v) {
     return (1ull << 63) | ((uint64_t)len << 40) | ((uint64_t)seg << 32) | v;
 }
@@ -193,36 +204,81 @@ __host__ __device__ __forceinline__ uint64_t even_range(uint32_t b0, uint32_t b1
 // bounds (optional): segment boundaries s * len / parts for every (len <= 32, s <= parts) as bytes at [len * SEED_BOUND_STRIDE + s]
 // (the resolver kernel keeps them in shared memory: the integer divisions were most of its instructions)
 constexpr uint32_t SEED_BOUND_STRIDE = 34;
-__device__ inline uint32_t resolve_seed_thread(const LibTables& T, int m, uint64_t key, uint32_t bad, uint32_t len, const uint8_t* bounds = nullptr) {
-    const int nbad = __popc(bad);
-    if (m <= 0 || nbad > m) return RES_NONE;
+// the key's segments: value and width (in bits) of each, which ones hold a non-ACGT symbol
+struct SeedSegs {
+    uint32_t v[SEED_MAX_PARTS], w[SEED_MAX_PARTS];
+    uint32_t badmask;
+};
+__device__ __forceinline__ void seed_segments(uint32_t parts, uint64_t key, uint64_t badeven, uint32_t len, const uint8_t* bl, SeedSegs& S) {
+    S.badmask = 0;
+    #pragma unroll
+    for (int s = 0; s < SEED_MAX_PARTS; s++) {
+        S.v[s] = 0; S.w[s] = 0;
+        if ((uint32_t)s < parts) {
+            const uint32_t b0 = bl ? bl[s] : (uint32_t)s * len / parts, b1 = bl ? bl[s + 1] : ((uint32_t)s + 1) * len / parts;
+            const uint64_t seg = even_range(b0, b1);
+            if (badeven & seg) S.badmask |= 1u << s;                   // a non-ACGT symbol can never agree exactly
+            S.w[s] = 2 * (b1 - b0);
+            S.v[s] = (uint32_t)((key >> (2 * b0)) & ((seg | (seg << 1)) >> (2 * b0)));     // (a segment is <= 16 symbols: seed_plan)
+        }
+    }
+}
+// seed `combo` of the key: the chosen segments' symbols, lowest segment on top
+__host__ __device__ __forceinline__ uint64_t seed_value(uint32_t combo, const uint32_t* v, const uint32_t* w) {
+    uint64_t x = 0;
+    #pragma unroll
+    for (int s = 0; s < SEED_MAX_PARTS; s++) if ((combo >> s) & 1u) x = (x << w[s]) | v[s];
+    return x;
+}
+// bucket of a seed: (first record, count)
+__device__ __forceinline__ uint2 seed_bucket(const LibTables& T, uint64_t tag) {
+    uint32_t h = seed_hash(tag) & T.seed_mask;
+    for (;;) {
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(T.seed_slots) + h);
+        const uint64_t t = ((uint64_t)raw.y << 32) | raw.x;
+        if (t == 0) return make_uint2(0, 0);
+        if (t == tag) return make_uint2(raw.z, raw.w);
+        h = (h + 1) & T.seed_mask;
+    }
+}
+
+// the classic plan (seed_ncombo == 0): miss + 1 one-segment seeds, any number of segments
+__device__ __noinline__ uint32_t resolve_seed_classic(const LibTables& T, int m, uint64_t key, uint32_t bad, uint32_t len) {
     const uint32_t parts = T.seed_parts;
     const uint64_t lenmask = even_range(0, len), badeven = spread_even(bad) & lenmask;
-    const uint8_t* bl = bounds ? bounds + len * SEED_BOUND_STRIDE : nullptr;
     Best b{m + 1, 0, 0};
     for (uint32_t s = 0; s < parts; s++) {
-        const uint32_t b0 = bl ? bl[s] : s * len / parts, b1 = bl ? bl[s + 1] : (s + 1) * len / parts;
+        const uint32_t b0 = s * len / parts, b1 = (s + 1) * len / parts;
         const uint64_t seg = even_range(b0, b1);
-        if (badeven & seg) continue;                                   // a non-ACGT symbol can never agree exactly
-        const uint64_t v = (key >> (2 * b0)) & ((seg | (seg << 1)) >> (2 * b0));
-        const uint64_t tag = seed_tag(len, s, v);
-        uint32_t h = seed_hash(tag) & T.seed_mask, start = 0, count = 0;
-        for (;;) {
-            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(T.seed_slots) + h);
-            const uint64_t t = ((uint64_t)raw.y << 32) | raw.x;
-            if (t == 0) break;
-            if (t == tag) { start = raw.z; count = raw.w; break; }
-            h = (h + 1) & T.seed_mask;
+        if (badeven & seg) continue;
+        const uint2 bk = seed_bucket(T, seed_tag(len, s, (key >> (2 * b0)) & ((seg | (seg << 1)) >> (2 * b0))));
+        for (uint32_t k = 0; k < bk.y; k++) {
+            const uint4 it = __ldg(T.seed_recs + bk.x + k);
+            const uint64_t x = key ^ (((uint64_t)it.y << 32) | it.x);
+            const uint64_t diff = (((x | (x >> 1)) & lenmask) | badeven);
+            b.add_once(__popcll(diff), it.z, m);
         }
-        for (uint32_t c = 0; c < count; c++) {
-            const uint4 it = __ldg(T.seed_recs + start + c);           // {key lo, key hi, feature index, -}: one load per candidate
+    }
+    return (b.d <= m && b.n == 1) ? b.idx : RES_NONE;
+}
+
+__device__ __noinline__ uint32_t resolve_seed_thread(const LibTables& T, int m, uint64_t key, uint32_t bad, uint32_t len, const uint8_t* bounds = nullptr) {
+    const int nbad = __popc(bad);
+    if (m <= 0 || nbad > m) return RES_NONE;
+    if (T.seed_ncombo == 0) return resolve_seed_classic(T, m, key, bad, len);
+    const uint64_t lenmask = even_range(0, len), badeven = spread_even(bad) & lenmask;
+    SeedSegs S;
+    seed_segments(T.seed_parts, key, badeven, len, bounds ? bounds + len * SEED_BOUND_STRIDE : nullptr, S);
+    Best b{m + 1, 0, 0};
+    for (uint32_t c = 0; c < T.seed_ncombo; c++) {
+        const uint32_t combo = T.seed_combo[c];
+        if (combo & S.badmask) continue;
+        const uint2 bk = seed_bucket(T, seed_tag(len, c, seed_value(combo, S.v, S.w)));
+        for (uint32_t k = 0; k < bk.y; k++) {
+            const uint4 it = __ldg(T.seed_recs + bk.x + k);            // {key lo, key hi, feature index, -}: one load per candidate
             const uint64_t x = key ^ (((uint64_t)it.y << 32) | it.x);
             const uint64_t diff = (((x | (x >> 1)) & lenmask) | badeven);     // even bit 2p: symbol p differs (or is bad)
-            bool dup = false;                                          // already seen through an earlier agreeing segment?
-            for (uint32_t s2 = 0; s2 < s; s2++)
-                if ((diff & even_range(bl ? bl[s2] : s2 * len / parts, bl ? bl[s2 + 1] : (s2 + 1) * len / parts)) == 0) { dup = true; break; }
-            if (dup) continue;
-            b.add(__popcll(diff), it.z, m);
+            b.add_once(__popcll(diff), it.z, m);                       // (an entry that agrees on more segments comes through several seeds)
         }
     }
     return (b.d <= m && b.n == 1) ? b.idx : RES_NONE;
@@ -255,8 +311,7 @@ __global__ void __launch_bounds__(256) k_resolve_seed(LibTables T, int m, const 
 }
 
 // ---- the same pigeonhole resolution, G lanes per key: they share the bucket probes, split the candidates and merge
-// (min distance, how many attain it, which) with shuffles.  With 100 000 guides and m = 2 a key meets ~36 candidates: one
-// thread per key walks them one dependent 16-byte load after the other, eight lanes take four or five each.  Resolved keys
+// (min distance, how many attain it, which) with shuffles: worth it when buckets are long (one-segment seeds of a big library).  Resolved keys
 // without bad symbols go through the memo (LibTables::memo) first.
 template <int G>
 __device__ __forceinline__ uint32_t resolve_seed_group(const LibTables& T, int m, uint64_t key, uint32_t bad, uint32_t len, bool act,
@@ -270,32 +325,18 @@ __device__ __forceinline__ uint32_t resolve_seed_group(const LibTables& T, int m
     const int nbad = __popc(bad);
     Best b{m + 1, 0, 0};
     if (act && !cached && m > 0 && nbad <= m) {
-        const uint32_t parts = T.seed_parts;
         const uint64_t lenmask = even_range(0, len), badeven = spread_even(bad) & lenmask;
-        const uint8_t* bl = bounds + len * SEED_BOUND_STRIDE;
-        for (uint32_t s = 0; s < parts; s++) {
-            const uint32_t b0 = bl[s], b1 = bl[s + 1];
-            const uint64_t seg = even_range(b0, b1);
-            if (badeven & seg) continue;
-            const uint64_t v = (key >> (2 * b0)) & ((seg | (seg << 1)) >> (2 * b0));
-            const uint64_t tag = seed_tag(len, s, v);
-            uint32_t h = seed_hash(tag) & T.seed_mask, start = 0, count = 0;
-            for (;;) {
-                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(T.seed_slots) + h);
-                const uint64_t t = ((uint64_t)raw.y << 32) | raw.x;
-                if (t == 0) break;
-                if (t == tag) { start = raw.z; count = raw.w; break; }
-                h = (h + 1) & T.seed_mask;
-            }
-            for (uint32_t c = gl; c < count; c += (uint32_t)G) {
-                const uint4 it = __ldg(T.seed_recs + start + c);
+        SeedSegs S;
+        seed_segments(T.seed_parts, key, badeven, len, bounds + len * SEED_BOUND_STRIDE, S);
+        for (uint32_t c = 0; c < T.seed_ncombo; c++) {
+            const uint32_t combo = T.seed_combo[c];
+            if (combo & S.badmask) continue;
+            const uint2 bk = seed_bucket(T, seed_tag(len, c, seed_value(combo, S.v, S.w)));
+            for (uint32_t k = gl; k < bk.y; k += (uint32_t)G) {
+                const uint4 it = __ldg(T.seed_recs + bk.x + k);
                 const uint64_t x = key ^ (((uint64_t)it.y << 32) | it.x);
                 const uint64_t diff = (((x | (x >> 1)) & lenmask) | badeven);
-                bool dup = false;
-                for (uint32_t s2 = 0; s2 < s; s2++)
-                    if ((diff & even_range(bl[s2], bl[s2 + 1])) == 0) { dup = true; break; }
-                if (dup) continue;
-                b.add(__popcll(diff), it.z, m);
+                b.add_once(__popcll(diff), it.z, m);
             }
         }
     }
@@ -304,7 +345,7 @@ __device__ __forceinline__ uint32_t resolve_seed_group(const LibTables& T, int m
         const int od = __shfl_xor_sync(0xffffffffu, b.d, o);
         const uint32_t on = __shfl_xor_sync(0xffffffffu, b.n, o), oi = __shfl_xor_sync(0xffffffffu, b.idx, o);
         if (od < b.d) { b.d = od; b.n = on; b.idx = oi; }
-        else if (od == b.d) b.n += on;
+        else if (od == b.d && !(b.n == 1 && on == 1 && oi == b.idx)) b.n += on;        // (the same entry found by two lanes is one entry)
     }
     uint32_t r = (b.d <= m && b.n == 1) ? b.idx : RES_NONE;
     if (cached) r = cached - 2u;                                        // stored: 1 = not aligned (RES_NONE = 1 - 2), idx + 2

@@ -97,6 +97,39 @@ def test_resolvers_on_fuzz(gu, resolver):
             gu.check_case(c, c["fastq"], resolver=resolver)
 
 
+@pytest.mark.parametrize("parts", [2, 3, 4, 5, 6, 8])
+def test_seed_plans_agree(gu, parts):
+    """the resolver's seed plan (P segments, seeds = every choice of P - m of them): every P the option accepts gives the
+    reference's answers — ties, N symbols, mixed key lengths, m = 1..3; a P that does not fit m falls back to m + 1 one-segment
+    seeds (the classic plan), which is covered here too"""
+    for c in G.fuzz()[::2] + G.kat():
+        if c["params"]["mode"] == "C":
+            gu.check_case(c, c["fastq"], seed_parts=parts)
+    for name in ("config3_slice", "config3_m3"):
+        c = [x for x in G.shaped() if x["name"] == name][0]
+        params, lib, data = cases.shaped_inputs(name)
+        gu.check_case(dict(c, library=lib), data, seed_parts=parts)
+        gu.check_case(dict(c, library=lib), data, seed_parts=parts, queue_entries=16)       # resolved inside the streaming kernel
+
+
+@pytest.mark.parametrize("miss,n_keys", [(9, 300), (5, 3000), (2, 100000), (3, 100000)])
+def test_seed_plans_on_large_libraries_and_many_mismatches(gu, oracle, miss, n_keys):
+    """what the automatic plan picks: two-segment seeds for 100 000 guides at m = 2, three-segment seeds at m = 3, the
+    classic one-segment seeds for m = 9 (more segments than a seed mask holds); against the oracle, keys resolved by the
+    resolver kernel and (16-entry queue) inside the streaming kernel"""
+    synth = importlib.import_module("2fast2q_b200.synth")
+    spec = synth.default_spec(3)
+    names, keys = synth.make_library(3, n_keys, 20)
+    data = synth.fixed_reads(keys, 0, 20000 if n_keys < 50000 else 6000, **spec)
+    want_c, want_s = oracle.count(oracle.make_config(miss=miss), keys, data)
+    cfg = gu.lib.make_config(miss=miss)
+    for opts in ({}, dict(queue_entries=16), dict(resolve_group=8)):
+        with gu.lib.Engine(cfg, 0, None, **opts) as e:
+            e.set_library(keys)
+            e.begin(); e.submit(data, True); c, s = e.end()
+        assert np.array_equal(c, want_c) and s == want_s, (miss, n_keys, opts)
+
+
 def test_queue_overflow_resolves_in_place(gu):
     """a 16-entry queue overflows immediately; results must not change"""
     c = [x for x in G.shaped() if x["name"] == "config2_slice"][0]
