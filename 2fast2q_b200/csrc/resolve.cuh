@@ -204,26 +204,24 @@ __host__ __device__ __forceinline__ uint64_t even_range(uint32_t b0, uint32_t b1
 // bounds (optional): segment boundaries s * len / parts for every (len <= 32, s <= parts) as bytes at [len * SEED_BOUND_STRIDE + s]
 // (the resolver kernel keeps them in shared memory: the integer divisions were most of its instructions)
 constexpr uint32_t SEED_BOUND_STRIDE = 34;
-// the key's segments: value and width (in bits) of each, which ones hold a non-ACGT symbol
-struct SeedSegs {
-    uint32_t v[SEED_MAX_PARTS], w[SEED_MAX_PARTS];
-    uint32_t badmask;
-};
-__device__ __forceinline__ void seed_segments(uint32_t parts, uint64_t key, uint64_t badeven, uint32_t len, const uint8_t* bl, SeedSegs& S) {
-    S.badmask = 0;
-    #pragma unroll
-    for (int s = 0; s < SEED_MAX_PARTS; s++) {
-        S.v[s] = 0; S.w[s] = 0;
-        if ((uint32_t)s < parts) {
-            const uint32_t b0 = bl ? bl[s] : (uint32_t)s * len / parts, b1 = bl ? bl[s + 1] : ((uint32_t)s + 1) * len / parts;
-            const uint64_t seg = even_range(b0, b1);
-            if (badeven & seg) S.badmask |= 1u << s;                   // a non-ACGT symbol can never agree exactly
-            S.w[s] = 2 * (b1 - b0);
-            S.v[s] = (uint32_t)((key >> (2 * b0)) & ((seg | (seg << 1)) >> (2 * b0)));     // (a segment is <= 16 symbols: seed_plan)
-        }
+// seed `combo` of a key on the device: the chosen segments' symbols, lowest segment on top (what seed_value builds on the
+// host); *skip when one of them holds a non-ACGT symbol (it can never agree exactly).  The work is per CHOSEN segment, so
+// the two one-segment seeds of m = 1 cost a fraction of the six two-segment seeds of m = 2
+__device__ __forceinline__ uint64_t seed_of(uint32_t combo, uint32_t parts, uint64_t key, uint64_t badeven, uint32_t len, const uint8_t* bl, bool* skip) {
+    uint64_t x = 0;
+    bool bad = false;
+    for (uint32_t s = 0; s < parts; s++) {
+        if (!((combo >> s) & 1u)) continue;
+        const uint32_t b0 = bl ? bl[s] : s * len / parts, b1 = bl ? bl[s + 1] : (s + 1) * len / parts;
+        const uint32_t w = 2 * (b1 - b0);                              // (<= 32 bits: seed_plan)
+        const uint64_t m = (1ull << w) - 1ull;
+        bad = bad || ((badeven >> (2 * b0)) & m) != 0;
+        x = (x << w) | ((key >> (2 * b0)) & m);
     }
+    *skip = bad;
+    return x;
 }
-// seed `combo` of the key: the chosen segments' symbols, lowest segment on top
+// the host's form (f2q_set_library), from per-segment values and widths
 __host__ __device__ __forceinline__ uint64_t seed_value(uint32_t combo, const uint32_t* v, const uint32_t* w) {
     uint64_t x = 0;
     #pragma unroll
@@ -262,18 +260,18 @@ __device__ __noinline__ uint32_t resolve_seed_classic(const LibTables& T, int m,
     return (b.d <= m && b.n == 1) ? b.idx : RES_NONE;
 }
 
-__device__ __noinline__ uint32_t resolve_seed_thread(const LibTables& T, int m, uint64_t key, uint32_t bad, uint32_t len, const uint8_t* bounds = nullptr) {
+__device__ __forceinline__ uint32_t resolve_seed_inline(const LibTables& T, int m, uint64_t key, uint32_t bad, uint32_t len, const uint8_t* bounds = nullptr) {
     const int nbad = __popc(bad);
     if (m <= 0 || nbad > m) return RES_NONE;
     if (T.seed_ncombo == 0) return resolve_seed_classic(T, m, key, bad, len);
     const uint64_t lenmask = even_range(0, len), badeven = spread_even(bad) & lenmask;
-    SeedSegs S;
-    seed_segments(T.seed_parts, key, badeven, len, bounds ? bounds + len * SEED_BOUND_STRIDE : nullptr, S);
+    const uint8_t* bl = bounds ? bounds + len * SEED_BOUND_STRIDE : nullptr;
     Best b{m + 1, 0, 0};
     for (uint32_t c = 0; c < T.seed_ncombo; c++) {
-        const uint32_t combo = T.seed_combo[c];
-        if (combo & S.badmask) continue;
-        const uint2 bk = seed_bucket(T, seed_tag(len, c, seed_value(combo, S.v, S.w)));
+        bool skip;
+        const uint64_t v = seed_of(T.seed_combo[c], T.seed_parts, key, badeven, len, bl, &skip);
+        if (skip) continue;
+        const uint2 bk = seed_bucket(T, seed_tag(len, c, v));
         for (uint32_t k = 0; k < bk.y; k++) {
             const uint4 it = __ldg(T.seed_recs + bk.x + k);            // {key lo, key hi, feature index, -}: one load per candidate
             const uint64_t x = key ^ (((uint64_t)it.y << 32) | it.x);
@@ -282,6 +280,11 @@ __device__ __noinline__ uint32_t resolve_seed_thread(const LibTables& T, int m, 
         }
     }
     return (b.d <= m && b.n == 1) ? b.idx : RES_NONE;
+}
+// out of line, for the callers in which resolving is the rare case (a full queue inside the streaming kernels): inlined
+// there it costs the hot loop registers (measured: streaming kernel 3.97 -> 3.69 ms with this call out of line)
+__device__ __noinline__ uint32_t resolve_seed_thread(const LibTables& T, int m, uint64_t key, uint32_t bad, uint32_t len, const uint8_t* bounds = nullptr) {
+    return resolve_seed_inline(T, m, key, bad, len, bounds);
 }
 
 __global__ void __launch_bounds__(256) k_resolve_seed(LibTables T, int m, const QEntry* __restrict__ queue, const uint32_t* __restrict__ seg_count,
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(256) k_resolve_seed(LibTables T, int m, const 
         const QEntry* __restrict__ q = queue + (size_t)seg * seg_cap;
         for (uint32_t i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {     // gridDim.y CTAs share a segment
             const QEntry e = q[i];
-            const uint32_t r = resolve_seed_thread(T, m, e.key, e.bad, e.len, e.len <= 32 ? s_bounds : nullptr);
+            const uint32_t r = resolve_seed_inline(T, m, e.key, e.bad, e.len, e.len <= 32 ? s_bounds : nullptr);     // (the kernel's own work: inlined, tables in the constant bank)
             if (r != RES_NONE) { atomicAdd(counts + r, 1ull); imperfect++; } else nonal++;
         }
     }
@@ -326,12 +329,12 @@ __device__ __forceinline__ uint32_t resolve_seed_group(const LibTables& T, int m
     Best b{m + 1, 0, 0};
     if (act && !cached && m > 0 && nbad <= m) {
         const uint64_t lenmask = even_range(0, len), badeven = spread_even(bad) & lenmask;
-        SeedSegs S;
-        seed_segments(T.seed_parts, key, badeven, len, bounds + len * SEED_BOUND_STRIDE, S);
+        const uint8_t* bl = bounds + len * SEED_BOUND_STRIDE;
         for (uint32_t c = 0; c < T.seed_ncombo; c++) {
-            const uint32_t combo = T.seed_combo[c];
-            if (combo & S.badmask) continue;
-            const uint2 bk = seed_bucket(T, seed_tag(len, c, seed_value(combo, S.v, S.w)));
+            bool skip;
+            const uint64_t v = seed_of(T.seed_combo[c], T.seed_parts, key, badeven, len, bl, &skip);
+            if (skip) continue;
+            const uint2 bk = seed_bucket(T, seed_tag(len, c, v));
             for (uint32_t k = gl; k < bk.y; k += (uint32_t)G) {
                 const uint4 it = __ldg(T.seed_recs + bk.x + k);
                 const uint64_t x = key ^ (((uint64_t)it.y << 32) | it.x);
