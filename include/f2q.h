@@ -128,6 +128,8 @@ const char* f2q_last_error(const f2q_ctx* ctx);   /* ctx may be NULL: last creat
  *   "gpu_inflate"     1 (default): f2q_submit_file inflates bgzip (BGZF) files ON THE DEVICE (k_inflate_bgzf_lanes: the 32
  *                     lanes of a warp inflate 32 blocks in lock step; only the compressed bytes cross PCIe) | 0: on host
  *                     threads, block-parallel | 2: on the device, one free-running thread per block (cross-check, slow)
+ *   "gpu_inflate_bits" 0 auto | 8 | 9: index bits of the GPU inflate's literal/length lookup table (8: 640 B of shared memory per
+ *                     lane, 11 warps per SM; 9: 1 280 B, 5 warps; auto takes 8 when a batch has more than 5 warps per SM)
  *   "seed_parts"      0 auto | P: segments of the resolver's seed plan (a key within m mismatches agrees with its library
  *                     entry on some P - m of P segments; seeds = all such choices; auto picks P from the library size);
  *                     set before f2q_set_library.  A P that does not fit (P <= m, more than 32 seeds, seeds longer than
