@@ -1077,7 +1077,7 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
     // pigeonhole seed index for <= miss mismatches (resolve.cuh)
     std::vector<uint4> seed_slots(16, make_uint4(0, 0, 0, 0));
     std::vector<uint4> seed_recs;
-    // seed plan: P segments, seeds = every choice of P - miss of them.  Cost of resolving one key ~ seeds x (1 probe + expected
+    // seed plan: P segments, seeds = every choice of K = P - miss of them.  Cost of resolving one key ~ seeds x (probe + expected
     // bucket length); a seed must fit the tag's 32 value bits (<= 16 symbols) for the longest key
     uint32_t parts = (uint32_t)std::max(1, std::min(c->cfg.miss, 32) + 1);
     std::vector<uint8_t> combos;
@@ -1094,7 +1094,8 @@ F2Q_EXPORT int f2q_set_library(f2q_ctx* c, const uint8_t* key_bytes, const uint6
                 const double seeds = n_choose(P, m);
                 if (seeds > SEED_MAX_COMBOS || K * ((maxlen + P - 1) / P) > 16) continue;
                 if (c->opt_seed_parts && (uint32_t)c->opt_seed_parts != P) continue;
-                const double cost = seeds * (1.0 + (double)fk.size() / std::pow(4.0, (double)K * meanlen / P));
+                // (measured at 100 000 guides, m = 1..3, P = m+1 .. m+3: a probe costs about 1.5 + K candidate compares)
+                const double cost = seeds * (1.5 + (double)K + (double)fk.size() / std::pow(4.0, (double)K * meanlen / P));
                 if (best < 0 || cost < best) { best = cost; parts = P; }
             }
         // (more than SEED_MAX_PARTS - 1 mismatches, or no plan that fits: the classic one-segment seeds, miss + 1 of them, no
